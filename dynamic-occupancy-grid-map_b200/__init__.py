@@ -1,0 +1,565 @@
+"""dogm_b200 — thin Python binding (ctypes + numpy) over the C ABI of libdogm_b200.so.
+
+The product is the shared library (hand-written sm_100a CUDA kernels behind ``include/dogm_b200.h``); this module
+only exists so that tests and ``bench.py`` can drive that ABI.  It mirrors the reference's ``dogm::DOGM`` class
+(reference ``dogm/include/dogm/dogm.h:20-199``): same method names in snake_case, same argument meaning, and the
+same tolerant error behaviour (CUDA errors are printed as ``GPU Kernel Error: ...`` by the library; here they
+additionally raise ``DogmError`` so that tests fail loudly).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present, construction raises.
+
+The directory name contains hyphens, so load it with ``tests/_loader.py`` (``load_dogm_b200()``), which registers
+it as the module ``dogm_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdogm_b200.so")
+
+# ----------------------------------------------------------------------------------------------------------
+# layouts (bit-identical to the reference's PODs, dogm_types.h:13-41 and dogm.h:26-60)
+# ----------------------------------------------------------------------------------------------------------
+GRID_CELL_DTYPE = np.dtype(
+    [
+        ("start_idx", "<i4"),
+        ("end_idx", "<i4"),
+        ("new_born_occ_mass", "<f4"),
+        ("pers_occ_mass", "<f4"),
+        ("free_mass", "<f4"),
+        ("occ_mass", "<f4"),
+        ("pred_occ_mass", "<f4"),
+        ("mu_A", "<f4"),
+        ("mu_UA", "<f4"),
+        ("w_A", "<f4"),
+        ("w_UA", "<f4"),
+        ("mean_x_vel", "<f4"),
+        ("mean_y_vel", "<f4"),
+        ("var_x_vel", "<f4"),
+        ("var_y_vel", "<f4"),
+        ("covar_xy_vel", "<f4"),
+    ]
+)
+MEAS_CELL_DTYPE = np.dtype([("free_mass", "<f4"), ("occ_mass", "<f4"), ("likelihood", "<f4"), ("p_A", "<f4")])
+DYNAMIC_CELL_DTYPE = np.dtype(
+    [
+        ("cell_idx", "<i4"),
+        ("occupancy", "<f4"),
+        ("mean_x_vel", "<f4"),
+        ("mean_y_vel", "<f4"),
+        ("var_x_vel", "<f4"),
+        ("var_y_vel", "<f4"),
+        ("covar_xy_vel", "<f4"),
+        ("mahalanobis", "<f4"),
+    ]
+)
+assert GRID_CELL_DTYPE.itemsize == 64 and MEAS_CELL_DTYPE.itemsize == 16 and DYNAMIC_CELL_DTYPE.itemsize == 32
+
+RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_INJECTED = 0, 1, 2
+NOISE_PHILOX, NOISE_INJECTED = 0, 1
+
+
+class Params(C.Structure):
+    """== dogm::DOGM::Params (dogm.h:26-60)."""
+
+    _fields_ = [
+        ("size", C.c_float),
+        ("resolution", C.c_float),
+        ("particle_count", C.c_int),
+        ("new_born_particle_count", C.c_int),
+        ("persistence_prob", C.c_float),
+        ("stddev_process_noise_position", C.c_float),
+        ("stddev_process_noise_velocity", C.c_float),
+        ("birth_prob", C.c_float),
+        ("stddev_velocity", C.c_float),
+        ("init_max_velocity", C.c_float),
+        ("freespace_discount", C.c_float),
+    ]
+
+
+GridParams = Params  # the name used by BASELINE.json's north_star
+
+
+class LaserSensorParams(C.Structure):
+    """== LaserMeasurementGrid::Params (laser_to_meas_grid.h:16-22)."""
+
+    _fields_ = [("max_range", C.c_float), ("resolution", C.c_float), ("fov", C.c_float), ("stddev_range", C.c_float)]
+
+
+class Options(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("resample_mode", C.c_int), ("noise_mode", C.c_int)]
+
+
+class DevicePtrs(C.Structure):
+    _fields_ = [
+        ("grid_cell_array", C.c_void_p),
+        ("particle_array", C.c_void_p),
+        ("particle_array_next", C.c_void_p),
+        ("birth_particle_array", C.c_void_p),
+        ("meas_cell_array", C.c_void_p),
+        ("weight_array", C.c_void_p),
+        ("born_masses_array", C.c_void_p),
+        ("resampled_idx_array", C.c_void_p),
+        ("joint_weight_accum", C.c_void_p),
+        ("cell_start_array", C.c_void_p),
+        ("cell_end_array", C.c_void_p),
+    ]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("total_ms", C.c_double), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_double)]
+
+
+class DogmError(RuntimeError):
+    pass
+
+
+# every symbol include/dogm_b200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SYMBOLS = [
+    ("dogm_create", C.c_int, [C.POINTER(Params), C.POINTER(_P)]),
+    ("dogm_destroy", None, [_P]),
+    ("dogm_update_grid", C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]),
+    ("dogm_update_grid_async", C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]),
+    ("dogm_synchronize", C.c_int, [_P]),
+    ("dogm_initialize_particles", C.c_int, [_P]),
+    ("dogm_particle_prediction", C.c_int, [_P, C.c_float]),
+    ("dogm_particle_assignment", C.c_int, [_P]),
+    ("dogm_grid_cell_occupancy_update", C.c_int, [_P, C.c_float]),
+    ("dogm_update_persistent_particles", C.c_int, [_P]),
+    ("dogm_initialize_new_particles", C.c_int, [_P]),
+    ("dogm_statistical_moments", C.c_int, [_P]),
+    ("dogm_resampling", C.c_int, [_P]),
+    ("dogm_get_grid_cells", C.c_int, [_P, _P]),
+    ("dogm_get_measurement_cells", C.c_int, [_P, _P]),
+    ("dogm_get_particles", C.c_int, [_P, _P]),
+    ("dogm_get_grid_size", C.c_int, [_P]),
+    ("dogm_get_grid_cell_count", C.c_int, [_P]),
+    ("dogm_get_particle_count", C.c_int, [_P]),
+    ("dogm_get_new_born_particle_count", C.c_int, [_P]),
+    ("dogm_get_resolution", C.c_float, [_P]),
+    ("dogm_get_position_x", C.c_float, [_P]),
+    ("dogm_get_position_y", C.c_float, [_P]),
+    ("dogm_get_yaw", C.c_float, [_P]),
+    ("dogm_get_device_ptrs", C.c_int, [_P, C.POINTER(DevicePtrs)]),
+    ("dogm_set_options", C.c_int, [_P, C.POINTER(Options)]),
+    ("dogm_get_options", C.c_int, [_P, C.POINTER(Options)]),
+    ("dogm_set_noise", C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
+    ("dogm_export_philox_noise", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    ("dogm_get_cycle_counter", C.c_uint32, [_P]),
+    ("dogm_set_particles", C.c_int, [_P, _P, C.c_int]),
+    ("dogm_set_birth_particles", C.c_int, [_P, _P, C.c_int]),
+    ("dogm_set_grid_cells", C.c_int, [_P, _P, C.c_int]),
+    ("dogm_set_measurement_cells", C.c_int, [_P, _P, C.c_int]),
+    ("dogm_set_pose", C.c_int, [_P, C.c_float, C.c_float, C.c_float]),
+    ("dogm_get_birth_particles", C.c_int, [_P, _P]),
+    ("dogm_get_weight_array", C.c_int, [_P, _P]),
+    ("dogm_get_born_masses", C.c_int, [_P, _P]),
+    ("dogm_get_resampled_indices", C.c_int, [_P, _P]),
+    ("dogm_get_joint_weight_accum", C.c_int, [_P, _P]),
+    ("dogm_get_cell_ranges", C.c_int, [_P, _P, _P]),
+    ("dogm_search_ancestors_f32", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
+    ("dogm_meas_create", C.c_int, [C.POINTER(LaserSensorParams), C.c_float, C.c_float, C.POINTER(_P)]),
+    ("dogm_meas_destroy", None, [_P]),
+    ("dogm_meas_generate", C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
+    ("dogm_meas_generate_into", C.c_int, [_P, _P, _P, C.c_int]),
+    ("dogm_meas_polar_grid", C.c_int, [_P, _P, C.c_int, _P]),
+    ("dogm_meas_get_grid_size", C.c_int, [_P]),
+    ("dogm_extract_dynamic_cells", C.c_int, [_P, C.c_float, C.c_float, _P, C.c_int, C.POINTER(C.c_int)]),
+    ("dogm_get_stream", _P, [_P]),
+    ("dogm_get_launch_count", C.c_uint64, [_P]),
+    ("dogm_kernel_timing_enable", C.c_int, [_P, C.c_int]),
+    ("dogm_kernel_timing_read", C.c_int, [_P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]),
+    ("dogm_host_alloc_pinned", C.c_int, [C.POINTER(_P), C.c_size_t]),
+    ("dogm_host_free_pinned", C.c_int, [_P]),
+    ("dogm_device_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
+    ("dogm_device_free", C.c_int, [_P]),
+    ("dogm_memcpy_h2d", C.c_int, [_P, _P, C.c_size_t]),
+    ("dogm_memcpy_d2h", C.c_int, [_P, _P, C.c_size_t]),
+    ("dogm_device_count", C.c_int, []),
+    ("dogm_set_device", C.c_int, [C.c_int]),
+    ("dogm_b200_version", C.c_char_p, []),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SYMBOLS]
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libdogm_b200.so in-tree for sm_100a (nvcc; cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise DogmError("building libdogm_b200.so failed")
+    return LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """dlopen the C-ABI library and bind every declared symbol.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DogmError(
+            f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+            "(or __graft_entry__.build()); there is no CPU fallback"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in _SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def _check(code: int, what: str) -> None:
+    if code != 0:
+        raise DogmError(f"{what} failed with code {code}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    assert isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+class ParticlesSoA:
+    """Host view of a particle block in the reference's layout (ParticlesSoA, dogm_types.h:51-144)."""
+
+    def __init__(self, n: int, block: np.ndarray | None = None):
+        self.size = n
+        self.block = np.zeros(n * 28, dtype=np.uint8) if block is None else block
+        assert self.block.dtype == np.uint8 and self.block.size == n * 28
+        b = self.block
+        self.state = b[: 16 * n].view("<f4").reshape(n, 4)
+        self.grid_cell_idx = b[16 * n : 20 * n].view("<i4")
+        self.weight = b[20 * n : 24 * n].view("<f4")
+        self.associated = b[24 * n : 25 * n].view(np.uint8)
+
+    @classmethod
+    def from_arrays(cls, state, grid_cell_idx, weight, associated=None) -> "ParticlesSoA":
+        n = len(weight)
+        p = cls(n)
+        p.state[:] = np.asarray(state, dtype=np.float32).reshape(n, 4)
+        p.grid_cell_idx[:] = np.asarray(grid_cell_idx, dtype=np.int32)
+        p.weight[:] = np.asarray(weight, dtype=np.float32)
+        if associated is not None:
+            p.associated[:] = np.asarray(associated, dtype=np.uint8)
+        return p
+
+
+class DOGM:
+    """Mirror of dogm::DOGM (dogm.h:20-199) over the C ABI."""
+
+    def __init__(self, params: Params):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = params
+        _check(self._lib.dogm_create(C.byref(params), C.byref(self._h)), "dogm_create")
+        self.grid_size = self._lib.dogm_get_grid_size(self._h)
+        self.grid_cell_count = self._lib.dogm_get_grid_cell_count(self._h)
+        self.particle_count = self._lib.dogm_get_particle_count(self._h)
+        self.new_born_particle_count = self._lib.dogm_get_new_born_particle_count(self._h)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.dogm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- the cycle (dogm.cu:115-131) -----------------------------------------------------------------------
+    def update_grid(self, measurement_grid, new_x, new_y, new_yaw, dt, device=True, sync=True) -> None:
+        """updateGrid(measurement_grid, new_x, new_y, new_yaw, dt, device).  `measurement_grid` is a device pointer
+        (int) when device=True, a MEAS_CELL_DTYPE array when device=False, or None (keep the previous grid)."""
+        if measurement_grid is not None and not device:
+            assert measurement_grid.dtype == MEAS_CELL_DTYPE and measurement_grid.size == self.grid_cell_count
+        fn = self._lib.dogm_update_grid if sync else self._lib.dogm_update_grid_async
+        _check(fn(self._h, _ptr(measurement_grid), new_x, new_y, new_yaw, dt, 1 if device else 0), "dogm_update_grid")
+
+    def synchronize(self) -> None:
+        _check(self._lib.dogm_synchronize(self._h), "dogm_synchronize")
+
+    def initialize_particles(self):
+        _check(self._lib.dogm_initialize_particles(self._h), "dogm_initialize_particles")
+
+    def particle_prediction(self, dt):
+        _check(self._lib.dogm_particle_prediction(self._h, dt), "dogm_particle_prediction")
+
+    def particle_assignment(self):
+        _check(self._lib.dogm_particle_assignment(self._h), "dogm_particle_assignment")
+
+    def grid_cell_occupancy_update(self, dt):
+        _check(self._lib.dogm_grid_cell_occupancy_update(self._h, dt), "dogm_grid_cell_occupancy_update")
+
+    def update_persistent_particles(self):
+        _check(self._lib.dogm_update_persistent_particles(self._h), "dogm_update_persistent_particles")
+
+    def initialize_new_particles(self):
+        _check(self._lib.dogm_initialize_new_particles(self._h), "dogm_initialize_new_particles")
+
+    def statistical_moments(self):
+        _check(self._lib.dogm_statistical_moments(self._h), "dogm_statistical_moments")
+
+    def resampling(self):
+        _check(self._lib.dogm_resampling(self._h), "dogm_resampling")
+
+    # --- read-out (dogm.cu:133-159) ------------------------------------------------------------------------
+    def get_grid_cells(self, out: np.ndarray | None = None) -> np.ndarray:
+        out = np.empty(self.grid_cell_count, dtype=GRID_CELL_DTYPE) if out is None else out
+        _check(self._lib.dogm_get_grid_cells(self._h, _ptr(out)), "dogm_get_grid_cells")
+        return out
+
+    def get_measurement_cells(self) -> np.ndarray:
+        out = np.empty(self.grid_cell_count, dtype=MEAS_CELL_DTYPE)
+        _check(self._lib.dogm_get_measurement_cells(self._h, _ptr(out)), "dogm_get_measurement_cells")
+        return out
+
+    def get_particles(self) -> ParticlesSoA:
+        p = ParticlesSoA(self.particle_count)
+        _check(self._lib.dogm_get_particles(self._h, _ptr(p.block)), "dogm_get_particles")
+        return p
+
+    def get_birth_particles(self) -> ParticlesSoA:
+        p = ParticlesSoA(self.new_born_particle_count)
+        _check(self._lib.dogm_get_birth_particles(self._h, _ptr(p.block)), "dogm_get_birth_particles")
+        return p
+
+    def get_weight_array(self) -> np.ndarray:
+        out = np.empty(self.particle_count, dtype=np.float32)
+        _check(self._lib.dogm_get_weight_array(self._h, _ptr(out)), "dogm_get_weight_array")
+        return out
+
+    def get_born_masses(self) -> np.ndarray:
+        out = np.empty(self.grid_cell_count, dtype=np.float32)
+        _check(self._lib.dogm_get_born_masses(self._h, _ptr(out)), "dogm_get_born_masses")
+        return out
+
+    def get_resampled_indices(self) -> np.ndarray:
+        out = np.empty(self.particle_count, dtype=np.int32)
+        _check(self._lib.dogm_get_resampled_indices(self._h, _ptr(out)), "dogm_get_resampled_indices")
+        return out
+
+    def get_joint_weight_accum(self) -> np.ndarray:
+        out = np.empty(self.particle_count + self.new_born_particle_count, dtype=np.float64)
+        _check(self._lib.dogm_get_joint_weight_accum(self._h, _ptr(out)), "dogm_get_joint_weight_accum")
+        return out
+
+    def get_cell_ranges(self):
+        s = np.empty(self.grid_cell_count, dtype=np.int32)
+        e = np.empty(self.grid_cell_count, dtype=np.int32)
+        _check(self._lib.dogm_get_cell_ranges(self._h, _ptr(s), _ptr(e)), "dogm_get_cell_ranges")
+        return s, e
+
+    def get_grid_size(self) -> int:
+        return self._lib.dogm_get_grid_size(self._h)
+
+    def get_resolution(self) -> float:
+        return self._lib.dogm_get_resolution(self._h)
+
+    def get_position_x(self) -> float:
+        return self._lib.dogm_get_position_x(self._h)
+
+    def get_position_y(self) -> float:
+        return self._lib.dogm_get_position_y(self._h)
+
+    def get_yaw(self) -> float:
+        return self._lib.dogm_get_yaw(self._h)
+
+    def device_ptrs(self) -> DevicePtrs:
+        d = DevicePtrs()
+        _check(self._lib.dogm_get_device_ptrs(self._h, C.byref(d)), "dogm_get_device_ptrs")
+        return d
+
+    # --- options / parity hooks ----------------------------------------------------------------------------
+    def set_options(self, seed=123456, resample_mode=RESAMPLE_SYSTEMATIC, noise_mode=NOISE_PHILOX) -> None:
+        o = Options(seed, resample_mode, noise_mode)
+        _check(self._lib.dogm_set_options(self._h, C.byref(o)), "dogm_set_options")
+
+    def set_noise(self, predict_noise=None, birth_noise=None, init_velocity=None, resample_u=None) -> None:
+        def prep(a, count):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.size == count, (a.size, count)
+            return a
+
+        N, B = self.particle_count, self.new_born_particle_count
+        bufs = [prep(predict_noise, 4 * N), prep(birth_noise, 2 * B), prep(init_velocity, 2 * N), prep(resample_u, N)]
+        _check(self._lib.dogm_set_noise(self._h, *[_ptr(b) for b in bufs], 0), "dogm_set_noise")
+
+    def export_philox_noise(self, cycle: int):
+        N, B = self.particle_count, self.new_born_particle_count
+        pn = np.empty((N, 4), np.float32)
+        bn = np.empty((B, 2), np.float32)
+        iv = np.empty((N, 2), np.float32)
+        ru = np.empty(N, np.float32)
+        _check(
+            self._lib.dogm_export_philox_noise(self._h, cycle, _ptr(pn), _ptr(bn), _ptr(iv), _ptr(ru)),
+            "dogm_export_philox_noise",
+        )
+        return pn, bn, iv, ru
+
+    def cycle_counter(self) -> int:
+        return self._lib.dogm_get_cycle_counter(self._h)
+
+    def set_particles(self, p: ParticlesSoA) -> None:
+        assert p.size == self.particle_count
+        _check(self._lib.dogm_set_particles(self._h, _ptr(p.block), 0), "dogm_set_particles")
+
+    def set_birth_particles(self, p: ParticlesSoA) -> None:
+        assert p.size == self.new_born_particle_count
+        _check(self._lib.dogm_set_birth_particles(self._h, _ptr(p.block), 0), "dogm_set_birth_particles")
+
+    def set_grid_cells(self, cells: np.ndarray) -> None:
+        assert cells.dtype == GRID_CELL_DTYPE and cells.size == self.grid_cell_count
+        _check(self._lib.dogm_set_grid_cells(self._h, _ptr(np.ascontiguousarray(cells)), 0), "dogm_set_grid_cells")
+
+    def set_measurement_cells(self, cells: np.ndarray) -> None:
+        assert cells.dtype == MEAS_CELL_DTYPE and cells.size == self.grid_cell_count
+        _check(
+            self._lib.dogm_set_measurement_cells(self._h, _ptr(np.ascontiguousarray(cells)), 0),
+            "dogm_set_measurement_cells",
+        )
+
+    def set_pose(self, x, y, yaw=0.0) -> None:
+        _check(self._lib.dogm_set_pose(self._h, x, y, yaw), "dogm_set_pose")
+
+    def search_ancestors_f32(self, cdf: np.ndarray, sorted_draws: np.ndarray) -> np.ndarray:
+        cdf = np.ascontiguousarray(cdf, dtype=np.float32)
+        draws = np.ascontiguousarray(sorted_draws, dtype=np.float32)
+        out = np.empty(draws.size, dtype=np.int32)
+        _check(
+            self._lib.dogm_search_ancestors_f32(self._h, _ptr(cdf), cdf.size, _ptr(draws), draws.size, _ptr(out)),
+            "dogm_search_ancestors_f32",
+        )
+        return out
+
+    def extract_dynamic_cells(self, min_occupancy: float, min_velocity: float, capacity: int = 1 << 16):
+        out = np.empty(capacity, dtype=DYNAMIC_CELL_DTYPE)
+        count = C.c_int(0)
+        _check(
+            self._lib.dogm_extract_dynamic_cells(self._h, min_occupancy, min_velocity, _ptr(out), capacity, C.byref(count)),
+            "dogm_extract_dynamic_cells",
+        )
+        return out[: min(count.value, capacity)], count.value
+
+    # --- instrumentation -----------------------------------------------------------------------------------
+    def stream(self) -> int:
+        return int(self._lib.dogm_get_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self._lib.dogm_get_launch_count(self._h))
+
+    def kernel_timing_enable(self, enable: bool) -> None:
+        _check(self._lib.dogm_kernel_timing_enable(self._h, 1 if enable else 0), "dogm_kernel_timing_enable")
+
+    def kernel_timing_read(self) -> dict:
+        arr = (KernelTime * 48)()
+        n = C.c_int(0)
+        _check(self._lib.dogm_kernel_timing_read(self._h, arr, 48, C.byref(n)), "dogm_kernel_timing_read")
+        return {
+            arr[i].name.decode(): {
+                "total_ms": arr[i].total_ms,
+                "launches": int(arr[i].launches),
+                "algorithmic_bytes": arr[i].algorithmic_bytes,
+            }
+            for i in range(n.value)
+        }
+
+
+class LaserMeasurementGrid:
+    """Mirror of LaserMeasurementGrid (laser_to_meas_grid.h:13-35): host beam ranges -> device MeasurementCell[]."""
+
+    def __init__(self, params: LaserSensorParams, grid_length: float, resolution: float):
+        self._lib = load_library()
+        self._m = C.c_void_p()
+        self.params = params
+        _check(self._lib.dogm_meas_create(C.byref(params), grid_length, resolution, C.byref(self._m)), "dogm_meas_create")
+        self.grid_size = self._lib.dogm_meas_get_grid_size(self._m)
+
+    def close(self) -> None:
+        if getattr(self, "_m", None) is not None and self._m:
+            self._lib.dogm_meas_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def generate_grid(self, measurements) -> int:
+        """generateGrid(measurements) -> device pointer owned by the generator (laser_to_meas_grid.cu:25-70)."""
+        beams = np.ascontiguousarray(measurements, dtype=np.float32)
+        out = C.c_void_p()
+        _check(self._lib.dogm_meas_generate(self._m, _ptr(beams), beams.size, C.byref(out)), "dogm_meas_generate")
+        return int(out.value)
+
+    def generate_grid_into(self, dogm: DOGM, measurements) -> None:
+        beams = np.ascontiguousarray(measurements, dtype=np.float32)
+        _check(self._lib.dogm_meas_generate_into(self._m, dogm._h, _ptr(beams), beams.size), "dogm_meas_generate_into")
+
+    def generate_grid_host(self, measurements) -> np.ndarray:
+        ptr = self.generate_grid(measurements)
+        out = np.empty(self.grid_size * self.grid_size, dtype=MEAS_CELL_DTYPE)
+        _check(self._lib.dogm_memcpy_d2h(_ptr(out), C.c_void_p(ptr), out.nbytes), "dogm_memcpy_d2h")
+        return out
+
+    def polar_grid(self, measurements) -> np.ndarray:
+        beams = np.ascontiguousarray(measurements, dtype=np.float32)
+        H = int(np.float32(self.params.max_range) / np.float32(self.params.resolution))
+        out = np.empty((H, beams.size, 2), dtype=np.float32)
+        _check(self._lib.dogm_meas_polar_grid(self._m, _ptr(beams), beams.size, _ptr(out)), "dogm_meas_polar_grid")
+        return out
+
+
+def device_count() -> int:
+    return load_library().dogm_device_count()
+
+
+def set_device(i: int) -> None:
+    _check(load_library().dogm_set_device(i), "dogm_set_device")
+
+
+def device_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load_library().dogm_device_alloc(C.byref(p), nbytes), "dogm_device_alloc")
+    return int(p.value)
+
+
+def device_free(ptr: int) -> None:
+    _check(load_library().dogm_device_free(C.c_void_p(ptr)), "dogm_device_free")
+
+
+def memcpy_h2d(dst: int, src: np.ndarray) -> None:
+    _check(load_library().dogm_memcpy_h2d(C.c_void_p(dst), _ptr(np.ascontiguousarray(src)), src.nbytes), "dogm_memcpy_h2d")
+
+
+def memcpy_d2h(dst: np.ndarray, src: int) -> None:
+    _check(load_library().dogm_memcpy_d2h(_ptr(dst), C.c_void_p(src), dst.nbytes), "dogm_memcpy_d2h")
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by cudaMallocHost memory (never freed explicitly: lives for the process)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(load_library().dogm_host_alloc_pinned(C.byref(p), max(n, 16)), "dogm_host_alloc_pinned")
+    buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

@@ -1,0 +1,848 @@
+// C ABI of libdogm_b200 (include/dogm_b200.h): host orchestration of the DOGM cycle.
+// One stream, every buffer allocated once in dogm_create, no allocation / host read-back inside a cycle
+// (the reference does ~26 cudaMalloc/cudaFree pairs and 3 blocking scalar copies per cycle).
+#include "dogm_internal.cuh"
+
+#include <cmath>
+#include <new>
+
+using namespace dogm_b200;
+
+namespace dogm_b200
+{
+
+void launch_begin(dogm_handle* h, int id, double algorithmic_bytes)
+{
+    if (id != K_MEMSET)
+        h->launch_count++;
+    h->last_bytes[id] = algorithmic_bytes;
+    if (!h->timing)
+        return;
+    TimedLaunch t;
+    t.id = id;
+    for (int k = 0; k < 2; k++)
+    {
+        cudaEvent_t e;
+        if (!h->event_pool.empty())
+        {
+            e = h->event_pool.back();
+            h->event_pool.pop_back();
+        }
+        else
+        {
+            cudaEventCreate(&e);
+        }
+        if (k == 0)
+            t.e0 = e;
+        else
+            t.e1 = e;
+    }
+    cudaEventRecord(t.e0, h->stream);
+    h->timed.push_back(t);
+}
+
+void launch_end(dogm_handle* h, int id)
+{
+    (void)id;
+    if (!h->timing)
+        return;
+    cudaEventRecord(h->timed.back().e1, h->stream);
+}
+
+} // namespace dogm_b200
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+static int alloc_zero(void** p, size_t bytes)
+{
+    if (bytes == 0)
+        bytes = 16;
+    DOGM_CHECK(cudaMalloc(p, bytes));
+    DOGM_CHECK(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+static void plan_sort(dogm_handle* h)
+{
+    int bits = 1;
+    while ((1ll << bits) < (long long)h->C)
+        bits++;
+    h->key_bits = bits;
+    int passes = (bits + kMaxDigitBits - 1) / kMaxDigitBits;
+    if (passes < 1)
+        passes = 1;
+    h->passes = passes;
+    int shift = 0;
+    for (int p = 0; p < passes; p++)
+    {
+        int d = (bits - shift + (passes - p) - 1) / (passes - p); // spread the remaining bits evenly
+        if (d < 5)
+            d = 5;
+        h->digit_shift[p] = shift;
+        h->digit_bins[p] = 1 << d;
+        shift += d;
+    }
+    h->tiles = div_up(h->N > 0 ? h->N : 1, kTileItems);
+}
+
+static int copy_in(void* dst_device, const void* src, size_t bytes, int on_device, cudaStream_t s)
+{
+    return (int)cudaMemcpyAsync(dst_device, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// life cycle
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
+{
+    if (!params || !out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!(params->resolution > 0.0f) || params->particle_count < 0 || params->new_born_particle_count < 0)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    const int gs = (int)(params->size / params->resolution); // dogm.cu:34
+    if (gs <= 0 || (long long)gs * gs > (1ll << 30))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if ((long long)params->particle_count + params->new_born_particle_count >= (1ll << 31))
+        return DOGM_ERR_INVALID_ARGUMENT;
+
+    int device = 0;
+    DOGM_CHECK(cudaGetDevice(&device)); // binds to the current device, dogm.cu:39-43
+    int sm_count = 0;
+    DOGM_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    DOGM_CHECK((cudaError_t)configure_kernels());
+
+    dogm_handle* h = new (std::nothrow) dogm_handle();
+    if (!h)
+        return (int)cudaErrorMemoryAllocation;
+    h->params = *params;
+    h->opts.seed = 123456ull; // the reference's seed, dogm.cu:101
+    h->opts.resample_mode = DOGM_RESAMPLE_SYSTEMATIC;
+    h->opts.noise_mode = DOGM_NOISE_PHILOX;
+    h->gs = gs;
+    h->C = gs * gs;
+    h->N = params->particle_count;
+    h->B = params->new_born_particle_count;
+    h->device = device;
+    h->sm_count = sm_count;
+    h->first_pose_received = false;
+    h->first_measurement_received = false;
+    h->position_x = h->position_y = h->yaw = 0.0f;
+    h->shift.active = 0;
+    h->shift.x_move = h->shift.y_move = 0;
+    h->shift_particles_pending = h->shift_grid_pending = false;
+    h->cycle = 0;
+    h->hist0_valid = false;
+    h->launch_count = 0;
+    h->timing = false;
+    h->predict_noise = nullptr;
+    h->birth_noise = nullptr;
+    h->init_velocity = nullptr;
+    h->resample_u = nullptr;
+    h->dyn_buf = nullptr;
+    h->dyn_capacity = 0;
+    h->dyn_count = nullptr;
+    h->dyn_count_host = nullptr;
+    for (int k = 0; k < K_COUNT; k++)
+    {
+        h->acc_ms[k] = 0.0;
+        h->acc_launches[k] = 0;
+        h->last_bytes[k] = 0.0;
+    }
+    plan_sort(h);
+    h->n_cell_blocks = div_up(h->C, kCellBlock);
+    h->n_chunks = div_up(h->N > 0 ? h->N : 1, kSegChunk);
+    h->n_cdf_tiles = div_up((long long)h->N + h->B > 0 ? (long long)h->N + h->B : 1, kCdfTile);
+
+    DOGM_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    const size_t C = (size_t)h->C, N = (size_t)h->N, B = (size_t)h->B;
+    void* blk;
+    int e = 0;
+    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
+    particle_set_assign(h->pa, blk, h->N);
+    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
+    particle_set_assign(h->pb, blk, h->N);
+    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(B));
+    particle_set_assign(h->birth, blk, h->B);
+    e |= alloc_zero((void**)&h->grid, C * sizeof(dogm_grid_cell));
+    e |= alloc_zero((void**)&h->meas, C * sizeof(dogm_meas_cell));
+    e |= alloc_zero((void**)&h->weight_array, N * sizeof(float));
+    e |= alloc_zero((void**)&h->born_masses, C * sizeof(float));
+    e |= alloc_zero((void**)&h->free_cur, C * sizeof(float));
+    e |= alloc_zero((void**)&h->free_next, C * sizeof(float));
+    e |= alloc_zero((void**)&h->cell_start, C * sizeof(int));
+    e |= alloc_zero((void**)&h->cell_end, C * sizeof(int));
+    e |= alloc_zero((void**)&h->cell_sums, C * sizeof(CellSums));
+    e |= alloc_zero((void**)&h->cell_coef, C * sizeof(float4));
+    e |= alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double));
+    e |= alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double));
+    e |= alloc_zero((void**)&h->slot_end, C * sizeof(int));
+    e |= alloc_zero((void**)&h->blk_slot_end, (size_t)h->n_cell_blocks * sizeof(int));
+    for (int p = 0; p < kMaxPasses; p++)
+    {
+        h->hist[p] = nullptr;
+        h->bin_tot[p] = nullptr;
+        h->bin_base[p] = nullptr;
+    }
+    for (int p = 0; p < h->passes; p++)
+    {
+        e |= alloc_zero((void**)&h->hist[p], (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t));
+        e |= alloc_zero((void**)&h->bin_tot[p], (size_t)h->digit_bins[p] * sizeof(uint32_t));
+        e |= alloc_zero((void**)&h->bin_base[p], (size_t)h->digit_bins[p] * sizeof(uint32_t));
+    }
+    e |= alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece));
+    e |= alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece));
+    e |= alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int));
+    e |= alloc_zero((void**)&h->cdf, (N + B) * sizeof(double));
+    e |= alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double));
+    e |= alloc_zero((void**)&h->tile_off, (size_t)h->n_cdf_tiles * sizeof(double));
+    e |= alloc_zero((void**)&h->ancestors, N * sizeof(int));
+    e |= alloc_zero((void**)&h->scal, sizeof(DeviceScalars));
+    if (e)
+    {
+        dogm_destroy(h);
+        return e;
+    }
+    e = run_init_grid(h); // DOGM::initialize, dogm.cu:95-113
+    if (e == 0)
+        e = (int)cudaStreamSynchronize(h->stream);
+    if (e)
+    {
+        dogm_destroy(h);
+        return e;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" void dogm_destroy(dogm_handle* h)
+{
+    if (!h)
+        return;
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->pa.block);
+    cudaFree(h->pb.block);
+    cudaFree(h->birth.block);
+    cudaFree(h->grid);
+    cudaFree(h->meas);
+    cudaFree(h->weight_array);
+    cudaFree(h->born_masses);
+    cudaFree(h->free_cur);
+    cudaFree(h->free_next);
+    cudaFree(h->cell_start);
+    cudaFree(h->cell_end);
+    cudaFree(h->cell_sums);
+    cudaFree(h->cell_coef);
+    cudaFree(h->blk_sum);
+    cudaFree(h->blk_off);
+    cudaFree(h->slot_end);
+    cudaFree(h->blk_slot_end);
+    for (int p = 0; p < kMaxPasses; p++)
+    {
+        cudaFree(h->hist[p]);
+        cudaFree(h->bin_tot[p]);
+        cudaFree(h->bin_base[p]);
+    }
+    cudaFree(h->seg_lead);
+    cudaFree(h->seg_trail);
+    cudaFree(h->seg_flags);
+    cudaFree(h->cdf);
+    cudaFree(h->tile_sum);
+    cudaFree(h->tile_off);
+    cudaFree(h->ancestors);
+    cudaFree(h->scal);
+    cudaFree(h->predict_noise);
+    cudaFree(h->birth_noise);
+    cudaFree(h->init_velocity);
+    cudaFree(h->resample_u);
+    cudaFree(h->dyn_buf);
+    cudaFree(h->dyn_count);
+    if (h->dyn_count_host)
+        cudaFreeHost(h->dyn_count_host);
+    for (auto& t : h->timed)
+    {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    for (auto& ev : h->event_pool)
+        cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the cycle
+// ---------------------------------------------------------------------------------------------------------
+static int noise_ready(const dogm_handle* h, bool first_cycle)
+{
+    if (h->opts.noise_mode != DOGM_NOISE_INJECTED)
+    {
+        if (h->opts.resample_mode == DOGM_RESAMPLE_INJECTED && !h->resample_u)
+            return DOGM_ERR_NOT_INITIALIZED;
+        return 0;
+    }
+    if ((h->N > 0 && !h->predict_noise) || (h->B > 0 && !h->birth_noise) || (h->N > 0 && !h->resample_u))
+        return DOGM_ERR_NOT_INITIALIZED;
+    if (first_cycle && h->N > 0 && !h->init_velocity)
+        return DOGM_ERR_NOT_INITIALIZED;
+    return 0;
+}
+
+// updatePose, dogm.cu:161-203: only the bookkeeping happens here; the particle shift is folded into the
+// prediction kernel and the grid shift into the cell kernel
+static void update_pose(dogm_handle* h, float new_x, float new_y, float new_yaw)
+{
+    h->shift.active = 0;
+    h->shift_particles_pending = h->shift_grid_pending = false;
+    if (!h->first_pose_received)
+    {
+        h->position_x = new_x;
+        h->position_y = new_y;
+        h->yaw = new_yaw;
+        h->first_pose_received = true;
+        return;
+    }
+    const float x_diff = new_x - h->position_x;
+    const float y_diff = new_y - h->position_y;
+    if (fabsf(x_diff) > h->params.resolution || fabsf(y_diff) > h->params.resolution)
+    {
+        h->shift.x_move = -(int)(x_diff / h->params.resolution);
+        h->shift.y_move = -(int)(y_diff / h->params.resolution);
+        h->shift.active = 1;
+        h->shift_particles_pending = h->shift_grid_pending = true;
+        h->position_x = new_x;
+        h->position_y = new_y;
+        h->yaw = new_yaw;
+    }
+}
+
+static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float new_x, float new_y, float new_yaw, float dt,
+                            int on_device, bool sync)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = noise_ready(h, !h->first_measurement_received);
+    if (e)
+        return e;
+    // updateMeasurementGrid, dogm.cu:205-215
+    if (meas && meas != h->meas)
+    {
+        LaunchScope ls(h, K_MEMSET, 32.0 * h->C);
+        DOGM_CHECK((cudaError_t)copy_in(h->meas, meas, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+    }
+    if (!h->first_measurement_received)
+    {
+        e = run_init_particles(h);
+        if (e)
+            return e;
+        h->first_measurement_received = true;
+    }
+    update_pose(h, new_x, new_y, new_yaw);
+
+    if ((e = run_predict(h, dt)))
+        return e;
+    if ((e = run_assignment(h)))
+        return e;
+    if ((e = run_occupancy_update(h, dt)))
+        return e;
+    if ((e = run_persistent_weights(h)))
+        return e;
+    if ((e = run_birth(h)))
+        return e;
+    if ((e = run_resampling(h)))
+        return e;
+    h->cycle++;
+    if (sync)
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_update_grid(dogm_handle* h, const dogm_meas_cell* measurement_grid, float new_x, float new_y,
+                                float new_yaw, float dt, int on_device)
+{
+    return update_grid_impl(h, measurement_grid, new_x, new_y, new_yaw, dt, on_device, true);
+}
+
+extern "C" int dogm_update_grid_async(dogm_handle* h, const dogm_meas_cell* measurement_grid, float new_x, float new_y,
+                                      float new_yaw, float dt, int on_device)
+{
+    return update_grid_impl(h, measurement_grid, new_x, new_y, new_yaw, dt, on_device, false);
+}
+
+extern "C" int dogm_synchronize(dogm_handle* h)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+#define STAGE_PROLOGUE()                                                                                               \
+    if (!h)                                                                                                            \
+        return DOGM_ERR_INVALID_ARGUMENT;                                                                              \
+    int e = 0;
+#define STAGE_EPILOGUE()                                                                                               \
+    if (e)                                                                                                             \
+        return e;                                                                                                      \
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));                                                                      \
+    return 0;
+
+extern "C" int dogm_initialize_particles(dogm_handle* h)
+{
+    STAGE_PROLOGUE();
+    if (h->opts.noise_mode == DOGM_NOISE_INJECTED && h->N > 0 && !h->init_velocity)
+        return DOGM_ERR_NOT_INITIALIZED;
+    e = run_init_particles(h);
+    h->first_measurement_received = true;
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_particle_prediction(dogm_handle* h, float dt)
+{
+    STAGE_PROLOGUE();
+    if (h->opts.noise_mode == DOGM_NOISE_INJECTED && h->N > 0 && !h->predict_noise)
+        return DOGM_ERR_NOT_INITIALIZED;
+    e = run_predict(h, dt);
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_particle_assignment(dogm_handle* h)
+{
+    STAGE_PROLOGUE();
+    e = run_assignment(h);
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_grid_cell_occupancy_update(dogm_handle* h, float dt)
+{
+    STAGE_PROLOGUE();
+    e = run_occupancy_update(h, dt);
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_update_persistent_particles(dogm_handle* h)
+{
+    STAGE_PROLOGUE();
+    e = run_persistent_weights(h);
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_initialize_new_particles(dogm_handle* h)
+{
+    STAGE_PROLOGUE();
+    if (h->opts.noise_mode == DOGM_NOISE_INJECTED && h->B > 0 && !h->birth_noise)
+        return DOGM_ERR_NOT_INITIALIZED;
+    e = run_birth(h);
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_statistical_moments(dogm_handle* h)
+{
+    // the velocity moments are produced by the fused cell kernel of dogm_grid_cell_occupancy_update
+    STAGE_PROLOGUE();
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_resampling(dogm_handle* h)
+{
+    STAGE_PROLOGUE();
+    if (h->N > 0 && !h->resample_u &&
+        (h->opts.noise_mode == DOGM_NOISE_INJECTED || h->opts.resample_mode == DOGM_RESAMPLE_INJECTED))
+        return DOGM_ERR_NOT_INITIALIZED;
+    e = run_resampling(h);
+    h->cycle++;
+    STAGE_EPILOGUE();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// read-out
+// ---------------------------------------------------------------------------------------------------------
+static int copy_out(dogm_handle* h, void* dst_host, const void* src_device, size_t bytes)
+{
+    if (!h || !dst_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (bytes == 0)
+        return 0;
+    DOGM_CHECK(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host)
+{
+    return copy_out(h, out_host, h ? h->grid : nullptr, h ? (size_t)h->C * sizeof(dogm_grid_cell) : 0);
+}
+extern "C" int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_host)
+{
+    return copy_out(h, out_host, h ? h->meas : nullptr, h ? (size_t)h->C * sizeof(dogm_meas_cell) : 0);
+}
+extern "C" int dogm_get_particles(dogm_handle* h, void* out_block)
+{
+    return copy_out(h, out_block, h ? h->pa.block : nullptr, h ? DOGM_PARTICLE_BLOCK_BYTES(h->N) : 0);
+}
+extern "C" int dogm_get_birth_particles(dogm_handle* h, void* out_block)
+{
+    return copy_out(h, out_block, h ? h->birth.block : nullptr, h ? DOGM_PARTICLE_BLOCK_BYTES(h->B) : 0);
+}
+extern "C" int dogm_get_weight_array(dogm_handle* h, float* out_host)
+{
+    return copy_out(h, out_host, h ? h->weight_array : nullptr, h ? (size_t)h->N * sizeof(float) : 0);
+}
+extern "C" int dogm_get_born_masses(dogm_handle* h, float* out_host)
+{
+    return copy_out(h, out_host, h ? h->born_masses : nullptr, h ? (size_t)h->C * sizeof(float) : 0);
+}
+extern "C" int dogm_get_resampled_indices(dogm_handle* h, int* out_host)
+{
+    return copy_out(h, out_host, h ? h->ancestors : nullptr, h ? (size_t)h->N * sizeof(int) : 0);
+}
+extern "C" int dogm_get_joint_weight_accum(dogm_handle* h, double* out_host)
+{
+    return copy_out(h, out_host, h ? h->cdf : nullptr, h ? ((size_t)h->N + h->B) * sizeof(double) : 0);
+}
+extern "C" int dogm_get_cell_ranges(dogm_handle* h, int* start_host, int* end_host)
+{
+    int e = copy_out(h, start_host, h ? h->cell_start : nullptr, h ? (size_t)h->C * sizeof(int) : 0);
+    if (e)
+        return e;
+    return copy_out(h, end_host, h->cell_end, (size_t)h->C * sizeof(int));
+}
+
+extern "C" int dogm_get_grid_size(const dogm_handle* h) { return h ? h->gs : 0; }
+extern "C" int dogm_get_grid_cell_count(const dogm_handle* h) { return h ? h->C : 0; }
+extern "C" int dogm_get_particle_count(const dogm_handle* h) { return h ? h->N : 0; }
+extern "C" int dogm_get_new_born_particle_count(const dogm_handle* h) { return h ? h->B : 0; }
+extern "C" float dogm_get_resolution(const dogm_handle* h) { return h ? h->params.resolution : 0.0f; }
+extern "C" float dogm_get_position_x(const dogm_handle* h) { return h ? h->position_x : 0.0f; }
+extern "C" float dogm_get_position_y(const dogm_handle* h) { return h ? h->position_y : 0.0f; }
+extern "C" float dogm_get_yaw(const dogm_handle* h) { return h ? h->yaw : 0.0f; }
+extern "C" uint32_t dogm_get_cycle_counter(const dogm_handle* h) { return h ? h->cycle : 0u; }
+
+extern "C" int dogm_get_device_ptrs(dogm_handle* h, dogm_device_ptrs* out)
+{
+    if (!h || !out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    out->grid_cell_array = h->grid;
+    out->particle_array = h->pa.block;
+    out->particle_array_next = h->pb.block;
+    out->birth_particle_array = h->birth.block;
+    out->meas_cell_array = h->meas;
+    out->weight_array = h->weight_array;
+    out->born_masses_array = h->born_masses;
+    out->resampled_idx_array = h->ancestors;
+    out->joint_weight_accum = h->cdf;
+    out->cell_start_array = h->cell_start;
+    out->cell_end_array = h->cell_end;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// options and parity hooks
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int dogm_set_options(dogm_handle* h, const dogm_options* opts)
+{
+    if (!h || !opts)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (opts->resample_mode < DOGM_RESAMPLE_SYSTEMATIC || opts->resample_mode > DOGM_RESAMPLE_INJECTED)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (opts->noise_mode != DOGM_NOISE_PHILOX && opts->noise_mode != DOGM_NOISE_INJECTED)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    h->opts = *opts;
+    return 0;
+}
+
+extern "C" int dogm_get_options(const dogm_handle* h, dogm_options* out)
+{
+    if (!h || !out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    *out = h->opts;
+    return 0;
+}
+
+static int set_buffer(dogm_handle* h, void** slot, const void* src, size_t bytes, int on_device)
+{
+    if (!src || bytes == 0)
+        return 0;
+    if (!*slot)
+        DOGM_CHECK(cudaMalloc(slot, bytes));
+    DOGM_CHECK((cudaError_t)copy_in(*slot, src, bytes, on_device, h->stream));
+    return 0;
+}
+
+extern "C" int dogm_set_noise(dogm_handle* h, const float* predict_noise, const float* birth_noise,
+                              const float* init_velocity, const float* resample_unit, int on_device)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = 0;
+    e |= set_buffer(h, (void**)&h->predict_noise, predict_noise, (size_t)h->N * sizeof(float4), on_device);
+    e |= set_buffer(h, (void**)&h->birth_noise, birth_noise, (size_t)h->B * sizeof(float2), on_device);
+    e |= set_buffer(h, (void**)&h->init_velocity, init_velocity, (size_t)h->N * sizeof(float2), on_device);
+    e |= set_buffer(h, (void**)&h->resample_u, resample_unit, (size_t)h->N * sizeof(float), on_device);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream)); // the caller may reuse its buffers
+    return 0;
+}
+
+extern "C" int dogm_export_philox_noise(dogm_handle* h, uint32_t cycle, float* predict_noise, float* birth_noise,
+                                        float* init_velocity, float* resample_unit)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    float4* d_p = nullptr;
+    float2 *d_b = nullptr, *d_i = nullptr;
+    float* d_r = nullptr;
+    const size_t N = (size_t)h->N, B = (size_t)h->B;
+    if (predict_noise && N)
+        DOGM_CHECK(cudaMalloc(&d_p, N * sizeof(float4)));
+    if (birth_noise && B)
+        DOGM_CHECK(cudaMalloc(&d_b, B * sizeof(float2)));
+    if (init_velocity && N)
+        DOGM_CHECK(cudaMalloc(&d_i, N * sizeof(float2)));
+    if (resample_unit && N)
+        DOGM_CHECK(cudaMalloc(&d_r, N * sizeof(float)));
+    int e = run_export_noise(h, cycle, d_p, d_b, d_i, d_r);
+    if (!e && d_p)
+        e = (int)cudaMemcpyAsync(predict_noise, d_p, N * sizeof(float4), cudaMemcpyDeviceToHost, h->stream);
+    if (!e && d_b)
+        e = (int)cudaMemcpyAsync(birth_noise, d_b, B * sizeof(float2), cudaMemcpyDeviceToHost, h->stream);
+    if (!e && d_i)
+        e = (int)cudaMemcpyAsync(init_velocity, d_i, N * sizeof(float2), cudaMemcpyDeviceToHost, h->stream);
+    if (!e && d_r)
+        e = (int)cudaMemcpyAsync(resample_unit, d_r, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+    if (!e)
+        e = (int)cudaStreamSynchronize(h->stream);
+    cudaFree(d_p);
+    cudaFree(d_b);
+    cudaFree(d_i);
+    cudaFree(d_r);
+    return e;
+}
+
+extern "C" int dogm_set_particles(dogm_handle* h, const void* block, int on_device)
+{
+    if (!h || !block)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK((cudaError_t)copy_in(h->pa.block, block, DOGM_PARTICLE_BLOCK_BYTES(h->N), on_device, h->stream));
+    h->hist0_valid = false;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_set_birth_particles(dogm_handle* h, const void* block, int on_device)
+{
+    if (!h || !block)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK((cudaError_t)copy_in(h->birth.block, block, DOGM_PARTICLE_BLOCK_BYTES(h->B), on_device, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_set_grid_cells(dogm_handle* h, const dogm_grid_cell* cells, int on_device)
+{
+    if (!h || !cells)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK((cudaError_t)copy_in(h->grid, cells, (size_t)h->C * sizeof(dogm_grid_cell), on_device, h->stream));
+    int e = run_extract_free_mass(h);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_set_measurement_cells(dogm_handle* h, const dogm_meas_cell* cells, int on_device)
+{
+    if (!h || !cells)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK((cudaError_t)copy_in(h->meas, cells, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_set_pose(dogm_handle* h, float x, float y, float yaw)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    h->position_x = x;
+    h->position_y = y;
+    h->yaw = yaw;
+    h->first_pose_received = true;
+    return 0;
+}
+
+extern "C" int dogm_search_ancestors_f32(dogm_handle* h, const float* cdf, int n_cdf, const float* sorted_draws,
+                                         int n_draws, int* out)
+{
+    if (!h || !cdf || !sorted_draws || !out || n_cdf <= 0 || n_draws < 0)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    float *d_cdf = nullptr, *d_draws = nullptr;
+    int* d_out = nullptr;
+    DOGM_CHECK(cudaMalloc(&d_cdf, (size_t)n_cdf * sizeof(float)));
+    DOGM_CHECK(cudaMalloc(&d_draws, (size_t)(n_draws > 0 ? n_draws : 1) * sizeof(float)));
+    DOGM_CHECK(cudaMalloc(&d_out, (size_t)(n_draws > 0 ? n_draws : 1) * sizeof(int)));
+    int e = (int)cudaMemcpyAsync(d_cdf, cdf, (size_t)n_cdf * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (!e)
+        e = (int)cudaMemcpyAsync(d_draws, sorted_draws, (size_t)n_draws * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (!e)
+        e = run_search_ancestors_f32(h, d_cdf, n_cdf, d_draws, n_draws, d_out);
+    if (!e)
+        e = (int)cudaMemcpyAsync(out, d_out, (size_t)n_draws * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (!e)
+        e = (int)cudaStreamSynchronize(h->stream);
+    cudaFree(d_cdf);
+    cudaFree(d_draws);
+    cudaFree(d_out);
+    return e;
+}
+
+extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_velocity,
+                                          dogm_dynamic_cell* out_host, int capacity, int* out_count)
+{
+    if (!h || !out_count || capacity < 0 || (capacity > 0 && !out_host))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (!h->dyn_count)
+    {
+        DOGM_CHECK(cudaMalloc(&h->dyn_count, sizeof(int)));
+        DOGM_CHECK(cudaMallocHost(&h->dyn_count_host, sizeof(int)));
+    }
+    if (capacity > h->dyn_capacity)
+    {
+        cudaFree(h->dyn_buf);
+        h->dyn_buf = nullptr;
+        h->dyn_capacity = 0;
+        DOGM_CHECK(cudaMalloc(&h->dyn_buf, (size_t)capacity * sizeof(dogm_dynamic_cell)));
+        h->dyn_capacity = capacity;
+    }
+    int e = run_extract_dynamic_cells(h, min_occupancy, min_velocity, h->dyn_buf, capacity, h->dyn_count);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    const int found = *h->dyn_count_host;
+    *out_count = found;
+    const int n_copy = found < capacity ? found : capacity;
+    if (n_copy > 0)
+    {
+        DOGM_CHECK(cudaMemcpyAsync(out_host, h->dyn_buf, (size_t)n_copy * sizeof(dogm_dynamic_cell), cudaMemcpyDeviceToHost,
+                                   h->stream));
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// instrumentation
+// ---------------------------------------------------------------------------------------------------------
+extern "C" void* dogm_get_stream(dogm_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" uint64_t dogm_get_launch_count(const dogm_handle* h) { return h ? h->launch_count : 0; }
+
+static void drain_timed(dogm_handle* h)
+{
+    cudaStreamSynchronize(h->stream);
+    for (auto& t : h->timed)
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess)
+        {
+            h->acc_ms[t.id] += (double)ms;
+            h->acc_launches[t.id] += 1;
+        }
+        h->event_pool.push_back(t.e0);
+        h->event_pool.push_back(t.e1);
+    }
+    h->timed.clear();
+}
+
+extern "C" int dogm_kernel_timing_enable(dogm_handle* h, int enable)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    drain_timed(h);
+    h->timing = enable != 0;
+    for (int k = 0; k < K_COUNT; k++)
+    {
+        h->acc_ms[k] = 0.0;
+        h->acc_launches[k] = 0;
+    }
+    return 0;
+}
+
+extern "C" int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, int capacity, int* out_count)
+{
+    if (!h || !out || !out_count)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    drain_timed(h);
+    int n = 0;
+    for (int k = 0; k < K_COUNT && n < capacity; k++)
+    {
+        if (h->acc_launches[k] == 0)
+            continue;
+        memset(&out[n], 0, sizeof(dogm_kernel_time));
+        strncpy(out[n].name, kKernelNames[k], sizeof(out[n].name) - 1);
+        out[n].total_ms = h->acc_ms[k];
+        out[n].launches = h->acc_launches[k];
+        out[n].algorithmic_bytes = h->last_bytes[k];
+        n++;
+        h->acc_ms[k] = 0.0;
+        h->acc_launches[k] = 0;
+    }
+    *out_count = n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small runtime helpers for callers without a CUDA binding
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int dogm_host_alloc_pinned(void** out, size_t bytes)
+{
+    if (!out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaMallocHost(out, bytes ? bytes : 16));
+    return 0;
+}
+extern "C" int dogm_host_free_pinned(void* p)
+{
+    DOGM_CHECK(cudaFreeHost(p));
+    return 0;
+}
+extern "C" int dogm_device_alloc(void** out, size_t bytes)
+{
+    if (!out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaMalloc(out, bytes ? bytes : 16));
+    return 0;
+}
+extern "C" int dogm_device_free(void* p)
+{
+    DOGM_CHECK(cudaFree(p));
+    return 0;
+}
+extern "C" int dogm_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes)
+{
+    DOGM_CHECK(cudaMemcpy(dst_device, src_host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes)
+{
+    DOGM_CHECK(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int dogm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+extern "C" int dogm_set_device(int device)
+{
+    DOGM_CHECK(cudaSetDevice(device));
+    return 0;
+}
+extern "C" const char* dogm_b200_version(void)
+{
+    return "dogm_b200 0.1 (sm_100a, ABI " /* DOGM_B200_ABI_VERSION */ "1)";
+}

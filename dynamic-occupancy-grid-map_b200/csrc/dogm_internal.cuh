@@ -1,0 +1,326 @@
+// Internal declarations of libdogm_b200: handle layout, device-side helpers, kernel launch entry points.
+#pragma once
+
+#include "../../include/dogm_b200.h"
+#include "philox.cuh"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+namespace dogm_b200
+{
+
+// ---------------------------------------------------------------------------------------------------------
+// error handling: same print format as the reference's CHECK_ERROR (cuda_utils.h:13-24), but the code is kept
+// ---------------------------------------------------------------------------------------------------------
+inline int check_cuda(cudaError_t code, const char* file, int line)
+{
+    if (code != cudaSuccess)
+        printf("GPU Kernel Error: %s %s %d\n", cudaGetErrorString(code), file, line);
+    return (int)code;
+}
+#define DOGM_CHECK(expr)                                                                                               \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int _e = ::dogm_b200::check_cuda((expr), __FILE__, __LINE__);                                                  \
+        if (_e != 0)                                                                                                   \
+            return _e;                                                                                                 \
+    } while (0)
+
+inline int div_up(long long a, long long b)
+{
+    return (int)((a + b - 1) / b);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// geometry constants
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBlock = 256;           // threads per CTA of every streaming kernel
+constexpr int kWarpsPerBlock = 8;
+constexpr int kTileItems = 4096;      // particles per sort tile (one CTA, 16 per thread, 512 per warp)
+constexpr int kItemsPerThread = kTileItems / kBlock;
+constexpr int kRoundsPerWarp = kTileItems / kWarpsPerBlock / 32;
+constexpr int kMaxDigitBits = 12;     // <= 4096 bins: 8 warps * 4096 * 2 B = 64 KB of rank counters
+constexpr int kMaxPasses = 3;
+constexpr int kSegChunk = 256;        // particles per warp in the segmented reduction
+constexpr int kCellBlock = 256;       // cells per CTA in the cell kernels (also the granularity of the born-mass scan)
+constexpr int kCdfItems = 8;          // CDF entries per thread
+constexpr int kCdfTile = kBlock * kCdfItems;
+
+// ---------------------------------------------------------------------------------------------------------
+// device-side views
+// ---------------------------------------------------------------------------------------------------------
+struct ParticleSet // ParticlesSoA, dogm_types.h:51-144: one block of n*28 bytes
+{
+    void* block;
+    float4* state;
+    int* idx;
+    float* weight;
+    uint8_t* assoc;
+    int n;
+};
+
+inline void particle_set_assign(ParticleSet& p, void* block, int n)
+{
+    p.block = block;
+    p.n = n;
+    char* b = (char*)block;
+    p.state = (float4*)(b + DOGM_PARTICLE_STATE_OFFSET(n));
+    p.idx = (int*)(b + DOGM_PARTICLE_IDX_OFFSET(n));
+    p.weight = (float*)(b + DOGM_PARTICLE_WEIGHT_OFFSET(n));
+    p.assoc = (uint8_t*)(b + DOGM_PARTICLE_ASSOC_OFFSET(n));
+}
+
+struct __align__(16) CellSums // per non-empty cell, written by the segmented reduction
+{
+    float s0; // sum w           (accumulated in double, rounded once)
+    float s1; // sum w*vx
+    float s2; // sum w*vy
+    float s3; // sum (w*vx)*vx
+    float s4; // sum (w*vy)*vy
+    float s5; // sum (w*vx)*vy
+    float pad0, pad1;
+};
+
+struct __align__(16) SegPiece // open piece of a segment at a chunk border
+{
+    double s0;
+    float s1, s2, s3, s4, s5;
+    int pad;
+};
+
+enum : int
+{
+    SEG_LEAD = 1,    // first particle of the chunk continues a segment of the previous chunk
+    SEG_TRAIL = 2,   // last particle of the chunk continues into the next chunk
+    SEG_THROUGH = 4, // the whole chunk is the inside of one segment
+};
+
+struct DeviceScalars // device-resident scalars: nothing is read back by the host inside a cycle
+{
+    double born_total;   // sum of born masses (normaliser of the birth / init slot distribution)
+    double weight_total; // last entry of the joint weight CDF
+    unsigned int ticket[4];
+};
+
+struct CycleShift // ego-motion compensation of this cycle (dogm.cu:175-178)
+{
+    int active;
+    int x_move;
+    int y_move;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel timing (bench instrumentation)
+// ---------------------------------------------------------------------------------------------------------
+enum KernelId : int
+{
+    K_PREDICT = 0,
+    K_TILE_HIST,
+    K_HIST_SCAN,
+    K_SCATTER,
+    K_SEGSUM,
+    K_SEGFIX,
+    K_CELL,
+    K_BLOCKSUM_SCAN,
+    K_WEIGHTS,
+    K_BIRTH_CELLS,
+    K_BIRTH_PARTICLES,
+    K_CDF_REDUCE,
+    K_CDF_WRITE,
+    K_RESAMPLE,
+    K_INIT_MASSES,
+    K_INIT_PARTICLES,
+    K_MEAS_GRID,
+    K_MISC,
+    K_MEMSET,
+    K_COUNT
+};
+
+static const char* const kKernelNames[K_COUNT] = {
+    "k_predict",       "k_tile_hist",       "k_hist_scan",  "k_scatter",   "k_segsum",      "k_segfix",
+    "k_cell",          "k_blocksum_scan",   "k_weights",    "k_birth_cells", "k_birth_particles", "k_cdf_reduce",
+    "k_cdf_write",     "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
+    "memset"};
+
+struct TimedLaunch
+{
+    int id;
+    cudaEvent_t e0, e1;
+};
+
+} // namespace dogm_b200
+
+// ---------------------------------------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------------------------------------
+struct dogm_handle
+{
+    dogm_params params;
+    dogm_options opts;
+    int gs, C, N, B;
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+
+    // reference-visible buffers (dogm.h:159-191)
+    dogm_b200::ParticleSet pa;    // particle_array
+    dogm_b200::ParticleSet pb;    // particle_array_next
+    dogm_b200::ParticleSet birth; // birth_particle_array
+    dogm_grid_cell* grid;
+    dogm_meas_cell* meas;
+    float* weight_array;
+    float* born_masses;
+
+    // per-cell working set
+    float* free_cur;  // GridCell.free_mass of the previous cycle (SoA copy; the cell kernel reads it at the shifted index)
+    float* free_next; // written by the cell kernel; swapped with free_cur
+    int* cell_start;
+    int* cell_end;
+    dogm_b200::CellSums* cell_sums;
+    float4* cell_coef; // {likelihood, p_A*mu_A, (1-p_A)*mu_UA, over-unit divisor or 0} for non-empty cells
+    double* blk_sum;   // born-mass sum per 256-cell block
+    double* blk_off;   // exclusive prefix of blk_sum
+    int* slot_end;     // exclusive end slot per cell of the last birth / init distribution
+    int* blk_slot_end; // slot_end of the last cell of every 256-cell block
+    int n_cell_blocks;
+
+    // counting sort
+    int key_bits, passes;
+    int digit_shift[dogm_b200::kMaxPasses];
+    int digit_bins[dogm_b200::kMaxPasses];
+    uint32_t* hist[dogm_b200::kMaxPasses];     // [tiles][bins] per pass
+    uint32_t* bin_tot[dogm_b200::kMaxPasses];  // [bins]
+    uint32_t* bin_base[dogm_b200::kMaxPasses]; // [bins]
+    int tiles;
+    bool hist0_valid; // pass-0 tile histograms were produced by the prediction kernel for the current keys
+
+    // segmented reduction
+    int n_chunks;
+    dogm_b200::SegPiece* seg_lead;
+    dogm_b200::SegPiece* seg_trail;
+    int* seg_flags;
+
+    // resampling
+    double* cdf;      // N + B
+    double* tile_sum; // per CDF tile
+    double* tile_off;
+    int n_cdf_tiles;
+    int* ancestors; // N
+
+    // noise (injected mode)
+    float4* predict_noise;
+    float2* birth_noise;
+    float2* init_velocity;
+    float* resample_u;
+
+    dogm_b200::DeviceScalars* scal;
+
+    // host-side state (dogm.h:193-198)
+    bool first_pose_received;
+    bool first_measurement_received;
+    float position_x, position_y, yaw;
+    dogm_b200::CycleShift shift; // pending ego-motion shift: consumed by prediction (particles) and the cell kernel (grid)
+    bool shift_particles_pending;
+    bool shift_grid_pending;
+    uint32_t cycle;
+
+    // dynamic-cell extraction (allocated on first use, grown on demand)
+    dogm_dynamic_cell* dyn_buf;
+    int dyn_capacity;
+    int* dyn_count;
+    int* dyn_count_host; // pinned
+
+    // instrumentation
+    uint64_t launch_count;
+    bool timing;
+    std::vector<dogm_b200::TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double acc_ms[dogm_b200::K_COUNT];
+    uint64_t acc_launches[dogm_b200::K_COUNT];
+    double last_bytes[dogm_b200::K_COUNT];
+};
+
+namespace dogm_b200
+{
+
+// instrumentation hooks around every launch
+void launch_begin(dogm_handle* h, int id, double algorithmic_bytes);
+void launch_end(dogm_handle* h, int id);
+
+struct LaunchScope
+{
+    dogm_handle* h;
+    int id;
+    LaunchScope(dogm_handle* h_, int id_, double bytes) : h(h_), id(id_) { launch_begin(h, id, bytes); }
+    ~LaunchScope() { launch_end(h, id); }
+};
+
+// stage launchers (kernels_particles.cu / kernels_cells.cu / kernels_meas.cu); all stream-ordered on h->stream
+int run_init_particles(dogm_handle* h);
+int run_predict(dogm_handle* h, float dt);
+int run_assignment(dogm_handle* h);
+int run_occupancy_update(dogm_handle* h, float dt);
+int run_persistent_weights(dogm_handle* h);
+int run_birth(dogm_handle* h);
+int run_resampling(dogm_handle* h);
+int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells
+int run_init_grid(dogm_handle* h);         // initGridCellsKernel
+int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out);
+int configure_kernels();                   // opt-in shared memory sizes
+int run_search_ancestors_f32(dogm_handle* h, const float* d_cdf, int n_cdf, const float* d_draws, int n_draws, int* d_out);
+int run_export_noise(dogm_handle* h, uint32_t cycle, float4* d_predict, float2* d_birth, float2* d_init, float* d_resample);
+int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm_dynamic_cell* d_out, int capacity,
+                              int* d_count);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------
+// device helpers shared by the kernels
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ unsigned lanemask_le()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+// inclusive scan of a double over the 256 threads of a CTA, fixed combination order.
+// smem: at least kWarpsPerBlock doubles.  Returns the inclusive prefix; *total receives the CTA sum.
+__device__ __forceinline__ double block_inclusive_scan_f64(double v, double* smem, double* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        double t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d)
+            v += t;
+    }
+    if (lane == 31)
+        smem[warp] = v;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; w++)
+    {
+        const double s = smem[w];
+        if (w < warp)
+            off += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + v;
+}
+#endif
+
+} // namespace dogm_b200

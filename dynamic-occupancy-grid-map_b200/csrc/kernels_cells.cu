@@ -1,0 +1,556 @@
+// Cell-side kernels of the DOGM cycle for sm_100a:
+//   fused per-cell update (ego-motion grid shift, Dempster-Shafer occupancy update, born/persistent split,
+//   persistent-weight normalisers, velocity moments, born-mass block sums), birth-slot distribution and
+//   birth-particle initialisation, first-cycle particle initialisation, dynamic-cell extraction.
+//
+// Reference behaviour restated here (paths relative to the reference's dogm/):
+//   src/kernel/ego_motion_compensation.cu:25-43, src/kernel/mass_update.cu:16-93,
+//   src/kernel/update_persistent_particles.cu:16-31,59-76, src/kernel/statistical_moments.cu:16-106,
+//   src/kernel/init_new_particles.cu:30-195, src/kernel/init.cu:46-93, demo/utils/image_creation.cpp:19-66.
+//
+// Compiled with -fmad=false: every operator below is one IEEE rounding, in the order written.
+#include "dogm_internal.cuh"
+
+namespace dogm_b200
+{
+
+// =========================================================================================================
+// the fused cell kernel (one thread per cell, 256 cells per CTA)
+// =========================================================================================================
+struct CellArgs
+{
+    int C, gs;
+    const int* cell_start;
+    const int* cell_end;
+    const CellSums* sums;
+    const dogm_meas_cell* meas;
+    const float* free_cur;
+    float* free_next;
+    dogm_grid_cell* grid;
+    float* born_masses;
+    float4* coef;
+    double* blk_sum;
+    float p_B, alpha;
+    int shift_active, x_move, y_move;
+};
+
+__global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
+{
+    __shared__ double s_scan[kWarpsPerBlock];
+    const int c = blockIdx.x * kCellBlock + threadIdx.x;
+    const bool valid = c < a.C;
+    float rho_b = 0.0f;
+    if (valid)
+    {
+        const int start = a.cell_start[c];
+        const bool occupied = start >= 0;
+        int end = -1;
+        CellSums cs;
+        cs.s0 = cs.s1 = cs.s2 = cs.s3 = cs.s4 = cs.s5 = 0.0f;
+        if (occupied)
+        {
+            end = a.cell_end[c];
+            const float4* sp = reinterpret_cast<const float4*>(a.sums + c);
+            const float4 lo = sp[0], hi = sp[1];
+            cs.s0 = lo.x;
+            cs.s1 = lo.y;
+            cs.s2 = lo.z;
+            cs.s3 = lo.w;
+            cs.s4 = hi.x;
+            cs.s5 = hi.y;
+        }
+        const float4 zq = *reinterpret_cast<const float4*>(a.meas + c);
+        const float z_free = zq.x, z_occ = zq.y, lik = zq.z, p_A = zq.w;
+
+        // ego-motion compensation of the grid (updatePose dogm.cu:175-193, moveMapKernel
+        // ego_motion_compensation.cu:25-43): of all cell fields only free_mass survives into the next cycle,
+        // so the shift is a shifted read of the previous free masses; vacated cells read 0 (dogm.cu:185)
+        float free_prev;
+        if (a.shift_active)
+        {
+            const int x = c % a.gs, y = c / a.gs;
+            const int nx = x + a.x_move, ny = y + a.y_move;
+            free_prev = (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs) ? a.free_cur[nx + a.gs * ny] : 0.0f;
+        }
+        else
+        {
+            free_prev = a.free_cur[c];
+        }
+
+        // gridCellPredictionUpdateKernel, mass_update.cu:61-93
+        float m_occ_pred = occupied ? cs.s0 : 0.0f;
+        float over_div = 0.0f;
+        if (m_occ_pred > 1.0f)
+        { // normalize_weights, mass_update.cu:51-59: applied per particle by k_weights
+            over_div = m_occ_pred;
+            m_occ_pred = 1.0f;
+        }
+        const float fa = a.alpha * free_prev;
+        const float fb = 1.0f - m_occ_pred;
+        const float m_free_pred = fminf(fa, fb);
+        const float unknown_pred = 1.0f - m_occ_pred - m_free_pred;
+        const float meas_unknown = 1.0f - z_free - z_occ;
+        const float K = m_free_pred * z_occ + m_occ_pred * z_free;
+        const float occ_up = (m_occ_pred * meas_unknown + unknown_pred * z_occ + m_occ_pred * z_occ) / (1.0f - K);
+        const float free_up = (m_free_pred * meas_unknown + unknown_pred * z_free + m_free_pred * z_free) / (1.0f - K);
+        rho_b = (occ_up * a.p_B * (1.0f - m_occ_pred)) / (m_occ_pred + a.p_B * (1.0f - m_occ_pred));
+        const float rho_p = occ_up - rho_b;
+
+        // updatePersistentParticlesKernel2, update_persistent_particles.cu:59-76 (sum of likelihood-weighted
+        // weights of the cell = likelihood * predicted occupancy: the likelihood is a per-cell constant)
+        float mu_A = 0.0f, mu_UA = 0.0f;
+        float mean_x = 0.0f, mean_y = 0.0f, var_x = 0.0f, var_y = 0.0f, covar = 0.0f;
+        if (occupied)
+        {
+            const float m_occ_accum = lik * m_occ_pred;
+            mu_A = m_occ_accum > 0.0f ? rho_p / m_occ_accum : 0.0f;
+            mu_UA = m_occ_pred > 0.0f ? rho_p / m_occ_pred : 0.0f;
+            const float cA = p_A * mu_A;
+            const float cUA = (1.0f - p_A) * mu_UA;
+            a.coef[c] = make_float4(lik, cA, cUA, over_div);
+
+            // statisticalMomentsKernel2, statistical_moments.cu:78-106: the updated weight of every particle of
+            // the cell is its predicted weight times one per-cell factor, so the moment sums of the predicted
+            // weights (k_segsum) are rescaled instead of summed again
+            if (rho_p > 0.0f)
+            {
+                float kfac = cA * lik + cUA;
+                if (over_div > 0.0f)
+                    kfac = kfac / over_div;
+                const float inv = 1.0f / rho_p;
+                mean_x = inv * (kfac * cs.s1);
+                mean_y = inv * (kfac * cs.s2);
+                var_x = inv * (kfac * cs.s3) - mean_x * mean_x;
+                var_y = inv * (kfac * cs.s4) - mean_y * mean_y;
+                covar = inv * (kfac * cs.s5) - mean_x * mean_y;
+            }
+        }
+
+        a.born_masses[c] = rho_b;
+        a.free_next[c] = free_up;
+        float4* g = reinterpret_cast<float4*>(a.grid + c);
+        g[0] = make_float4(__int_as_float(start), __int_as_float(end), rho_b, rho_p);
+        g[1] = make_float4(free_up, occ_up, m_occ_pred, mu_A);
+        g[2] = make_float4(mu_UA, 0.0f, 0.0f, mean_x); // w_A / w_UA are filled in by k_birth_cells for cells that own slots
+        g[3] = make_float4(mean_y, var_x, var_y, covar);
+    }
+    double total;
+    block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
+    if (threadIdx.x == 0)
+        a.blk_sum[blockIdx.x] = total;
+}
+
+// =========================================================================================================
+// slot distribution: accumulate + normalize_particle_orders + calc_start_idx/calc_end_idx
+// (init_new_particles.cu:30-43,66-74) and the per-cell part of initNewParticlesKernel1 (:126-143)
+// =========================================================================================================
+struct SlotArgs
+{
+    int C;
+    int count; // slots to distribute: B (birth) or N (first-cycle initialisation)
+    const float* masses;
+    const double* blk_off;
+    const DeviceScalars* scal;
+    int* slot_end;
+    int* blk_slot_end;
+    const dogm_meas_cell* meas;
+    dogm_grid_cell* grid; // w_A / w_UA are written when non-null
+};
+
+__global__ void __launch_bounds__(kCellBlock) k_birth_cells(SlotArgs a)
+{
+    __shared__ double s_scan[kWarpsPerBlock];
+    __shared__ int s_end[kCellBlock];
+    const int c = blockIdx.x * kCellBlock + threadIdx.x;
+    const bool valid = c < a.C;
+    const float m = valid ? a.masses[c] : 0.0f;
+    double total;
+    const double incl = block_inclusive_scan_f64((double)m, s_scan, &total);
+    const double off = a.blk_off[blockIdx.x];
+    const float maxf = (float)a.scal->born_total;
+    const float scale = (float)a.count / maxf;
+    const int e = __float2int_rz((float)(off + incl) * scale);
+    s_end[threadIdx.x] = e;
+    __syncthreads();
+    if (!valid)
+        return;
+    a.slot_end[c] = e;
+    const int last = min(kCellBlock, a.C - blockIdx.x * kCellBlock) - 1;
+    if (threadIdx.x == last)
+        a.blk_slot_end[blockIdx.x] = e;
+    if (a.grid)
+    {
+        int e_prev;
+        if (threadIdx.x > 0)
+            e_prev = s_end[threadIdx.x - 1];
+        else
+            e_prev = c == 0 ? 0 : __float2int_rz((float)off * scale);
+        const int num_new = e > e_prev ? e - e_prev : 0;
+        if (num_new > 0)
+        {
+            const float p_A = a.meas[c].p_A;
+            const int nu_A = __float2int_rz(roundf((float)num_new * p_A));
+            const int nu_UA = num_new - nu_A;
+            const float w_A = nu_A > 0 ? (p_A * m) / (float)nu_A : 0.0f;
+            const float w_UA = nu_UA > 0 ? ((1.0f - p_A) * m) / (float)nu_UA : 0.0f;
+            a.grid[c].w_A = w_A;
+            a.grid[c].w_UA = w_UA;
+        }
+    }
+}
+
+// owner cell of slot s: first cell j with slot_end[j] > s (two-level search: 256-cell blocks, then cells)
+__device__ __forceinline__ int find_slot_owner(const int* __restrict__ slot_end, const int* __restrict__ blk_slot_end,
+                                               int n_blocks, int C, int s)
+{
+    int lo = 0, hi = n_blocks;
+    while (lo < hi)
+    {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (blk_slot_end[mid] > s)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    if (lo >= n_blocks)
+        return -1;
+    int clo = lo * kCellBlock, chi = min(C, clo + kCellBlock);
+    while (clo < chi)
+    {
+        const int mid = clo + ((chi - clo) >> 1);
+        if (slot_end[mid] > s)
+            chi = mid;
+        else
+            clo = mid + 1;
+    }
+    return clo < C ? clo : -1;
+}
+
+struct BirthArgs
+{
+    int B, C, gs, n_blocks;
+    const int* slot_end;
+    const int* blk_slot_end;
+    const dogm_meas_cell* meas;
+    const dogm_grid_cell* grid;
+    ParticleSet birth;
+    const float2* noise;
+    int noise_injected;
+    float stddev_velocity;
+    uint64_t seed;
+    uint32_t cycle;
+};
+
+// initBirthParticlesKernel (init.cu:46-67) + slot ownership of initNewParticlesKernel1 (init_new_particles.cu:145-153,
+// with the deterministic rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
+__global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
+{
+    const int s = blockIdx.x * kBlock + threadIdx.x;
+    if (s >= a.B)
+        return;
+    int j = find_slot_owner(a.slot_end, a.blk_slot_end, a.n_blocks, a.C, s);
+    bool assoc = false;
+    float weight;
+    if (j >= 0)
+    {
+        const int start = j > 0 ? a.slot_end[j - 1] : 0;
+        const int num_new = a.slot_end[j] - start;
+        const float p_A = a.meas[j].p_A;
+        const int nu_A = __float2int_rz(roundf((float)num_new * p_A));
+        assoc = s <= start + nu_A;
+        weight = assoc ? a.grid[j].w_A : a.grid[j].w_UA;
+    }
+    else
+    { // a slot no cell owns keeps its previous cell index, as in the reference
+        j = a.birth.idx[s];
+        weight = a.grid[j].w_UA;
+    }
+    float2 v;
+    if (a.noise_injected)
+        v = a.noise[s];
+    else
+    {
+        const float4 g = philox_normal4(a.seed, (uint32_t)s, STAGE_BIRTH, a.cycle);
+        v = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
+    }
+    const float x = (float)(j % a.gs) + 0.5f;
+    const float y = (float)j / (float)a.gs + 0.5f; // float division, init_new_particles.cu:173
+    a.birth.idx[s] = j;
+    a.birth.assoc[s] = assoc ? 1 : 0;
+    a.birth.weight[s] = weight;
+    a.birth.state[s] = make_float4(x, y, v.x, v.y);
+}
+
+// =========================================================================================================
+// first-cycle initialisation: copyMassesKernel + initParticlesKernel1/2 (init_new_particles.cu:76-124)
+// =========================================================================================================
+__global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell* __restrict__ meas, float* masses, int C,
+                                                            double* blk_sum)
+{
+    __shared__ double s_scan[kWarpsPerBlock];
+    const int c = blockIdx.x * kCellBlock + threadIdx.x;
+    float m = 0.0f;
+    if (c < C)
+    {
+        m = meas[c].occ_mass;
+        masses[c] = m;
+    }
+    double total;
+    block_inclusive_scan_f64((double)m, s_scan, &total);
+    if (threadIdx.x == 0)
+        blk_sum[blockIdx.x] = total;
+}
+
+struct InitArgs
+{
+    int N, C, gs, n_blocks;
+    const int* slot_end;
+    const int* blk_slot_end;
+    ParticleSet p;
+    const float2* init_velocity;
+    int noise_injected;
+    float init_max_velocity;
+    uint64_t seed;
+    uint32_t cycle;
+};
+
+__global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.N)
+        return;
+    int j = find_slot_owner(a.slot_end, a.blk_slot_end, a.n_blocks, a.C, i);
+    if (j < 0)
+        j = a.p.idx[i];
+    float2 v;
+    if (a.noise_injected)
+        v = a.init_velocity[i];
+    else
+    { // curand_uniform(state, -v, v) = min + (max - min) * (1 - u), u in (0,1]  (cuda_utils.h:31-35)
+        const Philox4 r = philox4x32_10((uint32_t)i, STAGE_INIT, a.cycle, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const float lo = -a.init_max_velocity;
+        const float span = a.init_max_velocity - lo;
+        v = make_float2(lo + span * (1.0f - u01_open_low(r.x)), lo + span * (1.0f - u01_open_low(r.y)));
+    }
+    const float x = (float)(j % a.gs) + 0.5f;
+    const float y = (float)(j / a.gs) + 0.5f; // integer division, init_new_particles.cu:115
+    a.p.idx[i] = j;
+    a.p.weight[i] = 1.0f / (float)a.N;
+    a.p.state[i] = make_float4(x, y, v.x, v.y);
+}
+
+// =========================================================================================================
+// small utilities
+// =========================================================================================================
+__global__ void __launch_bounds__(kBlock) k_extract_free(const dogm_grid_cell* __restrict__ grid, float* free_cur, int C)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c < C)
+        free_cur[c] = grid[c].free_mass;
+}
+
+__global__ void __launch_bounds__(kBlock) k_init_grid(dogm_grid_cell* grid, dogm_meas_cell* meas, float* free_a,
+                                                      float* free_b, int* cell_start, int C)
+{ // initGridCellsKernel, init.cu:69-84 (all other GridCell fields start at 0 here; the reference leaves them uninitialised)
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= C)
+        return;
+    float4* g = reinterpret_cast<float4*>(grid + c);
+    g[0] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.f, 0.f);
+    g[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    g[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(meas + c) = make_float4(0.f, 0.f, 1.f, 1.f); // free, occ, likelihood, p_A
+    free_a[c] = 0.f;
+    free_b[c] = 0.f;
+    cell_start[c] = -1;
+}
+
+// computeCellsWithVelocity, demo/utils/image_creation.cpp:19-66, as a stream compaction on the device
+__global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell* __restrict__ grid, int C, float min_occ,
+                                                            float min_vel, dogm_dynamic_cell* out, int capacity,
+                                                            int* count)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    bool hit = false;
+    dogm_dynamic_cell rec;
+    if (c < C)
+    {
+        const float4* g = reinterpret_cast<const float4*>(grid + c);
+        const float4 q1 = g[1], q2 = g[2], q3 = g[3];
+        const float free_mass = q1.x, occ_mass = q1.y;
+        const float mx = q2.w, my = q3.x, vxx = q3.y, vyy = q3.z, cxy = q3.w;
+        const float occ = occ_mass + 0.5f * (1.0f - occ_mass - free_mass);
+        const float det = vxx * vyy - cxy * cxy;
+        const float maha = (vyy * mx * mx - 2.0f * cxy * mx * my + vxx * my * my) / det;
+        hit = occ >= min_occ && maha >= min_vel;
+        rec.cell_idx = c;
+        rec.occupancy = occ;
+        rec.mean_x_vel = mx;
+        rec.mean_y_vel = my;
+        rec.var_x_vel = vxx;
+        rec.var_y_vel = vyy;
+        rec.covar_xy_vel = cxy;
+        rec.mahalanobis = maha;
+    }
+    // warp-aggregated append
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m)
+    {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(m) - 1)
+            base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (hit)
+        {
+            const int at = base + __popc(m & lanemask_lt());
+            if (at < capacity)
+                out[at] = rec;
+        }
+    }
+}
+
+// =========================================================================================================
+// host-side launchers
+// =========================================================================================================
+static int run_slot_distribution(dogm_handle* h, int count, bool write_weights)
+{
+    int e0 = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
+    if (e0)
+        return e0;
+    SlotArgs a;
+    a.C = h->C;
+    a.count = count;
+    a.masses = h->born_masses;
+    a.blk_off = h->blk_off;
+    a.scal = h->scal;
+    a.slot_end = h->slot_end;
+    a.blk_slot_end = h->blk_slot_end;
+    a.meas = h->meas;
+    a.grid = write_weights ? h->grid : nullptr;
+    {
+        LaunchScope ls(h, K_BIRTH_CELLS, 8.0 * h->C);
+        k_birth_cells<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+int run_init_particles(dogm_handle* h)
+{
+    {
+        LaunchScope ls(h, K_INIT_MASSES, 8.0 * h->C);
+        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum);
+    }
+    int e = run_slot_distribution(h, h->N, false);
+    if (e)
+        return e;
+    if (h->N <= 0)
+        return 0;
+    InitArgs a;
+    a.N = h->N;
+    a.C = h->C;
+    a.gs = h->gs;
+    a.n_blocks = h->n_cell_blocks;
+    a.slot_end = h->slot_end;
+    a.blk_slot_end = h->blk_slot_end;
+    a.p = h->pa;
+    a.init_velocity = h->init_velocity;
+    a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
+    a.init_max_velocity = h->params.init_max_velocity;
+    a.seed = h->opts.seed;
+    a.cycle = h->cycle;
+    {
+        LaunchScope ls(h, K_INIT_PARTICLES, 24.0 * h->N);
+        k_init_particles<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(a);
+    }
+    h->hist0_valid = false;
+    return (int)cudaGetLastError();
+}
+
+int run_occupancy_update(dogm_handle* h, float dt)
+{
+    CellArgs a;
+    a.C = h->C;
+    a.gs = h->gs;
+    a.cell_start = h->cell_start;
+    a.cell_end = h->cell_end;
+    a.sums = h->cell_sums;
+    a.meas = h->meas;
+    a.free_cur = h->free_cur;
+    a.free_next = h->free_next;
+    a.grid = h->grid;
+    a.born_masses = h->born_masses;
+    a.coef = h->cell_coef;
+    a.blk_sum = h->blk_sum;
+    a.p_B = h->params.birth_prob;
+    a.alpha = powf(h->params.freespace_discount, dt); // std::pow(float, float), dogm.cu:291
+    a.shift_active = (h->shift_grid_pending && h->shift.active) ? 1 : 0;
+    a.x_move = h->shift.x_move;
+    a.y_move = h->shift.y_move;
+    {
+        LaunchScope ls(h, K_CELL, 96.0 * h->C);
+        k_cell<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);
+    }
+    h->shift_grid_pending = false;
+    float* t = h->free_cur;
+    h->free_cur = h->free_next;
+    h->free_next = t;
+    return (int)cudaGetLastError();
+}
+
+int run_birth(dogm_handle* h)
+{
+    int e = run_slot_distribution(h, h->B, true);
+    if (e)
+        return e;
+    if (h->B <= 0)
+        return 0;
+    BirthArgs a;
+    a.B = h->B;
+    a.C = h->C;
+    a.gs = h->gs;
+    a.n_blocks = h->n_cell_blocks;
+    a.slot_end = h->slot_end;
+    a.blk_slot_end = h->blk_slot_end;
+    a.meas = h->meas;
+    a.grid = h->grid;
+    a.birth = h->birth;
+    a.noise = h->birth_noise;
+    a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
+    a.stddev_velocity = h->params.stddev_velocity;
+    a.seed = h->opts.seed;
+    a.cycle = h->cycle;
+    {
+        LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B);
+        k_birth_particles<<<div_up(h->B, kBlock), kBlock, 0, h->stream>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+int run_extract_free_mass(dogm_handle* h)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    k_extract_free<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->free_cur, h->C);
+    return (int)cudaGetLastError();
+}
+
+int run_init_grid(dogm_handle* h)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    k_init_grid<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->meas, h->free_cur, h->free_next,
+                                                               h->cell_start, h->C);
+    return (int)cudaGetLastError();
+}
+
+int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm_dynamic_cell* d_out, int capacity,
+                              int* d_count)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    cudaMemsetAsync(d_count, 0, sizeof(int), h->stream);
+    k_extract_dynamic<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->C, min_occ, min_vel, d_out, capacity,
+                                                                     d_count);
+    return (int)cudaGetLastError();
+}
+
+} // namespace dogm_b200

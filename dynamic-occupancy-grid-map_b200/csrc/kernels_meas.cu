@@ -1,0 +1,297 @@
+// Measurement grid from one lidar scan, as a single CUDA kernel.
+//
+// Replaces the reference's three-step path (demo/simulator/mapping/laser_to_meas_grid.cu:25-70):
+//   createPolarGridTextureKernel  (kernel/measurement_grid.cu:33-89)   inverse sensor model -> polar RG32F GL texture
+//   OpenGL triangle-fan render    (opengl/renderer.cpp:11-31,50-54,66-84; opengl/shader.cpp:22-35)  polar -> cartesian
+//   cartesianGridToMeasurementGridKernel (kernel/measurement_grid.cu:115-132)  RGBA32F framebuffer -> MeasurementCell[]
+// Every cartesian cell finds its fan triangle, interpolates the texture coordinate exactly as the rasteriser would,
+// and takes a bilinear sample (mip level 0) of the inverse sensor model evaluated on the fly; no polar table, no GL.
+#include "dogm_internal.cuh"
+
+#include <cmath>
+#include <vector>
+
+struct dogm_meas_handle
+{
+    dogm_laser_params params;
+    float grid_length;
+    float resolution;
+    int gs;
+    int H; // polar range bins
+    int a0, wedges;
+    float radius, start_angle;
+    int max_beams;
+    float* d_beams;
+    float2* d_verts; // arc vertices (NDC offsets from the fan centre), wedges + 1 entries
+    dogm_meas_cell* d_grid;
+    float* h_beams_pinned;
+    cudaStream_t stream;
+};
+
+namespace dogm_b200
+{
+
+struct MeasArgs
+{
+    int gs, K, H;
+    int a0, wedges;
+    float radius, start_angle, fov;
+    float resolution, stddev_range;
+    const float* beams;
+    const float2* verts;
+    dogm_meas_cell* out;
+};
+
+// inverse_sensor_model + clamp, measurement_grid.cu:33-70,80-85
+__device__ __forceinline__ float2 polar_cell(const MeasArgs& a, float zk, int i)
+{
+    const float free_p = 0.15f + (float)i * (1.0f - 0.15f) / (float)a.H;
+    float occ_m, free_m;
+    if (isfinite(zk))
+    {
+        const int r = __float2int_rz(zk / a.resolution);
+        const float diff = (float)(i - r) * a.resolution;
+        const float occ = 0.95f * expf(-0.5f * diff * diff / (a.stddev_range * a.stddev_range));
+        if (i <= r)
+        {
+            const bool o = occ > free_p;
+            occ_m = o ? occ : 0.0f;
+            free_m = o ? 0.0f : 1.0f - free_p;
+        }
+        else
+        {
+            occ_m = occ > 0.5f ? occ : 0.0f;
+            free_m = 0.0f;
+        }
+    }
+    else
+    {
+        occ_m = 0.0f;
+        free_m = 1.0f - free_p;
+    }
+    const float eps = 0.00001f;
+    return make_float2(fmaxf(eps, fminf(1.0f - eps, occ_m)), fmaxf(eps, fminf(1.0f - eps, free_m)));
+}
+
+__device__ __forceinline__ float2 polar_texel(const MeasArgs& a, int bi, int ri)
+{
+    if (bi < 0 || bi >= a.K || ri < 0 || ri >= a.H) // GL_CLAMP_TO_BORDER, border R = G = 0 (texture.cpp:16-29)
+        return make_float2(0.0f, 0.0f);
+    return polar_cell(a, a.beams[bi], ri);
+}
+
+__global__ void __launch_bounds__(kBlock) k_meas_grid(MeasArgs a)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= a.gs * a.gs)
+        return;
+    const int px = c % a.gs;
+    const int py = a.gs - 1 - c / a.gs; // framebuffer row of this grid row (flip of measurement_grid.cu:120)
+    float occ_out = 0.0f, free_out = 0.0f;
+
+    const float X = ((float)px + 0.5f) * 2.0f / (float)a.gs - 1.0f;
+    const float Y = ((float)py + 0.5f) * 2.0f / (float)a.gs - 1.0f;
+    const float dx = X, dy = Y + 1.0f; // fan centre at NDC (0,-1), renderer.cpp:54
+    const float deg = atan2f(dy, dx) * (180.0f / 3.14159265358979323846f);
+    int k = (int)floorf(deg - (float)a.a0);
+    k = max(0, min(a.wedges - 1, k));
+    float beta = 0.0f, gamma = 0.0f;
+    bool found = false;
+    for (int attempt = 0; attempt < 3 && !found; attempt++)
+    {
+        const float2 e0 = a.verts[k], e1 = a.verts[k + 1];
+        const float det = e0.x * e1.y - e0.y * e1.x;
+        beta = (dx * e1.y - dy * e1.x) / det;
+        gamma = (e0.x * dy - e0.y * dx) / det;
+        if (gamma < 0.0f && k > 0)
+            k -= 1;
+        else if (beta < 0.0f && k < a.wedges - 1)
+            k += 1;
+        else
+            found = true;
+    }
+    if (found && beta >= 0.0f && gamma >= 0.0f && beta + gamma <= 1.0f)
+    {
+        // texcoords: ((angle - start) / fov, 1) on the arc, (0,0) at the centre (renderer.cpp:13,29)
+        const float s0 = ((float)(a.a0 + k) - a.start_angle) / a.fov;
+        const float s1 = ((float)(a.a0 + k + 1) - a.start_angle) / a.fov;
+        const float s = beta * s0 + gamma * s1;
+        const float t = beta + gamma;
+        const float u = 1.0f - s / (t + 1e-10f); // shader.cpp:29
+        const float v = t;
+        const float fu = u * (float)a.K - 0.5f;
+        const float fv = v * (float)a.H - 0.5f;
+        const float fu0 = floorf(fu), fv0 = floorf(fv);
+        const int i0 = (int)fu0, j0 = (int)fv0;
+        const float wu = fu - fu0, wv = fv - fv0;
+        const float2 t00 = polar_texel(a, i0, j0), t10 = polar_texel(a, i0 + 1, j0);
+        const float2 t01 = polar_texel(a, i0, j0 + 1), t11 = polar_texel(a, i0 + 1, j0 + 1);
+        const float ob = t00.x + wu * (t10.x - t00.x), ot = t01.x + wu * (t11.x - t01.x);
+        const float fb = t00.y + wu * (t10.y - t00.y), ft = t01.y + wu * (t11.y - t01.y);
+        occ_out = ob + wv * (ot - ob);
+        free_out = fb + wv * (ft - fb);
+    }
+    // MeasurementCell {free_mass, occ_mass, likelihood, p_A}, measurement_grid.cu:126-130
+    *reinterpret_cast<float4*>(a.out + c) = make_float4(free_out, occ_out, 1.0f, 1.0f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
+{
+    const int t = blockIdx.x * kBlock + threadIdx.x;
+    if (t >= a.K * a.H)
+        return;
+    const int b = t % a.K, i = t / a.K;
+    out[t] = polar_cell(a, a.beams[b], i);
+}
+
+static MeasArgs make_args(const dogm_meas_handle* m, int K, dogm_meas_cell* out)
+{
+    MeasArgs a;
+    a.gs = m->gs;
+    a.K = K;
+    a.H = m->H;
+    a.a0 = m->a0;
+    a.wedges = m->wedges;
+    a.radius = m->radius;
+    a.start_angle = m->start_angle;
+    a.fov = m->params.fov;
+    a.resolution = m->params.resolution;
+    a.stddev_range = m->params.stddev_range;
+    a.beams = m->d_beams;
+    a.verts = m->d_verts;
+    a.out = out;
+    return a;
+}
+
+static int upload_beams(dogm_meas_handle* m, const float* beams_host, int K, cudaStream_t stream)
+{
+    if (K <= 0 || !beams_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (K > m->max_beams)
+    {
+        cudaStreamSynchronize(stream);
+        cudaFree(m->d_beams);
+        cudaFreeHost(m->h_beams_pinned);
+        m->max_beams = K;
+        DOGM_CHECK(cudaMalloc(&m->d_beams, (size_t)K * sizeof(float)));
+        DOGM_CHECK(cudaMallocHost(&m->h_beams_pinned, (size_t)K * sizeof(float)));
+    }
+    memcpy(m->h_beams_pinned, beams_host, (size_t)K * sizeof(float));
+    DOGM_CHECK(cudaMemcpyAsync(m->d_beams, m->h_beams_pinned, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+} // namespace dogm_b200
+
+using namespace dogm_b200;
+
+extern "C" int dogm_meas_create(const dogm_laser_params* params, float grid_length, float resolution,
+                                dogm_meas_handle** out)
+{
+    if (!params || !out)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    dogm_meas_handle* m = new dogm_meas_handle();
+    m->params = *params;
+    m->grid_length = grid_length;
+    m->resolution = resolution;
+    m->gs = (int)(grid_length / resolution);                 // laser_to_meas_grid.cu:11
+    m->H = (int)(params->max_range / params->resolution);    // laser_to_meas_grid.cu:35
+    m->radius = 2.0f * (params->max_range / grid_length);    // renderer.cpp:52
+    const float half_fov = params->fov / 2.0f;               // renderer.cpp:15-17
+    m->start_angle = 90.0f - half_fov;
+    const float end_angle = 90.0f + half_fov;
+    m->a0 = (int)m->start_angle;
+    std::vector<float2> verts;
+    for (int angle = m->a0; (float)angle <= end_angle; angle++) // renderer.cpp:19-30
+    {
+        const float rad = (float)((double)angle * 3.14159265358979323846 / 180.0);
+        verts.push_back(make_float2(m->radius * cosf(rad), m->radius * sinf(rad)));
+    }
+    m->wedges = (int)verts.size() - 1;
+    m->max_beams = 0;
+    m->d_beams = nullptr;
+    m->h_beams_pinned = nullptr;
+    m->d_verts = nullptr;
+    m->d_grid = nullptr;
+    if (m->gs <= 0 || m->H <= 0 || m->wedges < 1)
+    {
+        delete m;
+        return DOGM_ERR_INVALID_ARGUMENT;
+    }
+    DOGM_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    DOGM_CHECK(cudaMalloc(&m->d_verts, verts.size() * sizeof(float2)));
+    DOGM_CHECK(cudaMemcpy(m->d_verts, verts.data(), verts.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    DOGM_CHECK(cudaMalloc(&m->d_grid, (size_t)m->gs * m->gs * sizeof(dogm_meas_cell)));
+    *out = m;
+    return 0;
+}
+
+extern "C" void dogm_meas_destroy(dogm_meas_handle* m)
+{
+    if (!m)
+        return;
+    cudaStreamSynchronize(m->stream);
+    cudaFree(m->d_beams);
+    cudaFreeHost(m->h_beams_pinned);
+    cudaFree(m->d_verts);
+    cudaFree(m->d_grid);
+    cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int dogm_meas_get_grid_size(const dogm_meas_handle* m)
+{
+    return m ? m->gs : 0;
+}
+
+extern "C" int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams,
+                                  dogm_meas_cell** out_device)
+{
+    if (!m)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = upload_beams(m, beam_ranges_host, num_beams, m->stream);
+    if (e)
+        return e;
+    const MeasArgs a = make_args(m, num_beams, m->d_grid);
+    k_meas_grid<<<div_up((long long)m->gs * m->gs, kBlock), kBlock, 0, m->stream>>>(a);
+    DOGM_CHECK(cudaGetLastError());
+    DOGM_CHECK(cudaStreamSynchronize(m->stream)); // laser_to_meas_grid.cu:67
+    if (out_device)
+        *out_device = m->d_grid;
+    return 0;
+}
+
+extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, const float* beam_ranges_host, int num_beams)
+{
+    if (!m || !h || m->gs != h->gs)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = upload_beams(m, beam_ranges_host, num_beams, h->stream);
+    if (e)
+        return e;
+    const MeasArgs a = make_args(m, num_beams, h->meas);
+    {
+        LaunchScope ls(h, K_MEAS_GRID, 16.0 * h->C);
+        k_meas_grid<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(a);
+    }
+    DOGM_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, float* out_host)
+{
+    if (!m || !out_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = upload_beams(m, beam_ranges_host, num_beams, m->stream);
+    if (e)
+        return e;
+    float2* d_out = nullptr;
+    const size_t count = (size_t)num_beams * m->H;
+    DOGM_CHECK(cudaMalloc(&d_out, count * sizeof(float2)));
+    const MeasArgs a = make_args(m, num_beams, nullptr);
+    k_meas_polar<<<div_up((long long)count, kBlock), kBlock, 0, m->stream>>>(a, d_out);
+    DOGM_CHECK(cudaGetLastError());
+    DOGM_CHECK(cudaMemcpyAsync(out_host, d_out, count * sizeof(float2), cudaMemcpyDeviceToHost, m->stream));
+    DOGM_CHECK(cudaStreamSynchronize(m->stream));
+    cudaFree(d_out);
+    return 0;
+}

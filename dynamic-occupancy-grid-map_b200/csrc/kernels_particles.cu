@@ -1,0 +1,964 @@
+// Particle-side kernels of the DOGM cycle for sm_100a:
+//   prediction (+ pass-0 digit histogram), stable LSD counting sort keyed on the bounded cell index,
+//   per-cell segmented sums, persistent-weight update, joint-weight CDF, resampling search + gather.
+//
+// Reference behaviour restated here (paths relative to the reference's dogm/):
+//   src/kernel/predict.cu:16-52, src/dogm.cu:262-281 (thrust::sort_by_key), src/kernel/particle_to_grid.cu:26-44,
+//   src/kernel/update_persistent_particles.cu:49-87, src/dogm.cu:386-423, src/kernel/resampling.cu:17-68.
+//
+// All float arithmetic that feeds an index (cell index, birth slot, ancestor) is written with explicit
+// round-to-nearest intrinsics and the file is compiled with -fmad=false, so the operation order below IS the
+// numerical contract.
+#include "dogm_internal.cuh"
+
+namespace dogm_b200
+{
+
+// =========================================================================================================
+// prediction
+// =========================================================================================================
+struct PredictArgs
+{
+    float4* state;
+    float* weight;
+    int* idx;
+    int n;
+    int gs;
+    float dt, p_S, sigma_pos, sigma_vel;
+    int shift_active, x_move, y_move;
+    const float4* noise;
+    uint64_t seed;
+    uint32_t cycle;
+    uint32_t* hist; // [tiles][bins] pass-0 histogram
+    int bins;
+    uint32_t mask;
+};
+
+__device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t slot, uint32_t cycle, float sigma_pos,
+                                                       float sigma_vel)
+{
+    const float4 g = philox_normal4(seed, slot, STAGE_PREDICT, cycle);
+    return make_float4(__fmul_rn(g.x, sigma_pos), __fmul_rn(g.y, sigma_pos), __fmul_rn(g.z, sigma_vel),
+                       __fmul_rn(g.w, sigma_vel));
+}
+
+// predictKernel, predict.cu:16-52.  The ego-motion particle shift of moveParticlesKernel
+// (ego_motion_compensation.cu:16-23) is applied first when a shift is pending: same two roundings as the
+// reference's separate kernel.  x' = (x + dt*vx) + noise: three roundings, the GLM mat4*vec4 grouping of predict.cu:33.
+template <bool INJECTED>
+__global__ void __launch_bounds__(kBlock) k_predict(PredictArgs a)
+{
+    extern __shared__ uint32_t s_hist[];
+    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+        s_hist[b] = 0u;
+    __syncthreads();
+
+    const int base = blockIdx.x * kTileItems;
+    const float hi = (float)(a.gs - 1);
+    const float xm = (float)a.x_move, ym = (float)a.y_move;
+#pragma unroll 4
+    for (int j = 0; j < kItemsPerThread; j++)
+    {
+        const int i = base + j * kBlock + threadIdx.x;
+        if (i < a.n)
+        {
+            float4 s = a.state[i];
+            float w = a.weight[i];
+            float4 nz;
+            if (INJECTED)
+                nz = a.noise[i];
+            else
+                nz = predict_noise_philox(a.seed, (uint32_t)i, a.cycle, a.sigma_pos, a.sigma_vel);
+            if (a.shift_active)
+            {
+                s.x = __fsub_rn(s.x, xm);
+                s.y = __fsub_rn(s.y, ym);
+            }
+            const float x = __fadd_rn(__fadd_rn(s.x, __fmul_rn(a.dt, s.z)), nz.x);
+            const float y = __fadd_rn(__fadd_rn(s.y, __fmul_rn(a.dt, s.w)), nz.y);
+            const float vx = __fadd_rn(s.z, nz.z);
+            const float vy = __fadd_rn(s.w, nz.w);
+            w = __fmul_rn(a.p_S, w);
+            if ((x > hi || x < 0.0f) || (y > hi || y < 0.0f))
+                w = 0.0f;
+            const int px = min(max(__float2int_rz(x), 0), a.gs - 1);
+            const int py = min(max(__float2int_rz(y), 0), a.gs - 1);
+            const int cell = px + a.gs * py;
+            a.state[i] = make_float4(x, y, vx, vy);
+            a.weight[i] = w;
+            a.idx[i] = cell;
+            atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t* row = a.hist + (size_t)blockIdx.x * a.bins;
+    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+        row[b] = s_hist[b];
+}
+
+// pass-0 histogram alone (used when the keys did not come from k_predict, e.g. after dogm_set_particles)
+__global__ void __launch_bounds__(kBlock) k_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
+                                                      int shift, uint32_t mask)
+{
+    extern __shared__ uint32_t s_hist[];
+    for (int b = threadIdx.x; b < bins; b += kBlock)
+        s_hist[b] = 0u;
+    __syncthreads();
+    const int base = blockIdx.x * kTileItems;
+#pragma unroll 4
+    for (int j = 0; j < kItemsPerThread; j++)
+    {
+        const int i = base + j * kBlock + threadIdx.x;
+        if (i < n)
+            atomicAdd(&s_hist[((uint32_t)key[i] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * bins;
+    for (int b = threadIdx.x; b < bins; b += kBlock)
+        row[b] = s_hist[b];
+}
+
+// =========================================================================================================
+// counting sort: scan of the [tiles][bins] digit histograms
+//   in : table[t][b] = number of keys of tile t whose digit is b
+//   out: table[t][b] = number of keys with digit b in tiles < t;   bin_base[b] = number of keys with digit < b
+// One CTA per 32 bins, lane = bin, warp w owns a contiguous range of tiles; the last CTA to finish scans the
+// bin totals.
+// =========================================================================================================
+__global__ void __launch_bounds__(kBlock) k_hist_scan(uint32_t* table, int tiles, int bins, uint32_t* bin_tot,
+                                                      uint32_t* bin_base, unsigned int* ticket)
+{
+    __shared__ uint32_t s_part[kWarpsPerBlock][32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bin = blockIdx.x * 32 + lane;
+    const int per = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int t0 = min(warp * per, tiles), t1 = min(t0 + per, tiles);
+
+    uint32_t sum = 0;
+    for (int t = t0; t < t1; t++)
+        sum += table[(size_t)t * bins + bin];
+    s_part[warp][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; w++)
+    {
+        const uint32_t p = s_part[w][lane];
+        if (w < warp)
+            run += p;
+        total += p;
+    }
+    for (int t = t0; t < t1; t++)
+    {
+        const size_t at = (size_t)t * bins + bin;
+        const uint32_t v = table[at];
+        table[at] = run;
+        run += v;
+    }
+    if (warp == 0)
+        bin_tot[bin] = total;
+
+    // last CTA: exclusive scan of the bin totals
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned int done = atomicAdd(ticket, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last)
+        return;
+    __threadfence();
+    __shared__ uint32_t s_warp_tot[kWarpsPerBlock];
+    const int per_thread = (bins + kBlock - 1) / kBlock;
+    const int b0 = min((int)threadIdx.x * per_thread, bins), b1 = min(b0 + per_thread, bins);
+    uint32_t local = 0;
+    for (int b = b0; b < b1; b++)
+        local += __ldcg(&bin_tot[b]);
+    uint32_t incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    if (lane == 31)
+        s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int w = 0; w < warp; w++)
+        off += s_warp_tot[w];
+    uint32_t excl = off + incl - local;
+    for (int b = b0; b < b1; b++)
+    {
+        bin_base[b] = excl;
+        excl += __ldcg(&bin_tot[b]);
+    }
+    if (threadIdx.x == 0)
+        *ticket = 0u;
+}
+
+// =========================================================================================================
+// counting sort: stable scatter of one digit pass (one CTA per tile of 4096 consecutive particles)
+// rank of a particle = bin_base[digit] + (same digit in earlier tiles) + (same digit in earlier warps of the tile)
+//                      + (same digit earlier in its own warp), the last term by __match_any ranking.
+// =========================================================================================================
+struct ScatterArgs
+{
+    const float4* src_state;
+    const int* src_idx;
+    const float* src_weight;
+    const uint8_t* src_assoc;
+    float4* dst_state;
+    int* dst_idx;
+    float* dst_weight;
+    uint8_t* dst_assoc;
+    int n;
+    int shift;
+    uint32_t mask;
+    int bins;
+    const uint32_t* table;    // this pass, exclusive over tiles
+    const uint32_t* bin_base; // this pass
+    uint32_t* next_table;     // next pass histogram (atomics) or nullptr
+    int next_shift;
+    uint32_t next_mask;
+    int next_bins;
+};
+
+__global__ void __launch_bounds__(kBlock) k_scatter(ScatterArgs a)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
+    unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+
+    for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
+        s_cnt[b] = 0;
+    __syncthreads();
+
+    const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
+    unsigned short* my_cnt = s_cnt + warp * a.bins;
+
+    int keys[kRoundsPerWarp];
+    uint32_t packed[kRoundsPerWarp]; // (rank within warp << 16) | digit
+
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const int i = warp_base + r * 32 + lane;
+        const bool valid = i < a.n;
+        const int key = valid ? a.src_idx[i] : 0;
+        const uint32_t digit = valid ? (((uint32_t)key >> a.shift) & a.mask) : 0xffffffffu;
+        const unsigned peers = __match_any_sync(full, digit);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader)
+        {
+            old = my_cnt[digit];
+            my_cnt[digit] = (unsigned short)(old + __popc(peers));
+        }
+        old = __shfl_sync(full, old, leader);
+        keys[r] = key;
+        packed[r] = ((old + __popc(peers & lt)) << 16) | (digit & 0xffffu);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // exclusive prefix over the warps of the tile, and the global offset of every bin for this tile
+    const uint32_t* row = a.table + (size_t)blockIdx.x * a.bins;
+    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++)
+        {
+            const uint32_t c = s_cnt[w * a.bins + b];
+            s_cnt[w * a.bins + b] = (unsigned short)run;
+            run += c;
+        }
+        s_binoff[b] = a.bin_base[b] + row[b];
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const int i = warp_base + r * 32 + lane;
+        if (i < a.n)
+        {
+            const uint32_t digit = packed[r] & 0xffffu;
+            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
+            const int key = keys[r];
+            a.dst_idx[dest] = key;
+            a.dst_state[dest] = a.src_state[i];
+            a.dst_weight[dest] = a.src_weight[i];
+            a.dst_assoc[dest] = a.src_assoc[i];
+            if (a.next_table)
+            {
+                const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
+                atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
+            }
+        }
+    }
+}
+
+// =========================================================================================================
+// per-cell sums over the sorted particles (one warp per 256 consecutive particles, fixed combination order)
+// replaces the reference's  weight scan + prefix differences (dogm.cu:287-288, common.h:25-32, mass_update.cu:76)
+// and the five moment scans (dogm.cu:359-377, statistical_moments.cu:58-76); also yields GridCell.start_idx /
+// end_idx (particle_to_grid.cu:33-40).
+// =========================================================================================================
+__global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, const float* __restrict__ wgt,
+                                                   const float4* __restrict__ st, int n, int* cell_start, int* cell_end,
+                                                   CellSums* sums, SegPiece* lead, SegPiece* trail, int* flags)
+{
+    const int lane = threadIdx.x & 31;
+    const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int base = chunk * kSegChunk;
+    if (base >= n)
+        return;
+    const unsigned full = 0xffffffffu;
+    const unsigned le = lanemask_le();
+
+    int last_key = (base > 0) ? key[base - 1] : -2;
+    bool from_before = true; // no segment head seen in this chunk yet
+    bool carry_open = false;
+    bool first_is_lead = false;
+    double c0 = 0.0;
+    float c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
+
+    for (int step = 0; step < kSegChunk / 32; step++)
+    {
+        const int i = base + step * 32 + lane;
+        const bool valid = i < n;
+        const int k = valid ? key[i] : -3;
+        float w = 0.f, vx = 0.f, vy = 0.f;
+        if (valid)
+        {
+            w = wgt[i];
+            const float4 s = st[i];
+            vx = s.z;
+            vy = s.w;
+        }
+        int kprev = __shfl_up_sync(full, k, 1);
+        if (lane == 0)
+            kprev = last_key;
+        int knext = __shfl_down_sync(full, k, 1);
+        if (lane == 31)
+            knext = (i + 1 < n) ? key[i + 1] : -3;
+        const bool head = valid && (k != kprev);
+        const bool tail = valid && (k != knext);
+        if (step == 0)
+            first_is_lead = (__shfl_sync(full, (int)(valid && !head), 0) != 0);
+
+        const unsigned hm = __ballot_sync(full, head);
+        const unsigned mine = hm & le;
+        const int start_lane = mine ? (31 - __clz(mine)) : -1;
+        const int lo = start_lane < 0 ? 0 : start_lane;
+
+        double v0 = (double)w;
+        const float wx = __fmul_rn(w, vx), wy = __fmul_rn(w, vy);
+        float v1 = wx, v2 = wy, v3 = __fmul_rn(wx, vx), v4 = __fmul_rn(wy, vy), v5 = __fmul_rn(wx, vy);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const double t0 = __shfl_up_sync(full, v0, d);
+            const float t1 = __shfl_up_sync(full, v1, d);
+            const float t2 = __shfl_up_sync(full, v2, d);
+            const float t3 = __shfl_up_sync(full, v3, d);
+            const float t4 = __shfl_up_sync(full, v4, d);
+            const float t5 = __shfl_up_sync(full, v5, d);
+            if (lane - d >= lo)
+            {
+                v0 += t0;
+                v1 += t1;
+                v2 += t2;
+                v3 += t3;
+                v4 += t4;
+                v5 += t5;
+            }
+        }
+        const bool cont = start_lane < 0; // continues the piece carried in from earlier steps / chunks
+        if (cont)
+        {
+            v0 = c0 + v0;
+            v1 = c1 + v1;
+            v2 = c2 + v2;
+            v3 = c3 + v3;
+            v4 = c4 + v4;
+            v5 = c5 + v5;
+        }
+        if (head)
+            cell_start[k] = i;
+        if (tail)
+        {
+            cell_end[k] = i;
+            if (!(cont && from_before))
+            {
+                CellSums cs;
+                cs.s0 = (float)v0;
+                cs.s1 = v1;
+                cs.s2 = v2;
+                cs.s3 = v3;
+                cs.s4 = v4;
+                cs.s5 = v5;
+                cs.pad0 = 0.f;
+                cs.pad1 = 0.f;
+                sums[k] = cs;
+            }
+            else
+            {
+                SegPiece p;
+                p.s0 = v0;
+                p.s1 = v1;
+                p.s2 = v2;
+                p.s3 = v3;
+                p.s4 = v4;
+                p.s5 = v5;
+                p.pad = 0;
+                lead[chunk] = p;
+            }
+        }
+        carry_open = (__shfl_sync(full, (int)(valid && !tail), 31) != 0);
+        const double n0 = __shfl_sync(full, v0, 31);
+        const float n1 = __shfl_sync(full, v1, 31);
+        const float n2 = __shfl_sync(full, v2, 31);
+        const float n3 = __shfl_sync(full, v3, 31);
+        const float n4 = __shfl_sync(full, v4, 31);
+        const float n5 = __shfl_sync(full, v5, 31);
+        if (carry_open)
+        {
+            c0 = n0;
+            c1 = n1;
+            c2 = n2;
+            c3 = n3;
+            c4 = n4;
+            c5 = n5;
+        }
+        else
+        {
+            c0 = 0.0;
+            c1 = c2 = c3 = c4 = c5 = 0.f;
+        }
+        if (hm)
+            from_before = false;
+        last_key = __shfl_sync(full, k, 31);
+    }
+    if (lane == 0)
+    {
+        int f = first_is_lead ? SEG_LEAD : 0;
+        if (carry_open)
+        {
+            SegPiece p;
+            p.s0 = c0;
+            p.s1 = c1;
+            p.s2 = c2;
+            p.s3 = c3;
+            p.s4 = c4;
+            p.s5 = c5;
+            p.pad = 0;
+            f |= SEG_TRAIL;
+            trail[chunk] = p;
+            if (from_before)
+            {
+                f |= SEG_THROUGH;
+                lead[chunk] = p;
+            }
+        }
+        flags[chunk] = f;
+    }
+}
+
+// segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
+__global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ key, int n_chunks, CellSums* sums,
+                                                   const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
+                                                   const int* __restrict__ flags)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= n_chunks)
+        return;
+    const int f = flags[c];
+    if (!(f & SEG_TRAIL) || (f & SEG_THROUGH))
+        return;
+    SegPiece acc = trail[c];
+    int c2 = c + 1;
+    while (c2 < n_chunks)
+    {
+        const SegPiece p = lead[c2];
+        acc.s0 += p.s0;
+        acc.s1 += p.s1;
+        acc.s2 += p.s2;
+        acc.s3 += p.s3;
+        acc.s4 += p.s4;
+        acc.s5 += p.s5;
+        if (!(flags[c2] & SEG_THROUGH))
+            break;
+        c2++;
+    }
+    const int k = key[(c + 1) * kSegChunk - 1];
+    CellSums cs;
+    cs.s0 = (float)acc.s0;
+    cs.s1 = acc.s1;
+    cs.s2 = acc.s2;
+    cs.s3 = acc.s3;
+    cs.s4 = acc.s4;
+    cs.s5 = acc.s5;
+    cs.pad0 = 0.f;
+    cs.pad1 = 0.f;
+    sums[k] = cs;
+}
+
+// =========================================================================================================
+// persistent-particle weights: updatePersistentParticlesKernel1 + 3 (update_persistent_particles.cu:33-57,78-87)
+// with the per-cell constants precomputed by the cell kernel; the over-unit normalisation of
+// normalize_weights (mass_update.cu:51-59) is applied on the fly.
+// =========================================================================================================
+__global__ void __launch_bounds__(kBlock) k_weights(const int* __restrict__ key, const float* __restrict__ wgt,
+                                                    const float4* __restrict__ coef, float* __restrict__ weight_array,
+                                                    int n)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4 c = coef[key[i]];
+    float w = wgt[i];
+    if (c.w > 0.0f)
+        w = __fdiv_rn(w, c.w);
+    const float unnorm = __fmul_rn(c.x, w);
+    weight_array[i] = __fadd_rn(__fmul_rn(c.y, unnorm), __fmul_rn(c.z, w));
+}
+
+// =========================================================================================================
+// joint weight CDF (dogm.cu:390-398): reduce-then-scan in double, fixed order
+// =========================================================================================================
+__device__ __forceinline__ float joint_entry(const float* __restrict__ wa, const float* __restrict__ bw, int N, int n,
+                                             int i)
+{
+    return i < N ? wa[i] : (i < n ? bw[i - N] : 0.0f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_cdf_reduce(const float* __restrict__ wa, const float* __restrict__ bw, int N,
+                                                       int n, double* tile_sum)
+{
+    __shared__ double s_scan[kWarpsPerBlock];
+    const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < kCdfItems; j++)
+        run += (double)joint_entry(wa, bw, N, n, i0 + j);
+    double total;
+    block_inclusive_scan_f64(run, s_scan, &total);
+    if (threadIdx.x == 0)
+        tile_sum[blockIdx.x] = total;
+}
+
+// exclusive scan of up to a few 10^5 block sums by one CTA (thread-serial chunks + one block scan)
+__global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict__ in, double* __restrict__ out_excl,
+                                                        int n, double* total_out)
+{
+    __shared__ double s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + 1023) / 1024;
+    const int b0 = min((int)threadIdx.x * per, n), b1 = min(b0 + per, n);
+    double local = 0.0;
+    for (int b = b0; b < b1; b++)
+        local += in[b];
+    double incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const double t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        double wv = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const double t = __shfl_up_sync(0xffffffffu, wv, d);
+            if (lane >= d)
+                wv += t;
+        }
+        s_warp[lane] = wv; // inclusive over warps
+    }
+    __syncthreads();
+    const double warp_off = warp > 0 ? s_warp[warp - 1] : 0.0;
+    double excl = warp_off + (incl - local);
+    for (int b = b0; b < b1; b++)
+    {
+        const double v = in[b];
+        out_excl[b] = excl;
+        excl += v;
+    }
+    if (threadIdx.x == 1023)
+        *total_out = s_warp[31];
+}
+
+__global__ void __launch_bounds__(kBlock) k_cdf_write(const float* __restrict__ wa, const float* __restrict__ bw, int N,
+                                                      int n, const double* __restrict__ tile_off, double* __restrict__ cdf)
+{
+    __shared__ double s_scan[kWarpsPerBlock];
+    const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
+    double loc[kCdfItems];
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < kCdfItems; j++)
+    {
+        run += (double)joint_entry(wa, bw, N, n, i0 + j);
+        loc[j] = run;
+    }
+    double total;
+    const double incl = block_inclusive_scan_f64(run, s_scan, &total);
+    const double off = tile_off[blockIdx.x] + (incl - run);
+#pragma unroll
+    for (int j = 0; j < kCdfItems; j++)
+        if (i0 + j < n)
+            cdf[i0 + j] = off + loc[j];
+}
+
+// =========================================================================================================
+// resampling: offsets -> ancestor by binary search in the CDF -> gather into the next particle set
+// (resampling.cu:34-68; dogm.cu:400-419).  weight_total stays on the device (no joint_max read-back).
+// =========================================================================================================
+struct ResampleArgs
+{
+    const double* cdf;
+    int n_cdf;
+    int N;
+    ParticleSet src;   // sorted persistent particles
+    ParticleSet birth; // birth particles
+    ParticleSet dst;   // next population
+    int* ancestors;
+    const DeviceScalars* scal;
+    int mode;           // DOGM_RESAMPLE_*
+    int noise_injected; // offsets come from resample_u
+    const float* resample_u;
+    uint64_t seed;
+    uint32_t cycle;
+};
+
+__device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_t slot, uint32_t cycle)
+{
+    const Philox4 p = philox4x32_10(slot, STAGE_RESAMPLE, cycle, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u01_half_open(p.x);
+}
+
+__global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= a.N)
+        return;
+    const double total = a.scal->weight_total;
+    const float joint_max = (float)total;
+    double r;
+    if (a.mode == DOGM_RESAMPLE_INJECTED)
+    {
+        r = (double)__fmul_rn(joint_max, a.resample_u[i]);
+    }
+    else
+    {
+        const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
+        float u;
+        if (a.noise_injected)
+            u = a.resample_u[strat ? i : 0];
+        else
+            u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
+        r = ((double)i + (double)u) * (total / (double)a.N);
+    }
+    int lo = 0, hi = a.n_cdf;
+    while (lo < hi)
+    {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (a.cdf[mid] < r)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const int anc = lo < a.n_cdf ? lo : a.n_cdf - 1;
+    a.ancestors[i] = anc;
+    float4 s;
+    int cell;
+    uint8_t as;
+    if (anc < a.N)
+    {
+        s = a.src.state[anc];
+        cell = a.src.idx[anc];
+        as = a.src.assoc[anc];
+    }
+    else
+    {
+        const int b = anc - a.N;
+        s = a.birth.state[b];
+        cell = a.birth.idx[b];
+        as = a.birth.assoc[b];
+    }
+    a.dst.state[i] = s;
+    a.dst.idx[i] = cell;
+    a.dst.assoc[i] = as;
+    a.dst.weight[i] = __fdiv_rn(joint_max, (float)a.N);
+}
+
+// ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
+__global__ void __launch_bounds__(kBlock) k_search_f32(const float* __restrict__ cdf, int n_cdf,
+                                                       const float* __restrict__ draws, int n_draws, int* out)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n_draws)
+        return;
+    const float r = draws[i];
+    int lo = 0, hi = n_cdf;
+    while (lo < hi)
+    {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (cdf[mid] < r)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[i] = lo < n_cdf ? lo : n_cdf - 1;
+}
+
+// the noise a Philox-mode cycle consumes, written out for a checker
+__global__ void __launch_bounds__(kBlock) k_export_noise(uint64_t seed, uint32_t cycle, int N, int B, float sigma_pos,
+                                                         float sigma_vel, float stddev_velocity, float init_max_velocity,
+                                                         int resample_mode, float4* predict, float2* birth, float2* init,
+                                                         float* resample)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < N)
+    {
+        if (predict)
+            predict[i] = predict_noise_philox(seed, (uint32_t)i, cycle, sigma_pos, sigma_vel);
+        if (init)
+        {
+            const Philox4 p = philox4x32_10((uint32_t)i, STAGE_INIT, cycle, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+            const float span = __fsub_rn(init_max_velocity, -init_max_velocity);
+            init[i] = make_float2(__fadd_rn(-init_max_velocity, __fmul_rn(span, __fsub_rn(1.0f, u01_open_low(p.x)))),
+                                  __fadd_rn(-init_max_velocity, __fmul_rn(span, __fsub_rn(1.0f, u01_open_low(p.y)))));
+        }
+        if (resample)
+            resample[i] = resample_fraction_philox(seed, resample_mode == DOGM_RESAMPLE_STRATIFIED ? (uint32_t)i : 0u, cycle);
+    }
+    if (i < B && birth)
+    {
+        const float4 g = philox_normal4(seed, (uint32_t)i, STAGE_BIRTH, cycle);
+        birth[i] = make_float2(__fmul_rn(g.x, stddev_velocity), __fmul_rn(g.y, stddev_velocity));
+    }
+}
+
+// =========================================================================================================
+// host-side launchers
+// =========================================================================================================
+int run_predict(dogm_handle* h, float dt)
+{
+    if (h->N <= 0)
+        return 0;
+    PredictArgs a;
+    a.state = h->pa.state;
+    a.weight = h->pa.weight;
+    a.idx = h->pa.idx;
+    a.n = h->N;
+    a.gs = h->gs;
+    a.dt = dt;
+    a.p_S = h->params.persistence_prob;
+    a.sigma_pos = h->params.stddev_process_noise_position;
+    a.sigma_vel = h->params.stddev_process_noise_velocity;
+    a.shift_active = (h->shift_particles_pending && h->shift.active) ? 1 : 0;
+    a.x_move = h->shift.x_move;
+    a.y_move = h->shift.y_move;
+    a.noise = h->predict_noise;
+    a.seed = h->opts.seed;
+    a.cycle = h->cycle;
+    a.hist = h->hist[0];
+    a.bins = h->digit_bins[0];
+    a.mask = (uint32_t)(h->digit_bins[0] - 1);
+    const size_t smem = (size_t)a.bins * sizeof(uint32_t);
+    {
+        LaunchScope ls(h, K_PREDICT, 44.0 * h->N);
+        if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
+            k_predict<true><<<h->tiles, kBlock, smem, h->stream>>>(a);
+        else
+            k_predict<false><<<h->tiles, kBlock, smem, h->stream>>>(a);
+    }
+    h->shift_particles_pending = false;
+    h->hist0_valid = true;
+    return (int)cudaGetLastError();
+}
+
+int run_assignment(dogm_handle* h)
+{
+    const int N = h->N;
+    if (N <= 0)
+        return 0;
+    // reinitGridParticleIndices (init.cu:86-93): start = -1 for every cell
+    {
+        LaunchScope ls(h, K_MEMSET, 4.0 * h->C);
+        cudaMemsetAsync(h->cell_start, 0xff, (size_t)h->C * sizeof(int), h->stream);
+    }
+    for (int p = 1; p < h->passes; p++)
+    {
+        LaunchScope ls(h, K_MEMSET, 0.0);
+        cudaMemsetAsync(h->hist[p], 0, (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t), h->stream);
+    }
+    if (!h->hist0_valid)
+    {
+        LaunchScope ls(h, K_TILE_HIST, 4.0 * N);
+        k_tile_hist<<<h->tiles, kBlock, (size_t)h->digit_bins[0] * sizeof(uint32_t), h->stream>>>(
+            h->pa.idx, N, h->hist[0], h->digit_bins[0], h->digit_shift[0], (uint32_t)(h->digit_bins[0] - 1));
+    }
+    for (int p = 0; p < h->passes; p++)
+    {
+        const int bins = h->digit_bins[p];
+        {
+            LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
+            k_hist_scan<<<bins / 32, kBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p], h->bin_base[p],
+                                                             &h->scal->ticket[0]);
+        }
+        ScatterArgs a;
+        a.src_state = h->pa.state;
+        a.src_idx = h->pa.idx;
+        a.src_weight = h->pa.weight;
+        a.src_assoc = h->pa.assoc;
+        a.dst_state = h->pb.state;
+        a.dst_idx = h->pb.idx;
+        a.dst_weight = h->pb.weight;
+        a.dst_assoc = h->pb.assoc;
+        a.n = N;
+        a.shift = h->digit_shift[p];
+        a.mask = (uint32_t)(bins - 1);
+        a.bins = bins;
+        a.table = h->hist[p];
+        a.bin_base = h->bin_base[p];
+        const bool has_next = p + 1 < h->passes;
+        a.next_table = has_next ? h->hist[p + 1] : nullptr;
+        a.next_shift = has_next ? h->digit_shift[p + 1] : 0;
+        a.next_mask = has_next ? (uint32_t)(h->digit_bins[p + 1] - 1) : 0u;
+        a.next_bins = has_next ? h->digit_bins[p + 1] : 0;
+        const size_t smem = (size_t)bins * sizeof(uint32_t) + (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
+        {
+            LaunchScope ls(h, K_SCATTER, 50.0 * N);
+            k_scatter<<<h->tiles, kBlock, smem, h->stream>>>(a);
+        }
+        // the sorted-so-far set becomes particle_array
+        ParticleSet t = h->pa;
+        h->pa = h->pb;
+        h->pb = t;
+    }
+    h->hist0_valid = false;
+    // per-cell sums + start/end over the sorted set
+    {
+        LaunchScope ls(h, K_SEGSUM, 24.0 * N);
+        k_segsum<<<div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->stream>>>(
+            h->pa.idx, h->pa.weight, h->pa.state, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail,
+            h->seg_flags);
+    }
+    {
+        LaunchScope ls(h, K_SEGFIX, 0.0);
+        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->pa.idx, h->n_chunks, h->cell_sums, h->seg_lead,
+                                                                      h->seg_trail, h->seg_flags);
+    }
+    return (int)cudaGetLastError();
+}
+
+int run_persistent_weights(dogm_handle* h)
+{
+    if (h->N <= 0)
+        return 0;
+    LaunchScope ls(h, K_WEIGHTS, 12.0 * h->N);
+    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->pa.idx, h->pa.weight, h->cell_coef, h->weight_array,
+                                                             h->N);
+    return (int)cudaGetLastError();
+}
+
+int run_resampling(dogm_handle* h)
+{
+    const int N = h->N, n = h->N + h->B;
+    if (N <= 0)
+        return 0;
+    {
+        LaunchScope ls(h, K_CDF_REDUCE, 4.0 * n);
+        k_cdf_reduce<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(h->weight_array, h->birth.weight, N, n, h->tile_sum);
+    }
+    {
+        int e = run_blocksum_scan(h, h->tile_sum, h->tile_off, h->n_cdf_tiles, &h->scal->weight_total);
+        if (e)
+            return e;
+    }
+    {
+        LaunchScope ls(h, K_CDF_WRITE, 12.0 * n);
+        k_cdf_write<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(h->weight_array, h->birth.weight, N, n, h->tile_off, h->cdf);
+    }
+    ResampleArgs a;
+    a.cdf = h->cdf;
+    a.n_cdf = n;
+    a.N = N;
+    a.src = h->pa;
+    a.birth = h->birth;
+    a.dst = h->pb;
+    a.ancestors = h->ancestors;
+    a.scal = h->scal;
+    a.mode = h->opts.resample_mode;
+    a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
+    a.resample_u = h->resample_u;
+    a.seed = h->opts.seed;
+    a.cycle = h->cycle;
+    {
+        LaunchScope ls(h, K_RESAMPLE, 58.0 * N);
+        k_resample<<<div_up(N, kBlock), kBlock, 0, h->stream>>>(a);
+    }
+    // publish: particle_array = particle_array_next (dogm.cu:128) by pointer swap
+    ParticleSet t = h->pa;
+    h->pa = h->pb;
+    h->pb = t;
+    return (int)cudaGetLastError();
+}
+
+int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out)
+{
+    LaunchScope ls(h, K_BLOCKSUM_SCAN, 16.0 * n);
+    k_blocksum_scan<<<1, 1024, 0, h->stream>>>(in, out_excl, n, total_out);
+    return (int)cudaGetLastError();
+}
+
+int configure_kernels()
+{
+    const int max_bins = 1 << kMaxDigitBits;
+    const int smem = max_bins * (int)sizeof(uint32_t) + max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
+    return (int)cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+int run_search_ancestors_f32(dogm_handle* h, const float* d_cdf, int n_cdf, const float* d_draws, int n_draws, int* d_out)
+{
+    if (n_draws <= 0)
+        return 0;
+    LaunchScope ls(h, K_MISC, 0.0);
+    k_search_f32<<<div_up(n_draws, kBlock), kBlock, 0, h->stream>>>(d_cdf, n_cdf, d_draws, n_draws, d_out);
+    return (int)cudaGetLastError();
+}
+
+int run_export_noise(dogm_handle* h, uint32_t cycle, float4* d_predict, float2* d_birth, float2* d_init,
+                     float* d_resample)
+{
+    const int m = h->N > h->B ? h->N : h->B;
+    if (m <= 0)
+        return 0;
+    LaunchScope ls(h, K_MISC, 0.0);
+    k_export_noise<<<div_up(m, kBlock), kBlock, 0, h->stream>>>(
+        h->opts.seed, cycle, h->N, h->B, h->params.stddev_process_noise_position, h->params.stddev_process_noise_velocity,
+        h->params.stddev_velocity, h->params.init_max_velocity, h->opts.resample_mode, d_predict, d_birth, d_init,
+        d_resample);
+    return (int)cudaGetLastError();
+}
+
+} // namespace dogm_b200

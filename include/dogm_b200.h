@@ -1,0 +1,306 @@
+/*
+ * dogm_b200.h — C ABI of the B200-native dynamic occupancy grid map (DOGM) update cycle.
+ *
+ * This is the drop-in boundary for the reference's per-cycle path.  The reference has no FFI layer:
+ * callers link its static library and use the C++ class dogm::DOGM (reference dogm/include/dogm/dogm.h:20-199).
+ * Every entry point below replaces one member of that class (file:line cited per entry) and uses plain
+ * pointers and sizes only.  The header-only C++ class in include/dogm/dogm.h re-creates dogm::DOGM on top
+ * of this ABI, so a reference user switches by changing the include path and linking libdogm_b200.so.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success or a cudaError_t value (> 0) / DOGM_ERR_* (< 0);
+ *     like the reference's CHECK_ERROR (cuda_utils.h:13-24) the library also prints
+ *     "GPU Kernel Error: <msg> <file> <line>" and carries on where the reference carries on.
+ *   - not thread-safe; one handle binds to the CUDA device that is current at dogm_create (dogm.cu:39-43).
+ *   - layouts of dogm_params / dogm_grid_cell / dogm_meas_cell and of the particle block are bit-identical to
+ *     DOGM::Params (dogm.h:26-60), GridCell / MeasurementCell / ParticlesSoA (dogm_types.h:13-144).
+ *   - there is no CPU fallback: without a CUDA device dogm_create fails with a cudaError_t.
+ */
+#ifndef DOGM_B200_H
+#define DOGM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOGM_B200_ABI_VERSION 1
+
+#define DOGM_ERR_INVALID_ARGUMENT (-1)
+#define DOGM_ERR_NOT_INITIALIZED (-2)
+#define DOGM_ERR_UNSUPPORTED (-3)
+
+/* == DOGM::Params, dogm.h:26-60 (11 fields, same order, same types) */
+typedef struct dogm_params
+{
+    float size;                          /* grid edge length [m] */
+    float resolution;                    /* cell edge length [m/cell] */
+    int particle_count;                  /* persistent particles N */
+    int new_born_particle_count;         /* birth particles B */
+    float persistence_prob;              /* p_S */
+    float stddev_process_noise_position; /* [cells] */
+    float stddev_process_noise_velocity; /* [cells/s] */
+    float birth_prob;                    /* p_B */
+    float stddev_velocity;               /* birth velocity sigma */
+    float init_max_velocity;             /* first-cycle velocity range */
+    float freespace_discount;            /* alpha; per-cycle factor is alpha^dt */
+} dogm_params;
+
+/* == GridCell, dogm_types.h:13-33 (64 bytes, row-major idx = x + grid_size * y) */
+typedef struct dogm_grid_cell
+{
+    int start_idx;
+    int end_idx;
+    float new_born_occ_mass;
+    float pers_occ_mass;
+    float free_mass;
+    float occ_mass;
+    float pred_occ_mass;
+    float mu_A;
+    float mu_UA;
+    float w_A;
+    float w_UA;
+    float mean_x_vel;
+    float mean_y_vel;
+    float var_x_vel;
+    float var_y_vel;
+    float covar_xy_vel;
+} dogm_grid_cell;
+
+/* == MeasurementCell, dogm_types.h:35-41 (16 bytes) */
+typedef struct dogm_meas_cell
+{
+    float free_mass;
+    float occ_mass;
+    float likelihood;
+    float p_A;
+} dogm_meas_cell;
+
+/* Particle block == ParticlesSoA::memory_block, dogm_types.h:69-85,136-142:
+ *   one block of n * 28 bytes: float4 state[n] (x, y, vx, vy) | int grid_cell_idx[n] | float weight[n] | bool associated[n]
+ *   (the tail n*3 bytes of the block are padding, as in the reference where sizeof(Particle) == 28). */
+#define DOGM_PARTICLE_BLOCK_BYTES(n) ((size_t)(n) * 28u)
+#define DOGM_PARTICLE_STATE_OFFSET(n) ((size_t)0)
+#define DOGM_PARTICLE_IDX_OFFSET(n) ((size_t)(n) * 16u)
+#define DOGM_PARTICLE_WEIGHT_OFFSET(n) ((size_t)(n) * 20u)
+#define DOGM_PARTICLE_ASSOC_OFFSET(n) ((size_t)(n) * 24u)
+
+typedef struct dogm_handle dogm_handle;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Life cycle
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* DOGM::DOGM(const Params&) + DOGM::initialize(), dogm.cu:33-71,95-113.
+ * Allocates every buffer once (no allocation happens in any later call), zero-fills the particle sets
+ * (the reference leaves them uninitialised), cells: masses 0 / indices -1, measurement cells (0,0,1,1). */
+int dogm_create(const dogm_params* params, dogm_handle** out);
+
+/* DOGM::~DOGM(), dogm.cu:73-93 */
+void dogm_destroy(dogm_handle* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The cycle
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* DOGM::updateGrid(measurement_grid, new_x, new_y, new_yaw, dt, device), dogm.cu:115-131.
+ * measurement_grid may be NULL (the reference tolerates the failing copy, dogm_spec.cpp:32; here it means
+ * "keep the previous measurement grid").  Returns after the whole cycle has finished on the device
+ * (the reference ends with cudaDeviceSynchronize, dogm.cu:130). */
+int dogm_update_grid(dogm_handle* h, const dogm_meas_cell* measurement_grid, float new_x, float new_y,
+                     float new_yaw, float dt, int on_device);
+
+/* Same cycle without the final synchronisation (stream-ordered; the host copy of a host measurement grid is
+ * taken before returning).  Pair with dogm_synchronize. */
+int dogm_update_grid_async(dogm_handle* h, const dogm_meas_cell* measurement_grid, float new_x, float new_y,
+                           float new_yaw, float dt, int on_device);
+int dogm_synchronize(dogm_handle* h);
+
+/* The eight public stage methods, dogm.h:148-156 / dogm.cu:217-423.  They run on the handle's stream and
+ * synchronise before returning.  Where this implementation fuses work across the reference's stage borders
+ * the observable state after the *last* stage of a cycle is the reference's; DESIGN.md lists what each stage
+ * leaves behind. */
+int dogm_initialize_particles(dogm_handle* h);                 /* dogm.cu:217-241 */
+int dogm_particle_prediction(dogm_handle* h, float dt);        /* dogm.cu:243-260 */
+int dogm_particle_assignment(dogm_handle* h);                  /* dogm.cu:262-281 */
+int dogm_grid_cell_occupancy_update(dogm_handle* h, float dt); /* dogm.cu:283-298 */
+int dogm_update_persistent_particles(dogm_handle* h);          /* dogm.cu:300-321 */
+int dogm_initialize_new_particles(dogm_handle* h);             /* dogm.cu:323-348 */
+int dogm_statistical_moments(dogm_handle* h);                  /* dogm.cu:350-384 */
+int dogm_resampling(dogm_handle* h);                           /* dogm.cu:386-423, plus the publish of dogm.cu:128 */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Read-out (blocking device-to-host copies, dogm.cu:133-159, dogm.h:111-139)
+ * ---------------------------------------------------------------------------------------------------------- */
+int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host);        /* getGridCells: grid_cell_count * 64 B */
+int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_host); /* getMeasurementCells: count * 16 B */
+int dogm_get_particles(dogm_handle* h, void* out_block);                  /* getParticles: particle block of N */
+int dogm_get_grid_size(const dogm_handle* h);                             /* getGridSize */
+int dogm_get_grid_cell_count(const dogm_handle* h);
+int dogm_get_particle_count(const dogm_handle* h);
+int dogm_get_new_born_particle_count(const dogm_handle* h);
+float dogm_get_resolution(const dogm_handle* h);
+float dogm_get_position_x(const dogm_handle* h);
+float dogm_get_position_y(const dogm_handle* h);
+float dogm_get_yaw(const dogm_handle* h);
+
+/* The reference's public device buffers (dogm.h:159-191).  particle_array / particle_array_next swap roles
+ * inside a cycle (pointer swap instead of the reference's 28*N-byte copy, dogm.cu:128), so re-read this
+ * struct after every call that runs a stage. */
+typedef struct dogm_device_ptrs
+{
+    dogm_grid_cell* grid_cell_array;
+    void* particle_array;           /* particle block of N */
+    void* particle_array_next;      /* particle block of N */
+    void* birth_particle_array;     /* particle block of B */
+    dogm_meas_cell* meas_cell_array;
+    float* weight_array;            /* N */
+    float* born_masses_array;       /* grid_cell_count */
+    int* resampled_idx_array;       /* N ancestors of the last resampling (a temporary in the reference, dogm.cu:413) */
+    double* joint_weight_accum;     /* N + B running sum of [weight_array, birth weights] of the last resampling */
+    int* cell_start_array;          /* grid_cell_count, -1 for empty cells (== GridCell.start_idx) */
+    int* cell_end_array;            /* grid_cell_count, valid where cell_start_array >= 0 */
+} dogm_device_ptrs;
+int dogm_get_device_ptrs(dogm_handle* h, dogm_device_ptrs* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Options and parity hooks (no equivalent in the reference: it hard-codes XORWOW seed 123456, dogm.cu:101)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* How the N sorted resampling offsets are produced */
+#define DOGM_RESAMPLE_SYSTEMATIC 0 /* (i + u0) * total / N with one Philox draw per cycle (default) */
+#define DOGM_RESAMPLE_STRATIFIED 1 /* (i + u_i) * total / N with one Philox draw per particle */
+#define DOGM_RESAMPLE_INJECTED 2   /* total * a_i with a caller-supplied ascending a_i in [0,1): the reference's
+                                      sorted multinomial draws (resampling.cu:17-47) fed from outside */
+
+/* Source of the Gaussian / uniform noise of prediction, birth and first-cycle initialisation */
+#define DOGM_NOISE_PHILOX 0   /* counter-based Philox4x32-10, counter = (slot, stage, cycle) */
+#define DOGM_NOISE_INJECTED 1 /* caller-supplied buffers (dogm_set_noise) */
+
+typedef struct dogm_options
+{
+    uint64_t seed;     /* Philox key (default 123456, the reference's seed) */
+    int resample_mode; /* DOGM_RESAMPLE_* */
+    int noise_mode;    /* DOGM_NOISE_* */
+} dogm_options;
+int dogm_set_options(dogm_handle* h, const dogm_options* opts);
+int dogm_get_options(const dogm_handle* h, dogm_options* out);
+
+/* Injected noise for the NEXT stages that need it (device or host pointers; copied into handle-owned buffers).
+ *   predict_noise : N * 4 floats, per particle (nx, ny, nvx, nvy) already scaled by the process-noise sigmas,
+ *                   i.e. the values predictKernel adds (predict.cu:27-33)
+ *   birth_noise   : B * 2 floats, per birth slot (vx, vy) already scaled by stddev_velocity (init_new_particles.cu:178-187)
+ *   init_velocity : N * 2 floats, first-cycle velocities in [-init_max_velocity, +) (init_new_particles.cu:116-117)
+ *   resample_unit : N floats, ascending, in [0,1): offsets as a fraction of the weight total
+ * Any pointer may be NULL (that buffer keeps its previous content). */
+int dogm_set_noise(dogm_handle* h, const float* predict_noise, const float* birth_noise, const float* init_velocity,
+                   const float* resample_unit, int on_device);
+
+/* Writes the noise the Philox stream of cycle `cycle` will produce into host buffers (same shapes as above;
+ * resample_unit gets the systematic/stratified fractions (i + u)/N).  Lets a checker replay a Philox-mode cycle. */
+int dogm_export_philox_noise(dogm_handle* h, uint32_t cycle, float* predict_noise, float* birth_noise,
+                             float* init_velocity, float* resample_unit);
+uint32_t dogm_get_cycle_counter(const dogm_handle* h);
+
+/* State injection for stage-wise checks */
+int dogm_set_particles(dogm_handle* h, const void* block, int on_device);              /* particle block of N */
+int dogm_set_birth_particles(dogm_handle* h, const void* block, int on_device);        /* particle block of B */
+int dogm_set_grid_cells(dogm_handle* h, const dogm_grid_cell* cells, int on_device);   /* grid_cell_count cells */
+int dogm_set_measurement_cells(dogm_handle* h, const dogm_meas_cell* cells, int on_device);
+int dogm_set_pose(dogm_handle* h, float x, float y, float yaw);                        /* as if a first pose had been received */
+int dogm_get_birth_particles(dogm_handle* h, void* out_block);                         /* particle block of B */
+int dogm_get_weight_array(dogm_handle* h, float* out_host);                            /* N */
+int dogm_get_born_masses(dogm_handle* h, float* out_host);                             /* grid_cell_count */
+int dogm_get_resampled_indices(dogm_handle* h, int* out_host);                         /* N */
+int dogm_get_joint_weight_accum(dogm_handle* h, double* out_host);                     /* N + B */
+int dogm_get_cell_ranges(dogm_handle* h, int* start_host, int* end_host);              /* grid_cell_count each */
+
+/* The ancestor search of the resampling stage on caller-supplied data (resampling.cu:34-47):
+ * out[i] = min(first j with cdf[j] >= draws[i], n_cdf - 1).  Host pointers; float CDF as in the reference. */
+int dogm_search_ancestors_f32(dogm_handle* h, const float* cdf, int n_cdf, const float* sorted_draws, int n_draws,
+                              int* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Measurement grid from a lidar scan (reference LaserMeasurementGrid, laser_to_meas_grid.h:13-35,
+ * laser_to_meas_grid.cu:10-70, kernels measurement_grid.cu:33-89,115-132, GL warp renderer.cpp:11-31,66-84 +
+ * shader.cpp:22-35 replaced by one CUDA kernel)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dogm_laser_params /* == LaserMeasurementGrid::Params, laser_to_meas_grid.h:16-22 */
+{
+    float max_range;    /* [m] */
+    float resolution;   /* [m/bin] */
+    float fov;          /* [deg] */
+    float stddev_range; /* [m] */
+} dogm_laser_params;
+
+typedef struct dogm_meas_handle dogm_meas_handle;
+
+/* LaserMeasurementGrid(params, grid_length, resolution), laser_to_meas_grid.cu:10-18 */
+int dogm_meas_create(const dogm_laser_params* params, float grid_length, float resolution, dogm_meas_handle** out);
+void dogm_meas_destroy(dogm_meas_handle* m);
+/* generateGrid(measurements), laser_to_meas_grid.cu:25-70: host beam ranges (inf = no return) -> device
+ * MeasurementCell[grid_size^2] owned by the generator.  Synchronous like the reference (:67). */
+int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, dogm_meas_cell** out_device);
+/* Same, stream-ordered on the stream of `h` and written straight into h's measurement buffer; the following
+ * dogm_update_grid(h, NULL, ...) then consumes it without the 16*C-byte copy of dogm.cu:207-208. */
+int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, const float* beam_ranges_host, int num_beams);
+/* The polar inverse-sensor-model grid alone (createPolarGridTextureKernel, measurement_grid.cu:72-89):
+ * out_host[(range_bin * num_beams + beam) * 2 + {0: occ, 1: free}], range bins = int(max_range / resolution). */
+int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, float* out_host);
+int dogm_meas_get_grid_size(const dogm_meas_handle* m);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * On-device extraction of dynamic cells (reference computeCellsWithVelocity, demo/utils/image_creation.cpp:19-66):
+ * cells with pignistic occupancy >= min_occupancy and Mahalanobis velocity v' S^-1 v >= min_velocity.
+ * out_host receives up to `capacity` records; returns the number found through *out_count.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dogm_dynamic_cell
+{
+    int cell_idx;
+    float occupancy;
+    float mean_x_vel;
+    float mean_y_vel;
+    float var_x_vel;
+    float var_y_vel;
+    float covar_xy_vel;
+    float mahalanobis;
+} dogm_dynamic_cell;
+int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_velocity, dogm_dynamic_cell* out_host,
+                               int capacity, int* out_count);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Instrumentation for bench.py
+ * ---------------------------------------------------------------------------------------------------------- */
+void* dogm_get_stream(dogm_handle* h);                 /* cudaStream_t every kernel of this handle is launched on */
+uint64_t dogm_get_launch_count(const dogm_handle* h);  /* kernels launched by this handle so far */
+/* Per-kernel device timing with CUDA events on the handle's stream.  enable=1 starts recording an event pair
+ * around every launch of subsequent cycles; dogm_kernel_timing_read sums them per kernel name since the last read. */
+#define DOGM_MAX_KERNEL_SLOTS 48
+typedef struct dogm_kernel_time
+{
+    char name[48];
+    double total_ms;
+    uint64_t launches;
+    double algorithmic_bytes; /* per-launch algorithmic bytes of the last launch */
+} dogm_kernel_time;
+int dogm_kernel_timing_enable(dogm_handle* h, int enable);
+int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, int capacity, int* out_count);
+
+/* Pinned host memory helpers so that callers without a CUDA runtime binding can stage inputs/outputs */
+int dogm_host_alloc_pinned(void** out, size_t bytes);
+int dogm_host_free_pinned(void* p);
+int dogm_device_alloc(void** out, size_t bytes);
+int dogm_device_free(void* p);
+int dogm_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
+int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int dogm_device_count(void);
+int dogm_set_device(int device);
+const char* dogm_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DOGM_B200_H */
