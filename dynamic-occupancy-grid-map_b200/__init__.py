@@ -127,6 +127,8 @@ _SYMBOLS = [
     ("dogm_update_grid", C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]),
     ("dogm_update_grid_async", C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]),
     ("dogm_synchronize", C.c_int, [_P]),
+    ("dogm_update_measurement_grid", C.c_int, [_P, _P, C.c_int]),
+    ("dogm_update_pose", C.c_int, [_P, C.c_float, C.c_float, C.c_float]),
     ("dogm_initialize_particles", C.c_int, [_P]),
     ("dogm_particle_prediction", C.c_int, [_P, C.c_float]),
     ("dogm_particle_assignment", C.c_int, [_P]),
@@ -175,6 +177,9 @@ _SYMBOLS = [
     ("dogm_get_launch_count", C.c_uint64, [_P]),
     ("dogm_kernel_timing_enable", C.c_int, [_P, C.c_int]),
     ("dogm_kernel_timing_read", C.c_int, [_P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]),
+    ("dogm_timer_start", C.c_int, [_P]),
+    ("dogm_timer_stop", C.c_int, [_P]),
+    ("dogm_timer_elapsed_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("dogm_host_alloc_pinned", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("dogm_host_free_pinned", C.c_int, [_P]),
     ("dogm_device_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
@@ -294,6 +299,15 @@ class DOGM:
 
     def synchronize(self) -> None:
         _check(self._lib.dogm_synchronize(self._h), "dogm_synchronize")
+
+    def update_measurement_grid(self, measurement_grid, device=False):
+        _check(
+            self._lib.dogm_update_measurement_grid(self._h, _ptr(measurement_grid), 1 if device else 0),
+            "dogm_update_measurement_grid",
+        )
+
+    def update_pose(self, new_x, new_y, new_yaw):
+        _check(self._lib.dogm_update_pose(self._h, new_x, new_y, new_yaw), "dogm_update_pose")
 
     def initialize_particles(self):
         _check(self._lib.dogm_initialize_particles(self._h), "dogm_initialize_particles")
@@ -465,6 +479,17 @@ class DOGM:
 
     def launch_count(self) -> int:
         return int(self._lib.dogm_get_launch_count(self._h))
+
+    def timer_start(self) -> None:
+        _check(self._lib.dogm_timer_start(self._h), "dogm_timer_start")
+
+    def timer_stop(self) -> None:
+        _check(self._lib.dogm_timer_stop(self._h), "dogm_timer_stop")
+
+    def timer_elapsed_ms(self) -> float:
+        ms = C.c_float(0)
+        _check(self._lib.dogm_timer_elapsed_ms(self._h, C.byref(ms)), "dogm_timer_elapsed_ms")
+        return float(ms.value)
 
     def kernel_timing_enable(self, enable: bool) -> None:
         _check(self._lib.dogm_kernel_timing_enable(self._h, 1 if enable else 0), "dogm_kernel_timing_enable")

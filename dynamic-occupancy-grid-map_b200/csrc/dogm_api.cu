@@ -136,6 +136,7 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     h->hist0_valid = false;
     h->launch_count = 0;
     h->timing = false;
+    h->timer_ready = false;
     h->predict_noise = nullptr;
     h->birth_noise = nullptr;
     h->init_velocity = nullptr;
@@ -268,6 +269,11 @@ extern "C" void dogm_destroy(dogm_handle* h)
     }
     for (auto& ev : h->event_pool)
         cudaEventDestroy(ev);
+    if (h->timer_ready)
+    {
+        cudaEventDestroy(h->timer_e0);
+        cudaEventDestroy(h->timer_e1);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -388,6 +394,29 @@ extern "C" int dogm_synchronize(dogm_handle* h)
         return e;                                                                                                      \
     DOGM_CHECK(cudaStreamSynchronize(h->stream));                                                                      \
     return 0;
+
+extern "C" int dogm_update_measurement_grid(dogm_handle* h, const dogm_meas_cell* measurement_grid, int on_device)
+{
+    STAGE_PROLOGUE();
+    if (h->opts.noise_mode == DOGM_NOISE_INJECTED && !h->first_measurement_received && h->N > 0 && !h->init_velocity)
+        return DOGM_ERR_NOT_INITIALIZED;
+    if (measurement_grid && measurement_grid != h->meas)
+        DOGM_CHECK((cudaError_t)copy_in(h->meas, measurement_grid, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+    if (!h->first_measurement_received)
+    {
+        e = run_init_particles(h);
+        h->first_measurement_received = true;
+    }
+    STAGE_EPILOGUE();
+}
+
+extern "C" int dogm_update_pose(dogm_handle* h, float new_x, float new_y, float new_yaw)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    update_pose(h, new_x, new_y, new_yaw);
+    return 0;
+}
 
 extern "C" int dogm_initialize_particles(dogm_handle* h)
 {
@@ -790,6 +819,48 @@ extern "C" int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, in
         h->acc_launches[k] = 0;
     }
     *out_count = n;
+    return 0;
+}
+
+static int ensure_timer(dogm_handle* h)
+{
+    if (!h->timer_ready)
+    {
+        DOGM_CHECK(cudaEventCreate(&h->timer_e0));
+        DOGM_CHECK(cudaEventCreate(&h->timer_e1));
+        h->timer_ready = true;
+    }
+    return 0;
+}
+
+extern "C" int dogm_timer_start(dogm_handle* h)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = ensure_timer(h);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaEventRecord(h->timer_e0, h->stream));
+    return 0;
+}
+
+extern "C" int dogm_timer_stop(dogm_handle* h)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = ensure_timer(h);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaEventRecord(h->timer_e1, h->stream));
+    return 0;
+}
+
+extern "C" int dogm_timer_elapsed_ms(dogm_handle* h, float* out_ms)
+{
+    if (!h || !out_ms || !h->timer_ready)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaEventSynchronize(h->timer_e1));
+    DOGM_CHECK(cudaEventElapsedTime(out_ms, h->timer_e0, h->timer_e1));
     return 0;
 }
 

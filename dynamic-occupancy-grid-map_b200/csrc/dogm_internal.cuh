@@ -235,6 +235,8 @@ struct dogm_handle
     int* dyn_count_host; // pinned
 
     // instrumentation
+    bool timer_ready;
+    cudaEvent_t timer_e0, timer_e1;
     uint64_t launch_count;
     bool timing;
     std::vector<dogm_b200::TimedLaunch> timed;

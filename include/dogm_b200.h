@@ -122,6 +122,12 @@ int dogm_synchronize(dogm_handle* h);
  * synchronise before returning.  Where this implementation fuses work across the reference's stage borders
  * the observable state after the *last* stage of a cycle is the reference's; DESIGN.md lists what each stage
  * leaves behind. */
+int dogm_update_measurement_grid(dogm_handle* h, const dogm_meas_cell* measurement_grid, int on_device);
+                                                               /* dogm.cu:205-215 (private in the reference) */
+int dogm_update_pose(dogm_handle* h, float new_x, float new_y, float new_yaw);
+                                                               /* dogm.cu:161-203 (private in the reference): records the
+                                                                  pose and arms the ego-motion shift that the next
+                                                                  prediction / occupancy-update stages apply */
 int dogm_initialize_particles(dogm_handle* h);                 /* dogm.cu:217-241 */
 int dogm_particle_prediction(dogm_handle* h, float dt);        /* dogm.cu:243-260 */
 int dogm_particle_assignment(dogm_handle* h);                  /* dogm.cu:262-281 */
@@ -287,6 +293,11 @@ typedef struct dogm_kernel_time
 } dogm_kernel_time;
 int dogm_kernel_timing_enable(dogm_handle* h, int enable);
 int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, int capacity, int* out_count);
+
+/* A CUDA-event stopwatch on the handle's stream (device time of everything enqueued between start and stop) */
+int dogm_timer_start(dogm_handle* h);
+int dogm_timer_stop(dogm_handle* h);
+int dogm_timer_elapsed_ms(dogm_handle* h, float* out_ms); /* synchronises on the stop event */
 
 /* Pinned host memory helpers so that callers without a CUDA runtime binding can stage inputs/outputs */
 int dogm_host_alloc_pinned(void** out, size_t bytes);

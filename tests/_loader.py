@@ -29,3 +29,14 @@ def load_oracle():
     sys.modules["dogm_oracle"] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_ref():
+    """Wrapper of oracle/_ref (the reference's own CUDA code); check `.available()` before use."""
+    if "dogm_ref" in sys.modules:
+        return sys.modules["dogm_ref"]
+    spec = importlib.util.spec_from_file_location("dogm_ref", os.path.join(ROOT, "oracle", "ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["dogm_ref"] = mod
+    spec.loader.exec_module(mod)
+    return mod

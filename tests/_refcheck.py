@@ -1,0 +1,270 @@
+"""Stage-wise comparison of an implementation against snapshots of the reference's own CUDA run
+(oracle/ref.py: RefDOGM.run_cycle_verbose), used with live snapshots on the GPU box and with the committed golden
+fixtures (tests/golden/ref_*.npz) on the CPU.
+
+What can and cannot be equal: prediction, cell indices and the stable sort are bit-exact; everything
+downstream of a thrust::inclusive_scan in the reference (per-cell sums as float prefix differences, birth slot
+boundaries, the joint CDF) carries the reference's own float error of a few ulp of the RUNNING TOTAL, so masses are
+compared with rtol 1e-4 plus that noise floor, and ancestor indices are compared bit-exactly with the reference's own
+CDF and sorted draws fed to the search."""
+import numpy as np
+
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def split_block(block, n):
+    b = np.ascontiguousarray(block).view(np.uint8)
+    state = b[: 16 * n].view("<f4").reshape(n, 4)
+    idx = b[16 * n : 20 * n].view("<i4")
+    weight = b[20 * n : 24 * n].view("<f4")
+    assoc = b[24 * n : 25 * n]
+    return state, idx, weight, assoc
+
+
+class OracleAdapter:
+    """Drives oracle.OracleDOGM (CPU)."""
+
+    def __init__(self, orc, params):
+        self.mod = orc
+        self.o = orc.OracleDOGM(params, resample_mode=orc.RESAMPLE_INJECTED)
+        self.N, self.B = self.o.particle_count, self.o.new_born_particle_count
+
+    def set_state(self, P0, G0, meas, pose0):
+        st, idx, w, a = split_block(P0, self.N)
+        p = self.o.particles
+        p.state[:], p.grid_cell_idx[:], p.weight[:], p.associated[:] = st, idx, w, a
+        self.o.grid_cells[:] = G0.view(self.mod.GRID_CELL_DTYPE)
+        self.o.set_first_measurement_received(True)
+        self.o.update_measurement_grid(meas.view(self.mod.MEAS_CELL_DTYPE))
+        self.o.set_pose(float(pose0[0]), float(pose0[1]), float(pose0[2]))
+
+    def fresh_init(self, meas, iv):
+        self.o.set_noise(init_velocity=iv)
+        self.o.update_measurement_grid(meas.view(self.mod.MEAS_CELL_DTYPE))
+        p = self.o.particles
+        return p.state.copy(), p.grid_cell_idx.copy(), p.weight.copy()
+
+    def set_noise(self, pn, bn, iv, ru):
+        self.o.set_noise(pn, bn, iv, ru)
+
+    def update_pose(self, x, y, yaw):
+        self.o.update_pose(x, y, yaw)
+
+    def predict(self, dt):
+        self.o.particle_prediction(dt)
+        p = self.o.particles
+        return p.state.copy(), p.grid_cell_idx.copy(), p.weight.copy(), p.associated.copy()
+
+    def assignment(self):
+        self.o.particle_assignment()
+        p, g = self.o.particles, self.o.grid_cells
+        return (p.state.copy(), p.grid_cell_idx.copy(), p.weight.copy(), p.associated.copy()), g["start_idx"].copy(), g["end_idx"].copy()
+
+    def occupancy(self, dt):
+        self.o.grid_cell_occupancy_update(dt)
+        return self.o.grid_cells.copy(), self.o.born_masses.copy()
+
+    def persistent(self):
+        self.o.update_persistent_particles()
+        return self.o.weight_array.copy(), self.o.grid_cells.copy()
+
+    def birth(self):
+        self.o.initialize_new_particles()
+        b = self.o.birth_particles
+        return (b.state.copy(), b.grid_cell_idx.copy(), b.weight.copy(), b.associated.copy()), self.o.grid_cells.copy()
+
+    def moments(self):
+        self.o.statistical_moments()
+        return self.o.grid_cells.copy()
+
+    def resampling(self):
+        self.o.resampling()
+        n = self.o.particles_next
+        return self.o.joint_weight_accum.copy(), self.o.resampled_idx.copy(), (n.state.copy(), n.grid_cell_idx.copy(), n.weight.copy(), n.associated.copy())
+
+    def search_f32(self, cdf, draws):
+        return self.mod.search_ancestors_f32(cdf, draws)
+
+    def position(self):
+        return self.o.position
+
+
+class GpuAdapter:
+    """Drives dogm_b200.DOGM (the CUDA library through its C ABI)."""
+
+    def __init__(self, gpu, params):
+        self.mod = gpu
+        self.params = params
+        self.d = gpu.DOGM(params)
+        self.d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
+        self.N, self.B = self.d.particle_count, self.d.new_born_particle_count
+
+    def set_state(self, P0, G0, meas, pose0):
+        self.d.set_particles(self.mod.ParticlesSoA(self.N, np.ascontiguousarray(P0).view(np.uint8).copy()))
+        self.d.set_grid_cells(np.ascontiguousarray(G0).view(self.mod.GRID_CELL_DTYPE))
+        self.d.set_measurement_cells(np.ascontiguousarray(meas).view(self.mod.MEAS_CELL_DTYPE))
+        self.d.set_pose(float(pose0[0]), float(pose0[1]), float(pose0[2]))
+
+    def fresh_init(self, meas, iv):
+        d = self.mod.DOGM(self.params)
+        d.set_options(noise_mode=self.mod.NOISE_INJECTED, resample_mode=self.mod.RESAMPLE_INJECTED)
+        d.set_noise(init_velocity=iv)
+        d.update_measurement_grid(np.ascontiguousarray(meas).view(self.mod.MEAS_CELL_DTYPE))
+        p = d.get_particles()
+        out = p.state.copy(), p.grid_cell_idx.copy(), p.weight.copy()
+        d.close()
+        return out
+
+    def set_noise(self, pn, bn, iv, ru):
+        self.d.set_noise(pn, bn, iv, ru)
+
+    def update_pose(self, x, y, yaw):
+        self.d.update_pose(x, y, yaw)
+
+    def _parts(self, p):
+        return p.state.copy(), p.grid_cell_idx.copy(), p.weight.copy(), p.associated.copy()
+
+    def predict(self, dt):
+        self.d.particle_prediction(dt)
+        return self._parts(self.d.get_particles())
+
+    def assignment(self):
+        self.d.particle_assignment()
+        s, e = self.d.get_cell_ranges()
+        e = np.where(s >= 0, e, -1)
+        return self._parts(self.d.get_particles()), s, e
+
+    def occupancy(self, dt):
+        self.d.grid_cell_occupancy_update(dt)
+        return self.d.get_grid_cells(), self.d.get_born_masses()
+
+    def persistent(self):
+        self.d.update_persistent_particles()
+        return self.d.get_weight_array(), self.d.get_grid_cells()
+
+    def birth(self):
+        self.d.initialize_new_particles()
+        return self._parts(self.d.get_birth_particles()), self.d.get_grid_cells()
+
+    def moments(self):
+        self.d.statistical_moments()
+        return self.d.get_grid_cells()
+
+    def resampling(self):
+        self.d.resampling()
+        return self.d.get_joint_weight_accum(), self.d.get_resampled_indices(), self._parts(self.d.get_particles())
+
+    def search_f32(self, cdf, draws):
+        return self.d.search_ancestors_f32(cdf, draws)
+
+    def position(self):
+        return self.d.get_position_x(), self.d.get_position_y(), self.d.get_yaw()
+
+
+def _close(a, b, rtol, atol):
+    return np.abs(a.astype(np.float64) - b.astype(np.float64)) <= rtol * np.abs(b.astype(np.float64)) + atol
+
+
+def check_first_cycle_init(impl, snap, meas, N, gs):
+    """initializeParticles (dogm.cu:217-241): particles per cell proportional to the measured occupancy (slot borders
+    may move by one against the reference's float scan), positions at cell centres, velocities = the injected draws."""
+    st, idx, w = impl.fresh_init(meas, snap["iv"])
+    rst, ridx, rw, _ = split_block(snap["P0"], N)
+    assert np.array_equal(st[:, 2:], rst[:, 2:]), "first-cycle velocities differ"
+    assert np.array_equal(w, rw), "first-cycle weights differ"
+    mine = np.bincount(idx, minlength=gs * gs).astype(np.int64)
+    ref = np.bincount(ridx, minlength=gs * gs).astype(np.int64)
+    assert np.max(np.abs(np.cumsum(mine) - np.cumsum(ref))) <= 1, "first-cycle slot borders differ by more than one slot"
+    assert np.array_equal(st[:, 0], (idx % gs).astype(np.float32) + np.float32(0.5))
+    assert np.array_equal(st[:, 1], (idx // gs).astype(np.float32) + np.float32(0.5))
+    return float(np.mean(idx == ridx))
+
+
+def check_cycle(impl, snap, meas, x, y, yaw, dt, p_A_is_one=True):
+    """Runs one cycle of `impl` from the reference's starting state and compares stage by stage.  Returns stats."""
+    N, B = impl.N, impl.B
+    stats = {}
+    impl.set_state(snap["P0"], snap["G0"], meas, snap["pose0"])
+    impl.set_noise(snap["pn"], snap["bn"], snap["iv"], snap["ru"])
+
+    # --- pose + prediction: bit-exact (predict.cu:16-52, ego_motion_compensation.cu:16-23)
+    impl.update_pose(x, y, yaw)
+    st, idx, w, _ = impl.predict(dt)
+    rst, ridx, rw, _ = split_block(snap["P1"], N)
+    assert np.array_equal(idx, ridx), "particle-to-cell indices differ from the reference"
+    assert np.array_equal(st.view(np.uint32), rst.view(np.uint32)), "predicted states differ from the reference"
+    assert np.array_equal(w.view(np.uint32), rw.view(np.uint32)), "predicted weights differ from the reference"
+    assert impl.position() == tuple(float(v) for v in snap["pose7"]), "pose bookkeeping differs"
+
+    # --- assignment: the stable sort permutation and the cell ranges are bit-exact (dogm.cu:262-281)
+    (st, idx, w, _), cs, ce = impl.assignment()
+    rst, ridx, rw, _ = split_block(snap["P2"], N)
+    assert np.array_equal(idx, ridx), "sorted cell indices differ"
+    assert np.array_equal(st.view(np.uint32), rst.view(np.uint32)), "sorted states differ (sort not stable?)"
+    assert np.array_equal(w.view(np.uint32), rw.view(np.uint32)), "sorted weights differ"
+    assert np.array_equal(cs, snap["G2"]["start_idx"]) and np.array_equal(ce, snap["G2"]["end_idx"]), "cell ranges differ"
+
+    # --- occupancy update: masses within 1e-4 relative + the reference's scan noise floor
+    total_w = float(np.sum(rw.astype(np.float64)))
+    floor = 8.0 * EPS32 * max(total_w, 1.0)
+    g, born = impl.occupancy(dt)
+    G3 = snap["G3"]
+    worst = 0.0
+    for f in ("pred_occ_mass", "occ_mass", "free_mass", "new_born_occ_mass", "pers_occ_mass"):
+        ok = _close(g[f], G3[f], 1e-4, floor)
+        assert np.all(ok), f"{f}: {np.count_nonzero(~ok)} cells outside tolerance, worst {np.max(np.abs(g[f] - G3[f]))}"
+        denom = np.maximum(np.abs(G3[f].astype(np.float64)), 1e-3)
+        worst = max(worst, float(np.max(np.abs(g[f].astype(np.float64) - G3[f]) / denom)))
+    stats["mass_worst_rel"] = worst
+    assert np.all(_close(born, snap["born3"], 1e-4, floor))
+
+    # --- persistent weights (update_persistent_particles.cu:49-87)
+    wa, g4 = impl.persistent()
+    W4 = snap["W4"]
+    rel = np.abs(wa.astype(np.float64) - W4) / np.maximum(np.abs(W4.astype(np.float64)), 1e-30)
+    per_cell_floor = floor / np.maximum(snap["G3"]["pred_occ_mass"][ridx].astype(np.float64), 1e-12)  # relative error of the cell sum
+    ok = rel <= 1e-4 + 2.0 * per_cell_floor
+    assert np.all(ok | (W4 == 0)), f"weight_array: {np.count_nonzero(~(ok | (W4 == 0)))} particles outside tolerance, worst {rel[~ok].max() if np.any(~ok) else 0}"
+    stats["weight_median_rel"] = float(np.median(rel[W4 > 0])) if np.any(W4 > 0) else 0.0
+
+    # --- birth: total born mass per cell is conserved; slot ownership is racy in the reference
+    (bst, bidx, bw, bas), g5 = impl.birth()
+    rbst, rbidx, rbw, rbas = split_block(snap["BP5"], B)
+    assert np.array_equal(bst[:, 2:], rbst[:, 2:]), "birth velocities differ"
+    C = g5.size
+    mine = np.bincount(bidx, weights=bw.astype(np.float64), minlength=C)
+    owners = np.nonzero(np.bincount(bidx, minlength=C))[0]
+    assert np.all(_close(mine[owners], born[owners], 2e-4, 1e-7)), "birth weights of a cell do not add up to its born mass"
+    assert abs(mine.sum() - float(np.sum(snap["born3"].astype(np.float64)))) <= 1e-3 * max(1.0, mine.sum())
+    stats["birth_slot_match"] = float(np.mean(bidx == rbidx))
+    cnt_m = np.cumsum(np.bincount(bidx, minlength=C))
+    cnt_r = np.cumsum(np.bincount(rbidx, minlength=C))
+    stats["birth_border_max_shift"] = int(np.max(np.abs(cnt_m - cnt_r)))
+
+    # --- moments: mean velocities within 1e-4 relative (+ floor), statistical_moments.cu:78-106
+    g6 = impl.moments()
+    G6 = snap["G6"]
+    occ = (G6["start_idx"] >= 0) & (G6["pers_occ_mass"] > 1e-4)
+    vel_floor = floor * 50.0 / np.maximum(G6["pers_occ_mass"][occ].astype(np.float64), 1e-6)
+    for f in ("mean_x_vel", "mean_y_vel"):
+        a, b = g6[f][occ].astype(np.float64), G6[f][occ].astype(np.float64)
+        ok = np.abs(a - b) <= 1e-4 * np.abs(b) + vel_floor + 1e-4
+        assert np.mean(ok) > 0.999, f"{f}: {np.count_nonzero(~ok)} of {ok.size} cells outside tolerance"
+    empty = G6["start_idx"] < 0
+    assert np.all(g6["mean_x_vel"][empty] == 0) and np.all(g6["var_x_vel"][empty] == 0)
+
+    # --- resampling: CDF within float tolerance; ancestors bit-exact on the reference's own CDF and draws
+    cdf, anc, (nst, nidx, nw, nas) = impl.resampling()
+    rcdf = snap["cdf7"].astype(np.float64)
+    assert np.all(np.abs(cdf[:-1] - rcdf[:-1]) <= 1e-4 * rcdf[:-1] + floor * 4), "joint CDF differs from the reference"
+    got = impl.search_f32(snap["cdf7"], snap["rand7"])
+    assert np.array_equal(got, snap["idx7"]), "ancestor indices differ from the reference (same CDF, same draws)"
+    stats["ancestor_match_own_cdf"] = float(np.mean(anc == snap["idx7"]))
+    jm = np.float32(snap["joint_max7"][0])
+    assert abs(float(nw[0]) - float(jm) / N) <= 1e-4 * float(jm) / N
+    # the gather itself: next[i] = particle[a_i] or birth[a_i - N] (resampling.cu:49-68), checked on own ancestors
+    pers = anc < N
+    assert np.array_equal(nst[pers], st[anc[pers]])
+    assert np.array_equal(nst[~pers], bst[anc[~pers] - N])
+    assert np.array_equal(nidx[pers], idx[anc[pers]])
+    return stats

@@ -1,0 +1,282 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs and identical
+injected noise, free-running over several cycles.
+
+Bar (BASELINE.json north_star): particle-to-cell indices and resample ancestor indices bit-exact; per-cell
+occupied/free masses and mean velocities within 1e-4 relative.  Because every order-dependent sum on both sides is
+accumulated in double and rounded once, the whole particle state is in fact expected to be bit-identical, which is
+what these tests assert; velocity moments (float sums in a different order) are compared with a tolerance."""
+import numpy as np
+import pytest
+
+from conftest import cycle_noise, make_params, synthetic_meas
+
+pytestmark = pytest.mark.gpu
+
+MASS_FIELDS = ["new_born_occ_mass", "pers_occ_mass", "free_mass", "occ_mass", "pred_occ_mass", "w_A", "w_UA"]
+MOMENT_FIELDS = ["mean_x_vel", "mean_y_vel", "var_x_vel", "var_y_vel", "covar_xy_vel"]
+
+
+def assert_particles_equal(got, exp, what, check_weight=True):
+    assert np.array_equal(got.grid_cell_idx, exp.grid_cell_idx), f"{what}: cell indices differ"
+    assert np.array_equal(got.state.view(np.uint32), exp.state.view(np.uint32)), f"{what}: states differ"
+    if check_weight:
+        assert np.array_equal(got.weight.view(np.uint32), exp.weight.view(np.uint32)), f"{what}: weights differ"
+    assert np.array_equal(got.associated, exp.associated), f"{what}: associated flags differ"
+
+
+def assert_cells_match(g, e, vel_scale):
+    assert np.array_equal(g["start_idx"], e["start_idx"])
+    assert np.array_equal(g["end_idx"], e["end_idx"])
+    for f in MASS_FIELDS:
+        # north_star tolerance is 1e-4 relative; the design gives bit-equality, so the check is much tighter
+        assert np.allclose(g[f], e[f], rtol=1e-6, atol=1e-9), f
+    occ = e["start_idx"] >= 0
+    for f in ("mu_A", "mu_UA"):  # defined on non-empty cells only
+        assert np.allclose(g[f][occ], e[f][occ], rtol=1e-6, atol=1e-9), f
+    for f in MOMENT_FIELDS[:2]:
+        assert np.allclose(g[f], e[f], rtol=1e-4, atol=1e-4 * vel_scale), f
+    for f in MOMENT_FIELDS[2:]:
+        assert np.allclose(g[f], e[f], rtol=1e-3, atol=1e-4 * vel_scale * vel_scale), f
+
+
+def compare_after_cycle(d, o, p, tag):
+    N = d.particle_count
+    assert_particles_equal(d.get_particles(), o.particles, f"{tag} particles")
+    assert_particles_equal(d.get_birth_particles(), o.birth_particles, f"{tag} birth particles")
+    assert np.array_equal(d.get_resampled_indices(), o.resampled_idx), f"{tag}: ancestor indices differ"
+    assert np.array_equal(d.get_weight_array().view(np.uint32), o.weight_array.view(np.uint32)), f"{tag}: weight_array"
+    assert np.array_equal(d.get_born_masses().view(np.uint32), o.born_masses.view(np.uint32)), f"{tag}: born masses"
+    assert np.allclose(d.get_joint_weight_accum(), o.joint_weight_accum, rtol=1e-13, atol=0), f"{tag}: cdf"
+    assert_cells_match(d.get_grid_cells(), o.grid_cells, p.stddev_velocity)
+    assert (d.get_position_x(), d.get_position_y(), d.get_yaw()) == o.position
+
+
+def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, **over):
+    rng = np.random.default_rng(seed)
+    p = make_params(gpu, size, res, n, b, **over)
+    po = make_params(orc, size, res, n, b, **over)
+    d = gpu.DOGM(p)
+    d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
+    o = orc.OracleDOGM(po, resample_mode=orc.RESAMPLE_INJECTED)
+    gs = d.grid_size
+    assert gs == o.grid_size
+    meas = None
+    for c in range(cycles):
+        if c % meas_every == 0:
+            meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, gs, rng)
+        pn, bn, iv, ru = cycle_noise(rng, n, b, p)
+        d.set_noise(pn, bn, iv, ru)
+        o.set_noise(pn, bn, iv, ru)
+        x, y = ego[0] * c, ego[1] * c
+        d.update_grid(meas, x, y, 0.0, dt, device=False)
+        o.update_grid(meas.view(orc.MEAS_CELL_DTYPE), x, y, 0.0, dt)
+        compare_after_cycle(d, o, p, f"cycle {c}")
+    d.close()
+    o.close()
+
+
+def test_free_running_single_pass_sort(gpu, orc):
+    # 40x40 cells -> 11 key bits -> one counting-sort pass; ego motion shifts the grid on most cycles
+    free_run(gpu, orc, 10.0, 0.25, 20000, 2000, cycles=6, seed=11)
+
+
+def test_free_running_two_pass_sort(gpu, orc):
+    # 128x128 cells -> 14 key bits -> two passes of 7 bits
+    free_run(gpu, orc, 64.0, 0.5, 100000, 10000, cycles=5, seed=12, ego=(0.3, 0.8))
+
+
+def test_free_running_config1_reference_demo(gpu, orc):
+    # BASELINE.json configs[0]: 250x250 grid, 3e5 persistent + 3e4 birth particles (README.md:20-22)
+    free_run(gpu, orc, 50.0, 0.2, 300000, 30000, cycles=4, seed=13, ego=(0.0, 0.4))
+
+
+def test_free_running_ragged_sizes(gpu, orc):
+    # particle counts that are not multiples of 4 / 32 / the tile sizes; x and y shifts of both signs
+    free_run(gpu, orc, 9.0, 0.3, 1001, 77, cycles=5, seed=14, ego=(-0.7, 0.35))
+    free_run(gpu, orc, 10.0, 1.0, 2, 1, cycles=4, seed=15, ego=(1.5, -2.5))
+    free_run(gpu, orc, 33.0, 0.5, 4097, 513, cycles=3, seed=16, ego=(0.0, 0.0))
+
+
+def test_free_running_dense_scene_over_unit_cells(gpu, orc):
+    # few cells, many particles, no process noise on position: predicted cell masses exceed 1 and get renormalised
+    free_run(gpu, orc, 4.0, 0.5, 30000, 3000, cycles=4, seed=17, ego=(0.0, 0.0),
+             stddev_process_noise_position=0.01, stddev_process_noise_velocity=0.1, stddev_velocity=0.5, init_max_velocity=0.5)
+
+
+def test_null_measurement_grid(gpu, orc):
+    """updateGrid(nullptr, ...) (dogm_spec.cpp:32): the initial measurement grid stays; the cycle still runs."""
+    p = make_params(gpu, 10.0, 1.0, 64, 8)
+    po = make_params(orc, 10.0, 1.0, 64, 8)
+    d = gpu.DOGM(p)
+    d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
+    o = orc.OracleDOGM(po)
+    rng = np.random.default_rng(18)
+    for c in range(3):
+        pn, bn, iv, ru = cycle_noise(rng, 64, 8, p)
+        d.set_noise(pn, bn, iv, ru)
+        o.set_noise(pn, bn, iv, ru)
+        d.update_grid(None, 1.0 * c, 0.0, 0.0, 0.1)
+        o.update_grid(None, 1.0 * c, 0.0, 0.0, 0.1)
+        compare_after_cycle(d, o, p, f"null-meas cycle {c}")
+    m = d.get_measurement_cells()
+    assert np.all(m["likelihood"] == 1.0) and np.all(m["p_A"] == 1.0) and np.all(m["occ_mass"] == 0.0)
+
+
+def test_stage_api_equals_update_grid(gpu, orc):
+    """The eight public stage methods (dogm.h:148-156) run one after the other give the same cycle as updateGrid."""
+    rng = np.random.default_rng(19)
+    n, b = 30000, 3000
+    p = make_params(gpu, 20.0, 0.5, n, b)
+    a, s = gpu.DOGM(p), gpu.DOGM(p)
+    for d in (a, s):
+        d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
+    meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, a.grid_size, rng)
+    for c in range(3):
+        pn, bn, iv, ru = cycle_noise(rng, n, b, p)
+        a.set_noise(pn, bn, iv, ru)
+        s.set_noise(pn, bn, iv, ru)
+        a.update_grid(meas, 0.0, 0.0, 0.0, 0.1, device=False)
+        s.set_measurement_cells(meas)
+        if c == 0:
+            s.initialize_particles()
+        s.particle_prediction(0.1)
+        s.particle_assignment()
+        s.grid_cell_occupancy_update(0.1)
+        s.update_persistent_particles()
+        s.initialize_new_particles()
+        s.statistical_moments()
+        s.resampling()
+        assert_particles_equal(s.get_particles(), a.get_particles(), f"stage-wise cycle {c}")
+        ga, gs_ = a.get_grid_cells(), s.get_grid_cells()
+        assert np.array_equal(ga.view(np.uint8), gs_.view(np.uint8))
+
+
+def test_spec_predict_on_gpu(gpu):
+    """DOGM.Predict, test/dogm_spec.cpp:68-103, against the CUDA library."""
+    p = make_params(gpu, 10.0, 1.0, 2, 1, persistence_prob=0.5, stddev_process_noise_position=0.0,
+                    stddev_process_noise_velocity=0.0, stddev_velocity=10.0)
+    d = gpu.DOGM(p)
+    parts = gpu.ParticlesSoA.from_arrays([[3.25, 4.5, 1.7, -2.3], [7.125, 1.0625, -30.0, 12.5]], [0, 0], [0.37, 0.63])
+    d.set_particles(parts)
+    dt = np.float32(0.1)
+    d.particle_prediction(float(dt))  # Philox noise with sigma = 0 adds exactly 0
+    q = d.get_particles()
+    pred = parts.state.copy()
+    pred[:, 0] = parts.state[:, 0] + dt * parts.state[:, 2]
+    pred[:, 1] = parts.state[:, 1] + dt * parts.state[:, 3]
+    assert np.array_equal(q.state, pred)
+    assert np.array_equal(q.weight, parts.weight * np.float32(0.5))
+
+
+def test_spec_ego_motion_compensation_on_gpu(gpu):
+    """DOGM.EgoMotionCompensation, test/dogm_spec.cpp:10-66: pose bookkeeping and the +3 cell particle shift."""
+    p = make_params(gpu, 10.0, 1.0, 2, 1, persistence_prob=0.5, stddev_process_noise_position=0.0,
+                    stddev_process_noise_velocity=0.0, stddev_velocity=10.0)
+    d = gpu.DOGM(p)
+    d.update_grid(None, 10.0, 10.0, 0.0, 0.0)
+    assert (d.get_position_x(), d.get_position_y()) == (10.0, 10.0)
+    d.update_grid(None, 10.5, 10.5, 0.0, 0.0)
+    assert (d.get_position_x(), d.get_position_y()) == (10.0, 10.0)
+    parts = gpu.ParticlesSoA.from_arrays([[3.25, 4.5, 0.0, 0.0], [5.5, 5.5, 0.0, 0.0]], [0, 0], [0.5, 0.5])
+    d.set_particles(parts)
+    d.update_grid(None, 13.0, 10.0, 0.0, 0.0)
+    assert (d.get_position_x(), d.get_position_y()) == (13.0, 10.0)
+    q = d.get_particles()
+    allowed = {(3.25 + 3.0, 4.5), (5.5 + 3.0, 5.5), (0.5, 0.5)}  # shifted survivors, or a newborn at cell 0's centre
+    for s in q.state:
+        assert (float(s[0]), float(s[1])) in allowed
+
+
+def philox4x32_10(ctr, key):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def test_philox_known_answers_and_device_stream(gpu):
+    # Random123 known-answer vectors for philox4x32-10
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert philox4x32_10((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert philox4x32_10((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == (
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+    # the device stream: resampling fractions are u = (word0 >> 8) * 2^-24 of counter (slot, STAGE_RESAMPLE=4, cycle, 0)
+    p = make_params(gpu, 10.0, 1.0, 64, 8)
+    d = gpu.DOGM(p)
+    seed = 0x1234ABCD5678
+    d.set_options(seed=seed, resample_mode=gpu.RESAMPLE_STRATIFIED)
+    _, _, _, ru = d.export_philox_noise(7)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    exp = np.array([(philox4x32_10((i, 4, 7, 0), key)[0] >> 8) / 2.0**24 for i in range(64)], np.float32)
+    assert np.array_equal(ru, exp)
+    pn, bn, iv, _ = d.export_philox_noise(7)
+    assert np.all(np.isfinite(pn)) and np.all(np.abs(iv) <= 30.0)
+
+
+@pytest.mark.parametrize("mode", ["systematic", "stratified"])
+def test_philox_mode_replayed_by_oracle(gpu, orc, mode):
+    """Production mode: Philox noise generated on the device; the same numbers exported and fed to the oracle."""
+    rng = np.random.default_rng(21)
+    n, b = 50000, 5000
+    p = make_params(gpu, 25.0, 0.5, n, b)
+    po = make_params(orc, 25.0, 0.5, n, b)
+    gmode = gpu.RESAMPLE_SYSTEMATIC if mode == "systematic" else gpu.RESAMPLE_STRATIFIED
+    omode = orc.RESAMPLE_SYSTEMATIC if mode == "systematic" else orc.RESAMPLE_STRATIFIED
+    d = gpu.DOGM(p)
+    d.set_options(seed=987654321, resample_mode=gmode, noise_mode=gpu.NOISE_PHILOX)
+    o = orc.OracleDOGM(po, resample_mode=omode)
+    for c in range(4):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, rng)
+        pn, bn, iv, ru = d.export_philox_noise(d.cycle_counter())
+        o.set_noise(pn, bn, iv, ru)
+        d.update_grid(meas, 0.0, 0.45 * c, 0.0, 0.1, device=False)
+        o.update_grid(meas.view(orc.MEAS_CELL_DTYPE), 0.0, 0.45 * c, 0.0, 0.1)
+        compare_after_cycle(d, o, p, f"philox {mode} cycle {c}")
+    # determinism: a second handle with the same seed reproduces the population bit for bit
+    d2 = gpu.DOGM(p)
+    d2.set_options(seed=987654321, resample_mode=gmode, noise_mode=gpu.NOISE_PHILOX)
+    rng = np.random.default_rng(21)
+    for c in range(4):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d2.grid_size, rng)
+        d2.update_grid(meas, 0.0, 0.45 * c, 0.0, 0.1, device=False)
+    assert np.array_equal(d2.get_particles().block, d.get_particles().block)
+
+
+def test_search_ancestors_f32_kernel(gpu, orc):
+    """resampling.cu:34-47 on a float CDF (the reference's data type), incl. zero-weight entries and ties."""
+    rng = np.random.default_rng(22)
+    w = rng.uniform(0, 1, 200000).astype(np.float32)
+    w[rng.integers(0, w.size, 20000)] = 0.0
+    cdf = np.cumsum(w, dtype=np.float32)
+    draws = np.sort(rng.uniform(0, cdf[-1], 150000).astype(np.float32))
+    draws[:10] = 0.0
+    draws[-1] = cdf[-1]
+    p = make_params(gpu, 10.0, 1.0, 4, 1)
+    d = gpu.DOGM(p)
+    got = d.search_ancestors_f32(cdf, draws)
+    assert np.array_equal(got, orc.search_ancestors_f32(cdf, draws))
+    assert np.array_equal(got, np.minimum(np.searchsorted(cdf, draws, side="left"), cdf.size - 1))
+
+
+def test_dynamic_cell_extraction(gpu, orc):
+    rng = np.random.default_rng(23)
+    n, b = 60000, 6000
+    p = make_params(gpu, 20.0, 0.5, n, b)
+    d = gpu.DOGM(p)
+    for c in range(6):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, np.random.default_rng(5))
+        d.update_grid(meas, 0.0, 0.0, 0.0, 0.1, device=False)
+    cells = d.get_grid_cells()
+    got, count = d.extract_dynamic_cells(0.6, 0.5)
+    rec, n_exp = orc.extract_dynamic_cells(cells.view(orc.GRID_CELL_DTYPE), 0.6, 0.5)
+    assert count == n_exp
+    order = np.argsort(got["cell_idx"])
+    exp_idx = rec[:, 0].copy().view(np.int32)
+    assert np.array_equal(got["cell_idx"][order], np.sort(exp_idx))
+    eo = np.argsort(exp_idx)
+    assert np.allclose(got["occupancy"][order], rec[eo, 1], rtol=1e-6)
+    assert np.allclose(got["mahalanobis"][order], rec[eo, 7], rtol=1e-4, atol=1e-5)

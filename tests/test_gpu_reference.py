@@ -1,0 +1,105 @@
+"""GPU parity against the REFERENCE's own CUDA implementation (oracle/_ref: the unmodified reference sources built
+for sm_100), on identical inputs and the same pre-generated noise (extracted from the reference's XORWOW states):
+particle-to-cell indices, the sorted particle order and resample ancestor indices bit-exact; per-cell masses and mean
+velocities within 1e-4 relative (plus the reference's own float-scan noise floor).  Also replays the committed
+golden fixtures through the CUDA library."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from _loader import ROOT, load_ref
+from _refcheck import GpuAdapter, check_cycle, check_first_cycle_init
+from conftest import make_params, synthetic_meas
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    mod = load_ref()
+    if not mod.available():
+        pytest.skip("oracle/_ref/libdogm_ref.so not built (needs /root/reference at build time)")
+    mod.load_library()
+    return mod
+
+
+def live_case(gpu, ref, size, res, n, b, cycles, ego, seed, dt=0.1):
+    rng = np.random.default_rng(seed)
+    params = make_params(gpu, size, res, n, b)
+    r = ref.RefDOGM(params, gpu.GRID_CELL_DTYPE, gpu.MEAS_CELL_DTYPE)
+    impl = GpuAdapter(gpu, params)
+    all_stats = []
+    for c in range(cycles):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, r.grid_size, rng)
+        x, y = float(np.float32(ego[0] * c)), float(np.float32(ego[1] * c))
+        snap = r.run_cycle_verbose(meas, x, y, 0.0, dt, first_cycle=(c == 0))
+        if c == 0:
+            check_first_cycle_init(impl, snap, meas, n, r.grid_size)
+        stats = check_cycle(impl, snap, meas, x, y, 0.0, dt)
+        all_stats.append(stats)
+        print(f"N={n} cycle {c}: {stats}")
+    r.close()
+    return all_stats
+
+
+def test_reference_small(gpu, ref):
+    live_case(gpu, ref, 16.0, 0.5, 4096, 512, cycles=4, ego=(0.0, 0.6), seed=31)
+
+
+def test_reference_ragged(gpu, ref):
+    live_case(gpu, ref, 9.0, 0.3, 1001, 77, cycles=4, ego=(-0.4, 0.35), seed=32)
+
+
+def test_reference_config1_demo_scale(gpu, ref):
+    # BASELINE.json configs[0]: 250x250 grid, 3e5 + 3e4 particles (the reference demo's grid, README.md:20-22)
+    live_case(gpu, ref, 50.0, 0.2, 300000, 30000, cycles=4, ego=(0.0, 0.4), seed=33)
+
+
+def test_reference_config2_nuss_scale(gpu, ref):
+    # BASELINE.json configs[1]: 1200x1200 grid, 2e6 + 2e5 particles
+    live_case(gpu, ref, 120.0, 0.1, 2000000, 200000, cycles=3, ego=(0.0, 0.4), seed=34)
+
+
+def test_whole_cycle_agrees_with_reference_update_grid(gpu, ref):
+    """The reference's own updateGrid (one call, nothing unrolled) against dogm_update_grid on the same inputs and
+    noise: cell indices of the resampled population's ancestors cannot be compared (different CDF rounding), so the
+    check is on the per-cell masses after three free-running cycles, statistically."""
+    rng = np.random.default_rng(35)
+    n, b = 200000, 20000
+    params = make_params(gpu, 50.0, 0.25, n, b)
+    r = ref.RefDOGM(params, gpu.GRID_CELL_DTYPE, gpu.MEAS_CELL_DTYPE)
+    d = gpu.DOGM(params)
+    d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
+    meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, rng, n_blobs=10)
+    for c in range(4):
+        iv, pn, bn, ru = r.extract_noise(c == 0)
+        d.set_noise(pn, bn, iv, ru)
+        r.update_grid(meas, 0.0, 0.5 * c, 0.0, 0.1)
+        d.update_grid(meas, 0.0, 0.5 * c, 0.0, 0.1, device=False)
+    g, e = d.get_grid_cells(), r.get_grid_cells()
+    # free-running populations differ particle by particle after the first resampling; the maps must still agree
+    assert abs(float(g["occ_mass"].sum()) - float(e["occ_mass"].sum())) <= 2e-2 * float(e["occ_mass"].sum())
+    assert np.mean(np.abs(g["occ_mass"] - e["occ_mass"])) < 5e-3
+    assert np.mean(np.abs(g["free_mass"] - e["free_mass"])) < 5e-3
+    assert (d.get_position_x(), d.get_position_y()) == r.get_pose()[:2]
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_cuda_path_replays_golden_fixture(gpu, path):
+    z = np.load(path)
+    a = z["params"]
+    params = gpu.Params(float(a[0]), float(a[1]), int(a[2]), int(a[3]), *[float(v) for v in a[4:]])
+    impl = GpuAdapter(gpu, params)
+    dt = float(z["dt"][0])
+    for c in range(int(z["cycles"][0])):
+        snap = {k[len(f"c{c}_"):]: z[k] for k in z.files if k.startswith(f"c{c}_")}
+        meas, pose = snap.pop("meas"), snap.pop("pose")
+        for k in ("G0", "G2", "G3", "G4", "G5", "G6"):
+            snap[k] = snap[k].view(gpu.GRID_CELL_DTYPE)
+        if c == 0:
+            check_first_cycle_init(impl, snap, meas, impl.N, impl.d.grid_size)
+        check_cycle(impl, snap, meas, float(pose[0]), float(pose[1]), float(pose[2]), dt)
