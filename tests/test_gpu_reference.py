@@ -39,7 +39,7 @@ def live_case(gpu, ref, size, res, n, b, cycles, ego, seed, dt=0.1):
         snap = r.run_cycle_verbose(meas, x, y, 0.0, dt, first_cycle=(c == 0))
         if c == 0:
             check_first_cycle_init(impl, snap, meas, n, r.grid_size)
-        stats = check_cycle(impl, snap, meas, x, y, 0.0, dt)
+        stats = check_cycle(impl, snap, meas, x, y, 0.0, dt, first_cycle=(c == 0))
         all_stats.append(stats)
         print(f"N={n} cycle {c}: {stats}")
     r.close()
@@ -75,16 +75,28 @@ def test_whole_cycle_agrees_with_reference_update_grid(gpu, ref):
     d = gpu.DOGM(params)
     d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
     meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, rng, n_blobs=10)
+    gs = d.grid_size
     for c in range(4):
         iv, pn, bn, ru = r.extract_noise(c == 0)
         d.set_noise(pn, bn, iv, ru)
         r.update_grid(meas, 0.0, 0.5 * c, 0.0, 0.1)
         d.update_grid(meas, 0.0, 0.5 * c, 0.0, 0.1, device=False)
-    g, e = d.get_grid_cells(), r.get_grid_cells()
-    # free-running populations differ particle by particle after the first resampling; the maps must still agree
-    assert abs(float(g["occ_mass"].sum()) - float(e["occ_mass"].sum())) <= 2e-2 * float(e["occ_mass"].sum())
-    assert np.mean(np.abs(g["occ_mass"] - e["occ_mass"])) < 5e-3
-    assert np.mean(np.abs(g["free_mass"] - e["free_mass"])) < 5e-3
+        g, e = d.get_grid_cells(), r.get_grid_cells()
+        if c == 0:
+            # same initial population up to +-1 slot at cell borders: the maps agree cell by cell
+            for f in ("occ_mass", "free_mass", "pred_occ_mass"):
+                close = np.abs(g[f] - e[f]) <= 1e-4 * np.abs(e[f]) + 1e-5
+                assert close.mean() > 0.995, (f, float(close.mean()))
+        # afterwards the two populations are different samples of the same posterior (the reference's float CDF and
+        # racy birth slots pick other ancestors): compare the maps summed over 10 x 10-cell blocks
+        blk = lambda a: a.reshape(gs // 10, 10, gs // 10, 10).sum(axis=(1, 3))  # noqa: E731
+        for f in ("occ_mass", "free_mass"):
+            gb, eb = blk(g[f].reshape(gs, gs).astype(np.float64)), blk(e[f].reshape(gs, gs).astype(np.float64))
+            big = eb > 5.0
+            rel = np.abs(gb[big] - eb[big]) / eb[big]
+            print(f"cycle {c} {f}: blocks {int(big.sum())}, median rel diff {np.median(rel):.4f}, max {rel.max():.4f}")
+            assert np.median(rel) < 0.02 and rel.max() < 0.15
+        assert abs(float(g["occ_mass"].sum()) - float(e["occ_mass"].sum())) <= 2e-2 * float(e["occ_mass"].sum())
     assert (d.get_position_x(), d.get_position_y()) == r.get_pose()[:2]
 
 
@@ -102,4 +114,4 @@ def test_cuda_path_replays_golden_fixture(gpu, path):
             snap[k] = snap[k].view(gpu.GRID_CELL_DTYPE)
         if c == 0:
             check_first_cycle_init(impl, snap, meas, impl.N, impl.d.grid_size)
-        check_cycle(impl, snap, meas, float(pose[0]), float(pose[1]), float(pose[2]), dt)
+        check_cycle(impl, snap, meas, float(pose[0]), float(pose[1]), float(pose[2]), dt, first_cycle=(c == 0))

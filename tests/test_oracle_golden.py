@@ -34,5 +34,5 @@ def test_oracle_replays_reference_run(orc, path):
             snap[k] = snap[k].view(orc.GRID_CELL_DTYPE)
         if c == 0:
             check_first_cycle_init(OracleAdapter(orc, params), snap, meas, impl.N, gs)
-        stats = check_cycle(impl, snap, meas, float(pose[0]), float(pose[1]), float(pose[2]), dt)
+        stats = check_cycle(impl, snap, meas, float(pose[0]), float(pose[1]), float(pose[2]), dt, first_cycle=(c == 0))
         print(os.path.basename(path), "cycle", c, stats)
