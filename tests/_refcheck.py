@@ -222,6 +222,13 @@ def check_cycle(impl, snap, meas, x, y, yaw, dt, first_cycle=False, p_B=0.02):
         worst = max(worst, float(np.max(np.abs(g[f].astype(np.float64) - G3[f]) / denom)))
     stats["mass_worst_rel"] = worst
     assert np.all(_close(born, snap["born3"], 1e-4, floor * 4.0 / p_B))
+    # arbitration: the predicted occupancy of a cell is the float64 sum of its particles' weights,
+    # capped at 1; this implementation must be within float rounding of it, whatever the reference's scan error is
+    truth = np.minimum(np.bincount(ridx, weights=rw.astype(np.float64), minlength=g.size), 1.0)
+    err_mine = np.abs(g["pred_occ_mass"].astype(np.float64) - truth)
+    err_ref = np.abs(G3["pred_occ_mass"].astype(np.float64) - truth)
+    assert np.all(err_mine <= 2.0 * EPS32 * np.maximum(truth, 1e-30)), "predicted occupancy is not the rounded exact cell sum"
+    stats["pred_occ_err_vs_f64"] = {"mine_max": float(err_mine.max()), "ref_max": float(err_ref.max())}
 
     # --- persistent weights (update_persistent_particles.cu:49-87)
     wa, g4 = impl.persistent()
@@ -268,7 +275,9 @@ def check_cycle(impl, snap, meas, x, y, yaw, dt, first_cycle=False, p_B=0.02):
     rcdf = snap["cdf7"].astype(np.float64)
     # persistent part of the CDF; the birth part [N, N+B) inherits the reference's racy slot ownership (it hands a few
     # percent of the slots to empty cells with weight 0, losing born mass) and is only reported
-    assert np.all(np.abs(cdf[:N] - rcdf[:N]) <= 1e-4 * rcdf[:N] + floor * 4), "joint CDF (persistent part) differs from the reference"
+    # every weight may be off by the relative error of its cell sum (see above) and those errors add up along the CDF
+    cum_tol = np.cumsum(np.abs(W4.astype(np.float64)) * (1e-4 + 6.0 * per_cell_floor)) + 16.0 * EPS32 * rcdf[:N] + floor * 4
+    assert np.all(np.abs(cdf[:N] - rcdf[:N]) <= cum_tol), "joint CDF (persistent part) differs from the reference"
     stats["cdf_birth_part_max_rel"] = float(np.max(np.abs(cdf[N:] - rcdf[N:]) / np.maximum(rcdf[N:], 1e-30))) if B > 0 else 0.0
     got = impl.search_f32(snap["cdf7"], snap["rand7"])
     assert np.array_equal(got, snap["idx7"]), "ancestor indices differ from the reference (same CDF, same draws)"
