@@ -333,10 +333,20 @@ static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float ne
     if (e)
         return e;
     // updateMeasurementGrid, dogm.cu:205-215
+    h->meas_src = nullptr;
     if (meas && meas != h->meas)
     {
-        LaunchScope ls(h, K_MEMSET, 32.0 * h->C);
-        DOGM_CHECK((cudaError_t)copy_in(h->meas, meas, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+        if (on_device && h->first_measurement_received)
+        {
+            // the cell kernel reads the caller's buffer and writes the handle's copy on the way: the reference's
+            // separate 16*C-byte device-to-device copy (dogm.cu:207-208) costs no extra pass
+            h->meas_src = meas;
+        }
+        else
+        {
+            LaunchScope ls(h, K_MEMSET, 32.0 * h->C);
+            DOGM_CHECK((cudaError_t)copy_in(h->meas, meas, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+        }
     }
     if (!h->first_measurement_received)
     {
@@ -533,10 +543,22 @@ extern "C" int dogm_get_joint_weight_accum(dogm_handle* h, double* out_host)
 }
 extern "C" int dogm_get_cell_ranges(dogm_handle* h, int* start_host, int* end_host)
 {
-    int e = copy_out(h, start_host, h ? h->cell_start : nullptr, h ? (size_t)h->C * sizeof(int) : 0);
-    if (e)
-        return e;
-    return copy_out(h, end_host, h->cell_end, (size_t)h->C * sizeof(int));
+    if (!h || !start_host || !end_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (h->ranges_in_soa)
+    { // between particleAssignment and gridCellOccupancyUpdate the ranges live in the compact arrays
+        int e = copy_out(h, start_host, h->cell_start, (size_t)h->C * sizeof(int));
+        if (e)
+            return e;
+        return copy_out(h, end_host, h->cell_end, (size_t)h->C * sizeof(int));
+    }
+    // afterwards they are GridCell.start_idx / end_idx (the cell kernel consumed and reset the compact arrays)
+    DOGM_CHECK(cudaMemcpy2DAsync(start_host, sizeof(int), &h->grid[0].start_idx, sizeof(dogm_grid_cell), sizeof(int),
+                                 (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaMemcpy2DAsync(end_host, sizeof(int), &h->grid[0].end_idx, sizeof(dogm_grid_cell), sizeof(int),
+                                 (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 extern "C" int dogm_get_grid_size(const dogm_handle* h) { return h ? h->gs : 0; }

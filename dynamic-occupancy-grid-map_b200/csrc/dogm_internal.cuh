@@ -40,6 +40,7 @@ inline int div_up(long long a, long long b)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kBlock = 256;           // threads per CTA of every streaming kernel
 constexpr int kWarpsPerBlock = 8;
+constexpr int kWideBlock = 1024;      // CTA size of the kernels that own a whole sort tile / a 32-bin column
 constexpr int kTileItems = 4096;      // particles per sort tile (one CTA, 16 per thread, 512 per warp)
 constexpr int kItemsPerThread = kTileItems / kBlock;
 constexpr int kRoundsPerWarp = kTileItems / kWarpsPerBlock / 32;
@@ -174,6 +175,8 @@ struct dogm_handle
     dogm_meas_cell* meas;
     float* weight_array;
     float* born_masses;
+    const dogm_meas_cell* meas_src; // caller's device measurement grid of the running cycle (copied by the cell kernel)
+    bool ranges_in_soa;             // cell_start / cell_end hold the ranges of the last assignment (not yet consumed)
 
     // per-cell working set
     float* free_cur;  // GridCell.free_mass of the previous cycle (SoA copy; the cell kernel reads it at the shifted index)

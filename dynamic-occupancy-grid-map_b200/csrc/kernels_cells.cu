@@ -20,10 +20,11 @@ namespace dogm_b200
 struct CellArgs
 {
     int C, gs;
-    const int* cell_start;
+    int* cell_start; // read, then reset to -1 for the next cycle's assignment (reinitGridParticleIndices, init.cu:86-93)
     const int* cell_end;
     const CellSums* sums;
-    const dogm_meas_cell* meas;
+    const dogm_meas_cell* meas;  // the measurement grid of this cycle (may be the caller's device buffer)
+    dogm_meas_cell* meas_copy;   // when non-null: the handle's own copy is written on the way (dogm.cu:207-208)
     const float* free_cur;
     float* free_next;
     dogm_grid_cell* grid;
@@ -37,12 +38,18 @@ struct CellArgs
 __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
 {
     __shared__ double s_scan[kWarpsPerBlock];
+    // staging for the 64-byte GridCell records: [warp][part][cell], row stride 34 float4 keeps both the per-thread
+    // writes and the transposed reads free of bank conflicts
+    __shared__ float4 s_out[kWarpsPerBlock][4][34];
     const int c = blockIdx.x * kCellBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = c < a.C;
     float rho_b = 0.0f;
     if (valid)
     {
         const int start = a.cell_start[c];
+        if (start >= 0)
+            a.cell_start[c] = -1;
         const bool occupied = start >= 0;
         int end = -1;
         CellSums cs;
@@ -60,6 +67,8 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
             cs.s5 = hi.y;
         }
         const float4 zq = *reinterpret_cast<const float4*>(a.meas + c);
+        if (a.meas_copy)
+            *reinterpret_cast<float4*>(a.meas_copy + c) = zq;
         const float z_free = zq.x, z_occ = zq.y, lik = zq.z, p_A = zq.w;
 
         // ego-motion compensation of the grid (updatePose dogm.cu:175-193, moveMapKernel
@@ -128,11 +137,23 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
 
         a.born_masses[c] = rho_b;
         a.free_next[c] = free_up;
-        float4* g = reinterpret_cast<float4*>(a.grid + c);
-        g[0] = make_float4(__int_as_float(start), __int_as_float(end), rho_b, rho_p);
-        g[1] = make_float4(free_up, occ_up, m_occ_pred, mu_A);
-        g[2] = make_float4(mu_UA, 0.0f, 0.0f, mean_x); // w_A / w_UA are filled in by k_birth_cells for cells that own slots
-        g[3] = make_float4(mean_y, var_x, var_y, covar);
+        s_out[warp][0][lane] = make_float4(__int_as_float(start), __int_as_float(end), rho_b, rho_p);
+        s_out[warp][1][lane] = make_float4(free_up, occ_up, m_occ_pred, mu_A);
+        s_out[warp][2][lane] = make_float4(mu_UA, 0.0f, 0.0f, mean_x); // w_A / w_UA: k_birth_cells, for cells that own slots
+        s_out[warp][3][lane] = make_float4(mean_y, var_x, var_y, covar);
+    }
+    // the warp's 32 GridCells are 2 KB of contiguous memory: write them as four fully coalesced 512-byte rows
+    __syncwarp();
+    {
+        const int warp_cell0 = blockIdx.x * kCellBlock + warp * 32;
+        float4* gw = reinterpret_cast<float4*>(a.grid + warp_cell0);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+        {
+            const int f = j * 32 + lane; // float4 index inside the warp's block: cell f/4, part f%4
+            if (warp_cell0 + (f >> 2) < a.C)
+                gw[f] = s_out[warp][f & 3][f >> 2];
+        }
     }
     double total;
     block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
@@ -476,7 +497,8 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.cell_start = h->cell_start;
     a.cell_end = h->cell_end;
     a.sums = h->cell_sums;
-    a.meas = h->meas;
+    a.meas = h->meas_src ? h->meas_src : h->meas;
+    a.meas_copy = h->meas_src ? h->meas : nullptr;
     a.free_cur = h->free_cur;
     a.free_next = h->free_next;
     a.grid = h->grid;
@@ -493,6 +515,8 @@ int run_occupancy_update(dogm_handle* h, float dt)
         k_cell<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);
     }
     h->shift_grid_pending = false;
+    h->meas_src = nullptr;
+    h->ranges_in_soa = false;
     float* t = h->free_cur;
     h->free_cur = h->free_next;
     h->free_next = t;

@@ -45,28 +45,33 @@ __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t s
 // predictKernel, predict.cu:16-52.  The ego-motion particle shift of moveParticlesKernel
 // (ego_motion_compensation.cu:16-23) is applied first when a shift is pending: same two roundings as the
 // reference's separate kernel.  x' = (x + dt*vx) + noise: three roundings, the GLM mat4*vec4 grouping of predict.cu:33.
+// One CTA of 1024 threads per sort tile (4 particles per thread): the tile's pass-0 digit histogram comes for free.
 template <bool INJECTED>
-__global__ void __launch_bounds__(kBlock) k_predict(PredictArgs a)
+__global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
     extern __shared__ uint32_t s_hist[];
-    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+    for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         s_hist[b] = 0u;
     __syncthreads();
 
+    float4* __restrict__ state = a.state;
+    float* __restrict__ weight = a.weight;
+    int* __restrict__ idx = a.idx;
+    const float4* __restrict__ noise = a.noise;
     const int base = blockIdx.x * kTileItems;
     const float hi = (float)(a.gs - 1);
     const float xm = (float)a.x_move, ym = (float)a.y_move;
-#pragma unroll 4
-    for (int j = 0; j < kItemsPerThread; j++)
+#pragma unroll
+    for (int j = 0; j < kTileItems / kWideBlock; j++)
     {
-        const int i = base + j * kBlock + threadIdx.x;
+        const int i = base + j * kWideBlock + threadIdx.x;
         if (i < a.n)
         {
-            float4 s = a.state[i];
-            float w = a.weight[i];
+            float4 s = state[i];
+            float w = weight[i];
             float4 nz;
             if (INJECTED)
-                nz = a.noise[i];
+                nz = noise[i];
             else
                 nz = predict_noise_philox(a.seed, (uint32_t)i, a.cycle, a.sigma_pos, a.sigma_vel);
             if (a.shift_active)
@@ -84,37 +89,37 @@ __global__ void __launch_bounds__(kBlock) k_predict(PredictArgs a)
             const int px = min(max(__float2int_rz(x), 0), a.gs - 1);
             const int py = min(max(__float2int_rz(y), 0), a.gs - 1);
             const int cell = px + a.gs * py;
-            a.state[i] = make_float4(x, y, vx, vy);
-            a.weight[i] = w;
-            a.idx[i] = cell;
+            state[i] = make_float4(x, y, vx, vy);
+            weight[i] = w;
+            idx[i] = cell;
             atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
         }
     }
     __syncthreads();
     uint32_t* row = a.hist + (size_t)blockIdx.x * a.bins;
-    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+    for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         row[b] = s_hist[b];
 }
 
 // pass-0 histogram alone (used when the keys did not come from k_predict, e.g. after dogm_set_particles)
-__global__ void __launch_bounds__(kBlock) k_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
-                                                      int shift, uint32_t mask)
+__global__ void __launch_bounds__(kWideBlock) k_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
+                                                          int shift, uint32_t mask)
 {
     extern __shared__ uint32_t s_hist[];
-    for (int b = threadIdx.x; b < bins; b += kBlock)
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
         s_hist[b] = 0u;
     __syncthreads();
     const int base = blockIdx.x * kTileItems;
-#pragma unroll 4
-    for (int j = 0; j < kItemsPerThread; j++)
+#pragma unroll
+    for (int j = 0; j < kTileItems / kWideBlock; j++)
     {
-        const int i = base + j * kBlock + threadIdx.x;
+        const int i = base + j * kWideBlock + threadIdx.x;
         if (i < n)
             atomicAdd(&s_hist[((uint32_t)key[i] >> shift) & mask], 1u);
     }
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * bins;
-    for (int b = threadIdx.x; b < bins; b += kBlock)
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
         row[b] = s_hist[b];
 }
 
@@ -122,39 +127,69 @@ __global__ void __launch_bounds__(kBlock) k_tile_hist(const int* __restrict__ ke
 // counting sort: scan of the [tiles][bins] digit histograms
 //   in : table[t][b] = number of keys of tile t whose digit is b
 //   out: table[t][b] = number of keys with digit b in tiles < t;   bin_base[b] = number of keys with digit < b
-// One CTA per 32 bins, lane = bin, warp w owns a contiguous range of tiles; the last CTA to finish scans the
-// bin totals.
+// One CTA of 32 warps per 32 bins (lane = bin, coalesced 128-byte rows); warp w owns a contiguous range of tiles
+// and keeps 16 independent loads in flight.  The last CTA to finish scans the bin totals.  As a side job every
+// CTA clears its share of the NEXT pass's table (filled with atomics by the scatter kernel that follows).
 // =========================================================================================================
-__global__ void __launch_bounds__(kBlock) k_hist_scan(uint32_t* table, int tiles, int bins, uint32_t* bin_tot,
-                                                      uint32_t* bin_base, unsigned int* ticket)
+constexpr int kScanWarps = kWideBlock / 32;
+constexpr int kScanBatch = 16;
+
+__global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__ table, int tiles, int bins,
+                                                          uint32_t* bin_tot, uint32_t* bin_base, unsigned int* ticket,
+                                                          uint4* __restrict__ zero_ptr, size_t zero_count)
 {
-    __shared__ uint32_t s_part[kWarpsPerBlock][32];
+    __shared__ uint32_t s_part[kScanWarps][32];
+    __shared__ uint32_t s_warp_tot[kScanWarps];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
-    const int per = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int per = (tiles + kScanWarps - 1) / kScanWarps;
     const int t0 = min(warp * per, tiles), t1 = min(t0 + per, tiles);
 
+    // side job: clear this CTA's share of the next table
+    if (zero_ptr)
+    {
+        const size_t share = (zero_count + gridDim.x - 1) / gridDim.x;
+        const size_t z0 = min((size_t)blockIdx.x * share, zero_count), z1 = min(z0 + share, zero_count);
+        for (size_t z = z0 + threadIdx.x; z < z1; z += kWideBlock)
+            zero_ptr[z] = make_uint4(0u, 0u, 0u, 0u);
+    }
+
     uint32_t sum = 0;
-    for (int t = t0; t < t1; t++)
-        sum += table[(size_t)t * bins + bin];
+    for (int tb = t0; tb < t1; tb += kScanBatch)
+    {
+        uint32_t v[kScanBatch];
+#pragma unroll
+        for (int k = 0; k < kScanBatch; k++)
+            v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
+#pragma unroll
+        for (int k = 0; k < kScanBatch; k++)
+            sum += v[k];
+    }
     s_part[warp][lane] = sum;
     __syncthreads();
     uint32_t run = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; w++)
+    for (int w = 0; w < kScanWarps; w++)
     {
         const uint32_t p = s_part[w][lane];
         if (w < warp)
             run += p;
         total += p;
     }
-    for (int t = t0; t < t1; t++)
+    for (int tb = t0; tb < t1; tb += kScanBatch)
     {
-        const size_t at = (size_t)t * bins + bin;
-        const uint32_t v = table[at];
-        table[at] = run;
-        run += v;
+        uint32_t v[kScanBatch];
+#pragma unroll
+        for (int k = 0; k < kScanBatch; k++)
+            v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
+#pragma unroll
+        for (int k = 0; k < kScanBatch; k++)
+            if (tb + k < t1)
+            {
+                table[(size_t)(tb + k) * bins + bin] = run;
+                run += v[k];
+            }
     }
     if (warp == 0)
         bin_tot[bin] = total;
@@ -171,8 +206,7 @@ __global__ void __launch_bounds__(kBlock) k_hist_scan(uint32_t* table, int tiles
     if (!s_last)
         return;
     __threadfence();
-    __shared__ uint32_t s_warp_tot[kWarpsPerBlock];
-    const int per_thread = (bins + kBlock - 1) / kBlock;
+    const int per_thread = (bins + kWideBlock - 1) / kWideBlock;
     const int b0 = min((int)threadIdx.x * per_thread, bins), b1 = min(b0 + per_thread, bins);
     uint32_t local = 0;
     for (int b = b0; b < b1; b++)
@@ -228,24 +262,41 @@ struct ScatterArgs
     int next_bins;
 };
 
-__global__ void __launch_bounds__(kBlock) k_scatter(ScatterArgs a)
+constexpr int kScatterBatch = 4; // rounds whose payload loads are issued together before the scattered stores
+
+__global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
     unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
 
+    const float4* __restrict__ src_state = a.src_state;
+    const int* __restrict__ src_idx = a.src_idx;
+    const float* __restrict__ src_weight = a.src_weight;
+    const uint8_t* __restrict__ src_assoc = a.src_assoc;
+    float4* __restrict__ dst_state = a.dst_state;
+    int* __restrict__ dst_idx = a.dst_idx;
+    float* __restrict__ dst_weight = a.dst_weight;
+    uint8_t* __restrict__ dst_assoc = a.dst_assoc;
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt = lanemask_lt();
+    const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
 
+    // all key loads of the warp's 16 rounds are in flight while the rank counters are cleared
+    int keys[kRoundsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const int i = warp_base + r * 32 + lane;
+        keys[r] = (i < a.n) ? src_idx[i] : 0;
+    }
     for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
         s_cnt[b] = 0;
     __syncthreads();
 
-    const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
     unsigned short* my_cnt = s_cnt + warp * a.bins;
-
-    int keys[kRoundsPerWarp];
     uint32_t packed[kRoundsPerWarp]; // (rank within warp << 16) | digit
 
 #pragma unroll
@@ -253,8 +304,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter(ScatterArgs a)
     {
         const int i = warp_base + r * 32 + lane;
         const bool valid = i < a.n;
-        const int key = valid ? a.src_idx[i] : 0;
-        const uint32_t digit = valid ? (((uint32_t)key >> a.shift) & a.mask) : 0xffffffffu;
+        const uint32_t digit = valid ? (((uint32_t)keys[r] >> a.shift) & a.mask) : 0xffffffffu;
         const unsigned peers = __match_any_sync(full, digit);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
@@ -264,14 +314,13 @@ __global__ void __launch_bounds__(kBlock) k_scatter(ScatterArgs a)
             my_cnt[digit] = (unsigned short)(old + __popc(peers));
         }
         old = __shfl_sync(full, old, leader);
-        keys[r] = key;
         packed[r] = ((old + __popc(peers & lt)) << 16) | (digit & 0xffffu);
         __syncwarp();
     }
     __syncthreads();
 
     // exclusive prefix over the warps of the tile, and the global offset of every bin for this tile
-    const uint32_t* row = a.table + (size_t)blockIdx.x * a.bins;
+    const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins;
     for (int b = threadIdx.x; b < a.bins; b += kBlock)
     {
         uint32_t run = 0;
@@ -287,22 +336,41 @@ __global__ void __launch_bounds__(kBlock) k_scatter(ScatterArgs a)
     __syncthreads();
 
 #pragma unroll
-    for (int r = 0; r < kRoundsPerWarp; r++)
+    for (int r0 = 0; r0 < kRoundsPerWarp; r0 += kScatterBatch)
     {
-        const int i = warp_base + r * 32 + lane;
-        if (i < a.n)
+        float4 st[kScatterBatch];
+        float wt[kScatterBatch];
+        uint8_t as[kScatterBatch];
+#pragma unroll
+        for (int q = 0; q < kScatterBatch; q++)
         {
-            const uint32_t digit = packed[r] & 0xffffu;
-            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
-            const int key = keys[r];
-            a.dst_idx[dest] = key;
-            a.dst_state[dest] = a.src_state[i];
-            a.dst_weight[dest] = a.src_weight[i];
-            a.dst_assoc[dest] = a.src_assoc[i];
-            if (a.next_table)
+            const int i = warp_base + (r0 + q) * 32 + lane;
+            if (i < a.n)
             {
-                const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
-                atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
+                st[q] = src_state[i];
+                wt[q] = src_weight[i];
+                as[q] = src_assoc[i];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kScatterBatch; q++)
+        {
+            const int r = r0 + q;
+            const int i = warp_base + r * 32 + lane;
+            if (i < a.n)
+            {
+                const uint32_t digit = packed[r] & 0xffffu;
+                const uint32_t dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
+                const int key = keys[r];
+                dst_idx[dest] = key;
+                dst_state[dest] = st[q];
+                dst_weight[dest] = wt[q];
+                dst_assoc[dest] = as[q];
+                if (a.next_table)
+                {
+                    const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
+                    atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
+                }
             }
         }
     }
@@ -787,9 +855,9 @@ int run_predict(dogm_handle* h, float dt)
     {
         LaunchScope ls(h, K_PREDICT, 44.0 * h->N);
         if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
-            k_predict<true><<<h->tiles, kBlock, smem, h->stream>>>(a);
+            k_predict<true><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
         else
-            k_predict<false><<<h->tiles, kBlock, smem, h->stream>>>(a);
+            k_predict<false><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
     }
     h->shift_particles_pending = false;
     h->hist0_valid = true;
@@ -801,20 +869,18 @@ int run_assignment(dogm_handle* h)
     const int N = h->N;
     if (N <= 0)
         return 0;
-    // reinitGridParticleIndices (init.cu:86-93): start = -1 for every cell
+    // reinitGridParticleIndices (init.cu:86-93): cell_start is all -1 here: k_init_grid set it and the cell kernel
+    // resets every entry it consumes; only when the ranges were never consumed (stage API) a memset is needed
+    if (h->ranges_in_soa)
     {
         LaunchScope ls(h, K_MEMSET, 4.0 * h->C);
         cudaMemsetAsync(h->cell_start, 0xff, (size_t)h->C * sizeof(int), h->stream);
     }
-    for (int p = 1; p < h->passes; p++)
-    {
-        LaunchScope ls(h, K_MEMSET, 0.0);
-        cudaMemsetAsync(h->hist[p], 0, (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t), h->stream);
-    }
+    h->ranges_in_soa = true;
     if (!h->hist0_valid)
     {
         LaunchScope ls(h, K_TILE_HIST, 4.0 * N);
-        k_tile_hist<<<h->tiles, kBlock, (size_t)h->digit_bins[0] * sizeof(uint32_t), h->stream>>>(
+        k_tile_hist<<<h->tiles, kWideBlock, (size_t)h->digit_bins[0] * sizeof(uint32_t), h->stream>>>(
             h->pa.idx, N, h->hist[0], h->digit_bins[0], h->digit_shift[0], (uint32_t)(h->digit_bins[0] - 1));
     }
     for (int p = 0; p < h->passes; p++)
@@ -822,8 +888,12 @@ int run_assignment(dogm_handle* h)
         const int bins = h->digit_bins[p];
         {
             LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
-            k_hist_scan<<<bins / 32, kBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p], h->bin_base[p],
-                                                             &h->scal->ticket[0]);
+            // the table of the next pass is cleared here, before the scatter below fills it with atomics
+            const bool nxt = p + 1 < h->passes;
+            const size_t zero_count = nxt ? ((size_t)h->tiles * h->digit_bins[p + 1] * sizeof(uint32_t)) / sizeof(uint4) : 0;
+            k_hist_scan<<<bins / 32, kWideBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p], h->bin_base[p],
+                                                               &h->scal->ticket[0], nxt ? (uint4*)h->hist[p + 1] : nullptr,
+                                                               zero_count);
         }
         ScatterArgs a;
         a.src_state = h->pa.state;

@@ -75,9 +75,11 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b)
 {
     const float u1 = u01_open_low(a);
     const float u2 = u01_half_open(b);
-    const float r = sqrtf(-2.0f * logf(u1));
+    // SFU intrinsics (the reference's curand_normal does the same, curand_normal.h:70-87): the noise is a pure
+    // function of the counter on the device; a checker gets the values through dogm_export_philox_noise
+    const float r = sqrtf(-2.0f * __logf(u1));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    __sincosf(6.283185307179586f * u2, &s, &c);
     return make_float2(r * c, r * s);
 }
 
