@@ -163,8 +163,13 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     int e = 0;
     e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
     particle_set_assign(h->pa, blk, h->N);
-    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
-    particle_set_assign(h->pb, blk, h->N);
+    e |= alloc_zero((void**)&h->rec_cur, (N ? N : 1) * sizeof(PRec));
+    e |= alloc_zero((void**)&h->rec_alt, (N ? N : 1) * sizeof(PRec));
+    e |= alloc_zero((void**)&h->skey, (N ? N : 1) * sizeof(int));
+    e |= alloc_zero((void**)&h->sw, (N ? N : 1) * sizeof(float));
+    h->pa_current = true;
+    h->rec_valid = false;
+    h->sorted_valid = false;
     e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(B));
     particle_set_assign(h->birth, blk, h->B);
     e |= alloc_zero((void**)&h->grid, C * sizeof(dogm_grid_cell));
@@ -224,7 +229,10 @@ extern "C" void dogm_destroy(dogm_handle* h)
         return;
     cudaStreamSynchronize(h->stream);
     cudaFree(h->pa.block);
-    cudaFree(h->pb.block);
+    cudaFree(h->rec_cur);
+    cudaFree(h->rec_alt);
+    cudaFree(h->skey);
+    cudaFree(h->sw);
     cudaFree(h->birth.block);
     cudaFree(h->grid);
     cudaFree(h->meas);
@@ -519,7 +527,12 @@ extern "C" int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_ho
 }
 extern "C" int dogm_get_particles(dogm_handle* h, void* out_block)
 {
-    return copy_out(h, out_block, h ? h->pa.block : nullptr, h ? DOGM_PARTICLE_BLOCK_BYTES(h->N) : 0);
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int e = ensure_soa(h); // between prediction and resampling the particles live in the record buffers
+    if (e)
+        return e;
+    return copy_out(h, out_block, h->pa.block, DOGM_PARTICLE_BLOCK_BYTES(h->N));
 }
 extern "C" int dogm_get_birth_particles(dogm_handle* h, void* out_block)
 {
@@ -576,8 +589,9 @@ extern "C" int dogm_get_device_ptrs(dogm_handle* h, dogm_device_ptrs* out)
     if (!h || !out)
         return DOGM_ERR_INVALID_ARGUMENT;
     out->grid_cell_array = h->grid;
+    ensure_soa(h);
     out->particle_array = h->pa.block;
-    out->particle_array_next = h->pb.block;
+    out->particle_array_next = h->pa.block; // resampling writes the next population in place (no 28*N-byte publish copy)
     out->birth_particle_array = h->birth.block;
     out->meas_cell_array = h->meas;
     out->weight_array = h->weight_array;
@@ -679,6 +693,9 @@ extern "C" int dogm_set_particles(dogm_handle* h, const void* block, int on_devi
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK((cudaError_t)copy_in(h->pa.block, block, DOGM_PARTICLE_BLOCK_BYTES(h->N), on_device, h->stream));
     h->hist0_valid = false;
+    h->pa_current = true;
+    h->rec_valid = false;
+    h->sorted_valid = false;
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -75,6 +75,15 @@ inline void particle_set_assign(ParticleSet& p, void* block, int n)
     p.assoc = (uint8_t*)(b + DOGM_PARTICLE_ASSOC_OFFSET(n));
 }
 
+struct __align__(16) PRec // a particle inside a cycle: one 32-byte DRAM sector
+{
+    float4 state;   // x, y, vx, vy
+    int key;        // grid_cell_idx
+    float weight;
+    uint32_t assoc; // associated flag
+    uint32_t pad;
+};
+
 struct __align__(16) CellSums // per non-empty cell, written by the segmented reduction
 {
     float s0; // sum w           (accumulated in double, rounded once)
@@ -168,8 +177,14 @@ struct dogm_handle
     cudaStream_t stream;
 
     // reference-visible buffers (dogm.h:159-191)
-    dogm_b200::ParticleSet pa;    // particle_array
-    dogm_b200::ParticleSet pb;    // particle_array_next
+    dogm_b200::ParticleSet pa;    // particle_array (== particle_array_next: the next population is written in place)
+    dogm_b200::PRec* rec_cur;     // the particles of the running cycle as 32-byte records (predicted, then sorted)
+    dogm_b200::PRec* rec_alt;     // ping-pong partner of rec_cur for the sort passes
+    int* skey;                    // sorted cell indices (compact copy, written by the segmented reduction)
+    float* sw;                    // sorted predicted weights (compact copy)
+    bool pa_current;              // the SoA block holds the current particles (false between prediction and resampling)
+    bool rec_valid;               // rec_cur holds the current particles
+    bool sorted_valid;            // rec_cur / skey / sw are sorted by cell and the per-cell sums exist
     dogm_b200::ParticleSet birth; // birth_particle_array
     dogm_grid_cell* grid;
     dogm_meas_cell* meas;
@@ -265,6 +280,7 @@ struct LaunchScope
 };
 
 // stage launchers (kernels_particles.cu / kernels_cells.cu / kernels_meas.cu); all stream-ordered on h->stream
+int ensure_soa(dogm_handle* h); // materialise the SoA block from the records when a caller wants to see it
 int run_init_particles(dogm_handle* h);
 int run_predict(dogm_handle* h, float dt);
 int run_assignment(dogm_handle* h);

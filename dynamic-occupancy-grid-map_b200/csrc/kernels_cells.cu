@@ -486,6 +486,9 @@ int run_init_particles(dogm_handle* h)
         k_init_particles<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(a);
     }
     h->hist0_valid = false;
+    h->pa_current = true;
+    h->rec_valid = false;
+    h->sorted_valid = false;
     return (int)cudaGetLastError();
 }
 

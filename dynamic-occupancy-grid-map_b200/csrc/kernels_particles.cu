@@ -6,6 +6,10 @@
 //   src/kernel/predict.cu:16-52, src/dogm.cu:262-281 (thrust::sort_by_key), src/kernel/particle_to_grid.cu:26-44,
 //   src/kernel/update_persistent_particles.cu:49-87, src/dogm.cu:386-423, src/kernel/resampling.cu:17-68.
 //
+// Data layout inside a cycle: the public population lives in the reference's ParticlesSoA block (`pa`); prediction
+// turns it into 32-byte records (PRec: one DRAM sector per particle) which the sort passes move, the segmented
+// reduction reads and the resampling gather fetches; resampling writes the next population back into `pa`.
+//
 // All float arithmetic that feeds an index (cell index, birth slot, ancestor) is written with explicit
 // round-to-nearest intrinsics and the file is compiled with -fmad=false, so the operation order below IS the
 // numerical contract.
@@ -15,13 +19,48 @@ namespace dogm_b200
 {
 
 // =========================================================================================================
+// record helpers
+// =========================================================================================================
+__device__ __forceinline__ float4 rec_hi(int key, float w, uint32_t assoc)
+{
+    return make_float4(__int_as_float(key), w, __uint_as_float(assoc), 0.0f);
+}
+
+__device__ __forceinline__ float4 shfl4(const float4& v, int src)
+{
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+
+// Every lane holds one record and its destination.  Written with two instructions that each cover 16 whole
+// records (lane l stores half l&1 of the record held by lane (l>>1) + 16*h): a store instruction then touches at
+// most 16 sectors instead of 32, which halves the L1TEX wavefronts of the scattered write.
+__device__ __forceinline__ void store_records_paired(PRec* __restrict__ dst, uint32_t dest, const float4& lo,
+                                                     const float4& hi, bool valid, int lane)
+{
+    const int part = lane & 1;
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+    {
+        const int src = (lane >> 1) + 16 * h;
+        const uint32_t d = __shfl_sync(0xffffffffu, dest, src);
+        const int v = __shfl_sync(0xffffffffu, (int)valid, src);
+        const float4 a = shfl4(lo, src);
+        const float4 b = shfl4(hi, src);
+        if (v)
+            reinterpret_cast<float4*>(dst + d)[part] = part ? b : a;
+    }
+}
+
+// =========================================================================================================
 // prediction
 // =========================================================================================================
 struct PredictArgs
 {
-    float4* state;
-    float* weight;
-    int* idx;
+    const float4* state;
+    const float* weight;
+    const uint8_t* assoc;
+    PRec* out;
     int n;
     int gs;
     float dt, p_S, sigma_pos, sigma_vel;
@@ -54,10 +93,11 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
         s_hist[b] = 0u;
     __syncthreads();
 
-    float4* __restrict__ state = a.state;
-    float* __restrict__ weight = a.weight;
-    int* __restrict__ idx = a.idx;
+    const float4* __restrict__ state = a.state;
+    const float* __restrict__ weight = a.weight;
+    const uint8_t* __restrict__ assoc = a.assoc;
     const float4* __restrict__ noise = a.noise;
+    PRec* __restrict__ out = a.out;
     const int base = blockIdx.x * kTileItems;
     const float hi = (float)(a.gs - 1);
     const float xm = (float)a.x_move, ym = (float)a.y_move;
@@ -69,6 +109,7 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
         {
             float4 s = state[i];
             float w = weight[i];
+            const uint32_t as = assoc[i];
             float4 nz;
             if (INJECTED)
                 nz = noise[i];
@@ -89,9 +130,9 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
             const int px = min(max(__float2int_rz(x), 0), a.gs - 1);
             const int py = min(max(__float2int_rz(y), 0), a.gs - 1);
             const int cell = px + a.gs * py;
-            state[i] = make_float4(x, y, vx, vy);
-            weight[i] = w;
-            idx[i] = cell;
+            float4* o = reinterpret_cast<float4*>(out + i);
+            o[0] = make_float4(x, y, vx, vy);
+            o[1] = rec_hi(cell, w, as);
             atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
         }
     }
@@ -101,9 +142,12 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
         row[b] = s_hist[b];
 }
 
-// pass-0 histogram alone (used when the keys did not come from k_predict, e.g. after dogm_set_particles)
-__global__ void __launch_bounds__(kWideBlock) k_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
-                                                          int shift, uint32_t mask)
+// SoA -> records without prediction (+ pass-0 histogram): the entry into the sort when the keys did not come from
+// k_predict, e.g. dogm_particle_assignment right after dogm_set_particles
+__global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restrict__ state, const int* __restrict__ idx,
+                                                           const float* __restrict__ weight,
+                                                           const uint8_t* __restrict__ assoc, PRec* __restrict__ out,
+                                                           int n, uint32_t* hist, int bins, uint32_t mask)
 {
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
@@ -115,12 +159,56 @@ __global__ void __launch_bounds__(kWideBlock) k_tile_hist(const int* __restrict_
     {
         const int i = base + j * kWideBlock + threadIdx.x;
         if (i < n)
-            atomicAdd(&s_hist[((uint32_t)key[i] >> shift) & mask], 1u);
+        {
+            const int key = idx[i];
+            float4* o = reinterpret_cast<float4*>(out + i);
+            o[0] = state[i];
+            o[1] = rec_hi(key, weight[i], assoc[i]);
+            atomicAdd(&s_hist[(uint32_t)key & mask], 1u);
+        }
     }
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * bins;
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
         row[b] = s_hist[b];
+}
+
+// pass-0 histogram of records that are already in place (assignment called twice in a row)
+__global__ void __launch_bounds__(kWideBlock) k_rec_tile_hist(const PRec* __restrict__ rec, int n, uint32_t* hist,
+                                                              int bins, uint32_t mask)
+{
+    extern __shared__ uint32_t s_hist[];
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
+        s_hist[b] = 0u;
+    __syncthreads();
+    const int base = blockIdx.x * kTileItems;
+#pragma unroll
+    for (int j = 0; j < kTileItems / kWideBlock; j++)
+    {
+        const int i = base + j * kWideBlock + threadIdx.x;
+        if (i < n)
+            atomicAdd(&s_hist[(uint32_t)rec[i].key & mask], 1u);
+    }
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * bins;
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
+        row[b] = s_hist[b];
+}
+
+// records -> the reference's SoA block (read-out between stages: getParticles after prediction / assignment)
+__global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ rec, float4* __restrict__ state,
+                                                       int* __restrict__ idx, float* __restrict__ weight,
+                                                       uint8_t* __restrict__ assoc, int n)
+{
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4* r = reinterpret_cast<const float4*>(rec + i);
+    const float4 lo = r[0], hi = r[1];
+    state[i] = lo;
+    idx[i] = __float_as_int(hi.x);
+    weight[i] = hi.y;
+    assoc[i] = (uint8_t)__float_as_uint(hi.z);
 }
 
 // =========================================================================================================
@@ -236,20 +324,14 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
 }
 
 // =========================================================================================================
-// counting sort: stable scatter of one digit pass (one CTA per tile of 4096 consecutive particles)
-// rank of a particle = bin_base[digit] + (same digit in earlier tiles) + (same digit in earlier warps of the tile)
-//                      + (same digit earlier in its own warp), the last term by __match_any ranking.
+// counting sort: stable scatter of one digit pass (one CTA per tile of 4096 consecutive records)
+// rank of a record = bin_base[digit] + (same digit in earlier tiles) + (same digit in earlier warps of the tile)
+//                    + (same digit earlier in its own warp), the last term by __match_any ranking.
 // =========================================================================================================
 struct ScatterArgs
 {
-    const float4* src_state;
-    const int* src_idx;
-    const float* src_weight;
-    const uint8_t* src_assoc;
-    float4* dst_state;
-    int* dst_idx;
-    float* dst_weight;
-    uint8_t* dst_assoc;
+    const PRec* src;
+    PRec* dst;
     int n;
     int shift;
     uint32_t mask;
@@ -262,7 +344,7 @@ struct ScatterArgs
     int next_bins;
 };
 
-constexpr int kScatterBatch = 4; // rounds whose payload loads are issued together before the scattered stores
+constexpr int kScatterBatch = 2; // rounds whose record loads are issued together before the scattered stores
 
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
@@ -270,14 +352,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
     unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
 
-    const float4* __restrict__ src_state = a.src_state;
-    const int* __restrict__ src_idx = a.src_idx;
-    const float* __restrict__ src_weight = a.src_weight;
-    const uint8_t* __restrict__ src_assoc = a.src_assoc;
-    float4* __restrict__ dst_state = a.dst_state;
-    int* __restrict__ dst_idx = a.dst_idx;
-    float* __restrict__ dst_weight = a.dst_weight;
-    uint8_t* __restrict__ dst_assoc = a.dst_assoc;
+    const PRec* __restrict__ src = a.src;
+    PRec* __restrict__ dst = a.dst;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
@@ -290,7 +366,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
         const int i = warp_base + r * 32 + lane;
-        keys[r] = (i < a.n) ? src_idx[i] : 0;
+        keys[r] = (i < a.n) ? src[i].key : 0;
     }
     for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
         s_cnt[b] = 0;
@@ -338,18 +414,16 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 #pragma unroll
     for (int r0 = 0; r0 < kRoundsPerWarp; r0 += kScatterBatch)
     {
-        float4 st[kScatterBatch];
-        float wt[kScatterBatch];
-        uint8_t as[kScatterBatch];
+        float4 lo[kScatterBatch], hi[kScatterBatch];
 #pragma unroll
         for (int q = 0; q < kScatterBatch; q++)
         {
             const int i = warp_base + (r0 + q) * 32 + lane;
             if (i < a.n)
             {
-                st[q] = src_state[i];
-                wt[q] = src_weight[i];
-                as[q] = src_assoc[i];
+                const float4* p = reinterpret_cast<const float4*>(src + i);
+                lo[q] = p[0];
+                hi[q] = p[1];
             }
         }
 #pragma unroll
@@ -357,34 +431,33 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
         {
             const int r = r0 + q;
             const int i = warp_base + r * 32 + lane;
-            if (i < a.n)
+            const bool valid = i < a.n;
+            uint32_t dest = 0;
+            if (valid)
             {
                 const uint32_t digit = packed[r] & 0xffffu;
-                const uint32_t dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
-                const int key = keys[r];
-                dst_idx[dest] = key;
-                dst_state[dest] = st[q];
-                dst_weight[dest] = wt[q];
-                dst_assoc[dest] = as[q];
+                dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
                 if (a.next_table)
                 {
-                    const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
+                    const uint32_t nd = ((uint32_t)keys[r] >> a.next_shift) & a.next_mask;
                     atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
                 }
             }
+            store_records_paired(dst, dest, lo[q], hi[q], valid, lane);
         }
     }
 }
 
 // =========================================================================================================
-// per-cell sums over the sorted particles (one warp per 256 consecutive particles, fixed combination order)
+// per-cell sums over the sorted records (one warp per 256 consecutive records, fixed combination order)
 // replaces the reference's  weight scan + prefix differences (dogm.cu:287-288, common.h:25-32, mass_update.cu:76)
 // and the five moment scans (dogm.cu:359-377, statistical_moments.cu:58-76); also yields GridCell.start_idx /
-// end_idx (particle_to_grid.cu:33-40).
+// end_idx (particle_to_grid.cu:33-40) and compact copies of the sorted keys / predicted weights for the kernels
+// that need nothing else of a particle.
 // =========================================================================================================
-__global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, const float* __restrict__ wgt,
-                                                   const float4* __restrict__ st, int n, int* cell_start, int* cell_end,
-                                                   CellSums* sums, SegPiece* lead, SegPiece* trail, int* flags)
+__global__ void __launch_bounds__(kBlock) k_segsum(const PRec* __restrict__ rec, int n, int* cell_start, int* cell_end,
+                                                   CellSums* sums, SegPiece* lead, SegPiece* trail, int* flags,
+                                                   int* __restrict__ skey, float* __restrict__ sw)
 {
     const int lane = threadIdx.x & 31;
     const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
@@ -394,7 +467,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, 
     const unsigned full = 0xffffffffu;
     const unsigned le = lanemask_le();
 
-    int last_key = (base > 0) ? key[base - 1] : -2;
+    int last_key = (base > 0) ? rec[base - 1].key : -2;
     bool from_before = true; // no segment head seen in this chunk yet
     bool carry_open = false;
     bool first_is_lead = false;
@@ -405,21 +478,25 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, 
     {
         const int i = base + step * 32 + lane;
         const bool valid = i < n;
-        const int k = valid ? key[i] : -3;
+        int k = -3;
         float w = 0.f, vx = 0.f, vy = 0.f;
         if (valid)
         {
-            w = wgt[i];
-            const float4 s = st[i];
-            vx = s.z;
-            vy = s.w;
+            const float4* p = reinterpret_cast<const float4*>(rec + i);
+            const float4 lo = p[0], hi = p[1];
+            k = __float_as_int(hi.x);
+            w = hi.y;
+            vx = lo.z;
+            vy = lo.w;
+            skey[i] = k;
+            sw[i] = w;
         }
         int kprev = __shfl_up_sync(full, k, 1);
         if (lane == 0)
             kprev = last_key;
         int knext = __shfl_down_sync(full, k, 1);
         if (lane == 31)
-            knext = (i + 1 < n) ? key[i + 1] : -3;
+            knext = (i + 1 < n) ? rec[i + 1].key : -3;
         const bool head = valid && (k != kprev);
         const bool tail = valid && (k != knext);
         if (step == 0)
@@ -428,7 +505,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, 
         const unsigned hm = __ballot_sync(full, head);
         const unsigned mine = hm & le;
         const int start_lane = mine ? (31 - __clz(mine)) : -1;
-        const int lo = start_lane < 0 ? 0 : start_lane;
+        const int lo_lane = start_lane < 0 ? 0 : start_lane;
 
         double v0 = (double)w;
         const float wx = __fmul_rn(w, vx), wy = __fmul_rn(w, vy);
@@ -442,7 +519,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, 
             const float t3 = __shfl_up_sync(full, v3, d);
             const float t4 = __shfl_up_sync(full, v4, d);
             const float t5 = __shfl_up_sync(full, v5, d);
-            if (lane - d >= lo)
+            if (lane - d >= lo_lane)
             {
                 v0 += t0;
                 v1 += t1;
@@ -544,7 +621,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int* __restrict__ key, 
 }
 
 // segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
-__global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ key, int n_chunks, CellSums* sums,
+__global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ skey, int n_chunks, CellSums* sums,
                                                    const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
                                                    const int* __restrict__ flags)
 {
@@ -569,7 +646,7 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ key, 
             break;
         c2++;
     }
-    const int k = key[(c + 1) * kSegChunk - 1];
+    const int k = skey[(c + 1) * kSegChunk - 1];
     CellSums cs;
     cs.s0 = (float)acc.s0;
     cs.s1 = acc.s1;
@@ -704,7 +781,7 @@ struct ResampleArgs
     const double* cdf;
     int n_cdf;
     int N;
-    ParticleSet src;   // sorted persistent particles
+    const PRec* src;   // sorted persistent particles
     ParticleSet birth; // birth particles
     ParticleSet dst;   // next population
     int* ancestors;
@@ -760,9 +837,11 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     uint8_t as;
     if (anc < a.N)
     {
-        s = a.src.state[anc];
-        cell = a.src.idx[anc];
-        as = a.src.assoc[anc];
+        const float4* p = reinterpret_cast<const float4*>(a.src + anc);
+        const float4 rlo = p[0], rhi = p[1];
+        s = rlo;
+        cell = __float_as_int(rhi.x);
+        as = (uint8_t)__float_as_uint(rhi.z);
     }
     else
     {
@@ -828,14 +907,34 @@ __global__ void __launch_bounds__(kBlock) k_export_noise(uint64_t seed, uint32_t
 // =========================================================================================================
 // host-side launchers
 // =========================================================================================================
+
+// make the SoA block `pa` current again (read-out / re-entry between stages)
+int ensure_soa(dogm_handle* h)
+{
+    if (h->pa_current || h->N <= 0)
+    {
+        h->pa_current = true;
+        return 0;
+    }
+    LaunchScope ls(h, K_MISC, 0.0);
+    k_rec_to_soa<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->rec_cur, h->pa.state, h->pa.idx, h->pa.weight,
+                                                                h->pa.assoc, h->N);
+    h->pa_current = true;
+    return (int)cudaGetLastError();
+}
+
 int run_predict(dogm_handle* h, float dt)
 {
     if (h->N <= 0)
         return 0;
+    int e = ensure_soa(h);
+    if (e)
+        return e;
     PredictArgs a;
     a.state = h->pa.state;
     a.weight = h->pa.weight;
-    a.idx = h->pa.idx;
+    a.assoc = h->pa.assoc;
+    a.out = h->rec_cur;
     a.n = h->N;
     a.gs = h->gs;
     a.dt = dt;
@@ -853,7 +952,7 @@ int run_predict(dogm_handle* h, float dt)
     a.mask = (uint32_t)(h->digit_bins[0] - 1);
     const size_t smem = (size_t)a.bins * sizeof(uint32_t);
     {
-        LaunchScope ls(h, K_PREDICT, 44.0 * h->N);
+        LaunchScope ls(h, K_PREDICT, 52.0 * h->N);
         if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
             k_predict<true><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
         else
@@ -861,6 +960,8 @@ int run_predict(dogm_handle* h, float dt)
     }
     h->shift_particles_pending = false;
     h->hist0_valid = true;
+    h->pa_current = false; // the predicted particles are the records now
+    h->rec_valid = true;
     return (int)cudaGetLastError();
 }
 
@@ -879,9 +980,15 @@ int run_assignment(dogm_handle* h)
     h->ranges_in_soa = true;
     if (!h->hist0_valid)
     {
-        LaunchScope ls(h, K_TILE_HIST, 4.0 * N);
-        k_tile_hist<<<h->tiles, kWideBlock, (size_t)h->digit_bins[0] * sizeof(uint32_t), h->stream>>>(
-            h->pa.idx, N, h->hist[0], h->digit_bins[0], h->digit_shift[0], (uint32_t)(h->digit_bins[0] - 1));
+        const size_t smem = (size_t)h->digit_bins[0] * sizeof(uint32_t);
+        const uint32_t mask = (uint32_t)(h->digit_bins[0] - 1);
+        LaunchScope ls(h, K_TILE_HIST, 57.0 * N);
+        if (h->pa_current || !h->rec_valid)
+            k_soa_to_rec<<<h->tiles, kWideBlock, smem, h->stream>>>(h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc,
+                                                                    h->rec_cur, N, h->hist[0], h->digit_bins[0], mask);
+        else
+            k_rec_tile_hist<<<h->tiles, kWideBlock, smem, h->stream>>>(h->rec_cur, N, h->hist[0], h->digit_bins[0], mask);
+        h->rec_valid = true;
     }
     for (int p = 0; p < h->passes; p++)
     {
@@ -896,14 +1003,8 @@ int run_assignment(dogm_handle* h)
                                                                zero_count);
         }
         ScatterArgs a;
-        a.src_state = h->pa.state;
-        a.src_idx = h->pa.idx;
-        a.src_weight = h->pa.weight;
-        a.src_assoc = h->pa.assoc;
-        a.dst_state = h->pb.state;
-        a.dst_idx = h->pb.idx;
-        a.dst_weight = h->pb.weight;
-        a.dst_assoc = h->pb.assoc;
+        a.src = h->rec_cur;
+        a.dst = h->rec_alt;
         a.n = N;
         a.shift = h->digit_shift[p];
         a.mask = (uint32_t)(bins - 1);
@@ -917,27 +1018,28 @@ int run_assignment(dogm_handle* h)
         a.next_bins = has_next ? h->digit_bins[p + 1] : 0;
         const size_t smem = (size_t)bins * sizeof(uint32_t) + (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
-            LaunchScope ls(h, K_SCATTER, 50.0 * N);
+            LaunchScope ls(h, K_SCATTER, 64.0 * N);
             k_scatter<<<h->tiles, kBlock, smem, h->stream>>>(a);
         }
-        // the sorted-so-far set becomes particle_array
-        ParticleSet t = h->pa;
-        h->pa = h->pb;
-        h->pb = t;
+        PRec* t = h->rec_cur;
+        h->rec_cur = h->rec_alt;
+        h->rec_alt = t;
     }
     h->hist0_valid = false;
-    // per-cell sums + start/end over the sorted set
+    h->pa_current = false;
+    // per-cell sums + start/end over the sorted records
     {
-        LaunchScope ls(h, K_SEGSUM, 24.0 * N);
+        LaunchScope ls(h, K_SEGSUM, 40.0 * N);
         k_segsum<<<div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->stream>>>(
-            h->pa.idx, h->pa.weight, h->pa.state, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail,
-            h->seg_flags);
+            h->rec_cur, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->skey,
+            h->sw);
     }
     {
         LaunchScope ls(h, K_SEGFIX, 0.0);
-        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->pa.idx, h->n_chunks, h->cell_sums, h->seg_lead,
+        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->skey, h->n_chunks, h->cell_sums, h->seg_lead,
                                                                       h->seg_trail, h->seg_flags);
     }
+    h->sorted_valid = true;
     return (int)cudaGetLastError();
 }
 
@@ -945,10 +1047,25 @@ int run_persistent_weights(dogm_handle* h)
 {
     if (h->N <= 0)
         return 0;
+    if (!h->sorted_valid)
+        return DOGM_ERR_NOT_INITIALIZED;
     LaunchScope ls(h, K_WEIGHTS, 12.0 * h->N);
-    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->pa.idx, h->pa.weight, h->cell_coef, h->weight_array,
-                                                             h->N);
+    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->skey, h->sw, h->cell_coef, h->weight_array, h->N);
     return (int)cudaGetLastError();
+}
+
+int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out)
+{
+    LaunchScope ls(h, K_BLOCKSUM_SCAN, 16.0 * n);
+    k_blocksum_scan<<<1, 1024, 0, h->stream>>>(in, out_excl, n, total_out);
+    return (int)cudaGetLastError();
+}
+
+int configure_kernels()
+{
+    const int max_bins = 1 << kMaxDigitBits;
+    const int smem = max_bins * (int)sizeof(uint32_t) + max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
+    return (int)cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int run_resampling(dogm_handle* h)
@@ -956,6 +1073,8 @@ int run_resampling(dogm_handle* h)
     const int N = h->N, n = h->N + h->B;
     if (N <= 0)
         return 0;
+    if (!h->sorted_valid)
+        return DOGM_ERR_NOT_INITIALIZED; // resampling gathers from the sorted records of dogm_particle_assignment
     {
         LaunchScope ls(h, K_CDF_REDUCE, 4.0 * n);
         k_cdf_reduce<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(h->weight_array, h->birth.weight, N, n, h->tile_sum);
@@ -973,9 +1092,9 @@ int run_resampling(dogm_handle* h)
     a.cdf = h->cdf;
     a.n_cdf = n;
     a.N = N;
-    a.src = h->pa;
+    a.src = h->rec_cur;
     a.birth = h->birth;
-    a.dst = h->pb;
+    a.dst = h->pa;
     a.ancestors = h->ancestors;
     a.scal = h->scal;
     a.mode = h->opts.resample_mode;
@@ -984,28 +1103,15 @@ int run_resampling(dogm_handle* h)
     a.seed = h->opts.seed;
     a.cycle = h->cycle;
     {
-        LaunchScope ls(h, K_RESAMPLE, 58.0 * N);
+        LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
         k_resample<<<div_up(N, kBlock), kBlock, 0, h->stream>>>(a);
     }
-    // publish: particle_array = particle_array_next (dogm.cu:128) by pointer swap
-    ParticleSet t = h->pa;
-    h->pa = h->pb;
-    h->pb = t;
+    // publish (dogm.cu:128): the next population was written straight into particle_array
+    h->pa_current = true;
+    h->rec_valid = false;
+    h->sorted_valid = false;
+    h->hist0_valid = false;
     return (int)cudaGetLastError();
-}
-
-int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out)
-{
-    LaunchScope ls(h, K_BLOCKSUM_SCAN, 16.0 * n);
-    k_blocksum_scan<<<1, 1024, 0, h->stream>>>(in, out_excl, n, total_out);
-    return (int)cudaGetLastError();
-}
-
-int configure_kernels()
-{
-    const int max_bins = 1 << kMaxDigitBits;
-    const int smem = max_bins * (int)sizeof(uint32_t) + max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
-    return (int)cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int run_search_ancestors_f32(dogm_handle* h, const float* d_cdf, int n_cdf, const float* d_draws, int n_draws, int* d_out)
