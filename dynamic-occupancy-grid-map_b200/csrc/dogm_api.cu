@@ -163,9 +163,11 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     int e = 0;
     e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
     particle_set_assign(h->pa, blk, h->N);
-    e |= alloc_zero((void**)&h->rec_cur, (N ? N : 1) * sizeof(PRec));
-    e |= alloc_zero((void**)&h->rec_alt, (N ? N : 1) * sizeof(PRec));
-    e |= alloc_zero((void**)&h->skey, (N ? N : 1) * sizeof(int));
+    e |= alloc_zero((void**)&h->rec, (N ? N : 1) * sizeof(PRec));
+    e |= alloc_zero((void**)&h->key0, (N ? N : 1) * sizeof(int));
+    e |= alloc_zero((void**)&h->pairs[0], (N ? N : 1) * sizeof(int2));
+    e |= alloc_zero((void**)&h->pairs[1], (N ? N : 1) * sizeof(int2));
+    h->spair = h->pairs[0];
     e |= alloc_zero((void**)&h->sw, (N ? N : 1) * sizeof(float));
     h->pa_current = true;
     h->rec_valid = false;
@@ -229,9 +231,10 @@ extern "C" void dogm_destroy(dogm_handle* h)
         return;
     cudaStreamSynchronize(h->stream);
     cudaFree(h->pa.block);
-    cudaFree(h->rec_cur);
-    cudaFree(h->rec_alt);
-    cudaFree(h->skey);
+    cudaFree(h->rec);
+    cudaFree(h->key0);
+    cudaFree(h->pairs[0]);
+    cudaFree(h->pairs[1]);
     cudaFree(h->sw);
     cudaFree(h->birth.block);
     cudaFree(h->grid);

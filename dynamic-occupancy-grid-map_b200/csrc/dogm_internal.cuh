@@ -75,12 +75,13 @@ inline void particle_set_assign(ParticleSet& p, void* block, int n)
     p.assoc = (uint8_t*)(b + DOGM_PARTICLE_ASSOC_OFFSET(n));
 }
 
-struct __align__(16) PRec // a particle inside a cycle: one 32-byte DRAM sector
+struct __align__(16) PRec // a particle inside a cycle: one 32-byte DRAM sector, written once by the prediction
 {
-    float4 state;   // x, y, vx, vy
+    float x, y;     // lo half: position, cell, flag
     int key;        // grid_cell_idx
-    float weight;
     uint32_t assoc; // associated flag
+    float vx, vy;   // hi half: what the per-cell sums need
+    float weight;
     uint32_t pad;
 };
 
@@ -178,13 +179,14 @@ struct dogm_handle
 
     // reference-visible buffers (dogm.h:159-191)
     dogm_b200::ParticleSet pa;    // particle_array (== particle_array_next: the next population is written in place)
-    dogm_b200::PRec* rec_cur;     // the particles of the running cycle as 32-byte records (predicted, then sorted)
-    dogm_b200::PRec* rec_alt;     // ping-pong partner of rec_cur for the sort passes
-    int* skey;                    // sorted cell indices (compact copy, written by the segmented reduction)
-    float* sw;                    // sorted predicted weights (compact copy)
+    dogm_b200::PRec* rec;         // the particles of the running cycle as 32-byte records in slot order
+    int* key0;                    // their cell indices in slot order (input of the first sort pass)
+    int2* pairs[2];               // (cell, slot) pairs: ping-pong buffers of the sort passes
+    int2* spair;                  // the sorted pairs (one of pairs[]): position p of the sorted set is record spair[p].y
+    float* sw;                    // predicted weights in sorted order (compact copy, written by the segmented reduction)
     bool pa_current;              // the SoA block holds the current particles (false between prediction and resampling)
-    bool rec_valid;               // rec_cur holds the current particles
-    bool sorted_valid;            // rec_cur / skey / sw are sorted by cell and the per-cell sums exist
+    bool rec_valid;               // rec / key0 hold the current particles
+    bool sorted_valid;            // spair / sw describe the current particles sorted by cell and the per-cell sums exist
     dogm_b200::ParticleSet birth; // birth_particle_array
     dogm_grid_cell* grid;
     dogm_meas_cell* meas;

@@ -19,37 +19,16 @@ namespace dogm_b200
 {
 
 // =========================================================================================================
-// record helpers
+// record helpers.  PRec halves: lo = (x, y, key, assoc), hi = (vx, vy, weight, pad): the segmented reduction only
+// needs the hi half, the cell index travels with the position.
 // =========================================================================================================
-__device__ __forceinline__ float4 rec_hi(int key, float w, uint32_t assoc)
+__device__ __forceinline__ float4 rec_lo(float x, float y, int key, uint32_t assoc)
 {
-    return make_float4(__int_as_float(key), w, __uint_as_float(assoc), 0.0f);
+    return make_float4(x, y, __int_as_float(key), __uint_as_float(assoc));
 }
-
-__device__ __forceinline__ float4 shfl4(const float4& v, int src)
+__device__ __forceinline__ float4 rec_hi(float vx, float vy, float w)
 {
-    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
-                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
-}
-
-// Every lane holds one record and its destination.  Written with two instructions that each cover 16 whole
-// records (lane l stores half l&1 of the record held by lane (l>>1) + 16*h): a store instruction then touches at
-// most 16 sectors instead of 32, which halves the L1TEX wavefronts of the scattered write.
-__device__ __forceinline__ void store_records_paired(PRec* __restrict__ dst, uint32_t dest, const float4& lo,
-                                                     const float4& hi, bool valid, int lane)
-{
-    const int part = lane & 1;
-#pragma unroll
-    for (int h = 0; h < 2; h++)
-    {
-        const int src = (lane >> 1) + 16 * h;
-        const uint32_t d = __shfl_sync(0xffffffffu, dest, src);
-        const int v = __shfl_sync(0xffffffffu, (int)valid, src);
-        const float4 a = shfl4(lo, src);
-        const float4 b = shfl4(hi, src);
-        if (v)
-            reinterpret_cast<float4*>(dst + d)[part] = part ? b : a;
-    }
+    return make_float4(vx, vy, w, 0.0f);
 }
 
 // =========================================================================================================
@@ -61,6 +40,7 @@ struct PredictArgs
     const float* weight;
     const uint8_t* assoc;
     PRec* out;
+    int* key_out;
     int n;
     int gs;
     float dt, p_S, sigma_pos, sigma_vel;
@@ -85,6 +65,8 @@ __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t s
 // (ego_motion_compensation.cu:16-23) is applied first when a shift is pending: same two roundings as the
 // reference's separate kernel.  x' = (x + dt*vx) + noise: three roundings, the GLM mat4*vec4 grouping of predict.cu:33.
 // One CTA of 1024 threads per sort tile (4 particles per thread): the tile's pass-0 digit histogram comes for free.
+// Output: the particle as a 32-byte record in slot order (it never moves again inside the cycle) and its cell
+// index in a compact key array (the only thing the sort passes touch).
 template <bool INJECTED>
 __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
@@ -98,6 +80,7 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
     const uint8_t* __restrict__ assoc = a.assoc;
     const float4* __restrict__ noise = a.noise;
     PRec* __restrict__ out = a.out;
+    int* __restrict__ key_out = a.key_out;
     const int base = blockIdx.x * kTileItems;
     const float hi = (float)(a.gs - 1);
     const float xm = (float)a.x_move, ym = (float)a.y_move;
@@ -131,8 +114,9 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
             const int py = min(max(__float2int_rz(y), 0), a.gs - 1);
             const int cell = px + a.gs * py;
             float4* o = reinterpret_cast<float4*>(out + i);
-            o[0] = make_float4(x, y, vx, vy);
-            o[1] = rec_hi(cell, w, as);
+            o[0] = rec_lo(x, y, cell, as);
+            o[1] = rec_hi(vx, vy, w);
+            key_out[i] = cell;
             atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
         }
     }
@@ -147,7 +131,8 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restrict__ state, const int* __restrict__ idx,
                                                            const float* __restrict__ weight,
                                                            const uint8_t* __restrict__ assoc, PRec* __restrict__ out,
-                                                           int n, uint32_t* hist, int bins, uint32_t mask)
+                                                           int* __restrict__ key_out, int n, uint32_t* hist, int bins,
+                                                           uint32_t mask)
 {
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
@@ -161,9 +146,11 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
         if (i < n)
         {
             const int key = idx[i];
+            const float4 s = state[i];
             float4* o = reinterpret_cast<float4*>(out + i);
-            o[0] = state[i];
-            o[1] = rec_hi(key, weight[i], assoc[i]);
+            o[0] = rec_lo(s.x, s.y, key, assoc[i]);
+            o[1] = rec_hi(s.z, s.w, weight[i]);
+            key_out[i] = key;
             atomicAdd(&s_hist[(uint32_t)key & mask], 1u);
         }
     }
@@ -173,9 +160,9 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
         row[b] = s_hist[b];
 }
 
-// pass-0 histogram of records that are already in place (assignment called twice in a row)
-__global__ void __launch_bounds__(kWideBlock) k_rec_tile_hist(const PRec* __restrict__ rec, int n, uint32_t* hist,
-                                                              int bins, uint32_t mask)
+// pass-0 histogram of keys that are already in place (assignment called twice in a row)
+__global__ void __launch_bounds__(kWideBlock) k_key_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
+                                                              uint32_t mask)
 {
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
@@ -187,7 +174,7 @@ __global__ void __launch_bounds__(kWideBlock) k_rec_tile_hist(const PRec* __rest
     {
         const int i = base + j * kWideBlock + threadIdx.x;
         if (i < n)
-            atomicAdd(&s_hist[(uint32_t)rec[i].key & mask], 1u);
+            atomicAdd(&s_hist[(uint32_t)key[i] & mask], 1u);
     }
     __syncthreads();
     uint32_t* row = hist + (size_t)blockIdx.x * bins;
@@ -195,20 +182,22 @@ __global__ void __launch_bounds__(kWideBlock) k_rec_tile_hist(const PRec* __rest
         row[b] = s_hist[b];
 }
 
-// records -> the reference's SoA block (read-out between stages: getParticles after prediction / assignment)
-__global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ rec, float4* __restrict__ state,
-                                                       int* __restrict__ idx, float* __restrict__ weight,
-                                                       uint8_t* __restrict__ assoc, int n)
+// records -> the reference's SoA block (read-out between stages: getParticles after prediction / assignment);
+// with `spair` the output is in sorted order (position p holds record spair[p].y)
+__global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ rec, const int2* __restrict__ spair,
+                                                       float4* __restrict__ state, int* __restrict__ idx,
+                                                       float* __restrict__ weight, uint8_t* __restrict__ assoc, int n)
 {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
-    const float4* r = reinterpret_cast<const float4*>(rec + i);
+    const int slot = spair ? spair[i].y : i;
+    const float4* r = reinterpret_cast<const float4*>(rec + slot);
     const float4 lo = r[0], hi = r[1];
-    state[i] = lo;
-    idx[i] = __float_as_int(hi.x);
-    weight[i] = hi.y;
-    assoc[i] = (uint8_t)__float_as_uint(hi.z);
+    state[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+    idx[i] = __float_as_int(lo.z);
+    weight[i] = hi.z;
+    assoc[i] = (uint8_t)__float_as_uint(lo.w);
 }
 
 // =========================================================================================================
@@ -324,14 +313,16 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
 }
 
 // =========================================================================================================
-// counting sort: stable scatter of one digit pass (one CTA per tile of 4096 consecutive records)
-// rank of a record = bin_base[digit] + (same digit in earlier tiles) + (same digit in earlier warps of the tile)
-//                    + (same digit earlier in its own warp), the last term by __match_any ranking.
+// counting sort: stable scatter of one digit pass over (key, slot) pairs (one CTA per tile of 4096 items).
+// Only these 8-byte pairs move; the 32-byte particle records stay where prediction wrote them.
+// rank of an item = bin_base[digit] + (same digit in earlier tiles) + (same digit in earlier warps of the tile)
+//                   + (same digit earlier in its own warp), the last term by __match_any ranking.
 // =========================================================================================================
 struct ScatterArgs
 {
-    const PRec* src;
-    PRec* dst;
+    const int* key_in;   // first pass: keys in slot order (slot = index)
+    const int2* pair_in; // later passes: (key, slot)
+    int2* pair_out;
     int n;
     int shift;
     uint32_t mask;
@@ -344,36 +335,44 @@ struct ScatterArgs
     int next_bins;
 };
 
-constexpr int kScatterBatch = 2; // rounds whose record loads are issued together before the scattered stores
-
+template <bool FIRST>
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
     unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
 
-    const PRec* __restrict__ src = a.src;
-    PRec* __restrict__ dst = a.dst;
+    const int* __restrict__ key_in = a.key_in;
+    const int2* __restrict__ pair_in = a.pair_in;
+    int2* __restrict__ pair_out = a.pair_out;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt = lanemask_lt();
     const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
 
-    // all key loads of the warp's 16 rounds are in flight while the rank counters are cleared
+    // all loads of the warp's 16 rounds are in flight while the rank counters are cleared
     int keys[kRoundsPerWarp];
+    int slots[FIRST ? 1 : kRoundsPerWarp];
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
         const int i = warp_base + r * 32 + lane;
-        keys[r] = (i < a.n) ? src[i].key : 0;
+        if (FIRST)
+            keys[r] = (i < a.n) ? key_in[i] : 0;
+        else
+        {
+            const int2 p = (i < a.n) ? pair_in[i] : make_int2(0, 0);
+            keys[r] = p.x;
+            slots[r] = p.y;
+        }
     }
     for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
         s_cnt[b] = 0;
     __syncthreads();
 
     unsigned short* my_cnt = s_cnt + warp * a.bins;
-    uint32_t packed[kRoundsPerWarp]; // (rank within warp << 16) | digit
+    unsigned short rank[kRoundsPerWarp];
 
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
             my_cnt[digit] = (unsigned short)(old + __popc(peers));
         }
         old = __shfl_sync(full, old, leader);
-        packed[r] = ((old + __popc(peers & lt)) << 16) | (digit & 0xffffu);
+        rank[r] = (unsigned short)(old + __popc(peers & lt));
         __syncwarp();
     }
     __syncthreads();
@@ -412,52 +411,79 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     __syncthreads();
 
 #pragma unroll
-    for (int r0 = 0; r0 < kRoundsPerWarp; r0 += kScatterBatch)
+    for (int r = 0; r < kRoundsPerWarp; r++)
     {
-        float4 lo[kScatterBatch], hi[kScatterBatch];
-#pragma unroll
-        for (int q = 0; q < kScatterBatch; q++)
+        const int i = warp_base + r * 32 + lane;
+        if (i < a.n)
         {
-            const int i = warp_base + (r0 + q) * 32 + lane;
-            if (i < a.n)
+            const int key = keys[r];
+            const uint32_t digit = ((uint32_t)key >> a.shift) & a.mask;
+            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + rank[r];
+            pair_out[dest] = make_int2(key, FIRST ? i : slots[r]);
+            if (a.next_table)
             {
-                const float4* p = reinterpret_cast<const float4*>(src + i);
-                lo[q] = p[0];
-                hi[q] = p[1];
+                const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
+                atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
             }
-        }
-#pragma unroll
-        for (int q = 0; q < kScatterBatch; q++)
-        {
-            const int r = r0 + q;
-            const int i = warp_base + r * 32 + lane;
-            const bool valid = i < a.n;
-            uint32_t dest = 0;
-            if (valid)
-            {
-                const uint32_t digit = packed[r] & 0xffffu;
-                dest = s_binoff[digit] + my_cnt[digit] + (packed[r] >> 16);
-                if (a.next_table)
-                {
-                    const uint32_t nd = ((uint32_t)keys[r] >> a.next_shift) & a.next_mask;
-                    atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
-                }
-            }
-            store_records_paired(dst, dest, lo[q], hi[q], valid, lane);
         }
     }
 }
 
 // =========================================================================================================
-// per-cell sums over the sorted records (one warp per 256 consecutive records, fixed combination order)
+// per-cell sums over the particles in sorted order (one warp per 256 consecutive sorted positions).
 // replaces the reference's  weight scan + prefix differences (dogm.cu:287-288, common.h:25-32, mass_update.cu:76)
 // and the five moment scans (dogm.cu:359-377, statistical_moments.cu:58-76); also yields GridCell.start_idx /
-// end_idx (particle_to_grid.cu:33-40) and compact copies of the sorted keys / predicted weights for the kernels
-// that need nothing else of a particle.
+// end_idx (particle_to_grid.cu:33-40) and a compact copy of the sorted predicted weights.
+//
+// Fixed combination order: the piece of a segment that is still open is accumulated lane-locally across the 32-wide
+// steps (no shuffles while a step lies inside one cell, the common case once particles have clustered) and
+// butterfly-reduced when it closes; segments that begin and end inside one step go through a segmented
+// Kogge-Stone scan.  The weight sum is carried in double and rounded once.
 // =========================================================================================================
-__global__ void __launch_bounds__(kBlock) k_segsum(const PRec* __restrict__ rec, int n, int* cell_start, int* cell_end,
-                                                   CellSums* sums, SegPiece* lead, SegPiece* trail, int* flags,
-                                                   int* __restrict__ skey, float* __restrict__ sw)
+struct Sum6
+{
+    double s0;
+    float s1, s2, s3, s4, s5;
+};
+
+__device__ __forceinline__ Sum6 warp_reduce6(Sum6 v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        v.s0 += __shfl_xor_sync(0xffffffffu, v.s0, d);
+        v.s1 += __shfl_xor_sync(0xffffffffu, v.s1, d);
+        v.s2 += __shfl_xor_sync(0xffffffffu, v.s2, d);
+        v.s3 += __shfl_xor_sync(0xffffffffu, v.s3, d);
+        v.s4 += __shfl_xor_sync(0xffffffffu, v.s4, d);
+        v.s5 += __shfl_xor_sync(0xffffffffu, v.s5, d);
+    }
+    return v;
+}
+
+__device__ __forceinline__ void store_cell_sums(CellSums* sums, int k, const Sum6& v)
+{
+    float4* p = reinterpret_cast<float4*>(sums + k);
+    p[0] = make_float4((float)v.s0, v.s1, v.s2, v.s3);
+    p[1] = make_float4(v.s4, v.s5, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void store_piece(SegPiece* dst, const Sum6& v)
+{
+    SegPiece p;
+    p.s0 = v.s0;
+    p.s1 = v.s1;
+    p.s2 = v.s2;
+    p.s3 = v.s3;
+    p.s4 = v.s4;
+    p.s5 = v.s5;
+    p.pad = 0;
+    *dst = p;
+}
+
+__global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
+                                                   int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
+                                                   SegPiece* trail, int* flags, float* __restrict__ sw)
 {
     const int lane = threadIdx.x & 31;
     const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
@@ -467,153 +493,154 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const PRec* __restrict__ rec,
     const unsigned full = 0xffffffffu;
     const unsigned le = lanemask_le();
 
-    int last_key = (base > 0) ? rec[base - 1].key : -2;
-    bool from_before = true; // no segment head seen in this chunk yet
-    bool carry_open = false;
+    int last_key = (base > 0) ? spair[base - 1].x : -2;
+    bool from_before = true; // no segment head seen in this chunk yet: an open piece began in an earlier chunk
+    bool have_open = false;
     bool first_is_lead = false;
-    double c0 = 0.0;
-    float c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
+    Sum6 acc; // lane-local share of the open piece
+    acc.s0 = 0.0;
+    acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.f;
 
     for (int step = 0; step < kSegChunk / 32; step++)
     {
         const int i = base + step * 32 + lane;
         const bool valid = i < n;
         int k = -3;
-        float w = 0.f, vx = 0.f, vy = 0.f;
+        Sum6 v;
+        v.s0 = 0.0;
+        v.s1 = v.s2 = v.s3 = v.s4 = v.s5 = 0.f;
         if (valid)
         {
-            const float4* p = reinterpret_cast<const float4*>(rec + i);
-            const float4 lo = p[0], hi = p[1];
-            k = __float_as_int(hi.x);
-            w = hi.y;
-            vx = lo.z;
-            vy = lo.w;
-            skey[i] = k;
+            const int2 pr = spair[i];
+            k = pr.x;
+            const float4 hi = reinterpret_cast<const float4*>(rec + pr.y)[1]; // (vx, vy, w, -)
+            const float w = hi.z;
             sw[i] = w;
+            const float wx = __fmul_rn(w, hi.x), wy = __fmul_rn(w, hi.y);
+            v.s0 = (double)w;
+            v.s1 = wx;
+            v.s2 = wy;
+            v.s3 = __fmul_rn(wx, hi.x);
+            v.s4 = __fmul_rn(wy, hi.y);
+            v.s5 = __fmul_rn(wx, hi.y);
         }
         int kprev = __shfl_up_sync(full, k, 1);
         if (lane == 0)
             kprev = last_key;
         int knext = __shfl_down_sync(full, k, 1);
         if (lane == 31)
-            knext = (i + 1 < n) ? rec[i + 1].key : -3;
+            knext = (i + 1 < n) ? spair[i + 1].x : -3;
         const bool head = valid && (k != kprev);
         const bool tail = valid && (k != knext);
-        if (step == 0)
-            first_is_lead = (__shfl_sync(full, (int)(valid && !head), 0) != 0);
-
         const unsigned hm = __ballot_sync(full, head);
-        const unsigned mine = hm & le;
-        const int start_lane = mine ? (31 - __clz(mine)) : -1;
-        const int lo_lane = start_lane < 0 ? 0 : start_lane;
-
-        double v0 = (double)w;
-        const float wx = __fmul_rn(w, vx), wy = __fmul_rn(w, vy);
-        float v1 = wx, v2 = wy, v3 = __fmul_rn(wx, vx), v4 = __fmul_rn(wy, vy), v5 = __fmul_rn(wx, vy);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
+        const unsigned tm = __ballot_sync(full, tail);
+        if (step == 0)
         {
-            const double t0 = __shfl_up_sync(full, v0, d);
-            const float t1 = __shfl_up_sync(full, v1, d);
-            const float t2 = __shfl_up_sync(full, v2, d);
-            const float t3 = __shfl_up_sync(full, v3, d);
-            const float t4 = __shfl_up_sync(full, v4, d);
-            const float t5 = __shfl_up_sync(full, v5, d);
-            if (lane - d >= lo_lane)
-            {
-                v0 += t0;
-                v1 += t1;
-                v2 += t2;
-                v3 += t3;
-                v4 += t4;
-                v5 += t5;
-            }
+            first_is_lead = !(hm & 1u); // base < n, so lane 0 is valid
+            have_open = first_is_lead;
         }
-        const bool cont = start_lane < 0; // continues the piece carried in from earlier steps / chunks
-        if (cont)
-        {
-            v0 = c0 + v0;
-            v1 = c1 + v1;
-            v2 = c2 + v2;
-            v3 = c3 + v3;
-            v4 = c4 + v4;
-            v5 = c5 + v5;
-        }
+        last_key = __shfl_sync(full, k, 31);
         if (head)
             cell_start[k] = i;
-        if (tail)
-        {
-            cell_end[k] = i;
-            if (!(cont && from_before))
-            {
-                CellSums cs;
-                cs.s0 = (float)v0;
-                cs.s1 = v1;
-                cs.s2 = v2;
-                cs.s3 = v3;
-                cs.s4 = v4;
-                cs.s5 = v5;
-                cs.pad0 = 0.f;
-                cs.pad1 = 0.f;
-                sums[k] = cs;
-            }
-            else
-            {
-                SegPiece p;
-                p.s0 = v0;
-                p.s1 = v1;
-                p.s2 = v2;
-                p.s3 = v3;
-                p.s4 = v4;
-                p.s5 = v5;
-                p.pad = 0;
-                lead[chunk] = p;
-            }
+
+        if (hm == 0u && tm == 0u)
+        { // the whole step lies inside the open piece
+            acc.s0 += v.s0;
+            acc.s1 += v.s1;
+            acc.s2 += v.s2;
+            acc.s3 += v.s3;
+            acc.s4 += v.s4;
+            acc.s5 += v.s5;
+            continue;
         }
-        carry_open = (__shfl_sync(full, (int)(valid && !tail), 31) != 0);
-        const double n0 = __shfl_sync(full, v0, 31);
-        const float n1 = __shfl_sync(full, v1, 31);
-        const float n2 = __shfl_sync(full, v2, 31);
-        const float n3 = __shfl_sync(full, v3, 31);
-        const float n4 = __shfl_sync(full, v4, 31);
-        const float n5 = __shfl_sync(full, v5, 31);
-        if (carry_open)
+
+        const int first_head = hm ? (__ffs(hm) - 1) : 32;
+        // 1. lanes in front of the first head extend the open piece; it ends at the one tail lane among them
+        if (lane < first_head)
         {
-            c0 = n0;
-            c1 = n1;
-            c2 = n2;
-            c3 = n3;
-            c4 = n4;
-            c5 = n5;
+            acc.s0 += v.s0;
+            acc.s1 += v.s1;
+            acc.s2 += v.s2;
+            acc.s3 += v.s3;
+            acc.s4 += v.s4;
+            acc.s5 += v.s5;
         }
-        else
+        const unsigned below = first_head >= 32 ? full : ((1u << first_head) - 1u);
+        const unsigned open_tail = tm & below;
+        if (open_tail)
         {
-            c0 = 0.0;
-            c1 = c2 = c3 = c4 = c5 = 0.f;
+            const Sum6 tot = warp_reduce6(acc);
+            if (lane == __ffs(open_tail) - 1)
+            {
+                cell_end[k] = i;
+                if (from_before)
+                    store_piece(&lead[chunk], tot);
+                else
+                    store_cell_sums(sums, k, tot);
+            }
+            acc.s0 = 0.0;
+            acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.f;
+            have_open = false;
         }
         if (hm)
+        {
             from_before = false;
-        last_key = __shfl_sync(full, k, 31);
+            // 2. segments that begin in this step: segmented inclusive scan over the lanes from the first head on
+            const unsigned mine = hm & le;
+            const int start_lane = mine ? (31 - __clz(mine)) : 32; // lanes in front of the first head take no part
+            Sum6 s = v;
+            if (lane < first_head)
+            {
+                s.s0 = 0.0;
+                s.s1 = s.s2 = s.s3 = s.s4 = s.s5 = 0.f;
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const double t0 = __shfl_up_sync(full, s.s0, d);
+                const float t1 = __shfl_up_sync(full, s.s1, d);
+                const float t2 = __shfl_up_sync(full, s.s2, d);
+                const float t3 = __shfl_up_sync(full, s.s3, d);
+                const float t4 = __shfl_up_sync(full, s.s4, d);
+                const float t5 = __shfl_up_sync(full, s.s5, d);
+                if (lane - d >= start_lane)
+                {
+                    s.s0 += t0;
+                    s.s1 += t1;
+                    s.s2 += t2;
+                    s.s3 += t3;
+                    s.s4 += t4;
+                    s.s5 += t5;
+                }
+            }
+            if (tail && lane >= first_head)
+            { // head and tail inside this step
+                cell_end[k] = i;
+                store_cell_sums(sums, k, s);
+            }
+            // 3. the segment of the last head stays open if no tail follows it
+            const int last_head = 31 - __clz(hm);
+            if ((tm >> last_head) == 0u)
+            {
+                have_open = true;
+                if (lane >= last_head)
+                    acc = v; // (invalid lanes hold zeros)
+            }
+        }
     }
+    // an open piece at the end of the chunk continues into the next one
+    const Sum6 tot = warp_reduce6(acc);
     if (lane == 0)
     {
         int f = first_is_lead ? SEG_LEAD : 0;
-        if (carry_open)
+        if (have_open)
         {
-            SegPiece p;
-            p.s0 = c0;
-            p.s1 = c1;
-            p.s2 = c2;
-            p.s3 = c3;
-            p.s4 = c4;
-            p.s5 = c5;
-            p.pad = 0;
             f |= SEG_TRAIL;
-            trail[chunk] = p;
+            store_piece(&trail[chunk], tot);
             if (from_before)
             {
                 f |= SEG_THROUGH;
-                lead[chunk] = p;
+                store_piece(&lead[chunk], tot);
             }
         }
         flags[chunk] = f;
@@ -621,7 +648,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const PRec* __restrict__ rec,
 }
 
 // segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
-__global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ skey, int n_chunks, CellSums* sums,
+__global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spair, int n_chunks, CellSums* sums,
                                                    const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
                                                    const int* __restrict__ flags)
 {
@@ -646,17 +673,15 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ skey,
             break;
         c2++;
     }
-    const int k = skey[(c + 1) * kSegChunk - 1];
-    CellSums cs;
-    cs.s0 = (float)acc.s0;
-    cs.s1 = acc.s1;
-    cs.s2 = acc.s2;
-    cs.s3 = acc.s3;
-    cs.s4 = acc.s4;
-    cs.s5 = acc.s5;
-    cs.pad0 = 0.f;
-    cs.pad1 = 0.f;
-    sums[k] = cs;
+    const int k = spair[(c + 1) * kSegChunk - 1].x;
+    Sum6 v;
+    v.s0 = acc.s0;
+    v.s1 = acc.s1;
+    v.s2 = acc.s2;
+    v.s3 = acc.s3;
+    v.s4 = acc.s4;
+    v.s5 = acc.s5;
+    store_cell_sums(sums, k, v);
 }
 
 // =========================================================================================================
@@ -664,14 +689,14 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int* __restrict__ skey,
 // with the per-cell constants precomputed by the cell kernel; the over-unit normalisation of
 // normalize_weights (mass_update.cu:51-59) is applied on the fly.
 // =========================================================================================================
-__global__ void __launch_bounds__(kBlock) k_weights(const int* __restrict__ key, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(kBlock) k_weights(const int2* __restrict__ spair, const float* __restrict__ wgt,
                                                     const float4* __restrict__ coef, float* __restrict__ weight_array,
                                                     int n)
 {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
-    const float4 c = coef[key[i]];
+    const float4 c = coef[spair[i].x];
     float w = wgt[i];
     if (c.w > 0.0f)
         w = __fdiv_rn(w, c.w);
@@ -781,8 +806,9 @@ struct ResampleArgs
     const double* cdf;
     int n_cdf;
     int N;
-    const PRec* src;   // sorted persistent particles
-    ParticleSet birth; // birth particles
+    const PRec* rec;    // persistent particles (records in slot order)
+    const int2* spair;  // sorted (cell, slot) pairs: position p of the sorted set is record spair[p].y
+    ParticleSet birth;  // birth particles
     ParticleSet dst;   // next population
     int* ancestors;
     const DeviceScalars* scal;
@@ -837,11 +863,11 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     uint8_t as;
     if (anc < a.N)
     {
-        const float4* p = reinterpret_cast<const float4*>(a.src + anc);
+        const float4* p = reinterpret_cast<const float4*>(a.rec + a.spair[anc].y);
         const float4 rlo = p[0], rhi = p[1];
-        s = rlo;
-        cell = __float_as_int(rhi.x);
-        as = (uint8_t)__float_as_uint(rhi.z);
+        s = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
+        cell = __float_as_int(rlo.z);
+        as = (uint8_t)__float_as_uint(rlo.w);
     }
     else
     {
@@ -917,8 +943,8 @@ int ensure_soa(dogm_handle* h)
         return 0;
     }
     LaunchScope ls(h, K_MISC, 0.0);
-    k_rec_to_soa<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->rec_cur, h->pa.state, h->pa.idx, h->pa.weight,
-                                                                h->pa.assoc, h->N);
+    k_rec_to_soa<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->rec, h->sorted_valid ? h->spair : nullptr, h->pa.state,
+                                                                h->pa.idx, h->pa.weight, h->pa.assoc, h->N);
     h->pa_current = true;
     return (int)cudaGetLastError();
 }
@@ -934,7 +960,8 @@ int run_predict(dogm_handle* h, float dt)
     a.state = h->pa.state;
     a.weight = h->pa.weight;
     a.assoc = h->pa.assoc;
-    a.out = h->rec_cur;
+    a.out = h->rec;
+    a.key_out = h->key0;
     a.n = h->N;
     a.gs = h->gs;
     a.dt = dt;
@@ -952,7 +979,7 @@ int run_predict(dogm_handle* h, float dt)
     a.mask = (uint32_t)(h->digit_bins[0] - 1);
     const size_t smem = (size_t)a.bins * sizeof(uint32_t);
     {
-        LaunchScope ls(h, K_PREDICT, 52.0 * h->N);
+        LaunchScope ls(h, K_PREDICT, 57.0 * h->N);
         if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
             k_predict<true><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
         else
@@ -962,6 +989,7 @@ int run_predict(dogm_handle* h, float dt)
     h->hist0_valid = true;
     h->pa_current = false; // the predicted particles are the records now
     h->rec_valid = true;
+    h->sorted_valid = false;
     return (int)cudaGetLastError();
 }
 
@@ -984,10 +1012,10 @@ int run_assignment(dogm_handle* h)
         const uint32_t mask = (uint32_t)(h->digit_bins[0] - 1);
         LaunchScope ls(h, K_TILE_HIST, 57.0 * N);
         if (h->pa_current || !h->rec_valid)
-            k_soa_to_rec<<<h->tiles, kWideBlock, smem, h->stream>>>(h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc,
-                                                                    h->rec_cur, N, h->hist[0], h->digit_bins[0], mask);
+            k_soa_to_rec<<<h->tiles, kWideBlock, smem, h->stream>>>(h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc, h->rec,
+                                                                    h->key0, N, h->hist[0], h->digit_bins[0], mask);
         else
-            k_rec_tile_hist<<<h->tiles, kWideBlock, smem, h->stream>>>(h->rec_cur, N, h->hist[0], h->digit_bins[0], mask);
+            k_key_tile_hist<<<h->tiles, kWideBlock, smem, h->stream>>>(h->key0, N, h->hist[0], h->digit_bins[0], mask);
         h->rec_valid = true;
     }
     for (int p = 0; p < h->passes; p++)
@@ -1003,8 +1031,9 @@ int run_assignment(dogm_handle* h)
                                                                zero_count);
         }
         ScatterArgs a;
-        a.src = h->rec_cur;
-        a.dst = h->rec_alt;
+        a.key_in = h->key0;
+        a.pair_in = p > 0 ? h->pairs[(p - 1) & 1] : nullptr;
+        a.pair_out = h->pairs[p & 1];
         a.n = N;
         a.shift = h->digit_shift[p];
         a.mask = (uint32_t)(bins - 1);
@@ -1018,25 +1047,25 @@ int run_assignment(dogm_handle* h)
         a.next_bins = has_next ? h->digit_bins[p + 1] : 0;
         const size_t smem = (size_t)bins * sizeof(uint32_t) + (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
-            LaunchScope ls(h, K_SCATTER, 64.0 * N);
-            k_scatter<<<h->tiles, kBlock, smem, h->stream>>>(a);
+            LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
+            if (p == 0)
+                k_scatter<true><<<h->tiles, kBlock, smem, h->stream>>>(a);
+            else
+                k_scatter<false><<<h->tiles, kBlock, smem, h->stream>>>(a);
         }
-        PRec* t = h->rec_cur;
-        h->rec_cur = h->rec_alt;
-        h->rec_alt = t;
     }
+    h->spair = h->pairs[(h->passes - 1) & 1];
     h->hist0_valid = false;
     h->pa_current = false;
-    // per-cell sums + start/end over the sorted records
+    // per-cell sums + start/end over the sorted order
     {
-        LaunchScope ls(h, K_SEGSUM, 40.0 * N);
+        LaunchScope ls(h, K_SEGSUM, 44.0 * N);
         k_segsum<<<div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->stream>>>(
-            h->rec_cur, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->skey,
-            h->sw);
+            h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw);
     }
     {
         LaunchScope ls(h, K_SEGFIX, 0.0);
-        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->skey, h->n_chunks, h->cell_sums, h->seg_lead,
+        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->spair, h->n_chunks, h->cell_sums, h->seg_lead,
                                                                       h->seg_trail, h->seg_flags);
     }
     h->sorted_valid = true;
@@ -1050,7 +1079,7 @@ int run_persistent_weights(dogm_handle* h)
     if (!h->sorted_valid)
         return DOGM_ERR_NOT_INITIALIZED;
     LaunchScope ls(h, K_WEIGHTS, 12.0 * h->N);
-    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->skey, h->sw, h->cell_coef, h->weight_array, h->N);
+    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->spair, h->sw, h->cell_coef, h->weight_array, h->N);
     return (int)cudaGetLastError();
 }
 
@@ -1065,7 +1094,10 @@ int configure_kernels()
 {
     const int max_bins = 1 << kMaxDigitBits;
     const int smem = max_bins * (int)sizeof(uint32_t) + max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
-    return (int)cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int e = (int)cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e)
+        return e;
+    return (int)cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int run_resampling(dogm_handle* h)
@@ -1092,7 +1124,8 @@ int run_resampling(dogm_handle* h)
     a.cdf = h->cdf;
     a.n_cdf = n;
     a.N = N;
-    a.src = h->rec_cur;
+    a.rec = h->rec;
+    a.spair = h->spair;
     a.birth = h->birth;
     a.dst = h->pa;
     a.ancestors = h->ancestors;
