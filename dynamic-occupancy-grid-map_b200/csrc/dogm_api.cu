@@ -374,7 +374,7 @@ static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float ne
         return e;
     if ((e = run_occupancy_update(h, dt)))
         return e;
-    if ((e = run_persistent_weights(h)))
+    if ((e = run_persistent_weights(h, true)))
         return e;
     if ((e = run_birth(h)))
         return e;
@@ -475,7 +475,7 @@ extern "C" int dogm_grid_cell_occupancy_update(dogm_handle* h, float dt)
 extern "C" int dogm_update_persistent_particles(dogm_handle* h)
 {
     STAGE_PROLOGUE();
-    e = run_persistent_weights(h);
+    e = run_persistent_weights(h, false);
     STAGE_EPILOGUE();
 }
 

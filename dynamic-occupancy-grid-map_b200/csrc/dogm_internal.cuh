@@ -186,6 +186,7 @@ struct dogm_handle
     float* sw;                    // predicted weights in sorted order (compact copy, written by the segmented reduction)
     bool pa_current;              // the SoA block holds the current particles (false between prediction and resampling)
     bool rec_valid;               // rec / key0 hold the current particles
+    bool weights_deferred;        // weight_array of this cycle is still to be produced (by the fused CDF kernels)
     bool sorted_valid;            // spair / sw describe the current particles sorted by cell and the per-cell sums exist
     dogm_b200::ParticleSet birth; // birth_particle_array
     dogm_grid_cell* grid;
@@ -287,7 +288,7 @@ int run_init_particles(dogm_handle* h);
 int run_predict(dogm_handle* h, float dt);
 int run_assignment(dogm_handle* h);
 int run_occupancy_update(dogm_handle* h, float dt);
-int run_persistent_weights(dogm_handle* h);
+int run_persistent_weights(dogm_handle* h, bool defer);
 int run_birth(dogm_handle* h);
 int run_resampling(dogm_handle* h);
 int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells

@@ -689,6 +689,14 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spai
 // with the per-cell constants precomputed by the cell kernel; the over-unit normalisation of
 // normalize_weights (mass_update.cu:51-59) is applied on the fly.
 // =========================================================================================================
+__device__ __forceinline__ float persistent_weight(const float4 c, float w)
+{
+    if (c.w > 0.0f)
+        w = __fdiv_rn(w, c.w);
+    const float unnorm = __fmul_rn(c.x, w);
+    return __fadd_rn(__fmul_rn(c.y, unnorm), __fmul_rn(c.z, w));
+}
+
 __global__ void __launch_bounds__(kBlock) k_weights(const int2* __restrict__ spair, const float* __restrict__ wgt,
                                                     const float4* __restrict__ coef, float* __restrict__ weight_array,
                                                     int n)
@@ -696,32 +704,46 @@ __global__ void __launch_bounds__(kBlock) k_weights(const int2* __restrict__ spa
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
-    const float4 c = coef[spair[i].x];
-    float w = wgt[i];
-    if (c.w > 0.0f)
-        w = __fdiv_rn(w, c.w);
-    const float unnorm = __fmul_rn(c.x, w);
-    weight_array[i] = __fadd_rn(__fmul_rn(c.y, unnorm), __fmul_rn(c.z, w));
+    weight_array[i] = persistent_weight(coef[spair[i].x], wgt[i]);
 }
 
 // =========================================================================================================
-// joint weight CDF (dogm.cu:390-398): reduce-then-scan in double, fixed order
+// joint weight CDF (dogm.cu:390-398): reduce-then-scan in double, fixed order.  FUSED: the persistent weights are
+// computed here from the sorted predicted weights (k_weights is skipped inside updateGrid); the write pass also
+// stores them to weight_array.
 // =========================================================================================================
-__device__ __forceinline__ float joint_entry(const float* __restrict__ wa, const float* __restrict__ bw, int N, int n,
-                                             int i)
+struct CdfArgs
 {
-    return i < N ? wa[i] : (i < n ? bw[i - N] : 0.0f);
+    const float* wa;     // weight_array (input when !fused, output when fused)
+    float* wa_out;
+    const float* bw;     // birth weights
+    const int2* spair;
+    const float* sw;
+    const float4* coef;
+    int N, n;
+};
+
+template <bool FUSED>
+__device__ __forceinline__ float joint_entry(const CdfArgs& a, int i)
+{
+    if (i < a.N)
+        return FUSED ? persistent_weight(a.coef[a.spair[i].x], a.sw[i]) : a.wa[i];
+    return i < a.n ? a.bw[i - a.N] : 0.0f;
 }
 
-__global__ void __launch_bounds__(kBlock) k_cdf_reduce(const float* __restrict__ wa, const float* __restrict__ bw, int N,
-                                                       int n, double* tile_sum)
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum)
 {
     __shared__ double s_scan[kWarpsPerBlock];
     const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
+    float e[kCdfItems];
+#pragma unroll
+    for (int j = 0; j < kCdfItems; j++)
+        e[j] = joint_entry<FUSED>(a, i0 + j);
     double run = 0.0;
 #pragma unroll
     for (int j = 0; j < kCdfItems; j++)
-        run += (double)joint_entry(wa, bw, N, n, i0 + j);
+        run += (double)e[j];
     double total;
     block_inclusive_scan_f64(run, s_scan, &total);
     if (threadIdx.x == 0)
@@ -775,17 +797,21 @@ __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict
         *total_out = s_warp[31];
 }
 
-__global__ void __launch_bounds__(kBlock) k_cdf_write(const float* __restrict__ wa, const float* __restrict__ bw, int N,
-                                                      int n, const double* __restrict__ tile_off, double* __restrict__ cdf)
+template <bool FUSED>
+__global__ void __launch_bounds__(kBlock) k_cdf_write(CdfArgs a, const double* __restrict__ tile_off, double* __restrict__ cdf)
 {
     __shared__ double s_scan[kWarpsPerBlock];
     const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
+    float e[kCdfItems];
+#pragma unroll
+    for (int j = 0; j < kCdfItems; j++)
+        e[j] = joint_entry<FUSED>(a, i0 + j);
     double loc[kCdfItems];
     double run = 0.0;
 #pragma unroll
     for (int j = 0; j < kCdfItems; j++)
     {
-        run += (double)joint_entry(wa, bw, N, n, i0 + j);
+        run += (double)e[j];
         loc[j] = run;
     }
     double total;
@@ -793,8 +819,12 @@ __global__ void __launch_bounds__(kBlock) k_cdf_write(const float* __restrict__ 
     const double off = tile_off[blockIdx.x] + (incl - run);
 #pragma unroll
     for (int j = 0; j < kCdfItems; j++)
-        if (i0 + j < n)
+        if (i0 + j < a.n)
+        {
             cdf[i0 + j] = off + loc[j];
+            if (FUSED && i0 + j < a.N)
+                a.wa_out[i0 + j] = e[j];
+        }
 }
 
 // =========================================================================================================
@@ -825,38 +855,84 @@ __device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_
     return u01_half_open(p.x);
 }
 
-__global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
+// One CTA resamples 256 consecutive outputs.  Their offsets ascend, so all ancestors lie in a short window of the
+// CDF behind the ancestor of the CTA's first offset: thread 0 finds that one by binary search in global memory,
+// the window is staged in shared memory with coalesced loads and every thread searches it there.  Offsets beyond
+// the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
+// to a search in global memory, so the result is lower_bound on the whole CDF in every case.
+constexpr int kResWindow = 768;
+
+__device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= a.N)
-        return;
-    const double total = a.scal->weight_total;
-    const float joint_max = (float)total;
-    double r;
-    if (a.mode == DOGM_RESAMPLE_INJECTED)
-    {
-        r = (double)__fmul_rn(joint_max, a.resample_u[i]);
-    }
-    else
-    {
-        const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
-        float u;
-        if (a.noise_injected)
-            u = a.resample_u[strat ? i : 0];
-        else
-            u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
-        r = ((double)i + (double)u) * (total / (double)a.N);
-    }
-    int lo = 0, hi = a.n_cdf;
     while (lo < hi)
     {
         const int mid = lo + ((hi - lo) >> 1);
-        if (a.cdf[mid] < r)
+        if (cdf[mid] < r)
             lo = mid + 1;
         else
             hi = mid;
     }
-    const int anc = lo < a.n_cdf ? lo : a.n_cdf - 1;
+    return lo;
+}
+
+__global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
+{
+    __shared__ double s_cdf[kResWindow];
+    __shared__ int s_lo;
+    __shared__ double s_first;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = i < a.N;
+    const double total = a.scal->weight_total;
+    const float joint_max = (float)total;
+    double r = 0.0;
+    if (valid)
+    {
+        if (a.mode == DOGM_RESAMPLE_INJECTED)
+        {
+            r = (double)__fmul_rn(joint_max, a.resample_u[i]);
+        }
+        else
+        {
+            const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
+            float u;
+            if (a.noise_injected)
+                u = a.resample_u[strat ? i : 0];
+            else
+                u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
+            r = ((double)i + (double)u) * (total / (double)a.N);
+        }
+    }
+    if (threadIdx.x == 0)
+    {
+        s_lo = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
+        s_first = r;
+    }
+    __syncthreads();
+    const int lo0 = s_lo;
+    for (int j = threadIdx.x; j < kResWindow; j += kBlock)
+        s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
+    __syncthreads();
+    if (!valid)
+        return;
+    int anc;
+    if (r < s_first)
+        anc = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
+    else if (r <= s_cdf[kResWindow - 1])
+    {
+        int l = 0, h = kResWindow;
+        while (l < h)
+        {
+            const int mid = l + ((h - l) >> 1);
+            if (s_cdf[mid] < r)
+                l = mid + 1;
+            else
+                h = mid;
+        }
+        anc = lo0 + l;
+    }
+    else
+        anc = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
+    anc = anc < a.n_cdf ? anc : a.n_cdf - 1;
     a.ancestors[i] = anc;
     float4 s;
     int cell;
@@ -1072,12 +1148,15 @@ int run_assignment(dogm_handle* h)
     return (int)cudaGetLastError();
 }
 
-int run_persistent_weights(dogm_handle* h)
+int run_persistent_weights(dogm_handle* h, bool defer)
 {
     if (h->N <= 0)
         return 0;
     if (!h->sorted_valid)
         return DOGM_ERR_NOT_INITIALIZED;
+    h->weights_deferred = defer; // inside updateGrid the CDF kernels compute the weights on the fly
+    if (defer)
+        return 0;
     LaunchScope ls(h, K_WEIGHTS, 12.0 * h->N);
     k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->spair, h->sw, h->cell_coef, h->weight_array, h->N);
     return (int)cudaGetLastError();
@@ -1107,9 +1186,22 @@ int run_resampling(dogm_handle* h)
         return 0;
     if (!h->sorted_valid)
         return DOGM_ERR_NOT_INITIALIZED; // resampling gathers from the sorted records of dogm_particle_assignment
+    CdfArgs ca;
+    ca.wa = h->weight_array;
+    ca.wa_out = h->weight_array;
+    ca.bw = h->birth.weight;
+    ca.spair = h->spair;
+    ca.sw = h->sw;
+    ca.coef = h->cell_coef;
+    ca.N = N;
+    ca.n = n;
+    const bool fused = h->weights_deferred;
     {
-        LaunchScope ls(h, K_CDF_REDUCE, 4.0 * n);
-        k_cdf_reduce<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(h->weight_array, h->birth.weight, N, n, h->tile_sum);
+        LaunchScope ls(h, K_CDF_REDUCE, fused ? 12.0 * N + 4.0 * h->B : 4.0 * n);
+        if (fused)
+            k_cdf_reduce<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
+        else
+            k_cdf_reduce<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
     }
     {
         int e = run_blocksum_scan(h, h->tile_sum, h->tile_off, h->n_cdf_tiles, &h->scal->weight_total);
@@ -1117,9 +1209,13 @@ int run_resampling(dogm_handle* h)
             return e;
     }
     {
-        LaunchScope ls(h, K_CDF_WRITE, 12.0 * n);
-        k_cdf_write<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(h->weight_array, h->birth.weight, N, n, h->tile_off, h->cdf);
+        LaunchScope ls(h, K_CDF_WRITE, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
+        if (fused)
+            k_cdf_write<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_off, h->cdf);
+        else
+            k_cdf_write<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_off, h->cdf);
     }
+    h->weights_deferred = false;
     ResampleArgs a;
     a.cdf = h->cdf;
     a.n_cdf = n;
