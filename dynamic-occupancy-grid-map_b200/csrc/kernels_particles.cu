@@ -481,6 +481,29 @@ __device__ __forceinline__ void store_piece(SegPiece* dst, const Sum6& v)
     *dst = p;
 }
 
+__device__ __forceinline__ void sum6_zero(Sum6& v)
+{
+    v.s0 = 0.0;
+    v.s1 = v.s2 = v.s3 = v.s4 = v.s5 = 0.f;
+}
+
+__device__ __forceinline__ void sum6_add(Sum6& a, const Sum6& b)
+{
+    a.s0 += b.s0;
+    a.s1 += b.s1;
+    a.s2 += b.s2;
+    a.s3 += b.s3;
+    a.s4 += b.s4;
+    a.s5 += b.s5;
+}
+
+constexpr int kSegPerLane = kSegChunk / 32; // 8 consecutive sorted positions per lane
+
+// Every lane walks its 8 consecutive positions serially: segments that begin and end inside the lane are finished
+// there; the piece in front of the lane's first head ("lead") and the piece behind its last tail ("trail") are
+// joined across lanes by ONE segmented warp scan per 256 particles.  Pieces that cross the chunk border go to the
+// lead / trail records of the chunk and are joined by k_segfix.  Fixed order: serial inside a lane, Kogge-Stone
+// across lanes, chunk order across chunks.
 __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
                                                    int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
                                                    SegPiece* trail, int* flags, float* __restrict__ sw)
@@ -491,156 +514,167 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spai
     if (base >= n)
         return;
     const unsigned full = 0xffffffffu;
-    const unsigned le = lanemask_le();
+    const int p0 = base + lane * kSegPerLane;
 
-    int last_key = (base > 0) ? spair[base - 1].x : -2;
-    bool from_before = true; // no segment head seen in this chunk yet: an open piece began in an earlier chunk
-    bool have_open = false;
-    bool first_is_lead = false;
-    Sum6 acc; // lane-local share of the open piece
-    acc.s0 = 0.0;
-    acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.f;
-
-    for (int step = 0; step < kSegChunk / 32; step++)
+    int key[kSegPerLane], slot[kSegPerLane];
+    if (p0 + kSegPerLane <= n)
     {
-        const int i = base + step * 32 + lane;
-        const bool valid = i < n;
-        int k = -3;
-        Sum6 v;
-        v.s0 = 0.0;
-        v.s1 = v.s2 = v.s3 = v.s4 = v.s5 = 0.f;
-        if (valid)
-        {
-            const int2 pr = spair[i];
-            k = pr.x;
-            const float4 hi = reinterpret_cast<const float4*>(rec + pr.y)[1]; // (vx, vy, w, -)
-            const float w = hi.z;
-            sw[i] = w;
-            const float wx = __fmul_rn(w, hi.x), wy = __fmul_rn(w, hi.y);
-            v.s0 = (double)w;
-            v.s1 = wx;
-            v.s2 = wy;
-            v.s3 = __fmul_rn(wx, hi.x);
-            v.s4 = __fmul_rn(wy, hi.y);
-            v.s5 = __fmul_rn(wx, hi.y);
-        }
-        int kprev = __shfl_up_sync(full, k, 1);
-        if (lane == 0)
-            kprev = last_key;
-        int knext = __shfl_down_sync(full, k, 1);
-        if (lane == 31)
-            knext = (i + 1 < n) ? spair[i + 1].x : -3;
-        const bool head = valid && (k != kprev);
-        const bool tail = valid && (k != knext);
-        const unsigned hm = __ballot_sync(full, head);
-        const unsigned tm = __ballot_sync(full, tail);
-        if (step == 0)
-        {
-            first_is_lead = !(hm & 1u); // base < n, so lane 0 is valid
-            have_open = first_is_lead;
-        }
-        last_key = __shfl_sync(full, k, 31);
-        if (head)
-            cell_start[k] = i;
-
-        if (hm == 0u && tm == 0u)
-        { // the whole step lies inside the open piece
-            acc.s0 += v.s0;
-            acc.s1 += v.s1;
-            acc.s2 += v.s2;
-            acc.s3 += v.s3;
-            acc.s4 += v.s4;
-            acc.s5 += v.s5;
-            continue;
-        }
-
-        const int first_head = hm ? (__ffs(hm) - 1) : 32;
-        // 1. lanes in front of the first head extend the open piece; it ends at the one tail lane among them
-        if (lane < first_head)
-        {
-            acc.s0 += v.s0;
-            acc.s1 += v.s1;
-            acc.s2 += v.s2;
-            acc.s3 += v.s3;
-            acc.s4 += v.s4;
-            acc.s5 += v.s5;
-        }
-        const unsigned below = first_head >= 32 ? full : ((1u << first_head) - 1u);
-        const unsigned open_tail = tm & below;
-        if (open_tail)
-        {
-            const Sum6 tot = warp_reduce6(acc);
-            if (lane == __ffs(open_tail) - 1)
-            {
-                cell_end[k] = i;
-                if (from_before)
-                    store_piece(&lead[chunk], tot);
-                else
-                    store_cell_sums(sums, k, tot);
-            }
-            acc.s0 = 0.0;
-            acc.s1 = acc.s2 = acc.s3 = acc.s4 = acc.s5 = 0.f;
-            have_open = false;
-        }
-        if (hm)
-        {
-            from_before = false;
-            // 2. segments that begin in this step: segmented inclusive scan over the lanes from the first head on
-            const unsigned mine = hm & le;
-            const int start_lane = mine ? (31 - __clz(mine)) : 32; // lanes in front of the first head take no part
-            Sum6 s = v;
-            if (lane < first_head)
-            {
-                s.s0 = 0.0;
-                s.s1 = s.s2 = s.s3 = s.s4 = s.s5 = 0.f;
-            }
+        const int4* q = reinterpret_cast<const int4*>(spair + p0);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
+        for (int j = 0; j < kSegPerLane / 2; j++)
+        {
+            const int4 t = q[j];
+            key[2 * j] = t.x;
+            slot[2 * j] = t.y;
+            key[2 * j + 1] = t.z;
+            slot[2 * j + 1] = t.w;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < kSegPerLane; j++)
+        {
+            key[j] = -3;
+            slot[j] = -1;
+            if (p0 + j < n)
             {
-                const double t0 = __shfl_up_sync(full, s.s0, d);
-                const float t1 = __shfl_up_sync(full, s.s1, d);
-                const float t2 = __shfl_up_sync(full, s.s2, d);
-                const float t3 = __shfl_up_sync(full, s.s3, d);
-                const float t4 = __shfl_up_sync(full, s.s4, d);
-                const float t5 = __shfl_up_sync(full, s.s5, d);
-                if (lane - d >= start_lane)
-                {
-                    s.s0 += t0;
-                    s.s1 += t1;
-                    s.s2 += t2;
-                    s.s3 += t3;
-                    s.s4 += t4;
-                    s.s5 += t5;
-                }
-            }
-            if (tail && lane >= first_head)
-            { // head and tail inside this step
-                cell_end[k] = i;
-                store_cell_sums(sums, k, s);
-            }
-            // 3. the segment of the last head stays open if no tail follows it
-            const int last_head = 31 - __clz(hm);
-            if ((tm >> last_head) == 0u)
-            {
-                have_open = true;
-                if (lane >= last_head)
-                    acc = v; // (invalid lanes hold zeros)
+                const int2 t = spair[p0 + j];
+                key[j] = t.x;
+                slot[j] = t.y;
             }
         }
     }
-    // an open piece at the end of the chunk continues into the next one
-    const Sum6 tot = warp_reduce6(acc);
+    float4 hi[kSegPerLane]; // (vx, vy, w, -) of the lane's particles: eight independent sector reads in flight
+#pragma unroll
+    for (int j = 0; j < kSegPerLane; j++)
+        hi[j] = slot[j] >= 0 ? reinterpret_cast<const float4*>(rec + slot[j])[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int kprev = __shfl_up_sync(full, key[kSegPerLane - 1], 1);
     if (lane == 0)
+        kprev = base > 0 ? spair[base - 1].x : -2;
+    int knext = __shfl_down_sync(full, key[0], 1);
+    if (lane == 31)
+        knext = base + kSegChunk < n ? spair[base + kSegChunk].x : -3;
+
+    // ---- serial walk over the lane's positions
+    Sum6 cur, leadv;
+    sum6_zero(cur);
+    sum6_zero(leadv);
+    bool seen_head = false, have_lead = false, open = false;
+    int lead_key = 0;
+    float wout[kSegPerLane];
+#pragma unroll
+    for (int j = 0; j < kSegPerLane; j++)
+    {
+        const int p = p0 + j;
+        wout[j] = hi[j].z;
+        if (p < n)
+        {
+            const int kj = key[j];
+            const int kp = j == 0 ? kprev : key[j - 1];
+            const int kn = j == kSegPerLane - 1 ? knext : key[j + 1];
+            if (kj != kp)
+            {
+                cell_start[kj] = p;
+                seen_head = true;
+            }
+            const float w = hi[j].z;
+            const float wx = __fmul_rn(w, hi[j].x), wy = __fmul_rn(w, hi[j].y);
+            cur.s0 += (double)w;
+            cur.s1 += wx;
+            cur.s2 += wy;
+            cur.s3 += __fmul_rn(wx, hi[j].x);
+            cur.s4 += __fmul_rn(wy, hi[j].y);
+            cur.s5 += __fmul_rn(wx, hi[j].y);
+            open = true;
+            if (kj != kn)
+            {
+                cell_end[kj] = p;
+                if (seen_head)
+                    store_cell_sums(sums, kj, cur); // began at a head inside this lane
+                else
+                {
+                    leadv = cur; // began in an earlier lane or chunk
+                    have_lead = true;
+                    lead_key = kj;
+                }
+                sum6_zero(cur);
+                open = false;
+            }
+        }
+    }
+    if (p0 + kSegPerLane <= n)
+    {
+        float4* o = reinterpret_cast<float4*>(sw + p0);
+        o[0] = make_float4(wout[0], wout[1], wout[2], wout[3]);
+        o[1] = make_float4(wout[4], wout[5], wout[6], wout[7]);
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < kSegPerLane; j++)
+            if (p0 + j < n)
+                sw[p0 + j] = wout[j];
+    }
+
+    // ---- join the pieces across lanes: segmented inclusive scan of the trail pieces, segments start at lanes
+    // that contain a head (their trail piece begins inside the lane)
+    const unsigned fm = __ballot_sync(full, seen_head);
+    const unsigned mine = fm & lanemask_le();
+    const int start_lane = mine ? (31 - __clz(mine)) : 0;
+    Sum6 sc = cur; // zero when the lane's last particle closed its segment
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const double t0 = __shfl_up_sync(full, sc.s0, d);
+        const float t1 = __shfl_up_sync(full, sc.s1, d);
+        const float t2 = __shfl_up_sync(full, sc.s2, d);
+        const float t3 = __shfl_up_sync(full, sc.s3, d);
+        const float t4 = __shfl_up_sync(full, sc.s4, d);
+        const float t5 = __shfl_up_sync(full, sc.s5, d);
+        if (lane - d >= start_lane)
+        {
+            sc.s0 += t0;
+            sc.s1 += t1;
+            sc.s2 += t2;
+            sc.s3 += t3;
+            sc.s4 += t4;
+            sc.s5 += t5;
+        }
+    }
+    // what arrives from the lanes in front: the scan value of the previous lane
+    Sum6 cin;
+    cin.s0 = __shfl_up_sync(full, sc.s0, 1);
+    cin.s1 = __shfl_up_sync(full, sc.s1, 1);
+    cin.s2 = __shfl_up_sync(full, sc.s2, 1);
+    cin.s3 = __shfl_up_sync(full, sc.s3, 1);
+    cin.s4 = __shfl_up_sync(full, sc.s4, 1);
+    cin.s5 = __shfl_up_sync(full, sc.s5, 1);
+    if (lane == 0)
+        sum6_zero(cin);
+    if (have_lead)
+    {
+        sum6_add(cin, leadv); // (pieces of earlier lanes) + (this lane's lead piece)
+        if (fm & lanemask_lt())
+            store_cell_sums(sums, lead_key, cin); // the segment began at a head in an earlier lane of this chunk
+        else
+            store_piece(&lead[chunk], cin); // it began in an earlier chunk
+    }
+    // ---- chunk summary
+    const int first_is_lead = __shfl_sync(full, (int)(key[0] == kprev), 0); // lane 0 always holds a particle
+    const int chunk_open = __shfl_sync(full, (int)open, 31);
+    if (lane == 31)
     {
         int f = first_is_lead ? SEG_LEAD : 0;
-        if (have_open)
+        if (chunk_open)
         {
             f |= SEG_TRAIL;
-            store_piece(&trail[chunk], tot);
-            if (from_before)
+            store_piece(&trail[chunk], sc);
+            if (fm == 0u)
             {
                 f |= SEG_THROUGH;
-                store_piece(&lead[chunk], tot);
+                store_piece(&lead[chunk], sc);
             }
         }
         flags[chunk] = f;
@@ -731,23 +765,38 @@ __device__ __forceinline__ float joint_entry(const CdfArgs& a, int i)
     return i < a.n ? a.bw[i - a.N] : 0.0f;
 }
 
+// A tile is 2048 consecutive entries; warp w owns entries [256 w, 256 w + 256) of it and reads them in 8 coalesced
+// rounds (entry = 256 w + 32 r + lane).
+constexpr int kCdfRounds = kCdfTile / kBlock; // 8
+
 template <bool FUSED>
 __global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum)
 {
-    __shared__ double s_scan[kWarpsPerBlock];
-    const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
-    float e[kCdfItems];
+    __shared__ double s_w[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
+    float e[kCdfRounds];
 #pragma unroll
-    for (int j = 0; j < kCdfItems; j++)
-        e[j] = joint_entry<FUSED>(a, i0 + j);
-    double run = 0.0;
+    for (int r = 0; r < kCdfRounds; r++)
+        e[r] = joint_entry<FUSED>(a, w0 + r * 32 + lane);
+    double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < kCdfItems; j++)
-        run += (double)e[j];
-    double total;
-    block_inclusive_scan_f64(run, s_scan, &total);
+    for (int r = 0; r < kCdfRounds; r++)
+        acc += (double)e[r];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0)
+        s_w[warp] = acc;
+    __syncthreads();
     if (threadIdx.x == 0)
-        tile_sum[blockIdx.x] = total;
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++)
+            t += s_w[w];
+        tile_sum[blockIdx.x] = t;
+    }
 }
 
 // exclusive scan of up to a few 10^5 block sums by one CTA (thread-serial chunks + one block scan)
@@ -800,31 +849,49 @@ __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict
 template <bool FUSED>
 __global__ void __launch_bounds__(kBlock) k_cdf_write(CdfArgs a, const double* __restrict__ tile_off, double* __restrict__ cdf)
 {
-    __shared__ double s_scan[kWarpsPerBlock];
-    const int i0 = blockIdx.x * kCdfTile + threadIdx.x * kCdfItems;
-    float e[kCdfItems];
+    __shared__ double s_w[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
+    float e[kCdfRounds];
 #pragma unroll
-    for (int j = 0; j < kCdfItems; j++)
-        e[j] = joint_entry<FUSED>(a, i0 + j);
-    double loc[kCdfItems];
-    double run = 0.0;
+    for (int r = 0; r < kCdfRounds; r++)
+        e[r] = joint_entry<FUSED>(a, w0 + r * 32 + lane);
+    // inclusive prefix inside the warp's 256 entries: warp scan per round + running carry
+    double p[kCdfRounds];
+    double carry = 0.0;
 #pragma unroll
-    for (int j = 0; j < kCdfItems; j++)
+    for (int r = 0; r < kCdfRounds; r++)
     {
-        run += (double)e[j];
-        loc[j] = run;
-    }
-    double total;
-    const double incl = block_inclusive_scan_f64(run, s_scan, &total);
-    const double off = tile_off[blockIdx.x] + (incl - run);
+        double v = (double)e[r];
 #pragma unroll
-    for (int j = 0; j < kCdfItems; j++)
-        if (i0 + j < a.n)
+        for (int d = 1; d < 32; d <<= 1)
         {
-            cdf[i0 + j] = off + loc[j];
-            if (FUSED && i0 + j < a.N)
-                a.wa_out[i0 + j] = e[j];
+            const double t = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d)
+                v += t;
         }
+        p[r] = carry + v;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0)
+        s_w[warp] = carry;
+    __syncthreads();
+    double off = tile_off[blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; w++)
+        if (w < warp)
+            off += s_w[w];
+#pragma unroll
+    for (int r = 0; r < kCdfRounds; r++)
+    {
+        const int i = w0 + r * 32 + lane;
+        if (i < a.n)
+        {
+            cdf[i] = off + p[r];
+            if (FUSED && i < a.N)
+                a.wa_out[i] = e[r];
+        }
+    }
 }
 
 // =========================================================================================================
@@ -875,47 +942,48 @@ __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, i
     return lo;
 }
 
+// the offset of output slot i into the joint weight total (dogm.cu:402-411; BASELINE.json: systematic resampling)
+__device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, double total, float joint_max)
+{
+    if (a.mode == DOGM_RESAMPLE_INJECTED)
+        return (double)__fmul_rn(joint_max, a.resample_u[i]);
+    const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
+    float u;
+    if (a.noise_injected)
+        u = a.resample_u[strat ? i : 0];
+    else
+        u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
+    return ((double)i + (double)u) * (total / (double)a.N);
+}
+
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
     __shared__ double s_cdf[kResWindow];
-    __shared__ int s_lo;
-    __shared__ double s_first;
     const int i = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < a.N;
     const double total = a.scal->weight_total;
     const float joint_max = (float)total;
-    double r = 0.0;
-    if (valid)
+    const double r = resample_offset(a, valid ? i : a.N - 1, total, joint_max);
+    const double r_first = resample_offset(a, blockIdx.x * kBlock, total, joint_max); // the CTA's first (smallest) offset
+    // lower_bound of the first offset by a 256-ary search: every thread probes one CDF entry per round
+    int lo0 = 0, hi0 = a.n_cdf;
+    while (lo0 < hi0)
     {
-        if (a.mode == DOGM_RESAMPLE_INJECTED)
-        {
-            r = (double)__fmul_rn(joint_max, a.resample_u[i]);
-        }
-        else
-        {
-            const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
-            float u;
-            if (a.noise_injected)
-                u = a.resample_u[strat ? i : 0];
-            else
-                u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
-            r = ((double)i + (double)u) * (total / (double)a.N);
-        }
+        const int stride = (hi0 - lo0 + kBlock - 1) / kBlock;
+        const int q = lo0 + threadIdx.x * stride;
+        const int cnt = __syncthreads_count(q < hi0 && a.cdf[q] < r_first); // monotone: the first cnt probes are below
+        const int nlo = cnt > 0 ? lo0 + (cnt - 1) * stride + 1 : lo0;
+        const long long qn = (long long)lo0 + (long long)cnt * stride;
+        hi0 = qn < hi0 ? (int)qn : hi0;
+        lo0 = nlo;
     }
-    if (threadIdx.x == 0)
-    {
-        s_lo = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
-        s_first = r;
-    }
-    __syncthreads();
-    const int lo0 = s_lo;
     for (int j = threadIdx.x; j < kResWindow; j += kBlock)
         s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
     __syncthreads();
     if (!valid)
         return;
     int anc;
-    if (r < s_first)
+    if (r < r_first)
         anc = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
     else if (r <= s_cdf[kResWindow - 1])
     {
