@@ -345,45 +345,6 @@ __device__ __forceinline__ double block_inclusive_scan_f64(double v, double* sme
     *total = tot;
     return off + v;
 }
-
-// "last CTA done" epilogue: every CTA of a kernel has written in[blockIdx.x]; the CTA that finishes last turns the
-// array into its exclusive prefix (out_excl) and total, in a fixed order, so that no separate single-CTA kernel has
-// to be launched.  Call with all 256 threads of the CTA.  s_scan: >= kWarpsPerBlock doubles, s_flag: one int.
-__device__ __forceinline__ void last_block_exclusive_scan_f64(const double* in, double* out_excl, int n,
-                                                              double* total_out, unsigned int* ticket, double* s_scan,
-                                                              int* s_flag)
-{
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        const unsigned int done = atomicAdd(ticket, 1u);
-        *s_flag = (done == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!*s_flag)
-        return;
-    __threadfence();
-    const int per = (n + kBlock - 1) / kBlock;
-    const int b0 = min((int)threadIdx.x * per, n), b1 = min(b0 + per, n);
-    double local = 0.0;
-    for (int b = b0; b < b1; b++)
-        local += __ldcg(&in[b]);
-    double total;
-    const double incl = block_inclusive_scan_f64(local, s_scan, &total);
-    double excl = incl - local;
-    for (int b = b0; b < b1; b++)
-    {
-        const double v = __ldcg(&in[b]);
-        out_excl[b] = excl;
-        excl += v;
-    }
-    if (threadIdx.x == 0)
-    {
-        *total_out = total;
-        *ticket = 0u;
-    }
-}
 #endif
 
 } // namespace dogm_b200

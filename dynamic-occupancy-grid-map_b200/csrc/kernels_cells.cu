@@ -31,8 +31,6 @@ struct CellArgs
     float* born_masses;
     float4* coef;
     double* blk_sum;
-    double* blk_off;      // exclusive prefix of blk_sum, produced by the last CTA
-    DeviceScalars* scal;  // born_total + ticket
     float p_B, alpha;
     int shift_active, x_move, y_move;
 };
@@ -157,12 +155,10 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
                 gw[f] = s_out[warp][f & 3][f >> 2];
         }
     }
-    __shared__ int s_flag;
     double total;
     block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
     if (threadIdx.x == 0)
         a.blk_sum[blockIdx.x] = total;
-    last_block_exclusive_scan_f64(a.blk_sum, a.blk_off, gridDim.x, &a.scal->born_total, &a.scal->ticket[1], s_scan, &s_flag);
 }
 
 // =========================================================================================================
@@ -310,10 +306,9 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 // first-cycle initialisation: copyMassesKernel + initParticlesKernel1/2 (init_new_particles.cu:76-124)
 // =========================================================================================================
 __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell* __restrict__ meas, float* masses, int C,
-                                                            double* blk_sum, double* blk_off, DeviceScalars* scal)
+                                                            double* blk_sum)
 {
     __shared__ double s_scan[kWarpsPerBlock];
-    __shared__ int s_flag;
     const int c = blockIdx.x * kCellBlock + threadIdx.x;
     float m = 0.0f;
     if (c < C)
@@ -325,7 +320,6 @@ __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell
     block_inclusive_scan_f64((double)m, s_scan, &total);
     if (threadIdx.x == 0)
         blk_sum[blockIdx.x] = total;
-    last_block_exclusive_scan_f64(blk_sum, blk_off, gridDim.x, &scal->born_total, &scal->ticket[1], s_scan, &s_flag);
 }
 
 struct InitArgs
@@ -443,6 +437,9 @@ __global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell
 // =========================================================================================================
 static int run_slot_distribution(dogm_handle* h, int count, bool write_weights)
 {
+    int e0 = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
+    if (e0)
+        return e0;
     SlotArgs a;
     a.C = h->C;
     a.count = count;
@@ -464,8 +461,7 @@ int run_init_particles(dogm_handle* h)
 {
     {
         LaunchScope ls(h, K_INIT_MASSES, 8.0 * h->C);
-        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum, h->blk_off,
-                                                                      h->scal);
+        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum);
     }
     int e = run_slot_distribution(h, h->N, false);
     if (e)
@@ -512,8 +508,6 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.born_masses = h->born_masses;
     a.coef = h->cell_coef;
     a.blk_sum = h->blk_sum;
-    a.blk_off = h->blk_off;
-    a.scal = h->scal;
     a.p_B = h->params.birth_prob;
     a.alpha = powf(h->params.freespace_discount, dt); // std::pow(float, float), dogm.cu:291
     a.shift_active = (h->shift_grid_pending && h->shift.active) ? 1 : 0;

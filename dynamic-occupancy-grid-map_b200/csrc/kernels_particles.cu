@@ -367,12 +367,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
             slots[r] = p.y;
         }
     }
-    {
-        uint4* z = reinterpret_cast<uint4*>(s_cnt); // bins is a multiple of 32: the counter block is a multiple of 16 B
-        const int nz = a.bins * kWarpsPerBlock * (int)sizeof(unsigned short) / (int)sizeof(uint4);
-        for (int b = threadIdx.x; b < nz; b += kBlock)
-            z[b] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
+        s_cnt[b] = 0;
     __syncthreads();
 
     unsigned short* my_cnt = s_cnt + warp * a.bins;
@@ -508,87 +504,15 @@ constexpr int kSegPerLane = kSegChunk / 32; // 8 consecutive sorted positions pe
 // joined across lanes by ONE segmented warp scan per 256 particles.  Pieces that cross the chunk border go to the
 // lead / trail records of the chunk and are joined by k_segfix.  Fixed order: serial inside a lane, Kogge-Stone
 // across lanes, chunk order across chunks.
-__device__ __forceinline__ SegPiece load_piece_cg(const SegPiece* p)
-{
-    const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldcg(q), b = __ldcg(q + 1);
-    SegPiece r;
-    r.s0 = __hiloint2double(__float_as_int(a.y), __float_as_int(a.x));
-    r.s1 = a.z;
-    r.s2 = a.w;
-    r.s3 = b.x;
-    r.s4 = b.y;
-    r.s5 = b.z;
-    r.pad = 0;
-    return r;
-}
-
-__device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
-                                             int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
-                                             SegPiece* trail, int* flags, float* __restrict__ sw, int chunk, int lane);
-
 __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
-                                                   int n_chunks, int* cell_start, int* cell_end, CellSums* sums,
-                                                   SegPiece* lead, SegPiece* trail, int* flags, float* __restrict__ sw,
-                                                   unsigned int* ticket)
+                                                   int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
+                                                   SegPiece* trail, int* flags, float* __restrict__ sw)
 {
-    __shared__ int s_last;
     const int lane = threadIdx.x & 31;
     const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    if (chunk * kSegChunk < n)
-        segsum_chunk(spair, rec, n, cell_start, cell_end, sums, lead, trail, flags, sw, chunk, lane);
-
-    // segments that span chunk borders: the last CTA to finish joins the pieces in chunk order (was k_segfix)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        const unsigned int done = atomicAdd(ticket, 1u);
-        s_last = (done == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last)
-        return;
-    __threadfence();
-    for (int c = threadIdx.x; c < n_chunks; c += kBlock)
-    {
-        const int f = __ldcg(&flags[c]);
-        if (!(f & SEG_TRAIL) || (f & SEG_THROUGH))
-            continue;
-        SegPiece acc = load_piece_cg(&trail[c]);
-        int c2 = c + 1;
-        while (c2 < n_chunks)
-        {
-            const SegPiece p = load_piece_cg(&lead[c2]);
-            acc.s0 += p.s0;
-            acc.s1 += p.s1;
-            acc.s2 += p.s2;
-            acc.s3 += p.s3;
-            acc.s4 += p.s4;
-            acc.s5 += p.s5;
-            if (!(__ldcg(&flags[c2]) & SEG_THROUGH))
-                break;
-            c2++;
-        }
-        const int k = spair[(c + 1) * kSegChunk - 1].x;
-        Sum6 v;
-        v.s0 = acc.s0;
-        v.s1 = acc.s1;
-        v.s2 = acc.s2;
-        v.s3 = acc.s3;
-        v.s4 = acc.s4;
-        v.s5 = acc.s5;
-        store_cell_sums(sums, k, v);
-    }
-    if (threadIdx.x == 0)
-        *ticket = 0u;
-}
-
-__device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
-                                             int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
-                                             SegPiece* trail, int* flags, float* __restrict__ sw, int chunk, int lane)
-{
     const int base = chunk * kSegChunk;
+    if (base >= n)
+        return;
     const unsigned full = 0xffffffffu;
     const int p0 = base + lane * kSegPerLane;
 
@@ -757,6 +681,43 @@ __device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, con
     }
 }
 
+// segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
+__global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spair, int n_chunks, CellSums* sums,
+                                                   const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
+                                                   const int* __restrict__ flags)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= n_chunks)
+        return;
+    const int f = flags[c];
+    if (!(f & SEG_TRAIL) || (f & SEG_THROUGH))
+        return;
+    SegPiece acc = trail[c];
+    int c2 = c + 1;
+    while (c2 < n_chunks)
+    {
+        const SegPiece p = lead[c2];
+        acc.s0 += p.s0;
+        acc.s1 += p.s1;
+        acc.s2 += p.s2;
+        acc.s3 += p.s3;
+        acc.s4 += p.s4;
+        acc.s5 += p.s5;
+        if (!(flags[c2] & SEG_THROUGH))
+            break;
+        c2++;
+    }
+    const int k = spair[(c + 1) * kSegChunk - 1].x;
+    Sum6 v;
+    v.s0 = acc.s0;
+    v.s1 = acc.s1;
+    v.s2 = acc.s2;
+    v.s3 = acc.s3;
+    v.s4 = acc.s4;
+    v.s5 = acc.s5;
+    store_cell_sums(sums, k, v);
+}
+
 // =========================================================================================================
 // persistent-particle weights: updatePersistentParticlesKernel1 + 3 (update_persistent_particles.cu:33-57,78-87)
 // with the per-cell constants precomputed by the cell kernel; the over-unit normalisation of
@@ -809,10 +770,9 @@ __device__ __forceinline__ float joint_entry(const CdfArgs& a, int i)
 constexpr int kCdfRounds = kCdfTile / kBlock; // 8
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum, double* tile_off, DeviceScalars* scal)
+__global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum)
 {
     __shared__ double s_w[kWarpsPerBlock];
-    __shared__ int s_flag;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
     float e[kCdfRounds];
@@ -837,8 +797,6 @@ __global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_s
             t += s_w[w];
         tile_sum[blockIdx.x] = t;
     }
-    // the last CTA turns the tile sums into tile offsets and the weight total (no separate scan kernel)
-    last_block_exclusive_scan_f64(tile_sum, tile_off, gridDim.x, &scal->weight_total, &scal->ticket[2], s_w, &s_flag);
 }
 
 // exclusive scan of up to a few 10^5 block sums by one CTA (thread-serial chunks + one block scan)
@@ -964,15 +922,12 @@ __device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_
     return u01_half_open(p.x);
 }
 
-// One CTA resamples 1024 consecutive outputs (4 per thread).  Their offsets ascend, so all ancestors lie in a short
-// window of the CDF behind the ancestor of the CTA's first offset: that one is found by a 256-ary search in which
-// every thread probes one CDF entry per round (3 rounds for 2.2e6 entries), the window is staged in shared memory
-// with coalesced loads and every thread searches it there.  Offsets beyond the window (long runs of zero weights) or
-// out of order (caller-supplied fractions that do not ascend) fall back to a search in global memory, so the result
-// is lower_bound on the whole CDF in every case.
-constexpr int kResPerThread = 4;
-constexpr int kResTile = kBlock * kResPerThread;
-constexpr int kResWindow = 1536;
+// One CTA resamples 256 consecutive outputs.  Their offsets ascend, so all ancestors lie in a short window of the
+// CDF behind the ancestor of the CTA's first offset: thread 0 finds that one by binary search in global memory,
+// the window is staged in shared memory with coalesced loads and every thread searches it there.  Offsets beyond
+// the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
+// to a search in global memory, so the result is lower_bound on the whole CDF in every case.
+constexpr int kResWindow = 768;
 
 __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
@@ -988,28 +943,29 @@ __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, i
 }
 
 // the offset of output slot i into the joint weight total (dogm.cu:402-411; BASELINE.json: systematic resampling)
-__device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, double total, float joint_max, float u0)
+__device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, double total, float joint_max)
 {
     if (a.mode == DOGM_RESAMPLE_INJECTED)
         return (double)__fmul_rn(joint_max, a.resample_u[i]);
-    float u = u0;
-    if (a.mode == DOGM_RESAMPLE_STRATIFIED)
-        u = a.noise_injected ? a.resample_u[i] : resample_fraction_philox(a.seed, (uint32_t)i, a.cycle);
+    const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
+    float u;
+    if (a.noise_injected)
+        u = a.resample_u[strat ? i : 0];
+    else
+        u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
     return ((double)i + (double)u) * (total / (double)a.N);
 }
 
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
     __shared__ double s_cdf[kResWindow];
-    const int tile0 = blockIdx.x * kResTile;
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = i < a.N;
     const double total = a.scal->weight_total;
     const float joint_max = (float)total;
-    // systematic resampling: one fraction for the whole population
-    float u0 = 0.0f;
-    if (a.mode == DOGM_RESAMPLE_SYSTEMATIC)
-        u0 = a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle);
-    const double r_first = resample_offset(a, tile0, total, joint_max, u0); // the CTA's first (smallest) offset
-    // lower_bound of the first offset by a 256-ary search
+    const double r = resample_offset(a, valid ? i : a.N - 1, total, joint_max);
+    const double r_first = resample_offset(a, blockIdx.x * kBlock, total, joint_max); // the CTA's first (smallest) offset
+    // lower_bound of the first offset by a 256-ary search: every thread probes one CDF entry per round
     int lo0 = 0, hi0 = a.n_cdf;
     while (lo0 < hi0)
     {
@@ -1024,81 +980,50 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     for (int j = threadIdx.x; j < kResWindow; j += kBlock)
         s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
     __syncthreads();
-
-    int anc[kResPerThread];
-#pragma unroll
-    for (int k = 0; k < kResPerThread; k++)
+    if (!valid)
+        return;
+    int anc;
+    if (r < r_first)
+        anc = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
+    else if (r <= s_cdf[kResWindow - 1])
     {
-        const int i = tile0 + k * kBlock + threadIdx.x;
-        anc[k] = -1;
-        if (i < a.N)
+        int l = 0, h = kResWindow;
+        while (l < h)
         {
-            const double r = resample_offset(a, i, total, joint_max, u0);
-            int x;
-            if (r < r_first)
-                x = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
-            else if (r <= s_cdf[kResWindow - 1])
-            {
-                int l = 0, h = kResWindow;
-                while (l < h)
-                {
-                    const int mid = l + ((h - l) >> 1);
-                    if (s_cdf[mid] < r)
-                        l = mid + 1;
-                    else
-                        h = mid;
-                }
-                x = lo0 + l;
-            }
+            const int mid = l + ((h - l) >> 1);
+            if (s_cdf[mid] < r)
+                l = mid + 1;
             else
-                x = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
-            anc[k] = x < a.n_cdf ? x : a.n_cdf - 1;
+                h = mid;
         }
+        anc = lo0 + l;
     }
-    // gather: all four record fetches of a thread are in flight together
-    int slot[kResPerThread];
-#pragma unroll
-    for (int k = 0; k < kResPerThread; k++)
-        slot[k] = (anc[k] >= 0 && anc[k] < a.N) ? a.spair[anc[k]].y : -1;
-    float4 rlo[kResPerThread], rhi[kResPerThread];
-#pragma unroll
-    for (int k = 0; k < kResPerThread; k++)
-        if (slot[k] >= 0)
-        {
-            const float4* p = reinterpret_cast<const float4*>(a.rec + slot[k]);
-            rlo[k] = p[0];
-            rhi[k] = p[1];
-        }
-    const float new_weight = __fdiv_rn(joint_max, (float)a.N);
-#pragma unroll
-    for (int k = 0; k < kResPerThread; k++)
+    else
+        anc = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
+    anc = anc < a.n_cdf ? anc : a.n_cdf - 1;
+    a.ancestors[i] = anc;
+    float4 s;
+    int cell;
+    uint8_t as;
+    if (anc < a.N)
     {
-        const int i = tile0 + k * kBlock + threadIdx.x;
-        if (i < a.N)
-        {
-            float4 s;
-            int cell;
-            uint8_t as;
-            if (slot[k] >= 0)
-            {
-                s = make_float4(rlo[k].x, rlo[k].y, rhi[k].x, rhi[k].y);
-                cell = __float_as_int(rlo[k].z);
-                as = (uint8_t)__float_as_uint(rlo[k].w);
-            }
-            else
-            {
-                const int b = anc[k] - a.N;
-                s = a.birth.state[b];
-                cell = a.birth.idx[b];
-                as = a.birth.assoc[b];
-            }
-            a.ancestors[i] = anc[k];
-            a.dst.state[i] = s;
-            a.dst.idx[i] = cell;
-            a.dst.assoc[i] = as;
-            a.dst.weight[i] = new_weight;
-        }
+        const float4* p = reinterpret_cast<const float4*>(a.rec + a.spair[anc].y);
+        const float4 rlo = p[0], rhi = p[1];
+        s = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
+        cell = __float_as_int(rlo.z);
+        as = (uint8_t)__float_as_uint(rlo.w);
     }
+    else
+    {
+        const int b = anc - a.N;
+        s = a.birth.state[b];
+        cell = a.birth.idx[b];
+        as = a.birth.assoc[b];
+    }
+    a.dst.state[i] = s;
+    a.dst.idx[i] = cell;
+    a.dst.assoc[i] = as;
+    a.dst.weight[i] = __fdiv_rn(joint_max, (float)a.N);
 }
 
 // ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
@@ -1280,8 +1205,12 @@ int run_assignment(dogm_handle* h)
     {
         LaunchScope ls(h, K_SEGSUM, 44.0 * N);
         k_segsum<<<div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->stream>>>(
-            h->spair, h->rec, N, h->n_chunks, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail,
-            h->seg_flags, h->sw, &h->scal->ticket[3]);
+            h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw);
+    }
+    {
+        LaunchScope ls(h, K_SEGFIX, 0.0);
+        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->spair, h->n_chunks, h->cell_sums, h->seg_lead,
+                                                                      h->seg_trail, h->seg_flags);
     }
     h->sorted_valid = true;
     return (int)cudaGetLastError();
@@ -1338,9 +1267,14 @@ int run_resampling(dogm_handle* h)
     {
         LaunchScope ls(h, K_CDF_REDUCE, fused ? 12.0 * N + 4.0 * h->B : 4.0 * n);
         if (fused)
-            k_cdf_reduce<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum, h->tile_off, h->scal);
+            k_cdf_reduce<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
         else
-            k_cdf_reduce<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum, h->tile_off, h->scal);
+            k_cdf_reduce<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
+    }
+    {
+        int e = run_blocksum_scan(h, h->tile_sum, h->tile_off, h->n_cdf_tiles, &h->scal->weight_total);
+        if (e)
+            return e;
     }
     {
         LaunchScope ls(h, K_CDF_WRITE, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
@@ -1367,7 +1301,7 @@ int run_resampling(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
-        k_resample<<<div_up(N, kResTile), kBlock, 0, h->stream>>>(a);
+        k_resample<<<div_up(N, kBlock), kBlock, 0, h->stream>>>(a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;
