@@ -351,28 +351,24 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     const unsigned lt = lanemask_lt();
     const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
 
-    // all loads of the warp's 16 rounds are in flight while the rank counters are cleared
+    // all key loads of the warp's 16 rounds are in flight while the rank counters are cleared
     int keys[kRoundsPerWarp];
-    int slots[FIRST ? 1 : kRoundsPerWarp];
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
         const int i = warp_base + r * 32 + lane;
-        if (FIRST)
-            keys[r] = (i < a.n) ? key_in[i] : 0;
-        else
-        {
-            const int2 p = (i < a.n) ? pair_in[i] : make_int2(0, 0);
-            keys[r] = p.x;
-            slots[r] = p.y;
-        }
+        keys[r] = (i < a.n) ? (FIRST ? key_in[i] : pair_in[i].x) : 0;
     }
-    for (int b = threadIdx.x; b < a.bins * kWarpsPerBlock; b += kBlock)
-        s_cnt[b] = 0;
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt); // bins is a multiple of 32: the counter block is a multiple of 16 B
+        const int nz = a.bins * kWarpsPerBlock * (int)sizeof(unsigned short) / (int)sizeof(uint4);
+        for (int b = threadIdx.x; b < nz; b += kBlock)
+            z[b] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
 
     unsigned short* my_cnt = s_cnt + warp * a.bins;
-    unsigned short rank[kRoundsPerWarp];
+    uint32_t rank2[kRoundsPerWarp / 2]; // ranks inside the warp's 512 items, two per register
 
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
@@ -389,7 +385,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
             my_cnt[digit] = (unsigned short)(old + __popc(peers));
         }
         old = __shfl_sync(full, old, leader);
-        rank[r] = (unsigned short)(old + __popc(peers & lt));
+        const uint32_t rk = old + __popc(peers & lt);
+        if (r & 1)
+            rank2[r >> 1] |= rk << 16;
+        else
+            rank2[r >> 1] = rk;
         __syncwarp();
     }
     __syncthreads();
@@ -410,16 +410,29 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     }
     __syncthreads();
 
+    // store phase: the (key, slot) inputs are read again (L1 / L2 hits) instead of being kept in registers
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
         const int i = warp_base + r * 32 + lane;
         if (i < a.n)
         {
-            const int key = keys[r];
+            int key, slot;
+            if (FIRST)
+            {
+                key = key_in[i];
+                slot = i;
+            }
+            else
+            {
+                const int2 p = pair_in[i];
+                key = p.x;
+                slot = p.y;
+            }
             const uint32_t digit = ((uint32_t)key >> a.shift) & a.mask;
-            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + rank[r];
-            pair_out[dest] = make_int2(key, FIRST ? i : slots[r]);
+            const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
+            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + rk;
+            pair_out[dest] = make_int2(key, slot);
             if (a.next_table)
             {
                 const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
@@ -927,7 +940,7 @@ __device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_
 // the window is staged in shared memory with coalesced loads and every thread searches it there.  Offsets beyond
 // the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
 // to a search in global memory, so the result is lower_bound on the whole CDF in every case.
-constexpr int kResWindow = 768;
+constexpr int kResWindow = 512;
 
 __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
@@ -942,29 +955,42 @@ __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, i
     return lo;
 }
 
-// the offset of output slot i into the joint weight total (dogm.cu:402-411; BASELINE.json: systematic resampling)
-__device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, double total, float joint_max)
+// the offset of output slot i into the joint weight total (dogm.cu:402-411; BASELINE.json: systematic resampling).
+// `u0` (the one fraction of systematic resampling) and `step` = total / N are computed once per CTA.
+__device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, float joint_max, float u0, double step)
 {
     if (a.mode == DOGM_RESAMPLE_INJECTED)
         return (double)__fmul_rn(joint_max, a.resample_u[i]);
-    const bool strat = (a.mode == DOGM_RESAMPLE_STRATIFIED);
-    float u;
-    if (a.noise_injected)
-        u = a.resample_u[strat ? i : 0];
-    else
-        u = resample_fraction_philox(a.seed, strat ? (uint32_t)i : 0u, a.cycle);
-    return ((double)i + (double)u) * (total / (double)a.N);
+    float u = u0;
+    if (a.mode == DOGM_RESAMPLE_STRATIFIED)
+        u = a.noise_injected ? a.resample_u[i] : resample_fraction_philox(a.seed, (uint32_t)i, a.cycle);
+    return ((double)i + (double)u) * step;
 }
 
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
     __shared__ double s_cdf[kResWindow];
+    __shared__ double s_step, s_first;
+    __shared__ float s_u0, s_jm;
     const int i = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < a.N;
-    const double total = a.scal->weight_total;
-    const float joint_max = (float)total;
-    const double r = resample_offset(a, valid ? i : a.N - 1, total, joint_max);
-    const double r_first = resample_offset(a, blockIdx.x * kBlock, total, joint_max); // the CTA's first (smallest) offset
+    if (threadIdx.x == 0)
+    {
+        const double total = a.scal->weight_total;
+        const float jm = (float)total;
+        float u0 = 0.0f;
+        if (a.mode == DOGM_RESAMPLE_SYSTEMATIC)
+            u0 = a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle);
+        const double step = total / (double)a.N;
+        s_step = step;
+        s_u0 = u0;
+        s_jm = jm;
+        s_first = resample_offset(a, blockIdx.x * kBlock, jm, u0, step); // the CTA's first (smallest) offset
+    }
+    __syncthreads();
+    const float joint_max = s_jm;
+    const double r_first = s_first;
+    const double r = resample_offset(a, valid ? i : a.N - 1, joint_max, s_u0, s_step);
     // lower_bound of the first offset by a 256-ary search: every thread probes one CDF entry per round
     int lo0 = 0, hi0 = a.n_cdf;
     while (lo0 < hi0)
