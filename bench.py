@@ -161,26 +161,35 @@ class Dist:
             import torch.distributed as dist
 
             self.torch = torch
-            torch.cuda.set_device(self.local_rank)
-            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            # NCCL on the GPU box; gloo only for the CPU test of this plumbing (tests/test_dist_cpu.py)
+            self.backend = os.environ.get("DOGM_BENCH_DIST_BACKEND", "nccl")
+            if self.backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+                dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(backend=self.backend)
             self.dist = dist
+
+    def _device(self):
+        return "cuda" if self.backend == "nccl" else "cpu"
 
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
-            self.torch.cuda.synchronize()
+            if self.backend == "nccl":
+                self.torch.cuda.synchronize()
 
     def max(self, v: float) -> float:
         if self.world == 1:
             return v
-        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self._device())
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
     def sum(self, v: float) -> float:
         if self.world == 1:
             return v
-        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self._device())
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
 
