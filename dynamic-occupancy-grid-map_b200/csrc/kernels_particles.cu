@@ -935,13 +935,13 @@ __device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_
     return u01_half_open(p.x);
 }
 
-// Resampling is organised by CDF tile, not by output: the CTA of tile t stages its 2048 CDF entries in shared memory
-// (one coalesced read, no search in global memory) and serves exactly the outputs whose offset r_i falls into the
-// tile, P_t < r_i <= L_t with P_t / L_t the last CDF entry of the previous / this tile.  The offsets ascend with i, so
-// these outputs are one contiguous range [i_start, i_end) whose ends are found by bisection on i with the very
-// predicate (r_i > P_t, r_i > L_t) that defines membership — pure arithmetic for the systematic and stratified
-// offsets.  Inside the tile every thread runs lower_bound in shared memory, so the ancestor is
-// min(lower_bound(cdf, r_i), n - 1) on the whole CDF, as in resampling.cu:34-47.
+// One CTA resamples 256 consecutive outputs.  Their offsets ascend, so all ancestors lie in a short window of the
+// CDF behind the ancestor of the CTA's first offset: thread 0 finds that one by binary search in global memory,
+// the window is staged in shared memory with coalesced loads and every thread searches it there.  Offsets beyond
+// the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
+// to a search in global memory, so the result is lower_bound on the whole CDF in every case.
+constexpr int kResWindow = 512;
+
 __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
     while (lo < hi)
@@ -967,32 +967,13 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
     return ((double)i + (double)u) * step;
 }
 
-// first output index in [0, N] whose offset exceeds x (the offsets do not decrease with i)
-__device__ __forceinline__ int first_offset_above(const ResampleArgs& a, double x, float joint_max, float u0, double step)
-{
-    int lo = 0, hi = a.N;
-    while (lo < hi)
-    {
-        const int mid = lo + ((hi - lo) >> 1);
-        if (resample_offset(a, mid, joint_max, u0, step) > x)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    return lo;
-}
-
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
-    __shared__ double s_cdf[kCdfTile];
-    __shared__ double s_step;
+    __shared__ double s_cdf[kResWindow];
+    __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
-    __shared__ int s_range[2];
-    const int e0 = blockIdx.x * kCdfTile;
-    const int cnt = min(kCdfTile, a.n_cdf - e0);
-    const bool last_tile = (e0 + cnt >= a.n_cdf);
-    for (int j = threadIdx.x; j < cnt; j += kBlock)
-        s_cdf[j] = a.cdf[e0 + j];
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = i < a.N;
     if (threadIdx.x == 0)
     {
         const double total = a.scal->weight_total;
@@ -1000,24 +981,39 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         float u0 = 0.0f;
         if (a.mode == DOGM_RESAMPLE_SYSTEMATIC)
             u0 = a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle);
-        s_step = total / (double)a.N;
+        const double step = total / (double)a.N;
+        s_step = step;
         s_u0 = u0;
         s_jm = jm;
+        s_first = resample_offset(a, blockIdx.x * kBlock, jm, u0, step); // the CTA's first (smallest) offset
     }
     __syncthreads();
-    const float joint_max = s_jm, u0 = s_u0;
-    const double step = s_step;
-    if (threadIdx.x == 0) // outputs in front of this tile: r_i <= last entry of the previous tile
-        s_range[0] = e0 == 0 ? 0 : first_offset_above(a, a.cdf[e0 - 1], joint_max, u0, step);
-    if (threadIdx.x == 32) // outputs behind it: r_i > last entry of this tile (the last tile takes whatever is left)
-        s_range[1] = last_tile ? a.N : first_offset_above(a, s_cdf[cnt - 1], joint_max, u0, step);
-    __syncthreads();
-    const int i_start = s_range[0], i_end = s_range[1];
-    const float new_weight = __fdiv_rn(joint_max, (float)a.N);
-    for (int i = i_start + threadIdx.x; i < i_end; i += kBlock)
+    const float joint_max = s_jm;
+    const double r_first = s_first;
+    const double r = resample_offset(a, valid ? i : a.N - 1, joint_max, s_u0, s_step);
+    // lower_bound of the first offset by a 256-ary search: every thread probes one CDF entry per round
+    int lo0 = 0, hi0 = a.n_cdf;
+    while (lo0 < hi0)
     {
-        const double r = resample_offset(a, i, joint_max, u0, step);
-        int l = 0, h = cnt;
+        const int stride = (hi0 - lo0 + kBlock - 1) / kBlock;
+        const int q = lo0 + threadIdx.x * stride;
+        const int cnt = __syncthreads_count(q < hi0 && a.cdf[q] < r_first); // monotone: the first cnt probes are below
+        const int nlo = cnt > 0 ? lo0 + (cnt - 1) * stride + 1 : lo0;
+        const long long qn = (long long)lo0 + (long long)cnt * stride;
+        hi0 = qn < hi0 ? (int)qn : hi0;
+        lo0 = nlo;
+    }
+    for (int j = threadIdx.x; j < kResWindow; j += kBlock)
+        s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
+    __syncthreads();
+    if (!valid)
+        return;
+    int anc;
+    if (r < r_first)
+        anc = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
+    else if (r <= s_cdf[kResWindow - 1])
+    {
+        int l = 0, h = kResWindow;
         while (l < h)
         {
             const int mid = l + ((h - l) >> 1);
@@ -1026,31 +1022,34 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             else
                 h = mid;
         }
-        const int anc = min(e0 + l, a.n_cdf - 1);
-        a.ancestors[i] = anc;
-        float4 s;
-        int cell;
-        uint8_t as;
-        if (anc < a.N)
-        {
-            const float4* p = reinterpret_cast<const float4*>(a.rec + a.spair[anc].y);
-            const float4 rlo = p[0], rhi = p[1];
-            s = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
-            cell = __float_as_int(rlo.z);
-            as = (uint8_t)__float_as_uint(rlo.w);
-        }
-        else
-        {
-            const int b = anc - a.N;
-            s = a.birth.state[b];
-            cell = a.birth.idx[b];
-            as = a.birth.assoc[b];
-        }
-        a.dst.state[i] = s;
-        a.dst.idx[i] = cell;
-        a.dst.assoc[i] = as;
-        a.dst.weight[i] = new_weight;
+        anc = lo0 + l;
     }
+    else
+        anc = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
+    anc = anc < a.n_cdf ? anc : a.n_cdf - 1;
+    a.ancestors[i] = anc;
+    float4 s;
+    int cell;
+    uint8_t as;
+    if (anc < a.N)
+    {
+        const float4* p = reinterpret_cast<const float4*>(a.rec + a.spair[anc].y);
+        const float4 rlo = p[0], rhi = p[1];
+        s = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
+        cell = __float_as_int(rlo.z);
+        as = (uint8_t)__float_as_uint(rlo.w);
+    }
+    else
+    {
+        const int b = anc - a.N;
+        s = a.birth.state[b];
+        cell = a.birth.idx[b];
+        as = a.birth.assoc[b];
+    }
+    a.dst.state[i] = s;
+    a.dst.idx[i] = cell;
+    a.dst.assoc[i] = as;
+    a.dst.weight[i] = __fdiv_rn(joint_max, (float)a.N);
 }
 
 // ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
@@ -1328,7 +1327,7 @@ int run_resampling(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
-        k_resample<<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(a);
+        k_resample<<<div_up(N, kBlock), kBlock, 0, h->stream>>>(a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;
