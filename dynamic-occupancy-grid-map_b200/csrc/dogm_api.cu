@@ -184,6 +184,7 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     e |= alloc_zero((void**)&h->cell_end, C * sizeof(int));
     e |= alloc_zero((void**)&h->cell_sums, C * sizeof(CellSums));
     e |= alloc_zero((void**)&h->cell_coef, C * sizeof(float4));
+    e |= alloc_zero((void**)&h->cell_prefix, C * sizeof(double));
     e |= alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double));
     e |= alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double));
     e |= alloc_zero((void**)&h->slot_end, C * sizeof(int));
@@ -247,6 +248,7 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->cell_end);
     cudaFree(h->cell_sums);
     cudaFree(h->cell_coef);
+    cudaFree(h->cell_prefix);
     cudaFree(h->blk_sum);
     cudaFree(h->blk_off);
     cudaFree(h->slot_end);

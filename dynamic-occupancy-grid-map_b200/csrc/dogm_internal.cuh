@@ -203,6 +203,7 @@ struct dogm_handle
     int* cell_end;
     dogm_b200::CellSums* cell_sums;
     float4* cell_coef; // {likelihood, p_A*mu_A, (1-p_A)*mu_UA, over-unit divisor or 0} for non-empty cells
+    double* cell_prefix; // block-local inclusive prefix (double) of the born / initial masses, per cell
     double* blk_sum;   // born-mass sum per 256-cell block
     double* blk_off;   // exclusive prefix of blk_sum
     int* slot_end;     // exclusive end slot per cell of the last birth / init distribution

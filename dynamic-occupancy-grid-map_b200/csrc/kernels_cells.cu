@@ -31,6 +31,7 @@ struct CellArgs
     float* born_masses;
     float4* coef;
     double* blk_sum;
+    double* prefix; // block-local inclusive prefix of the born masses (double), for the birth slot distribution
     float p_B, alpha;
     int shift_active, x_move, y_move;
 };
@@ -156,104 +157,97 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
         }
     }
     double total;
-    block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
+    const double incl = block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
+    if (valid)
+        a.prefix[c] = incl;
     if (threadIdx.x == 0)
         a.blk_sum[blockIdx.x] = total;
 }
 
 // =========================================================================================================
 // slot distribution: accumulate + normalize_particle_orders + calc_start_idx/calc_end_idx
-// (init_new_particles.cu:30-43,66-74) and the per-cell part of initNewParticlesKernel1 (:126-143)
+// (init_new_particles.cu:30-43,66-74).  The running sum over all cells is  blk_off[block] + prefix[cell]  (doubles:
+// block-local prefix from the cell kernel, block offsets from one small scan); the exclusive end slot of a cell,
+// int(float(sum) * (count / total)), is evaluated where it is needed instead of being stored per cell.
 // =========================================================================================================
-struct SlotArgs
+struct SlotView
 {
-    int C;
-    int count; // slots to distribute: B (birth) or N (first-cycle initialisation)
-    const float* masses;
     const double* blk_off;
-    const DeviceScalars* scal;
-    int* slot_end;
-    int* blk_slot_end;
-    const dogm_meas_cell* meas;
-    dogm_grid_cell* grid; // w_A / w_UA are written when non-null
+    const double* blk_sum;
+    const double* prefix;
+    int n_blocks, C;
+    float scale; // (float)count / (float)total
 };
 
-__global__ void __launch_bounds__(kCellBlock) k_birth_cells(SlotArgs a)
+__device__ __forceinline__ int slot_end_of_block(const SlotView& v, int b)
 {
-    __shared__ double s_scan[kWarpsPerBlock];
-    __shared__ int s_end[kCellBlock];
-    const int c = blockIdx.x * kCellBlock + threadIdx.x;
-    const bool valid = c < a.C;
-    const float m = valid ? a.masses[c] : 0.0f;
-    double total;
-    const double incl = block_inclusive_scan_f64((double)m, s_scan, &total);
-    const double off = a.blk_off[blockIdx.x];
-    const float maxf = (float)a.scal->born_total;
-    const float scale = (float)a.count / maxf;
-    const int e = __float2int_rz((float)(off + incl) * scale);
-    s_end[threadIdx.x] = e;
-    __syncthreads();
-    if (!valid)
-        return;
-    a.slot_end[c] = e;
-    const int last = min(kCellBlock, a.C - blockIdx.x * kCellBlock) - 1;
-    if (threadIdx.x == last)
-        a.blk_slot_end[blockIdx.x] = e;
-    if (a.grid)
-    {
-        int e_prev;
-        if (threadIdx.x > 0)
-            e_prev = s_end[threadIdx.x - 1];
-        else
-            e_prev = c == 0 ? 0 : __float2int_rz((float)off * scale);
-        const int num_new = e > e_prev ? e - e_prev : 0;
-        if (num_new > 0)
-        {
-            const float p_A = a.meas[c].p_A;
-            const int nu_A = __float2int_rz(roundf((float)num_new * p_A));
-            const int nu_UA = num_new - nu_A;
-            const float w_A = nu_A > 0 ? (p_A * m) / (float)nu_A : 0.0f;
-            const float w_UA = nu_UA > 0 ? ((1.0f - p_A) * m) / (float)nu_UA : 0.0f;
-            a.grid[c].w_A = w_A;
-            a.grid[c].w_UA = w_UA;
-        }
-    }
+    return __float2int_rz((float)(v.blk_off[b] + v.blk_sum[b]) * v.scale);
+}
+__device__ __forceinline__ int slot_end_of_cell(const SlotView& v, int c)
+{
+    return __float2int_rz((float)(v.blk_off[c / kCellBlock] + v.prefix[c]) * v.scale);
+}
+__device__ __forceinline__ int slot_start_of_cell(const SlotView& v, int c)
+{
+    if (c == 0)
+        return 0;
+    // the cell in front of the first cell of a block ends where that block's offset puts it
+    return (c % kCellBlock) ? slot_end_of_cell(v, c - 1) : __float2int_rz((float)v.blk_off[c / kCellBlock] * v.scale);
 }
 
-// owner cell of slot s: first cell j with slot_end[j] > s (two-level search: 256-cell blocks, then cells)
-__device__ __forceinline__ int find_slot_owner(const int* __restrict__ slot_end, const int* __restrict__ blk_slot_end,
-                                               int n_blocks, int C, int s)
+// owner cell of slot s: first cell j whose end slot exceeds s (two-level search: 256-cell blocks, then cells)
+__device__ __forceinline__ int find_slot_owner(const SlotView& v, int s)
 {
-    int lo = 0, hi = n_blocks;
+    int lo = 0, hi = v.n_blocks;
     while (lo < hi)
     {
         const int mid = lo + ((hi - lo) >> 1);
-        if (blk_slot_end[mid] > s)
+        if (slot_end_of_block(v, mid) > s)
             hi = mid;
         else
             lo = mid + 1;
     }
-    if (lo >= n_blocks)
+    if (lo >= v.n_blocks)
         return -1;
-    int clo = lo * kCellBlock, chi = min(C, clo + kCellBlock);
+    int clo = lo * kCellBlock, chi = min(v.C, clo + kCellBlock);
     while (clo < chi)
     {
         const int mid = clo + ((chi - clo) >> 1);
-        if (slot_end[mid] > s)
+        if (slot_end_of_cell(v, mid) > s)
             chi = mid;
         else
             clo = mid + 1;
     }
-    return clo < C ? clo : -1;
+    return clo < v.C ? clo : -1;
+}
+
+// per-cell part of initNewParticlesKernel1 (init_new_particles.cu:134-143)
+struct BirthWeights
+{
+    int start, nu_A;
+    float w_A, w_UA;
+};
+__device__ __forceinline__ BirthWeights birth_weights_of_cell(const SlotView& v, int j, float p_A, float born_mass)
+{
+    BirthWeights r;
+    r.start = slot_start_of_cell(v, j);
+    const int e = slot_end_of_cell(v, j);
+    const int num_new = e > r.start ? e - r.start : 0;
+    r.nu_A = __float2int_rz(roundf((float)num_new * p_A));
+    const int nu_UA = num_new - r.nu_A;
+    r.w_A = r.nu_A > 0 ? (p_A * born_mass) / (float)r.nu_A : 0.0f;
+    r.w_UA = nu_UA > 0 ? ((1.0f - p_A) * born_mass) / (float)nu_UA : 0.0f;
+    return r;
 }
 
 struct BirthArgs
 {
-    int B, C, gs, n_blocks;
-    const int* slot_end;
-    const int* blk_slot_end;
+    int B, gs;
+    SlotView slots;
+    const DeviceScalars* scal;
+    const float* born_masses;
     const dogm_meas_cell* meas;
-    const dogm_grid_cell* grid;
+    dogm_grid_cell* grid;
     ParticleSet birth;
     const float2* noise;
     int noise_injected;
@@ -262,51 +256,55 @@ struct BirthArgs
     uint32_t cycle;
 };
 
-// initBirthParticlesKernel (init.cu:46-67) + slot ownership of initNewParticlesKernel1 (init_new_particles.cu:145-153,
-// with the deterministic rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
+// initBirthParticlesKernel (init.cu:46-67) + initNewParticlesKernel1 (init_new_particles.cu:126-155, with the
+// deterministic ownership rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
 __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 {
     const int s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= a.B)
         return;
-    int j = find_slot_owner(a.slot_end, a.blk_slot_end, a.n_blocks, a.C, s);
+    SlotView v = a.slots;
+    v.scale = (float)a.B / (float)a.scal->born_total;
+    int j = find_slot_owner(v, s);
     bool assoc = false;
     float weight;
     if (j >= 0)
     {
-        const int start = j > 0 ? a.slot_end[j - 1] : 0;
-        const int num_new = a.slot_end[j] - start;
-        const float p_A = a.meas[j].p_A;
-        const int nu_A = __float2int_rz(roundf((float)num_new * p_A));
-        assoc = s <= start + nu_A;
-        weight = assoc ? a.grid[j].w_A : a.grid[j].w_UA;
+        const BirthWeights bw = birth_weights_of_cell(v, j, a.meas[j].p_A, a.born_masses[j]);
+        assoc = s <= bw.start + bw.nu_A;
+        weight = assoc ? bw.w_A : bw.w_UA;
+        if (s == bw.start)
+        { // the cell's first slot also records the weights in the grid cell (store_weights, :60-64)
+            a.grid[j].w_A = bw.w_A;
+            a.grid[j].w_UA = bw.w_UA;
+        }
     }
     else
     { // a slot no cell owns keeps its previous cell index, as in the reference
         j = a.birth.idx[s];
-        weight = a.grid[j].w_UA;
+        weight = birth_weights_of_cell(v, j, a.meas[j].p_A, a.born_masses[j]).w_UA;
     }
-    float2 v;
+    float2 vel;
     if (a.noise_injected)
-        v = a.noise[s];
+        vel = a.noise[s];
     else
     {
         const float4 g = philox_normal4(a.seed, (uint32_t)s, STAGE_BIRTH, a.cycle);
-        v = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
+        vel = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
     }
     const float x = (float)(j % a.gs) + 0.5f;
     const float y = (float)j / (float)a.gs + 0.5f; // float division, init_new_particles.cu:173
     a.birth.idx[s] = j;
     a.birth.assoc[s] = assoc ? 1 : 0;
     a.birth.weight[s] = weight;
-    a.birth.state[s] = make_float4(x, y, v.x, v.y);
+    a.birth.state[s] = make_float4(x, y, vel.x, vel.y);
 }
 
 // =========================================================================================================
 // first-cycle initialisation: copyMassesKernel + initParticlesKernel1/2 (init_new_particles.cu:76-124)
 // =========================================================================================================
 __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell* __restrict__ meas, float* masses, int C,
-                                                            double* blk_sum)
+                                                            double* blk_sum, double* prefix)
 {
     __shared__ double s_scan[kWarpsPerBlock];
     const int c = blockIdx.x * kCellBlock + threadIdx.x;
@@ -317,16 +315,18 @@ __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell
         masses[c] = m;
     }
     double total;
-    block_inclusive_scan_f64((double)m, s_scan, &total);
+    const double incl = block_inclusive_scan_f64((double)m, s_scan, &total);
+    if (c < C)
+        prefix[c] = incl;
     if (threadIdx.x == 0)
         blk_sum[blockIdx.x] = total;
 }
 
 struct InitArgs
 {
-    int N, C, gs, n_blocks;
-    const int* slot_end;
-    const int* blk_slot_end;
+    int N, gs;
+    SlotView slots;
+    const DeviceScalars* scal;
     ParticleSet p;
     const float2* init_velocity;
     int noise_injected;
@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.N)
         return;
-    int j = find_slot_owner(a.slot_end, a.blk_slot_end, a.n_blocks, a.C, i);
+    SlotView sv = a.slots;
+    sv.scale = (float)a.N / (float)a.scal->born_total;
+    int j = find_slot_owner(sv, i);
     if (j < 0)
         j = a.p.idx[i];
     float2 v;
@@ -435,46 +437,35 @@ __global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell
 // =========================================================================================================
 // host-side launchers
 // =========================================================================================================
-static int run_slot_distribution(dogm_handle* h, int count, bool write_weights)
+static SlotView make_slot_view(dogm_handle* h)
 {
-    int e0 = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
-    if (e0)
-        return e0;
-    SlotArgs a;
-    a.C = h->C;
-    a.count = count;
-    a.masses = h->born_masses;
-    a.blk_off = h->blk_off;
-    a.scal = h->scal;
-    a.slot_end = h->slot_end;
-    a.blk_slot_end = h->blk_slot_end;
-    a.meas = h->meas;
-    a.grid = write_weights ? h->grid : nullptr;
-    {
-        LaunchScope ls(h, K_BIRTH_CELLS, 8.0 * h->C);
-        k_birth_cells<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);
-    }
-    return (int)cudaGetLastError();
+    SlotView v;
+    v.blk_off = h->blk_off;
+    v.blk_sum = h->blk_sum;
+    v.prefix = h->cell_prefix;
+    v.n_blocks = h->n_cell_blocks;
+    v.C = h->C;
+    v.scale = 0.0f;
+    return v;
 }
 
 int run_init_particles(dogm_handle* h)
 {
     {
         LaunchScope ls(h, K_INIT_MASSES, 8.0 * h->C);
-        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum);
+        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum,
+                                                                      h->cell_prefix);
     }
-    int e = run_slot_distribution(h, h->N, false);
+    int e = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
     if (e)
         return e;
     if (h->N <= 0)
         return 0;
     InitArgs a;
     a.N = h->N;
-    a.C = h->C;
     a.gs = h->gs;
-    a.n_blocks = h->n_cell_blocks;
-    a.slot_end = h->slot_end;
-    a.blk_slot_end = h->blk_slot_end;
+    a.slots = make_slot_view(h);
+    a.scal = h->scal;
     a.p = h->pa;
     a.init_velocity = h->init_velocity;
     a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
@@ -508,6 +499,7 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.born_masses = h->born_masses;
     a.coef = h->cell_coef;
     a.blk_sum = h->blk_sum;
+    a.prefix = h->cell_prefix;
     a.p_B = h->params.birth_prob;
     a.alpha = powf(h->params.freespace_discount, dt); // std::pow(float, float), dogm.cu:291
     a.shift_active = (h->shift_grid_pending && h->shift.active) ? 1 : 0;
@@ -528,18 +520,17 @@ int run_occupancy_update(dogm_handle* h, float dt)
 
 int run_birth(dogm_handle* h)
 {
-    int e = run_slot_distribution(h, h->B, true);
+    int e = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
     if (e)
         return e;
     if (h->B <= 0)
         return 0;
     BirthArgs a;
     a.B = h->B;
-    a.C = h->C;
     a.gs = h->gs;
-    a.n_blocks = h->n_cell_blocks;
-    a.slot_end = h->slot_end;
-    a.blk_slot_end = h->blk_slot_end;
+    a.slots = make_slot_view(h);
+    a.scal = h->scal;
+    a.born_masses = h->born_masses;
     a.meas = h->meas;
     a.grid = h->grid;
     a.birth = h->birth;
