@@ -307,8 +307,8 @@ def run_ours(args, dist):
         d.synchronize()
         t_wall = time.perf_counter() - t_wall0
         dist.barrier()
-        if ms_dev < 300.0:  # keep the GPU under the same load a little longer so that nvidia-smi gets samples
-            t_end = time.perf_counter() + 1.0
+        if ms_dev < 3000.0:  # keep the GPU under the same load a little longer so that nvidia-smi gets samples
+            t_end = time.perf_counter() + 3.0
             while time.perf_counter() < t_end:
                 cycle_resident(True)
     ms_max = dist.max(ms_dev)

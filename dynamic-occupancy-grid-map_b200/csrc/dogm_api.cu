@@ -18,6 +18,7 @@ void launch_begin(dogm_handle* h, int id, double algorithmic_bytes)
     h->last_bytes[id] = algorithmic_bytes;
     if (!h->timing)
         return;
+    h->acc_bytes[id] += algorithmic_bytes;
     TimedLaunch t;
     t.id = id;
     for (int k = 0; k < 2; k++)
@@ -150,6 +151,7 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
         h->acc_ms[k] = 0.0;
         h->acc_launches[k] = 0;
         h->last_bytes[k] = 0.0;
+        h->acc_bytes[k] = 0.0;
     }
     plan_sort(h);
     h->n_cell_blocks = div_up(h->C, kCellBlock);
@@ -839,6 +841,7 @@ extern "C" int dogm_kernel_timing_enable(dogm_handle* h, int enable)
     {
         h->acc_ms[k] = 0.0;
         h->acc_launches[k] = 0;
+        h->acc_bytes[k] = 0.0;
     }
     return 0;
 }
@@ -857,10 +860,11 @@ extern "C" int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, in
         strncpy(out[n].name, kKernelNames[k], sizeof(out[n].name) - 1);
         out[n].total_ms = h->acc_ms[k];
         out[n].launches = h->acc_launches[k];
-        out[n].algorithmic_bytes = h->last_bytes[k];
+        out[n].algorithmic_bytes = h->acc_bytes[k] / (double)h->acc_launches[k]; // average over the launches timed
         n++;
         h->acc_ms[k] = 0.0;
         h->acc_launches[k] = 0;
+        h->acc_bytes[k] = 0.0;
     }
     *out_count = n;
     return 0;

@@ -266,6 +266,7 @@ struct dogm_handle
     double acc_ms[dogm_b200::K_COUNT];
     uint64_t acc_launches[dogm_b200::K_COUNT];
     double last_bytes[dogm_b200::K_COUNT];
+    double acc_bytes[dogm_b200::K_COUNT];
 };
 
 namespace dogm_b200
