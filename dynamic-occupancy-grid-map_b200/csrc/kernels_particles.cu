@@ -212,12 +212,10 @@ constexpr int kScanWarps = kWideBlock / 32;
 constexpr int kScanBatch = 16;
 
 __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__ table, int tiles, int bins,
-                                                          uint32_t* bin_tot, uint32_t* bin_base, unsigned int* ticket,
-                                                          uint4* __restrict__ zero_ptr, size_t zero_count)
+                                                          uint32_t* __restrict__ bin_tot, uint4* __restrict__ zero_ptr,
+                                                          size_t zero_count)
 {
     __shared__ uint32_t s_part[kScanWarps][32];
-    __shared__ uint32_t s_warp_tot[kScanWarps];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
     const int per = (tiles + kScanWarps - 1) / kScanWarps;
@@ -232,16 +230,30 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
             zero_ptr[z] = make_uint4(0u, 0u, 0u, 0u);
     }
 
+    // the common case (at most 16 tiles per warp, i.e. up to 2e6 particles): one batch of loads, kept in registers
+    uint32_t v[kScanBatch];
+    const bool single = (t1 - t0) <= kScanBatch;
     uint32_t sum = 0;
-    for (int tb = t0; tb < t1; tb += kScanBatch)
+    if (single)
     {
-        uint32_t v[kScanBatch];
 #pragma unroll
         for (int k = 0; k < kScanBatch; k++)
-            v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
+            v[k] = (t0 + k < t1) ? table[(size_t)(t0 + k) * bins + bin] : 0u;
 #pragma unroll
         for (int k = 0; k < kScanBatch; k++)
             sum += v[k];
+    }
+    else
+    {
+        for (int tb = t0; tb < t1; tb += kScanBatch)
+        {
+#pragma unroll
+            for (int k = 0; k < kScanBatch; k++)
+                v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
+#pragma unroll
+            for (int k = 0; k < kScanBatch; k++)
+                sum += v[k];
+        }
     }
     s_part[warp][lane] = sum;
     __syncthreads();
@@ -254,62 +266,34 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
             run += p;
         total += p;
     }
-    for (int tb = t0; tb < t1; tb += kScanBatch)
+    if (single)
     {
-        uint32_t v[kScanBatch];
 #pragma unroll
         for (int k = 0; k < kScanBatch; k++)
-            v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
-#pragma unroll
-        for (int k = 0; k < kScanBatch; k++)
-            if (tb + k < t1)
+            if (t0 + k < t1)
             {
-                table[(size_t)(tb + k) * bins + bin] = run;
+                table[(size_t)(t0 + k) * bins + bin] = run;
                 run += v[k];
             }
     }
-    if (warp == 0)
-        bin_tot[bin] = total;
-
-    // last CTA: exclusive scan of the bin totals
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
+    else
     {
-        const unsigned int done = atomicAdd(ticket, 1u);
-        s_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last)
-        return;
-    __threadfence();
-    const int per_thread = (bins + kWideBlock - 1) / kWideBlock;
-    const int b0 = min((int)threadIdx.x * per_thread, bins), b1 = min(b0 + per_thread, bins);
-    uint32_t local = 0;
-    for (int b = b0; b < b1; b++)
-        local += __ldcg(&bin_tot[b]);
-    uint32_t incl = local;
+        for (int tb = t0; tb < t1; tb += kScanBatch)
+        {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d)
-            incl += t;
+            for (int k = 0; k < kScanBatch; k++)
+                v[k] = (tb + k < t1) ? table[(size_t)(tb + k) * bins + bin] : 0u;
+#pragma unroll
+            for (int k = 0; k < kScanBatch; k++)
+                if (tb + k < t1)
+                {
+                    table[(size_t)(tb + k) * bins + bin] = run;
+                    run += v[k];
+                }
+        }
     }
-    if (lane == 31)
-        s_warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t off = 0;
-    for (int w = 0; w < warp; w++)
-        off += s_warp_tot[w];
-    uint32_t excl = off + incl - local;
-    for (int b = b0; b < b1; b++)
-    {
-        bin_base[b] = excl;
-        excl += __ldcg(&bin_tot[b]);
-    }
-    if (threadIdx.x == 0)
-        *ticket = 0u;
+    if (warp == 0)
+        bin_tot[bin] = total; // the exclusive scan over the bins is done by every scatter CTA (cheap, no serial tail here)
 }
 
 // =========================================================================================================
@@ -328,7 +312,7 @@ struct ScatterArgs
     uint32_t mask;
     int bins;
     const uint32_t* table;    // this pass, exclusive over tiles
-    const uint32_t* bin_base; // this pass
+    const uint32_t* bin_tot;  // this pass: number of keys per digit (all tiles)
     uint32_t* next_table;     // next pass histogram (atomics) or nullptr
     int next_shift;
     uint32_t next_mask;
@@ -394,19 +378,48 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     }
     __syncthreads();
 
-    // exclusive prefix over the warps of the tile, and the global offset of every bin for this tile
-    const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins;
-    for (int b = threadIdx.x; b < a.bins; b += kBlock)
+    // exclusive prefix over the warps of the tile, and the global offset of every bin for this tile:
+    // (keys with a smaller digit) + (same digit in earlier tiles).  Thread t owns the contiguous bins
+    // [t * per, (t + 1) * per): its share of the exclusive scan over the bin totals is a block scan of per-thread sums.
     {
-        uint32_t run = 0;
+        __shared__ uint32_t s_wtot[kWarpsPerBlock];
+        const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins;
+        const uint32_t* __restrict__ tot = a.bin_tot;
+        const int per = a.bins / kBlock > 0 ? a.bins / kBlock : 1; // bins is a power of two >= 32
+        const int b0 = threadIdx.x * per;
+        uint32_t local = 0;
+        if (b0 < a.bins)
+            for (int k = 0; k < per; k++)
+                local += tot[b0 + k];
+        uint32_t incl = local;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerBlock; w++)
+        for (int d = 1; d < 32; d <<= 1)
         {
-            const uint32_t c = s_cnt[w * a.bins + b];
-            s_cnt[w * a.bins + b] = (unsigned short)run;
-            run += c;
+            const uint32_t t = __shfl_up_sync(full, incl, d);
+            if (lane >= d)
+                incl += t;
         }
-        s_binoff[b] = a.bin_base[b] + row[b];
+        if (lane == 31)
+            s_wtot[warp] = incl;
+        __syncthreads();
+        uint32_t base = incl - local;
+        for (int w = 0; w < warp; w++)
+            base += s_wtot[w];
+        if (b0 < a.bins)
+            for (int k = 0; k < per; k++)
+            {
+                const int b = b0 + k;
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < kWarpsPerBlock; w++)
+                {
+                    const uint32_t c = s_cnt[w * a.bins + b];
+                    s_cnt[w * a.bins + b] = (unsigned short)run;
+                    run += c;
+                }
+                s_binoff[b] = base + row[b];
+                base += tot[b];
+            }
     }
     __syncthreads();
 
@@ -1196,9 +1209,8 @@ int run_assignment(dogm_handle* h)
             // the table of the next pass is cleared here, before the scatter below fills it with atomics
             const bool nxt = p + 1 < h->passes;
             const size_t zero_count = nxt ? ((size_t)h->tiles * h->digit_bins[p + 1] * sizeof(uint32_t)) / sizeof(uint4) : 0;
-            k_hist_scan<<<bins / 32, kWideBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p], h->bin_base[p],
-                                                               &h->scal->ticket[0], nxt ? (uint4*)h->hist[p + 1] : nullptr,
-                                                               zero_count);
+            k_hist_scan<<<bins / 32, kWideBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p],
+                                                               nxt ? (uint4*)h->hist[p + 1] : nullptr, zero_count);
         }
         ScatterArgs a;
         a.key_in = h->key0;
@@ -1209,7 +1221,7 @@ int run_assignment(dogm_handle* h)
         a.mask = (uint32_t)(bins - 1);
         a.bins = bins;
         a.table = h->hist[p];
-        a.bin_base = h->bin_base[p];
+        a.bin_tot = h->bin_tot[p];
         const bool has_next = p + 1 < h->passes;
         a.next_table = has_next ? h->hist[p + 1] : nullptr;
         a.next_shift = has_next ? h->digit_shift[p + 1] : 0;
