@@ -327,12 +327,13 @@ def run_ours(args, dist):
         beam_pinned[:] = beams[step % len(beams)]
         gen.generate_grid_into(d, beam_pinned)
         x, y = pose_at(step)
-        d.update_grid(None, float(x), float(y), 0.0, DT)
+        d.update_grid(None, float(x), float(y), 0.0, DT, sync=False)  # dogm_extract_dynamic_cells is the one sync
         rc = lib.dogm_extract_dynamic_cells(d._h, 0.7, 4.0, C_.c_void_p(dyn_out.ctypes.data), dyn_capacity, C_.byref(dyn_count))
         assert rc == 0
         d2h_bytes.append(4 + 32 * min(dyn_count.value, dyn_capacity))
         step += 1
 
+    d.set_dynamic_cell_filter(0.7, 4.0, dyn_capacity)  # the cycle's cell kernel compacts the result list itself
     for _ in range(max(3, W // 2)):
         cycle_e2e()
     d2h_bytes.clear()
@@ -342,6 +343,7 @@ def run_ours(args, dist):
         cycle_e2e()
     t_e2e = dist.max(time.perf_counter() - t0)
     e2e_value = dist.world * K / t_e2e
+    d.set_dynamic_cell_filter(0.0, 0.0, 0)
 
     # the same loop with the reference API's own full transfers: host MeasurementCell[] in, all GridCells out
     meas_pinned = gpu.pinned_empty((C,), gpu.MEAS_CELL_DTYPE)
@@ -425,7 +427,7 @@ def run_ours(args, dist):
             "unit": UNIT,
             "h2d_bytes_per_step": 4 * cfg["beams"],
             "d2h_bytes_per_step": float(np.mean(d2h_bytes)),
-            "path": "beams(host, pinned) -> dogm_meas_generate_into -> dogm_update_grid -> dogm_extract_dynamic_cells(host)",
+            "path": "beams(host, pinned) -> dogm_meas_generate_into -> dogm_update_grid_async -> dogm_extract_dynamic_cells(host, syncs)",
             "full_readback": {
                 "value": dist.world * k_full / t_full,
                 "unit": UNIT,

@@ -173,6 +173,7 @@ _SYMBOLS = [
     ("dogm_meas_polar_grid", C.c_int, [_P, _P, C.c_int, _P]),
     ("dogm_meas_get_grid_size", C.c_int, [_P]),
     ("dogm_extract_dynamic_cells", C.c_int, [_P, C.c_float, C.c_float, _P, C.c_int, C.POINTER(C.c_int)]),
+    ("dogm_set_dynamic_cell_filter", C.c_int, [_P, C.c_float, C.c_float, C.c_int]),
     ("dogm_get_stream", _P, [_P]),
     ("dogm_get_launch_count", C.c_uint64, [_P]),
     ("dogm_kernel_timing_enable", C.c_int, [_P, C.c_int]),
@@ -463,6 +464,12 @@ class DOGM:
             "dogm_search_ancestors_f32",
         )
         return out
+
+    def set_dynamic_cell_filter(self, min_occupancy: float, min_velocity: float, capacity: int = 1 << 16) -> None:
+        _check(
+            self._lib.dogm_set_dynamic_cell_filter(self._h, min_occupancy, min_velocity, capacity),
+            "dogm_set_dynamic_cell_filter",
+        )
 
     def extract_dynamic_cells(self, min_occupancy: float, min_velocity: float, capacity: int = 1 << 16):
         out = np.empty(capacity, dtype=DYNAMIC_CELL_DTYPE)

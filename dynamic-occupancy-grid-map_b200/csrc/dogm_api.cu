@@ -146,6 +146,9 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     h->dyn_capacity = 0;
     h->dyn_count = nullptr;
     h->dyn_count_host = nullptr;
+    h->dyn_filter_on = h->dyn_list_valid = false;
+    h->dyn_filter_capacity = 0;
+    h->dyn_mapped_host = h->dyn_mapped_dev = nullptr;
     for (int k = 0; k < K_COUNT; k++)
     {
         h->acc_ms[k] = 0.0;
@@ -277,6 +280,8 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->dyn_count);
     if (h->dyn_count_host)
         cudaFreeHost(h->dyn_count_host);
+    if (h->dyn_mapped_host)
+        cudaFreeHost(h->dyn_mapped_host);
     for (auto& t : h->timed)
     {
         cudaEventDestroy(t.e0);
@@ -720,6 +725,7 @@ extern "C" int dogm_set_grid_cells(dogm_handle* h, const dogm_grid_cell* cells, 
 {
     if (!h || !cells)
         return DOGM_ERR_INVALID_ARGUMENT;
+    h->dyn_list_valid = false;
     DOGM_CHECK((cudaError_t)copy_in(h->grid, cells, (size_t)h->C * sizeof(dogm_grid_cell), on_device, h->stream));
     int e = run_extract_free_mass(h);
     if (e)
@@ -773,15 +779,68 @@ extern "C" int dogm_search_ancestors_f32(dogm_handle* h, const float* cdf, int n
     return e;
 }
 
+static int ensure_dyn_counter(dogm_handle* h)
+{
+    if (!h->dyn_count)
+    {
+        DOGM_CHECK(cudaMalloc(&h->dyn_count, 2 * sizeof(int))); // [0] fused into the cycle, [1] stand-alone pass
+        DOGM_CHECK(cudaMallocHost(&h->dyn_count_host, sizeof(int)));
+    }
+    return 0;
+}
+
+extern "C" int dogm_set_dynamic_cell_filter(dogm_handle* h, float min_occupancy, float min_velocity, int capacity)
+{
+    if (!h || capacity < 0)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    h->dyn_filter_on = false;
+    h->dyn_list_valid = false;
+    if (capacity == 0)
+        return 0; // filter switched off
+    int e = ensure_dyn_counter(h);
+    if (e)
+        return e;
+    if (capacity > h->dyn_filter_capacity || !h->dyn_mapped_host)
+    {
+        if (h->dyn_mapped_host)
+            cudaFreeHost(h->dyn_mapped_host);
+        h->dyn_mapped_host = nullptr;
+        DOGM_CHECK(cudaHostAlloc((void**)&h->dyn_mapped_host, (size_t)capacity * sizeof(dogm_dynamic_cell), cudaHostAllocMapped));
+        DOGM_CHECK(cudaHostGetDevicePointer((void**)&h->dyn_mapped_dev, h->dyn_mapped_host, 0));
+    }
+    h->dyn_filter_capacity = capacity;
+    h->dyn_filter_occ = min_occupancy;
+    h->dyn_filter_vel = min_velocity;
+    h->dyn_filter_on = true;
+    return 0;
+}
+
 extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_velocity,
                                           dogm_dynamic_cell* out_host, int capacity, int* out_count)
 {
     if (!h || !out_count || capacity < 0 || (capacity > 0 && !out_host))
         return DOGM_ERR_INVALID_ARGUMENT;
-    if (!h->dyn_count)
+    int e0 = ensure_dyn_counter(h);
+    if (e0)
+        return e0;
+    // fast path: the cell kernel of the last cycle already produced the list for exactly this filter
+    if (h->dyn_filter_on && h->dyn_list_valid && h->dyn_list_cycle + 1 == h->cycle && min_occupancy == h->dyn_filter_occ &&
+        min_velocity == h->dyn_filter_vel)
     {
-        DOGM_CHECK(cudaMalloc(&h->dyn_count, sizeof(int)));
-        DOGM_CHECK(cudaMallocHost(&h->dyn_count_host, sizeof(int)));
+        DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+        const int found = *h->dyn_count_host;
+        if (found <= h->dyn_filter_capacity || capacity <= h->dyn_filter_capacity)
+        {
+            *out_count = found;
+            int n_copy = found < capacity ? found : capacity;
+            if (n_copy > h->dyn_filter_capacity)
+                n_copy = h->dyn_filter_capacity;
+            if (n_copy > 0)
+                memcpy(out_host, h->dyn_mapped_host, (size_t)n_copy * sizeof(dogm_dynamic_cell));
+            return 0;
+        }
     }
     if (capacity > h->dyn_capacity)
     {
@@ -791,10 +850,10 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
         DOGM_CHECK(cudaMalloc(&h->dyn_buf, (size_t)capacity * sizeof(dogm_dynamic_cell)));
         h->dyn_capacity = capacity;
     }
-    int e = run_extract_dynamic_cells(h, min_occupancy, min_velocity, h->dyn_buf, capacity, h->dyn_count);
+    int e = run_extract_dynamic_cells(h, min_occupancy, min_velocity, h->dyn_buf, capacity, h->dyn_count + 1);
     if (e)
         return e;
-    DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     const int found = *h->dyn_count_host;
     *out_count = found;

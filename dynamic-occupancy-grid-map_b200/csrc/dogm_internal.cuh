@@ -138,7 +138,7 @@ enum KernelId : int
     K_CELL,
     K_BLOCKSUM_SCAN,
     K_WEIGHTS,
-    K_BIRTH_CELLS,
+    K_MEAS_POLAR,
     K_BIRTH_PARTICLES,
     K_CDF_REDUCE,
     K_CDF_WRITE,
@@ -153,7 +153,7 @@ enum KernelId : int
 
 static const char* const kKernelNames[K_COUNT] = {
     "k_predict",       "k_tile_hist",       "k_hist_scan",  "k_scatter",   "k_segsum",      "k_segfix",
-    "k_cell",          "k_blocksum_scan",   "k_weights",    "k_birth_cells", "k_birth_particles", "k_cdf_reduce",
+    "k_cell",          "k_blocksum_scan",   "k_weights",    "k_meas_polar", "k_birth_particles", "k_cdf_reduce",
     "k_cdf_write",     "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
     "memset"};
 
@@ -255,6 +255,14 @@ struct dogm_handle
     int dyn_capacity;
     int* dyn_count;
     int* dyn_count_host; // pinned
+    // filter registered with dogm_set_dynamic_cell_filter: the cell kernel then appends matching cells straight into a
+    // host-mapped pinned buffer, so that the read-out after a cycle costs one small copy and no extra kernel
+    bool dyn_filter_on, dyn_list_valid;
+    float dyn_filter_occ, dyn_filter_vel;
+    int dyn_filter_capacity;
+    uint32_t dyn_list_cycle;
+    dogm_dynamic_cell* dyn_mapped_host;
+    dogm_dynamic_cell* dyn_mapped_dev;
 
     // instrumentation
     bool timer_ready;

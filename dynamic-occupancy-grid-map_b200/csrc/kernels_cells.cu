@@ -32,6 +32,11 @@ struct CellArgs
     float4* coef;
     double* blk_sum;
     double* prefix; // block-local inclusive prefix of the born masses (double), for the birth slot distribution
+    // optional fused extraction of dynamic cells (computeCellsWithVelocity, demo/utils/image_creation.cpp:19-66)
+    dogm_dynamic_cell* dyn_out; // device-visible (host-mapped) record buffer, or null
+    int* dyn_count;
+    int dyn_capacity;
+    float dyn_min_occ, dyn_min_vel;
     float p_B, alpha;
     int shift_active, x_move, y_move;
 };
@@ -46,6 +51,8 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool valid = c < a.C;
     float rho_b = 0.0f;
+    bool dyn_hit = false;
+    dogm_dynamic_cell dyn_rec;
     if (valid)
     {
         const int start = a.cell_start[c];
@@ -138,10 +145,45 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
 
         a.born_masses[c] = rho_b;
         a.free_next[c] = free_up;
+        if (a.dyn_out)
+        {
+            const float occ = occ_up + 0.5f * (1.0f - occ_up - free_up);
+            const float det = var_x * var_y - covar * covar;
+            const float maha = (var_y * mean_x * mean_x - 2.0f * covar * mean_x * mean_y + var_x * mean_y * mean_y) / det;
+            if (occ >= a.dyn_min_occ && maha >= a.dyn_min_vel)
+            {
+                dyn_hit = true;
+                dyn_rec.cell_idx = c;
+                dyn_rec.occupancy = occ;
+                dyn_rec.mean_x_vel = mean_x;
+                dyn_rec.mean_y_vel = mean_y;
+                dyn_rec.var_x_vel = var_x;
+                dyn_rec.var_y_vel = var_y;
+                dyn_rec.covar_xy_vel = covar;
+                dyn_rec.mahalanobis = maha;
+            }
+        }
         s_out[warp][0][lane] = make_float4(__int_as_float(start), __int_as_float(end), rho_b, rho_p);
         s_out[warp][1][lane] = make_float4(free_up, occ_up, m_occ_pred, mu_A);
         s_out[warp][2][lane] = make_float4(mu_UA, 0.0f, 0.0f, mean_x); // w_A / w_UA: k_birth_cells, for cells that own slots
         s_out[warp][3][lane] = make_float4(mean_y, var_x, var_y, covar);
+    }
+    if (a.dyn_out)
+    { // warp-aggregated append of the cells that pass the filter
+        const unsigned m = __ballot_sync(0xffffffffu, dyn_hit);
+        if (m)
+        {
+            int base = 0;
+            if (lane == __ffs(m) - 1)
+                base = atomicAdd(a.dyn_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (dyn_hit)
+            {
+                const int at = base + __popc(m & lanemask_lt());
+                if (at < a.dyn_capacity)
+                    a.dyn_out[at] = dyn_rec;
+            }
+        }
     }
     // the warp's 32 GridCells are 2 KB of contiguous memory: write them as four fully coalesced 512-byte rows
     __syncwarp();
@@ -505,6 +547,18 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.shift_active = (h->shift_grid_pending && h->shift.active) ? 1 : 0;
     a.x_move = h->shift.x_move;
     a.y_move = h->shift.y_move;
+    a.dyn_out = nullptr;
+    a.dyn_count = h->dyn_count;
+    a.dyn_capacity = h->dyn_filter_capacity;
+    a.dyn_min_occ = h->dyn_filter_occ;
+    a.dyn_min_vel = h->dyn_filter_vel;
+    if (h->dyn_filter_on)
+    {
+        a.dyn_out = h->dyn_mapped_dev;
+        cudaMemsetAsync(h->dyn_count, 0, sizeof(int), h->stream);
+        h->dyn_list_cycle = h->cycle;
+        h->dyn_list_valid = true;
+    }
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
         k_cell<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);

@@ -5,7 +5,10 @@
 //   OpenGL triangle-fan render    (opengl/renderer.cpp:11-31,50-54,66-84; opengl/shader.cpp:22-35)  polar -> cartesian
 //   cartesianGridToMeasurementGridKernel (kernel/measurement_grid.cu:115-132)  RGBA32F framebuffer -> MeasurementCell[]
 // Every cartesian cell finds its fan triangle, interpolates the texture coordinate exactly as the rasteriser would,
-// and takes a bilinear sample (mip level 0) of the inverse sensor model evaluated on the fly; no polar table, no GL.
+// and takes a bilinear sample (mip level 0) of the inverse sensor model; no GL.
+// The geometry of that lookup (fan triangle, texel pair, bilinear weights) depends only on the sensor, the grid and the
+// number of beams, so it is computed once per beam count (k_meas_geom) and a scan costs two small kernels:
+// k_meas_polar (inverse sensor model, K x H texels, L2-resident) and k_meas_apply (16 B in, 4 cached texels, 16 B out).
 #include "dogm_internal.cuh"
 
 #include <cmath>
@@ -25,6 +28,10 @@ struct dogm_meas_handle
     float2* d_verts; // arc vertices (NDC offsets from the fan centre), wedges + 1 entries
     dogm_meas_cell* d_grid;
     float* h_beams_pinned;
+    float4* d_geom;  // per cartesian cell: (i0, j0, wu, wv) of its bilinear lookup, i0 = kNoTexel outside the fan
+    int geom_beams;  // beam count d_geom was built for (0 = none)
+    float2* d_polar; // K x H polar table of the current scan
+    size_t polar_capacity;
     cudaStream_t stream;
 };
 
@@ -73,21 +80,18 @@ __device__ __forceinline__ float2 polar_cell(const MeasArgs& a, float zk, int i)
     return make_float2(fmaxf(eps, fminf(1.0f - eps, occ_m)), fmaxf(eps, fminf(1.0f - eps, free_m)));
 }
 
-__device__ __forceinline__ float2 polar_texel(const MeasArgs& a, int bi, int ri)
-{
-    if (bi < 0 || bi >= a.K || ri < 0 || ri >= a.H) // GL_CLAMP_TO_BORDER, border R = G = 0 (texture.cpp:16-29)
-        return make_float2(0.0f, 0.0f);
-    return polar_cell(a, a.beams[bi], ri);
-}
+constexpr int kNoTexel = -(1 << 30);
 
-__global__ void __launch_bounds__(kBlock) k_meas_grid(MeasArgs a)
+// Scan-independent part of the lookup: which fan triangle the cell centre falls into and where the rasteriser's
+// interpolated texture coordinate lands in the K x H polar texture.
+__global__ void __launch_bounds__(kBlock) k_meas_geom(MeasArgs a, float4* geom)
 {
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.gs * a.gs)
         return;
     const int px = c % a.gs;
     const int py = a.gs - 1 - c / a.gs; // framebuffer row of this grid row (flip of measurement_grid.cu:120)
-    float occ_out = 0.0f, free_out = 0.0f;
+    float4 g = make_float4(__int_as_float(kNoTexel), __int_as_float(kNoTexel), 0.0f, 0.0f);
 
     const float X = ((float)px + 0.5f) * 2.0f / (float)a.gs - 1.0f;
     const float Y = ((float)py + 0.5f) * 2.0f / (float)a.gs - 1.0f;
@@ -122,17 +126,40 @@ __global__ void __launch_bounds__(kBlock) k_meas_grid(MeasArgs a)
         const float fu = u * (float)a.K - 0.5f;
         const float fv = v * (float)a.H - 0.5f;
         const float fu0 = floorf(fu), fv0 = floorf(fv);
-        const int i0 = (int)fu0, j0 = (int)fv0;
-        const float wu = fu - fu0, wv = fv - fv0;
-        const float2 t00 = polar_texel(a, i0, j0), t10 = polar_texel(a, i0 + 1, j0);
-        const float2 t01 = polar_texel(a, i0, j0 + 1), t11 = polar_texel(a, i0 + 1, j0 + 1);
+        g = make_float4(__int_as_float((int)fu0), __int_as_float((int)fv0), fu - fu0, fv - fv0);
+    }
+    geom[c] = g;
+}
+
+__device__ __forceinline__ float2 polar_fetch(const float2* __restrict__ table, int K, int H, int bi, int ri)
+{
+    if (bi < 0 || bi >= K || ri < 0 || ri >= H) // GL_CLAMP_TO_BORDER, border R = G = 0 (texture.cpp:16-29)
+        return make_float2(0.0f, 0.0f);
+    return __ldg(table + (size_t)ri * K + bi);
+}
+
+// Per scan: bilinear sample (GL_LINEAR, mip level 0) of the polar table at the precomputed position.
+__global__ void __launch_bounds__(kBlock)
+    k_meas_apply(const float4* __restrict__ geom, const float2* __restrict__ table, int K, int H, int C, dogm_meas_cell* out)
+{
+    const int c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= C)
+        return;
+    const float4 g = __ldcs(geom + c);
+    const int i0 = __float_as_int(g.x), j0 = __float_as_int(g.y);
+    float occ_out = 0.0f, free_out = 0.0f;
+    if (i0 != kNoTexel)
+    {
+        const float wu = g.z, wv = g.w;
+        const float2 t00 = polar_fetch(table, K, H, i0, j0), t10 = polar_fetch(table, K, H, i0 + 1, j0);
+        const float2 t01 = polar_fetch(table, K, H, i0, j0 + 1), t11 = polar_fetch(table, K, H, i0 + 1, j0 + 1);
         const float ob = t00.x + wu * (t10.x - t00.x), ot = t01.x + wu * (t11.x - t01.x);
         const float fb = t00.y + wu * (t10.y - t00.y), ft = t01.y + wu * (t11.y - t01.y);
         occ_out = ob + wv * (ot - ob);
         free_out = fb + wv * (ft - fb);
     }
     // MeasurementCell {free_mass, occ_mass, likelihood, p_A}, measurement_grid.cu:126-130
-    *reinterpret_cast<float4*>(a.out + c) = make_float4(free_out, occ_out, 1.0f, 1.0f);
+    __stcs(reinterpret_cast<float4*>(out + c), make_float4(free_out, occ_out, 1.0f, 1.0f));
 }
 
 __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
@@ -181,6 +208,45 @@ static int upload_beams(dogm_meas_handle* m, const float* beams_host, int K, cud
     return 0;
 }
 
+// polar table of this scan + cartesian resampling; rebuilds the geometry when the beam count changes
+static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStream_t stream, dogm_handle* timing)
+{
+    const long long C = (long long)m->gs * m->gs;
+    const size_t texels = (size_t)K * m->H;
+    const MeasArgs a = make_args(m, K, out);
+    if (texels > m->polar_capacity)
+    {
+        cudaStreamSynchronize(stream);
+        cudaFree(m->d_polar);
+        m->d_polar = nullptr;
+        m->polar_capacity = 0;
+        DOGM_CHECK(cudaMalloc(&m->d_polar, texels * sizeof(float2)));
+        m->polar_capacity = texels;
+    }
+    if (m->geom_beams != K)
+    {
+        k_meas_geom<<<div_up(C, kBlock), kBlock, 0, stream>>>(a, m->d_geom);
+        DOGM_CHECK(cudaGetLastError());
+        m->geom_beams = K;
+    }
+    if (timing)
+    {
+        LaunchScope ls(timing, K_MEAS_POLAR, 8.0 * (double)texels);
+        k_meas_polar<<<div_up((long long)texels, kBlock), kBlock, 0, stream>>>(a, m->d_polar);
+    }
+    else
+        k_meas_polar<<<div_up((long long)texels, kBlock), kBlock, 0, stream>>>(a, m->d_polar);
+    if (timing)
+    {
+        LaunchScope ls(timing, K_MEAS_GRID, 32.0 * (double)C);
+        k_meas_apply<<<div_up(C, kBlock), kBlock, 0, stream>>>(m->d_geom, m->d_polar, K, m->H, (int)C, out);
+    }
+    else
+        k_meas_apply<<<div_up(C, kBlock), kBlock, 0, stream>>>(m->d_geom, m->d_polar, K, m->H, (int)C, out);
+    DOGM_CHECK(cudaGetLastError());
+    return 0;
+}
+
 } // namespace dogm_b200
 
 using namespace dogm_b200;
@@ -213,6 +279,10 @@ extern "C" int dogm_meas_create(const dogm_laser_params* params, float grid_leng
     m->h_beams_pinned = nullptr;
     m->d_verts = nullptr;
     m->d_grid = nullptr;
+    m->d_geom = nullptr;
+    m->geom_beams = 0;
+    m->d_polar = nullptr;
+    m->polar_capacity = 0;
     if (m->gs <= 0 || m->H <= 0 || m->wedges < 1)
     {
         delete m;
@@ -222,6 +292,7 @@ extern "C" int dogm_meas_create(const dogm_laser_params* params, float grid_leng
     DOGM_CHECK(cudaMalloc(&m->d_verts, verts.size() * sizeof(float2)));
     DOGM_CHECK(cudaMemcpy(m->d_verts, verts.data(), verts.size() * sizeof(float2), cudaMemcpyHostToDevice));
     DOGM_CHECK(cudaMalloc(&m->d_grid, (size_t)m->gs * m->gs * sizeof(dogm_meas_cell)));
+    DOGM_CHECK(cudaMalloc(&m->d_geom, (size_t)m->gs * m->gs * sizeof(float4)));
     *out = m;
     return 0;
 }
@@ -235,6 +306,8 @@ extern "C" void dogm_meas_destroy(dogm_meas_handle* m)
     cudaFreeHost(m->h_beams_pinned);
     cudaFree(m->d_verts);
     cudaFree(m->d_grid);
+    cudaFree(m->d_geom);
+    cudaFree(m->d_polar);
     cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -252,9 +325,9 @@ extern "C" int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_
     int e = upload_beams(m, beam_ranges_host, num_beams, m->stream);
     if (e)
         return e;
-    const MeasArgs a = make_args(m, num_beams, m->d_grid);
-    k_meas_grid<<<div_up((long long)m->gs * m->gs, kBlock), kBlock, 0, m->stream>>>(a);
-    DOGM_CHECK(cudaGetLastError());
+    e = launch_scan(m, num_beams, m->d_grid, m->stream, nullptr);
+    if (e)
+        return e;
     DOGM_CHECK(cudaStreamSynchronize(m->stream)); // laser_to_meas_grid.cu:67
     if (out_device)
         *out_device = m->d_grid;
@@ -268,13 +341,7 @@ extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, cons
     int e = upload_beams(m, beam_ranges_host, num_beams, h->stream);
     if (e)
         return e;
-    const MeasArgs a = make_args(m, num_beams, h->meas);
-    {
-        LaunchScope ls(h, K_MEAS_GRID, 16.0 * h->C);
-        k_meas_grid<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(a);
-    }
-    DOGM_CHECK(cudaGetLastError());
-    return 0;
+    return launch_scan(m, num_beams, h->meas, h->stream, h);
 }
 
 extern "C" int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, float* out_host)

@@ -89,6 +89,11 @@ class DOGM
         out.resize(static_cast<size_t>(count < capacity ? count : capacity));
         return out;
     }
+    // registers the filter so that each updateGrid compacts the list itself (capacity 0 = off)
+    void setDynamicCellFilter(float min_occupancy, float min_velocity, int capacity = 1 << 16)
+    {
+        last_error = dogm_set_dynamic_cell_filter(handle, min_occupancy, min_velocity, capacity);
+    }
     void setOptions(const ::dogm_options& o) { last_error = dogm_set_options(handle, &o); }
     ::dogm_handle* native() { return handle; }
 

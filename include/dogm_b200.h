@@ -275,6 +275,10 @@ typedef struct dogm_dynamic_cell
 } dogm_dynamic_cell;
 int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_velocity, dogm_dynamic_cell* out_host,
                                int capacity, int* out_count);
+/* Registers the filter ahead of time (capacity 0 switches it off): every following cycle then compacts the matching
+ * cells inside its per-cell kernel, straight into pinned host memory, and dogm_extract_dynamic_cells with the same
+ * thresholds returns that list with one 4-byte copy instead of a pass over all 64*C bytes of grid cells. */
+int dogm_set_dynamic_cell_filter(dogm_handle* h, float min_occupancy, float min_velocity, int capacity);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Instrumentation for bench.py

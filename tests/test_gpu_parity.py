@@ -280,3 +280,42 @@ def test_dynamic_cell_extraction(gpu, orc):
     eo = np.argsort(exp_idx)
     assert np.allclose(got["occupancy"][order], rec[eo, 1], rtol=1e-6)
     assert np.allclose(got["mahalanobis"][order], rec[eo, 7], rtol=1e-4, atol=1e-5)
+
+
+def test_dynamic_cell_filter_fused_into_cycle(gpu, orc):
+    """dogm_set_dynamic_cell_filter: the list compacted by the cycle's own cell kernel equals the stand-alone pass over
+    the published grid cells (computeCellsWithVelocity, demo/utils/image_creation.cpp:19-66), with ego-motion shifts
+    between the cycles; other thresholds fall back to the stand-alone pass; a too small capacity truncates only."""
+    n, b = 60000, 6000
+    p = make_params(gpu, 20.0, 0.5, n, b)
+    d = gpu.DOGM(p)
+    d.set_dynamic_cell_filter(0.6, 0.5, 4096)
+    for c in range(6):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, np.random.default_rng(5 + c))
+        d.update_grid(meas, 0.7 * c, -0.4 * c, 0.0, 0.1, device=False)
+        got, count = d.extract_dynamic_cells(0.6, 0.5, capacity=4096)  # fast path
+        cells = d.get_grid_cells()
+        rec, n_exp = orc.extract_dynamic_cells(cells.view(orc.GRID_CELL_DTYPE), 0.6, 0.5)
+        assert count == n_exp
+        order = np.argsort(got["cell_idx"])
+        exp_idx = rec[:, 0].copy().view(np.int32)
+        eo = np.argsort(exp_idx)
+        assert np.array_equal(got["cell_idx"][order], exp_idx[eo])
+        assert np.allclose(got["occupancy"][order], rec[eo, 1], rtol=1e-6)
+        assert np.allclose(got["mean_x_vel"][order], rec[eo, 2], rtol=1e-6, atol=1e-7)
+        assert np.allclose(got["mahalanobis"][order], rec[eo, 7], rtol=1e-4, atol=1e-5)
+    assert count > 0
+    # different thresholds: stand-alone pass, same answer as the oracle
+    got2, count2 = d.extract_dynamic_cells(0.5, 0.25)
+    rec2, n2 = orc.extract_dynamic_cells(cells.view(orc.GRID_CELL_DTYPE), 0.5, 0.25)
+    assert count2 == n2 and np.array_equal(np.sort(got2["cell_idx"]), np.sort(rec2[:, 0].copy().view(np.int32)))
+    # truncation: the count is the number found, the records are a subset
+    small = max(1, count // 2)
+    got3, count3 = d.extract_dynamic_cells(0.6, 0.5, capacity=small)
+    assert count3 == count and len(got3) == small and set(got3["cell_idx"]) <= set(exp_idx.tolist())
+    # switching the filter off restores the stand-alone behaviour
+    d.set_dynamic_cell_filter(0.0, 0.0, 0)
+    d.update_grid(meas, 4.0, -2.0, 0.0, 0.1, device=False)
+    got4, count4 = d.extract_dynamic_cells(0.6, 0.5)
+    rec4, n4 = orc.extract_dynamic_cells(d.get_grid_cells().view(orc.GRID_CELL_DTYPE), 0.6, 0.5)
+    assert count4 == n4
