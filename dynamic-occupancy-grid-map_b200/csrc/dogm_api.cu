@@ -809,6 +809,7 @@ extern "C" int dogm_set_dynamic_cell_filter(dogm_handle* h, float min_occupancy,
         DOGM_CHECK(cudaHostAlloc((void**)&h->dyn_mapped_host, (size_t)capacity * sizeof(dogm_dynamic_cell), cudaHostAllocMapped));
         DOGM_CHECK(cudaHostGetDevicePointer((void**)&h->dyn_mapped_dev, h->dyn_mapped_host, 0));
     }
+    DOGM_CHECK(cudaMemset(h->dyn_count, 0, 2 * sizeof(int)));
     h->dyn_filter_capacity = capacity;
     h->dyn_filter_occ = min_occupancy;
     h->dyn_filter_vel = min_velocity;

@@ -284,6 +284,33 @@ namespace dogm_b200
 void launch_begin(dogm_handle* h, int id, double algorithmic_bytes);
 void launch_end(dogm_handle* h, int id);
 
+// Programmatic dependent launch: every kernel of the library starts with pdl_prologue() and is launched with
+// launch_chained(), so the next kernel's CTAs are scheduled into the SM slots the running kernel's tail leaves free and
+// wait (griddepcontrol.wait) until the whole predecessor has finished and its writes are visible.  Since every kernel
+// waits, completion stays transitive along the stream.
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(cudaStream_t stream, void (*kernel)(KArgs...), long long grid, int block, size_t smem,
+                                  Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct LaunchScope
 {
     dogm_handle* h;

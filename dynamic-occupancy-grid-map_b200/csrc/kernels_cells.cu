@@ -43,6 +43,7 @@ struct CellArgs
 
 __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
 {
+    pdl_prologue();
     __shared__ double s_scan[kWarpsPerBlock];
     // staging for the 64-byte GridCell records: [warp][part][cell], row stride 34 float4 keeps both the per-thread
     // writes and the transposed reads free of bank conflicts
@@ -302,6 +303,7 @@ struct BirthArgs
 // deterministic ownership rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
 __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 {
+    pdl_prologue();
     const int s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= a.B)
         return;
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell* __restrict__ meas, float* masses, int C,
                                                             double* blk_sum, double* prefix)
 {
+    pdl_prologue();
     __shared__ double s_scan[kWarpsPerBlock];
     const int c = blockIdx.x * kCellBlock + threadIdx.x;
     float m = 0.0f;
@@ -379,6 +382,7 @@ struct InitArgs
 
 __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
 {
+    pdl_prologue();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.N)
         return;
@@ -409,6 +413,7 @@ __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
 // =========================================================================================================
 __global__ void __launch_bounds__(kBlock) k_extract_free(const dogm_grid_cell* __restrict__ grid, float* free_cur, int C)
 {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c < C)
         free_cur[c] = grid[c].free_mass;
@@ -417,6 +422,7 @@ __global__ void __launch_bounds__(kBlock) k_extract_free(const dogm_grid_cell* _
 __global__ void __launch_bounds__(kBlock) k_init_grid(dogm_grid_cell* grid, dogm_meas_cell* meas, float* free_a,
                                                       float* free_b, int* cell_start, int C)
 { // initGridCellsKernel, init.cu:69-84 (all other GridCell fields start at 0 here; the reference leaves them uninitialised)
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= C)
         return;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell
                                                             float min_vel, dogm_dynamic_cell* out, int capacity,
                                                             int* count)
 {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     bool hit = false;
     dogm_dynamic_cell rec;
@@ -495,7 +502,7 @@ int run_init_particles(dogm_handle* h)
 {
     {
         LaunchScope ls(h, K_INIT_MASSES, 8.0 * h->C);
-        k_init_masses<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(h->meas, h->born_masses, h->C, h->blk_sum,
+        launch_chained(h->stream, k_init_masses, h->n_cell_blocks, kCellBlock, 0, h->meas, h->born_masses, h->C, h->blk_sum,
                                                                       h->cell_prefix);
     }
     int e = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
@@ -516,7 +523,7 @@ int run_init_particles(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_INIT_PARTICLES, 24.0 * h->N);
-        k_init_particles<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(a);
+        launch_chained(h->stream, k_init_particles, div_up(h->N, kBlock), kBlock, 0, a);
     }
     h->hist0_valid = false;
     h->pa_current = true;
@@ -555,13 +562,14 @@ int run_occupancy_update(dogm_handle* h, float dt)
     if (h->dyn_filter_on)
     {
         a.dyn_out = h->dyn_mapped_dev;
-        cudaMemsetAsync(h->dyn_count, 0, sizeof(int), h->stream);
+        if (h->N <= 0) // otherwise k_segfix cleared the counter
+            cudaMemsetAsync(h->dyn_count, 0, sizeof(int), h->stream);
         h->dyn_list_cycle = h->cycle;
         h->dyn_list_valid = true;
     }
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
-        k_cell<<<h->n_cell_blocks, kCellBlock, 0, h->stream>>>(a);
+        launch_chained(h->stream, k_cell, h->n_cell_blocks, kCellBlock, 0, a);
     }
     h->shift_grid_pending = false;
     h->meas_src = nullptr;
@@ -595,7 +603,7 @@ int run_birth(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B);
-        k_birth_particles<<<div_up(h->B, kBlock), kBlock, 0, h->stream>>>(a);
+        launch_chained(h->stream, k_birth_particles, div_up(h->B, kBlock), kBlock, 0, a);
     }
     return (int)cudaGetLastError();
 }
@@ -603,14 +611,14 @@ int run_birth(dogm_handle* h)
 int run_extract_free_mass(dogm_handle* h)
 {
     LaunchScope ls(h, K_MISC, 0.0);
-    k_extract_free<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->free_cur, h->C);
+    launch_chained(h->stream, k_extract_free, div_up(h->C, kBlock), kBlock, 0, h->grid, h->free_cur, h->C);
     return (int)cudaGetLastError();
 }
 
 int run_init_grid(dogm_handle* h)
 {
     LaunchScope ls(h, K_MISC, 0.0);
-    k_init_grid<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->meas, h->free_cur, h->free_next,
+    launch_chained(h->stream, k_init_grid, div_up(h->C, kBlock), kBlock, 0, h->grid, h->meas, h->free_cur, h->free_next,
                                                                h->cell_start, h->C);
     return (int)cudaGetLastError();
 }
@@ -620,7 +628,7 @@ int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm
 {
     LaunchScope ls(h, K_MISC, 0.0);
     cudaMemsetAsync(d_count, 0, sizeof(int), h->stream);
-    k_extract_dynamic<<<div_up(h->C, kBlock), kBlock, 0, h->stream>>>(h->grid, h->C, min_occ, min_vel, d_out, capacity,
+    launch_chained(h->stream, k_extract_dynamic, div_up(h->C, kBlock), kBlock, 0, h->grid, h->C, min_occ, min_vel, d_out, capacity,
                                                                      d_count);
     return (int)cudaGetLastError();
 }

@@ -86,6 +86,7 @@ constexpr int kNoTexel = -(1 << 30);
 // interpolated texture coordinate lands in the K x H polar texture.
 __global__ void __launch_bounds__(kBlock) k_meas_geom(MeasArgs a, float4* geom)
 {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.gs * a.gs)
         return;
@@ -142,6 +143,7 @@ __device__ __forceinline__ float2 polar_fetch(const float2* __restrict__ table, 
 __global__ void __launch_bounds__(kBlock)
     k_meas_apply(const float4* __restrict__ geom, const float2* __restrict__ table, int K, int H, int C, dogm_meas_cell* out)
 {
+    pdl_prologue();
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= C)
         return;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(kBlock)
 
 __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
 {
+    pdl_prologue();
     const int t = blockIdx.x * kBlock + threadIdx.x;
     if (t >= a.K * a.H)
         return;
@@ -225,24 +228,24 @@ static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStre
     }
     if (m->geom_beams != K)
     {
-        k_meas_geom<<<div_up(C, kBlock), kBlock, 0, stream>>>(a, m->d_geom);
+        launch_chained(stream, k_meas_geom, div_up(C, kBlock), kBlock, 0, a, m->d_geom);
         DOGM_CHECK(cudaGetLastError());
         m->geom_beams = K;
     }
     if (timing)
     {
         LaunchScope ls(timing, K_MEAS_POLAR, 8.0 * (double)texels);
-        k_meas_polar<<<div_up((long long)texels, kBlock), kBlock, 0, stream>>>(a, m->d_polar);
+        launch_chained(stream, k_meas_polar, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
     }
     else
-        k_meas_polar<<<div_up((long long)texels, kBlock), kBlock, 0, stream>>>(a, m->d_polar);
+        launch_chained(stream, k_meas_polar, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
     if (timing)
     {
         LaunchScope ls(timing, K_MEAS_GRID, 32.0 * (double)C);
-        k_meas_apply<<<div_up(C, kBlock), kBlock, 0, stream>>>(m->d_geom, m->d_polar, K, m->H, (int)C, out);
+        launch_chained(stream, k_meas_apply, div_up(C, kBlock), kBlock, 0, m->d_geom, m->d_polar, K, m->H, (int)C, out);
     }
     else
-        k_meas_apply<<<div_up(C, kBlock), kBlock, 0, stream>>>(m->d_geom, m->d_polar, K, m->H, (int)C, out);
+        launch_chained(stream, k_meas_apply, div_up(C, kBlock), kBlock, 0, m->d_geom, m->d_polar, K, m->H, (int)C, out);
     DOGM_CHECK(cudaGetLastError());
     return 0;
 }
@@ -355,7 +358,7 @@ extern "C" int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_range
     const size_t count = (size_t)num_beams * m->H;
     DOGM_CHECK(cudaMalloc(&d_out, count * sizeof(float2)));
     const MeasArgs a = make_args(m, num_beams, nullptr);
-    k_meas_polar<<<div_up((long long)count, kBlock), kBlock, 0, m->stream>>>(a, d_out);
+    launch_chained(m->stream, k_meas_polar, div_up((long long)count, kBlock), kBlock, 0, a, d_out);
     DOGM_CHECK(cudaGetLastError());
     DOGM_CHECK(cudaMemcpyAsync(out_host, d_out, count * sizeof(float2), cudaMemcpyDeviceToHost, m->stream));
     DOGM_CHECK(cudaStreamSynchronize(m->stream));

@@ -70,6 +70,7 @@ __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t s
 template <bool INJECTED>
 __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
+    pdl_prologue();
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
                                                            int* __restrict__ key_out, int n, uint32_t* hist, int bins,
                                                            uint32_t mask)
 {
+    pdl_prologue();
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
 __global__ void __launch_bounds__(kWideBlock) k_key_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
                                                               uint32_t mask)
 {
+    pdl_prologue();
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ 
                                                        float4* __restrict__ state, int* __restrict__ idx,
                                                        float* __restrict__ weight, uint8_t* __restrict__ assoc, int n)
 {
+    pdl_prologue();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
                                                           uint32_t* __restrict__ bin_tot, uint4* __restrict__ zero_ptr,
                                                           size_t zero_count)
 {
+    pdl_prologue();
     __shared__ uint32_t s_part[kScanWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
@@ -322,6 +327,7 @@ struct ScatterArgs
 template <bool FIRST>
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
     unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
@@ -534,6 +540,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spai
                                                    int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
                                                    SegPiece* trail, int* flags, float* __restrict__ sw)
 {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int base = chunk * kSegChunk;
@@ -710,8 +717,11 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spai
 // segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
 __global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spair, int n_chunks, CellSums* sums,
                                                    const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
-                                                   const int* __restrict__ flags)
+                                                   const int* __restrict__ flags, int* zero_word)
 {
+    pdl_prologue();
+    if (zero_word && blockIdx.x == 0 && threadIdx.x == 0)
+        *zero_word = 0; // the dynamic-cell counter the cell kernel appends to (no memset node between the kernels)
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= n_chunks)
         return;
@@ -761,6 +771,7 @@ __global__ void __launch_bounds__(kBlock) k_weights(const int2* __restrict__ spa
                                                     const float4* __restrict__ coef, float* __restrict__ weight_array,
                                                     int n)
 {
+    pdl_prologue();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
@@ -798,6 +809,7 @@ constexpr int kCdfRounds = kCdfTile / kBlock; // 8
 template <bool FUSED>
 __global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum)
 {
+    pdl_prologue();
     __shared__ double s_w[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
@@ -829,6 +841,7 @@ __global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_s
 __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict__ in, double* __restrict__ out_excl,
                                                         int n, double* total_out)
 {
+    pdl_prologue();
     __shared__ double s_warp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (n + 1023) / 1024;
@@ -875,6 +888,7 @@ __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict
 template <bool FUSED>
 __global__ void __launch_bounds__(kBlock) k_cdf_write(CdfArgs a, const double* __restrict__ tile_off, double* __restrict__ cdf)
 {
+    pdl_prologue();
     __shared__ double s_w[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
@@ -982,6 +996,7 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
 
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
+    pdl_prologue();
     __shared__ double s_cdf[kResWindow];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
@@ -1069,6 +1084,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 __global__ void __launch_bounds__(kBlock) k_search_f32(const float* __restrict__ cdf, int n_cdf,
                                                        const float* __restrict__ draws, int n_draws, int* out)
 {
+    pdl_prologue();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n_draws)
         return;
@@ -1091,6 +1107,7 @@ __global__ void __launch_bounds__(kBlock) k_export_noise(uint64_t seed, uint32_t
                                                          int resample_mode, float4* predict, float2* birth, float2* init,
                                                          float* resample)
 {
+    pdl_prologue();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i < N)
     {
@@ -1126,7 +1143,7 @@ int ensure_soa(dogm_handle* h)
         return 0;
     }
     LaunchScope ls(h, K_MISC, 0.0);
-    k_rec_to_soa<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->rec, h->sorted_valid ? h->spair : nullptr, h->pa.state,
+    launch_chained(h->stream, k_rec_to_soa, div_up(h->N, kBlock), kBlock, 0, h->rec, h->sorted_valid ? h->spair : nullptr, h->pa.state,
                                                                 h->pa.idx, h->pa.weight, h->pa.assoc, h->N);
     h->pa_current = true;
     return (int)cudaGetLastError();
@@ -1164,9 +1181,9 @@ int run_predict(dogm_handle* h, float dt)
     {
         LaunchScope ls(h, K_PREDICT, 57.0 * h->N);
         if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
-            k_predict<true><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
+            launch_chained(h->stream, k_predict<true>, h->tiles, kWideBlock, smem, a);
         else
-            k_predict<false><<<h->tiles, kWideBlock, smem, h->stream>>>(a);
+            launch_chained(h->stream, k_predict<false>, h->tiles, kWideBlock, smem, a);
     }
     h->shift_particles_pending = false;
     h->hist0_valid = true;
@@ -1195,10 +1212,10 @@ int run_assignment(dogm_handle* h)
         const uint32_t mask = (uint32_t)(h->digit_bins[0] - 1);
         LaunchScope ls(h, K_TILE_HIST, 57.0 * N);
         if (h->pa_current || !h->rec_valid)
-            k_soa_to_rec<<<h->tiles, kWideBlock, smem, h->stream>>>(h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc, h->rec,
+            launch_chained(h->stream, k_soa_to_rec, h->tiles, kWideBlock, smem, h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc, h->rec,
                                                                     h->key0, N, h->hist[0], h->digit_bins[0], mask);
         else
-            k_key_tile_hist<<<h->tiles, kWideBlock, smem, h->stream>>>(h->key0, N, h->hist[0], h->digit_bins[0], mask);
+            launch_chained(h->stream, k_key_tile_hist, h->tiles, kWideBlock, smem, h->key0, N, h->hist[0], h->digit_bins[0], mask);
         h->rec_valid = true;
     }
     for (int p = 0; p < h->passes; p++)
@@ -1209,7 +1226,7 @@ int run_assignment(dogm_handle* h)
             // the table of the next pass is cleared here, before the scatter below fills it with atomics
             const bool nxt = p + 1 < h->passes;
             const size_t zero_count = nxt ? ((size_t)h->tiles * h->digit_bins[p + 1] * sizeof(uint32_t)) / sizeof(uint4) : 0;
-            k_hist_scan<<<bins / 32, kWideBlock, 0, h->stream>>>(h->hist[p], h->tiles, bins, h->bin_tot[p],
+            launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[p], h->tiles, bins, h->bin_tot[p],
                                                                nxt ? (uint4*)h->hist[p + 1] : nullptr, zero_count);
         }
         ScatterArgs a;
@@ -1231,9 +1248,9 @@ int run_assignment(dogm_handle* h)
         {
             LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
             if (p == 0)
-                k_scatter<true><<<h->tiles, kBlock, smem, h->stream>>>(a);
+                launch_chained(h->stream, k_scatter<true>, h->tiles, kBlock, smem, a);
             else
-                k_scatter<false><<<h->tiles, kBlock, smem, h->stream>>>(a);
+                launch_chained(h->stream, k_scatter<false>, h->tiles, kBlock, smem, a);
         }
     }
     h->spair = h->pairs[(h->passes - 1) & 1];
@@ -1242,13 +1259,13 @@ int run_assignment(dogm_handle* h)
     // per-cell sums + start/end over the sorted order
     {
         LaunchScope ls(h, K_SEGSUM, 44.0 * N);
-        k_segsum<<<div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->stream>>>(
+        launch_chained(h->stream, k_segsum, div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, 
             h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw);
     }
     {
         LaunchScope ls(h, K_SEGFIX, 0.0);
-        k_segfix<<<div_up(h->n_chunks, kBlock), kBlock, 0, h->stream>>>(h->spair, h->n_chunks, h->cell_sums, h->seg_lead,
-                                                                      h->seg_trail, h->seg_flags);
+        launch_chained(h->stream, k_segfix, div_up(h->n_chunks, kBlock), kBlock, 0, h->spair, h->n_chunks, h->cell_sums, h->seg_lead,
+                                                                      h->seg_trail, h->seg_flags, h->dyn_filter_on ? h->dyn_count : nullptr);
     }
     h->sorted_valid = true;
     return (int)cudaGetLastError();
@@ -1264,14 +1281,14 @@ int run_persistent_weights(dogm_handle* h, bool defer)
     if (defer)
         return 0;
     LaunchScope ls(h, K_WEIGHTS, 12.0 * h->N);
-    k_weights<<<div_up(h->N, kBlock), kBlock, 0, h->stream>>>(h->spair, h->sw, h->cell_coef, h->weight_array, h->N);
+    launch_chained(h->stream, k_weights, div_up(h->N, kBlock), kBlock, 0, h->spair, h->sw, h->cell_coef, h->weight_array, h->N);
     return (int)cudaGetLastError();
 }
 
 int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out)
 {
     LaunchScope ls(h, K_BLOCKSUM_SCAN, 16.0 * n);
-    k_blocksum_scan<<<1, 1024, 0, h->stream>>>(in, out_excl, n, total_out);
+    launch_chained(h->stream, k_blocksum_scan, 1, 1024, 0, in, out_excl, n, total_out);
     return (int)cudaGetLastError();
 }
 
@@ -1305,9 +1322,9 @@ int run_resampling(dogm_handle* h)
     {
         LaunchScope ls(h, K_CDF_REDUCE, fused ? 12.0 * N + 4.0 * h->B : 4.0 * n);
         if (fused)
-            k_cdf_reduce<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
+            launch_chained(h->stream, k_cdf_reduce<true>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_sum);
         else
-            k_cdf_reduce<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_sum);
+            launch_chained(h->stream, k_cdf_reduce<false>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_sum);
     }
     {
         int e = run_blocksum_scan(h, h->tile_sum, h->tile_off, h->n_cdf_tiles, &h->scal->weight_total);
@@ -1317,9 +1334,9 @@ int run_resampling(dogm_handle* h)
     {
         LaunchScope ls(h, K_CDF_WRITE, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
         if (fused)
-            k_cdf_write<true><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_off, h->cdf);
+            launch_chained(h->stream, k_cdf_write<true>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_off, h->cdf);
         else
-            k_cdf_write<false><<<h->n_cdf_tiles, kBlock, 0, h->stream>>>(ca, h->tile_off, h->cdf);
+            launch_chained(h->stream, k_cdf_write<false>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_off, h->cdf);
     }
     h->weights_deferred = false;
     ResampleArgs a;
@@ -1339,7 +1356,7 @@ int run_resampling(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
-        k_resample<<<div_up(N, kBlock), kBlock, 0, h->stream>>>(a);
+        launch_chained(h->stream, k_resample, div_up(N, kBlock), kBlock, 0, a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;
@@ -1354,7 +1371,7 @@ int run_search_ancestors_f32(dogm_handle* h, const float* d_cdf, int n_cdf, cons
     if (n_draws <= 0)
         return 0;
     LaunchScope ls(h, K_MISC, 0.0);
-    k_search_f32<<<div_up(n_draws, kBlock), kBlock, 0, h->stream>>>(d_cdf, n_cdf, d_draws, n_draws, d_out);
+    launch_chained(h->stream, k_search_f32, div_up(n_draws, kBlock), kBlock, 0, d_cdf, n_cdf, d_draws, n_draws, d_out);
     return (int)cudaGetLastError();
 }
 
@@ -1365,7 +1382,7 @@ int run_export_noise(dogm_handle* h, uint32_t cycle, float4* d_predict, float2* 
     if (m <= 0)
         return 0;
     LaunchScope ls(h, K_MISC, 0.0);
-    k_export_noise<<<div_up(m, kBlock), kBlock, 0, h->stream>>>(
+    launch_chained(h->stream, k_export_noise, div_up(m, kBlock), kBlock, 0, 
         h->opts.seed, cycle, h->N, h->B, h->params.stddev_process_noise_position, h->params.stddev_process_noise_velocity,
         h->params.stddev_velocity, h->params.init_max_velocity, h->opts.resample_mode, d_predict, d_birth, d_init,
         d_resample);
