@@ -20,7 +20,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdogm_b200.so")
+LIB_PATH = os.environ.get("DOGM_B200_LIB") or os.path.join(_HERE, "libdogm_b200.so")  # override: A/B builds of the same ABI
 
 # ----------------------------------------------------------------------------------------------------------
 # layouts (bit-identical to the reference's PODs, dogm_types.h:13-41 and dogm.h:26-60)
@@ -177,6 +177,8 @@ _SYMBOLS = [
     ("dogm_get_stream", _P, [_P]),
     ("dogm_get_launch_count", C.c_uint64, [_P]),
     ("dogm_kernel_timing_enable", C.c_int, [_P, C.c_int]),
+    ("dogm_trace_arm", C.c_int, [_P, C.c_int]),
+    ("dogm_trace_read", C.c_int, [_P, C.POINTER(C.c_uint64), C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     ("dogm_kernel_timing_read", C.c_int, [_P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]),
     ("dogm_timer_start", C.c_int, [_P]),
     ("dogm_timer_stop", C.c_int, [_P]),
@@ -497,6 +499,19 @@ class DOGM:
         ms = C.c_float(0)
         _check(self._lib.dogm_timer_elapsed_ms(self._h, C.byref(ms)), "dogm_timer_elapsed_ms")
         return float(ms.value)
+
+    def trace_arm(self, enable: bool = True) -> None:
+        _check(self._lib.dogm_trace_arm(self._h, 1 if enable else 0), "dogm_trace_arm")
+
+    def trace_read(self) -> list:
+        """[(kernel name, start stamp in ns)] of the launches since the last read, in time order."""
+        cap = 64
+        stamps = (C.c_uint64 * cap)()
+        names = C.create_string_buffer(48 * cap)
+        n = C.c_int(0)
+        _check(self._lib.dogm_trace_read(self._h, stamps, names, cap, C.byref(n)), "dogm_trace_read")
+        out = [(names.raw[48 * i : 48 * i + 48].split(b"\0")[0].decode(), int(stamps[i])) for i in range(n.value)]
+        return sorted(out, key=lambda kv: kv[1])
 
     def kernel_timing_enable(self, enable: bool) -> None:
         _check(self._lib.dogm_kernel_timing_enable(self._h, 1 if enable else 0), "dogm_kernel_timing_enable")

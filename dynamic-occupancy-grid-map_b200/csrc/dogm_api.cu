@@ -4,6 +4,8 @@
 #include "dogm_internal.cuh"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 
 using namespace dogm_b200;
@@ -211,7 +213,16 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     e |= alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int));
     e |= alloc_zero((void**)&h->cdf, (N + B) * sizeof(double));
     e |= alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double));
-    e |= alloc_zero((void**)&h->tile_off, (size_t)h->n_cdf_tiles * sizeof(double));
+    e |= alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 1) * sizeof(double));
+    e |= alloc_zero((void**)&h->chain_flags, (2 * (size_t)h->n_cdf_tiles + 2) * sizeof(uint32_t));
+    {
+        const char* sk = getenv("DOGM_B200_SKIP");
+        h->skip_mask = sk ? (unsigned)strtoul(sk, nullptr, 0) : 0u;
+    }
+    h->trace_buf = nullptr;
+    h->chain_epoch = 0;
+    h->chain_ticket_base = 0;
+    h->chain_capacity = chain_blocks_per_sm() * sm_count;
     e |= alloc_zero((void**)&h->ancestors, N * sizeof(int));
     e |= alloc_zero((void**)&h->scal, sizeof(DeviceScalars));
     if (e)
@@ -270,6 +281,14 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->cdf);
     cudaFree(h->tile_sum);
     cudaFree(h->tile_off);
+    cudaFree(h->chain_flags);
+    if (h->trace_buf)
+    {
+        trace_bind_particles(nullptr);
+        trace_bind_cells(nullptr);
+        trace_bind_meas(nullptr);
+        cudaFree(h->trace_buf);
+    }
     cudaFree(h->ancestors);
     cudaFree(h->scal);
     cudaFree(h->predict_noise);
@@ -889,6 +908,43 @@ static void drain_timed(dogm_handle* h)
         h->event_pool.push_back(t.e1);
     }
     h->timed.clear();
+}
+
+extern "C" int dogm_trace_arm(dogm_handle* h, int enable)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaDeviceSynchronize());
+    if (enable && !h->trace_buf)
+        DOGM_CHECK(cudaMalloc(&h->trace_buf, kTraceSlots * sizeof(unsigned long long)));
+    if (h->trace_buf)
+        DOGM_CHECK(cudaMemset(h->trace_buf, 0xff, kTraceSlots * sizeof(unsigned long long)));
+    unsigned long long* p = enable ? h->trace_buf : nullptr;
+    int e = trace_bind_particles(p);
+    e = e ? e : trace_bind_cells(p);
+    e = e ? e : trace_bind_meas(p);
+    return e;
+}
+
+extern "C" int dogm_trace_read(dogm_handle* h, uint64_t* out_start_ns, char* out_names, int capacity, int* out_count)
+{
+    if (!h || !out_start_ns || !out_names || !out_count || !h->trace_buf)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    unsigned long long host[kTraceSlots];
+    DOGM_CHECK(cudaMemcpy(host, h->trace_buf, sizeof(host), cudaMemcpyDeviceToHost));
+    DOGM_CHECK(cudaMemset(h->trace_buf, 0xff, sizeof(host)));
+    int n = 0;
+    for (int s = 0; s < kTraceSlots && n < capacity; s++)
+    {
+        if (host[s] == ~0ull)
+            continue;
+        out_start_ns[n] = host[s];
+        snprintf(out_names + 48 * n, 48, "%s%s", kKernelNames[s / 2], (s & 1) ? "#2" : "");
+        n++;
+    }
+    *out_count = n;
+    return 0;
 }
 
 extern "C" int dogm_kernel_timing_enable(dogm_handle* h, int enable)

@@ -48,7 +48,7 @@ constexpr int kMaxDigitBits = 12;     // <= 4096 bins: 8 warps * 4096 * 2 B = 64
 constexpr int kMaxPasses = 3;
 constexpr int kSegChunk = 256;        // particles per warp in the segmented reduction
 constexpr int kCellBlock = 256;       // cells per CTA in the cell kernels (also the granularity of the born-mass scan)
-constexpr int kCdfItems = 8;          // CDF entries per thread
+constexpr int kCdfItems = 16;         // CDF entries per thread
 constexpr int kCdfTile = kBlock * kCdfItems;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -140,8 +140,8 @@ enum KernelId : int
     K_WEIGHTS,
     K_MEAS_POLAR,
     K_BIRTH_PARTICLES,
-    K_CDF_REDUCE,
-    K_CDF_WRITE,
+    K_CDF_CHAIN,
+    K_CDF_SPARE,
     K_RESAMPLE,
     K_INIT_MASSES,
     K_INIT_PARTICLES,
@@ -153,8 +153,8 @@ enum KernelId : int
 
 static const char* const kKernelNames[K_COUNT] = {
     "k_predict",       "k_tile_hist",       "k_hist_scan",  "k_scatter",   "k_segsum",      "k_segfix",
-    "k_cell",          "k_blocksum_scan",   "k_weights",    "k_meas_polar", "k_birth_particles", "k_cdf_reduce",
-    "k_cdf_write",     "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
+    "k_cell",          "k_blocksum_scan",   "k_weights",    "k_meas_polar", "k_birth_particles", "k_cdf_chain",
+    "k_cdf_spare",     "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
     "memset"};
 
 struct TimedLaunch
@@ -229,7 +229,12 @@ struct dogm_handle
     // resampling
     double* cdf;      // N + B
     double* tile_sum; // per CDF tile
-    double* tile_off;
+    double* tile_off; // prefix of the tile groups before (k_cdf_chain)
+    uint32_t* chain_flags; // [tiles] tile flags | [tiles + 1] group flags | ticket
+    uint32_t chain_epoch, chain_ticket_base;
+    int chain_capacity; // CTAs of k_cdf_chain the device holds at once
+    unsigned skip_mask;  // DOGM_B200_SKIP (developer ablation)
+    unsigned long long* trace_buf; // kTraceSlots start stamps (dogm_trace_arm)
     int n_cdf_tiles;
     int* ancestors; // N
 
@@ -288,16 +293,37 @@ void launch_end(dogm_handle* h, int id);
 // launch_chained(), so the next kernel's CTAs are scheduled into the SM slots the running kernel's tail leaves free and
 // wait (griddepcontrol.wait) until the whole predecessor has finished and its writes are visible.  Since every kernel
 // waits, completion stays transitive along the stream.
-__device__ __forceinline__ void pdl_prologue()
+// Optional timeline (dogm_trace_arm): the first CTA of every launch to get past the wait stamps %globaltimer into its
+// slot (KernelId * 2 + pass).  With every kernel chained, the gap between two stamps is what the earlier kernel costs
+// inside the free-running cycle - tail, flush and launch gap included - without events that would break the chain.
+constexpr int kTraceSlots = 2 * K_COUNT;
+static __constant__ unsigned long long* c_trace; // one copy per translation unit, bound by trace_bind_*()
+
+__device__ __forceinline__ void pdl_prologue(int trace_slot)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0 && c_trace)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMin(c_trace + trace_slot, t);
+    }
 }
+
+// developer ablation switch (DOGM_B200_SKIP=<bit mask of KernelId>, effective from cycle 12 on): LaunchScope arms it for
+// the launch it brackets; results are garbage, only the timing of the remaining kernels is of interest
+inline bool g_skip_next_launch = false;
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chained(cudaStream_t stream, void (*kernel)(KArgs...), long long grid, int block, size_t smem,
                                   Args&&... args)
 {
+    if (g_skip_next_launch)
+    {
+        g_skip_next_launch = false;
+        return cudaSuccess;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3((unsigned)block, 1, 1);
@@ -315,7 +341,11 @@ struct LaunchScope
 {
     dogm_handle* h;
     int id;
-    LaunchScope(dogm_handle* h_, int id_, double bytes) : h(h_), id(id_) { launch_begin(h, id, bytes); }
+    LaunchScope(dogm_handle* h_, int id_, double bytes) : h(h_), id(id_)
+    {
+        launch_begin(h, id, bytes);
+        g_skip_next_launch = h->skip_mask != 0 && h->cycle >= 12 && ((h->skip_mask >> id) & 1u);
+    }
     ~LaunchScope() { launch_end(h, id); }
 };
 
@@ -331,7 +361,11 @@ int run_resampling(dogm_handle* h);
 int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells
 int run_init_grid(dogm_handle* h);         // initGridCellsKernel
 int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out);
-int configure_kernels();                   // opt-in shared memory sizes
+int configure_kernels();
+int chain_blocks_per_sm();
+int trace_bind_particles(unsigned long long* p);
+int trace_bind_cells(unsigned long long* p);
+int trace_bind_meas(unsigned long long* p);                   // opt-in shared memory sizes
 int run_search_ancestors_f32(dogm_handle* h, const float* d_cdf, int n_cdf, const float* d_draws, int n_draws, int* d_out);
 int run_export_noise(dogm_handle* h, uint32_t cycle, float4* d_predict, float2* d_birth, float2* d_init, float* d_resample);
 int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm_dynamic_cell* d_out, int capacity,

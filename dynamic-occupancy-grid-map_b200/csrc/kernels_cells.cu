@@ -43,7 +43,7 @@ struct CellArgs
 
 __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_CELL * 2);
     __shared__ double s_scan[kWarpsPerBlock];
     // staging for the 64-byte GridCell records: [warp][part][cell], row stride 34 float4 keeps both the per-thread
     // writes and the transposed reads free of bank conflicts
@@ -303,7 +303,7 @@ struct BirthArgs
 // deterministic ownership rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
 __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_BIRTH_PARTICLES * 2);
     const int s = blockIdx.x * kBlock + threadIdx.x;
     if (s >= a.B)
         return;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell* __restrict__ meas, float* masses, int C,
                                                             double* blk_sum, double* prefix)
 {
-    pdl_prologue();
+    pdl_prologue(K_INIT_MASSES * 2);
     __shared__ double s_scan[kWarpsPerBlock];
     const int c = blockIdx.x * kCellBlock + threadIdx.x;
     float m = 0.0f;
@@ -382,7 +382,7 @@ struct InitArgs
 
 __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_INIT_PARTICLES * 2);
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= a.N)
         return;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
 // =========================================================================================================
 __global__ void __launch_bounds__(kBlock) k_extract_free(const dogm_grid_cell* __restrict__ grid, float* free_cur, int C)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c < C)
         free_cur[c] = grid[c].free_mass;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kBlock) k_extract_free(const dogm_grid_cell* _
 __global__ void __launch_bounds__(kBlock) k_init_grid(dogm_grid_cell* grid, dogm_meas_cell* meas, float* free_a,
                                                       float* free_b, int* cell_start, int C)
 { // initGridCellsKernel, init.cu:69-84 (all other GridCell fields start at 0 here; the reference leaves them uninitialised)
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= C)
         return;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell
                                                             float min_vel, dogm_dynamic_cell* out, int capacity,
                                                             int* count)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int c = blockIdx.x * kBlock + threadIdx.x;
     bool hit = false;
     dogm_dynamic_cell rec;
@@ -631,6 +631,11 @@ int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm
     launch_chained(h->stream, k_extract_dynamic, div_up(h->C, kBlock), kBlock, 0, h->grid, h->C, min_occ, min_vel, d_out, capacity,
                                                                      d_count);
     return (int)cudaGetLastError();
+}
+
+int trace_bind_cells(unsigned long long* p)
+{
+    return (int)cudaMemcpyToSymbol(c_trace, &p, sizeof(p));
 }
 
 } // namespace dogm_b200

@@ -86,7 +86,7 @@ constexpr int kNoTexel = -(1 << 30);
 // interpolated texture coordinate lands in the K x H polar texture.
 __global__ void __launch_bounds__(kBlock) k_meas_geom(MeasArgs a, float4* geom)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= a.gs * a.gs)
         return;
@@ -143,7 +143,7 @@ __device__ __forceinline__ float2 polar_fetch(const float2* __restrict__ table, 
 __global__ void __launch_bounds__(kBlock)
     k_meas_apply(const float4* __restrict__ geom, const float2* __restrict__ table, int K, int H, int C, dogm_meas_cell* out)
 {
-    pdl_prologue();
+    pdl_prologue(K_MEAS_GRID * 2);
     const int c = blockIdx.x * kBlock + threadIdx.x;
     if (c >= C)
         return;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kBlock)
 
 __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
 {
-    pdl_prologue();
+    pdl_prologue(K_MEAS_POLAR * 2);
     const int t = blockIdx.x * kBlock + threadIdx.x;
     if (t >= a.K * a.H)
         return;
@@ -248,6 +248,11 @@ static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStre
         launch_chained(stream, k_meas_apply, div_up(C, kBlock), kBlock, 0, m->d_geom, m->d_polar, K, m->H, (int)C, out);
     DOGM_CHECK(cudaGetLastError());
     return 0;
+}
+
+int trace_bind_meas(unsigned long long* p)
+{
+    return (int)cudaMemcpyToSymbol(c_trace, &p, sizeof(p));
 }
 
 } // namespace dogm_b200

@@ -70,7 +70,7 @@ __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t s
 template <bool INJECTED>
 __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_PREDICT * 2);
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
                                                            int* __restrict__ key_out, int n, uint32_t* hist, int bins,
                                                            uint32_t mask)
 {
-    pdl_prologue();
+    pdl_prologue(K_TILE_HIST * 2);
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
 __global__ void __launch_bounds__(kWideBlock) k_key_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
                                                               uint32_t mask)
 {
-    pdl_prologue();
+    pdl_prologue(K_TILE_HIST * 2);
     extern __shared__ uint32_t s_hist[];
     for (int b = threadIdx.x; b < bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -185,13 +185,41 @@ __global__ void __launch_bounds__(kWideBlock) k_key_tile_hist(const int* __restr
         row[b] = s_hist[b];
 }
 
+// histogram of a later pass over the pairs the previous pass has just written (they are still in L2); cheaper than
+// 2e6 global atomics issued from the previous scatter (21 us against 6 us at 2e6 particles)
+__global__ void __launch_bounds__(kWideBlock) k_pair_tile_hist(const int2* __restrict__ pair, int n, uint32_t* hist, int bins,
+                                                               int shift, uint32_t mask)
+{
+    pdl_prologue(K_TILE_HIST * 2 + 1);
+    extern __shared__ uint32_t s_hist[];
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
+        s_hist[b] = 0u;
+    __syncthreads();
+    const int base = blockIdx.x * kTileItems;
+    int keys[kTileItems / kWideBlock];
+#pragma unroll
+    for (int j = 0; j < kTileItems / kWideBlock; j++)
+    {
+        const int i = base + j * kWideBlock + threadIdx.x;
+        keys[j] = i < n ? __ldg(&pair[i].x) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < kTileItems / kWideBlock; j++)
+        if (keys[j] >= 0)
+            atomicAdd(&s_hist[((uint32_t)keys[j] >> shift) & mask], 1u);
+    __syncthreads();
+    uint32_t* row = hist + (size_t)blockIdx.x * bins;
+    for (int b = threadIdx.x; b < bins; b += kWideBlock)
+        row[b] = s_hist[b];
+}
+
 // records -> the reference's SoA block (read-out between stages: getParticles after prediction / assignment);
 // with `spair` the output is in sorted order (position p holds record spair[p].y)
 __global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ rec, const int2* __restrict__ spair,
                                                        float4* __restrict__ state, int* __restrict__ idx,
                                                        float* __restrict__ weight, uint8_t* __restrict__ assoc, int n)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
                                                           uint32_t* __restrict__ bin_tot, uint4* __restrict__ zero_ptr,
                                                           size_t zero_count)
 {
-    pdl_prologue();
+    pdl_prologue(K_HIST_SCAN * 2 + (bins > 1024 ? 0 : 1));
     __shared__ uint32_t s_part[kScanWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
@@ -327,7 +355,7 @@ struct ScatterArgs
 template <bool FIRST>
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_SCATTER * 2 + (FIRST ? 0 : 1));
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
     unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
@@ -452,7 +480,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
             const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
             const uint32_t dest = s_binoff[digit] + my_cnt[digit] + rk;
             pair_out[dest] = make_int2(key, slot);
+#ifndef DOGM_ABLATE_NEXT_ATOMICS
             if (a.next_table)
+#else
+            if (false)
+#endif
             {
                 const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
                 atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
@@ -540,7 +572,7 @@ __global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spai
                                                    int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
                                                    SegPiece* trail, int* flags, float* __restrict__ sw)
 {
-    pdl_prologue();
+    pdl_prologue(K_SEGSUM * 2);
     const int lane = threadIdx.x & 31;
     const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int base = chunk * kSegChunk;
@@ -719,7 +751,7 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spai
                                                    const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
                                                    const int* __restrict__ flags, int* zero_word)
 {
-    pdl_prologue();
+    pdl_prologue(K_SEGFIX * 2);
     if (zero_word && blockIdx.x == 0 && threadIdx.x == 0)
         *zero_word = 0; // the dynamic-cell counter the cell kernel appends to (no memset node between the kernels)
     const int c = blockIdx.x * kBlock + threadIdx.x;
@@ -771,7 +803,7 @@ __global__ void __launch_bounds__(kBlock) k_weights(const int2* __restrict__ spa
                                                     const float4* __restrict__ coef, float* __restrict__ weight_array,
                                                     int n)
 {
-    pdl_prologue();
+    pdl_prologue(K_WEIGHTS * 2);
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n)
         return;
@@ -802,38 +834,184 @@ __device__ __forceinline__ float joint_entry(const CdfArgs& a, int i)
     return i < a.n ? a.bw[i - a.N] : 0.0f;
 }
 
-// A tile is 2048 consecutive entries; warp w owns entries [256 w, 256 w + 256) of it and reads them in 8 coalesced
-// rounds (entry = 256 w + 32 r + lane).
-constexpr int kCdfRounds = kCdfTile / kBlock; // 8
+// One kernel, one pass: a tile is 4096 consecutive entries (warp w owns entries [512 w, 512 w + 512) and reads them in
+// 16 coalesced rounds, entry = 512 w + 32 r + lane, which stay in registers).  Tiles are handed out by an atomic
+// ticket, so every tile with a lower number is running or done when a CTA waits for it; a tile publishes its total,
+// sums the totals of the tiles before it in a fixed order - the tiles of its own group of
+// 256 plus the published prefix of the groups before - and writes its part of the CDF.  The order of every double
+// addition is fixed by the tile number alone, so the CDF is identical from run to run.
+constexpr int kChainRounds = kCdfTile / kBlock; // 16
+constexpr int kChainWarpSpan = kCdfTile / kWarpsPerBlock; // 512
+constexpr int kChainGroup = 256;                // tiles per group
+
+struct ChainArgs
+{
+    CdfArgs c;
+    double* cdf;
+    double* tile_sum;     // [tiles]       published tile totals (publish_f64 / await_f64)
+    double* group_base;   // [groups + 1]  published sum of all tiles of the groups before
+    uint32_t* ticket;
+    uint32_t ticket_base;
+    uint32_t epoch;
+    int tiles;
+    double* total_out;
+};
+
+// A published sum travels as one 64-bit word: the sums are non-negative, so the sign bit carries the parity of the
+// launch epoch.  Every launch publishes every word exactly once, hence a word whose sign bit differs from the epoch's
+// parity still holds the previous launch's value.  One relaxed 64-bit load is both the flag and the payload.
+__device__ __forceinline__ void publish_f64(double* p, double v, uint32_t epoch)
+{
+    const unsigned long long bits =
+        ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull) | ((unsigned long long)(epoch & 1u) << 63);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(bits) : "memory");
+}
+__device__ __forceinline__ double await_f64(const double* p, uint32_t epoch)
+{
+    unsigned long long bits;
+    for (;;)
+    {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+        if ((uint32_t)(bits >> 63) == (epoch & 1u))
+            break;
+        __nanosleep(40);
+    }
+    return __longlong_as_double((long long)(bits & 0x7fffffffffffffffull));
+}
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_sum)
+__global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_CDF_CHAIN * 2);
     __shared__ double s_w[kWarpsPerBlock];
+    __shared__ double s_red[kWarpsPerBlock];
+    __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
-    float e[kCdfRounds];
-#pragma unroll
-    for (int r = 0; r < kCdfRounds; r++)
-        e[r] = joint_entry<FUSED>(a, w0 + r * 32 + lane);
-    double acc = 0.0;
-#pragma unroll
-    for (int r = 0; r < kCdfRounds; r++)
-        acc += (double)e[r];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-        acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0)
-        s_w[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0)
+    for (;;)
     {
-        double t = 0.0;
+        __syncthreads(); // s_tile / s_w / s_red of the previous tile are no longer read
+        if (threadIdx.x == 0)
+            s_tile = atomicAdd(a.ticket, 1u) - a.ticket_base;
+        __syncthreads();
+        const uint32_t t = s_tile;
+        if (t >= (uint32_t)a.tiles)
+            return;
+        const int w0 = (int)t * kCdfTile + warp * kChainWarpSpan;
+        // the entries are fetched in two batches of 8: all (cell, weight) loads of a batch are issued before the
+        // first dependent coefficient load, all coefficient loads before the first use
+        float e[kChainRounds];
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+        {
+            int cell[8];
+            float w[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+            {
+                const int i = w0 + (half * 8 + r) * 32 + lane;
+                cell[r] = -1;
+                if (FUSED)
+                {
+                    if (i < a.c.N)
+                        cell[r] = __ldg(&a.c.spair[i].x);
+                    w[r] = i < a.c.N ? __ldg(a.c.sw + i) : (i < a.c.n ? __ldg(a.c.bw + (i - a.c.N)) : 0.0f);
+                }
+                else
+                {
+                    w[r] = i < a.c.N ? a.c.wa[i] : (i < a.c.n ? __ldg(a.c.bw + (i - a.c.N)) : 0.0f);
+                }
+            }
+            if (FUSED)
+            {
+                float4 cf[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    cf[r] = cell[r] >= 0 ? __ldg(a.c.coef + cell[r]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    e[half * 8 + r] = cell[r] >= 0 ? persistent_weight(cf[r], w[r]) : w[r];
+            }
+            else
+            {
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    e[half * 8 + r] = w[r];
+            }
+        }
+        // the warp's total, accumulated exactly as the scan below accumulates its carry
+        double carry = 0.0;
+#pragma unroll
+        for (int r = 0; r < kChainRounds; r++)
+        {
+            double v = (double)e[r];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const double u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d)
+                    v += u;
+            }
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0)
+            s_w[warp] = carry;
+        __syncthreads();
+        double tot = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; w++)
-            t += s_w[w];
-        tile_sum[blockIdx.x] = t;
+            tot += s_w[w];
+        if (threadIdx.x == 0)
+            publish_f64(a.tile_sum + t, tot, a.epoch);
+        // totals of the tiles before this one inside its group, in a fixed order
+        const uint32_t group = t / kChainGroup, first = group * kChainGroup;
+        // (a group has at most 256 tiles: one word per thread, all polls in flight together)
+        double part = 0.0;
+        if (first + threadIdx.x < t)
+            part = await_f64(a.tile_sum + first + threadIdx.x, a.epoch);
+        else if (group > 0 && first + threadIdx.x == t)
+            part = await_f64(a.group_base + group, a.epoch); // prefix of the groups before
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            part += __shfl_xor_sync(0xffffffffu, part, d);
+        if (lane == 0)
+            s_red[warp] = part;
+        __syncthreads();
+        double off = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++)
+            off += s_red[w];
+        if (threadIdx.x == 0 && (t + 1) % kChainGroup == 0 && t + 1 < (uint32_t)a.tiles)
+        { // last tile of its group: publish the prefix the next group starts from
+            publish_f64(a.group_base + group + 1, off + tot, a.epoch);
+        }
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++)
+            if (w < warp)
+                off += s_w[w];
+        carry = 0.0;
+#pragma unroll
+        for (int r = 0; r < kChainRounds; r++)
+        {
+            double v = (double)e[r];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const double u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d)
+                    v += u;
+            }
+            const int i = w0 + r * 32 + lane;
+            if (i < a.c.n)
+            {
+                const double val = off + (carry + v);
+                __stcs(a.cdf + i, val);
+                if (FUSED && i < a.c.N)
+                    a.c.wa_out[i] = e[r];
+                if (i == a.c.n - 1)
+                    *a.total_out = val;
+            }
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
     }
 }
 
@@ -841,7 +1019,7 @@ __global__ void __launch_bounds__(kBlock) k_cdf_reduce(CdfArgs a, double* tile_s
 __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict__ in, double* __restrict__ out_excl,
                                                         int n, double* total_out)
 {
-    pdl_prologue();
+    pdl_prologue(K_BLOCKSUM_SCAN * 2);
     __shared__ double s_warp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (n + 1023) / 1024;
@@ -883,55 +1061,6 @@ __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict
     }
     if (threadIdx.x == 1023)
         *total_out = s_warp[31];
-}
-
-template <bool FUSED>
-__global__ void __launch_bounds__(kBlock) k_cdf_write(CdfArgs a, const double* __restrict__ tile_off, double* __restrict__ cdf)
-{
-    pdl_prologue();
-    __shared__ double s_w[kWarpsPerBlock];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int w0 = blockIdx.x * kCdfTile + warp * (kCdfTile / kWarpsPerBlock);
-    float e[kCdfRounds];
-#pragma unroll
-    for (int r = 0; r < kCdfRounds; r++)
-        e[r] = joint_entry<FUSED>(a, w0 + r * 32 + lane);
-    // inclusive prefix inside the warp's 256 entries: warp scan per round + running carry
-    double p[kCdfRounds];
-    double carry = 0.0;
-#pragma unroll
-    for (int r = 0; r < kCdfRounds; r++)
-    {
-        double v = (double)e[r];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const double t = __shfl_up_sync(0xffffffffu, v, d);
-            if (lane >= d)
-                v += t;
-        }
-        p[r] = carry + v;
-        carry += __shfl_sync(0xffffffffu, v, 31);
-    }
-    if (lane == 0)
-        s_w[warp] = carry;
-    __syncthreads();
-    double off = tile_off[blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; w++)
-        if (w < warp)
-            off += s_w[w];
-#pragma unroll
-    for (int r = 0; r < kCdfRounds; r++)
-    {
-        const int i = w0 + r * 32 + lane;
-        if (i < a.n)
-        {
-            cdf[i] = off + p[r];
-            if (FUSED && i < a.N)
-                a.wa_out[i] = e[r];
-        }
-    }
 }
 
 // =========================================================================================================
@@ -996,7 +1125,7 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
 
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
-    pdl_prologue();
+    pdl_prologue(K_RESAMPLE * 2);
     __shared__ double s_cdf[kResWindow];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
@@ -1084,7 +1213,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 __global__ void __launch_bounds__(kBlock) k_search_f32(const float* __restrict__ cdf, int n_cdf,
                                                        const float* __restrict__ draws, int n_draws, int* out)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n_draws)
         return;
@@ -1107,7 +1236,7 @@ __global__ void __launch_bounds__(kBlock) k_export_noise(uint64_t seed, uint32_t
                                                          int resample_mode, float4* predict, float2* birth, float2* init,
                                                          float* resample)
 {
-    pdl_prologue();
+    pdl_prologue(K_MISC * 2);
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i < N)
     {
@@ -1221,13 +1350,16 @@ int run_assignment(dogm_handle* h)
     for (int p = 0; p < h->passes; p++)
     {
         const int bins = h->digit_bins[p];
+        if (p > 0)
+        {
+            LaunchScope ls(h, K_TILE_HIST, 8.0 * N);
+            launch_chained(h->stream, k_pair_tile_hist, h->tiles, kWideBlock, (size_t)bins * sizeof(uint32_t), h->pairs[(p - 1) & 1],
+                           N, h->hist[p], bins, h->digit_shift[p], (uint32_t)(bins - 1));
+        }
         {
             LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
-            // the table of the next pass is cleared here, before the scatter below fills it with atomics
-            const bool nxt = p + 1 < h->passes;
-            const size_t zero_count = nxt ? ((size_t)h->tiles * h->digit_bins[p + 1] * sizeof(uint32_t)) / sizeof(uint4) : 0;
             launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[p], h->tiles, bins, h->bin_tot[p],
-                                                               nxt ? (uint4*)h->hist[p + 1] : nullptr, zero_count);
+                           (uint4*)nullptr, (size_t)0);
         }
         ScatterArgs a;
         a.key_in = h->key0;
@@ -1240,7 +1372,7 @@ int run_assignment(dogm_handle* h)
         a.table = h->hist[p];
         a.bin_tot = h->bin_tot[p];
         const bool has_next = p + 1 < h->passes;
-        a.next_table = has_next ? h->hist[p + 1] : nullptr;
+        a.next_table = nullptr; // the next pass counts its own digits (k_pair_tile_hist)
         a.next_shift = has_next ? h->digit_shift[p + 1] : 0;
         a.next_mask = has_next ? (uint32_t)(h->digit_bins[p + 1] - 1) : 0u;
         a.next_bins = has_next ? h->digit_bins[p + 1] : 0;
@@ -1292,6 +1424,15 @@ int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n,
     return (int)cudaGetLastError();
 }
 
+int chain_blocks_per_sm()
+{
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_cdf_chain<true>, kBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_cdf_chain<false>, kBlock, 0);
+    const int m = a < b ? a : b;
+    return m > 0 ? m : 1;
+}
+
 int configure_kernels()
 {
     const int max_bins = 1 << kMaxDigitBits;
@@ -1320,23 +1461,23 @@ int run_resampling(dogm_handle* h)
     ca.n = n;
     const bool fused = h->weights_deferred;
     {
-        LaunchScope ls(h, K_CDF_REDUCE, fused ? 12.0 * N + 4.0 * h->B : 4.0 * n);
+        ChainArgs ch;
+        ch.c = ca;
+        ch.cdf = h->cdf;
+        ch.tile_sum = h->tile_sum;
+        ch.group_base = h->tile_off;
+        ch.ticket = h->chain_flags;
+        ch.ticket_base = h->chain_ticket_base;
+        ch.epoch = ++h->chain_epoch;
+        ch.tiles = h->n_cdf_tiles;
+        ch.total_out = &h->scal->weight_total;
+        const int grid = h->n_cdf_tiles < h->chain_capacity ? h->n_cdf_tiles : h->chain_capacity;
+        h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
+        LaunchScope ls(h, K_CDF_CHAIN, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
         if (fused)
-            launch_chained(h->stream, k_cdf_reduce<true>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_sum);
+            launch_chained(h->stream, k_cdf_chain<true>, grid, kBlock, 0, ch);
         else
-            launch_chained(h->stream, k_cdf_reduce<false>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_sum);
-    }
-    {
-        int e = run_blocksum_scan(h, h->tile_sum, h->tile_off, h->n_cdf_tiles, &h->scal->weight_total);
-        if (e)
-            return e;
-    }
-    {
-        LaunchScope ls(h, K_CDF_WRITE, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
-        if (fused)
-            launch_chained(h->stream, k_cdf_write<true>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_off, h->cdf);
-        else
-            launch_chained(h->stream, k_cdf_write<false>, h->n_cdf_tiles, kBlock, 0, ca, h->tile_off, h->cdf);
+            launch_chained(h->stream, k_cdf_chain<false>, grid, kBlock, 0, ch);
     }
     h->weights_deferred = false;
     ResampleArgs a;
@@ -1387,6 +1528,11 @@ int run_export_noise(dogm_handle* h, uint32_t cycle, float4* d_predict, float2* 
         h->params.stddev_velocity, h->params.init_max_velocity, h->opts.resample_mode, d_predict, d_birth, d_init,
         d_resample);
     return (int)cudaGetLastError();
+}
+
+int trace_bind_particles(unsigned long long* p)
+{
+    return (int)cudaMemcpyToSymbol(c_trace, &p, sizeof(p));
 }
 
 } // namespace dogm_b200

@@ -296,6 +296,12 @@ typedef struct dogm_kernel_time
     double algorithmic_bytes; /* per-launch algorithmic bytes of the last launch */
 } dogm_kernel_time;
 int dogm_kernel_timing_enable(dogm_handle* h, int enable);
+/* Timeline of the free-running cycle without events between the kernels: while armed, the first CTA of every launch
+ * stamps the GPU's nanosecond timer once its predecessor has completed; dogm_trace_read returns the stamps (48-byte
+ * names, "#2" = second pass of the same kernel) of the launches since the last read and re-arms.  The difference of
+ * two consecutive stamps is the earlier kernel's share of the cycle.  One handle per process at a time. */
+int dogm_trace_arm(dogm_handle* h, int enable);
+int dogm_trace_read(dogm_handle* h, uint64_t* out_start_ns, char* out_names, int capacity, int* out_count);
 int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, int capacity, int* out_count);
 
 /* A CUDA-event stopwatch on the handle's stream (device time of everything enqueued between start and stop) */
