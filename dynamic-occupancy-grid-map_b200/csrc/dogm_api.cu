@@ -201,6 +201,7 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
         h->hist[p] = nullptr;
         h->bin_tot[p] = nullptr;
         h->bin_base[p] = nullptr;
+        h->scan_epoch[p] = 0;
     }
     for (int p = 0; p < h->passes; p++)
     {

@@ -216,7 +216,8 @@ struct dogm_handle
     int digit_bins[dogm_b200::kMaxPasses];
     uint32_t* hist[dogm_b200::kMaxPasses];     // [tiles][bins] per pass
     uint32_t* bin_tot[dogm_b200::kMaxPasses];  // [bins]
-    uint32_t* bin_base[dogm_b200::kMaxPasses]; // [bins]
+    uint32_t* bin_base[dogm_b200::kMaxPasses]; // chain words of k_hist_scan (bins / 32 x u64)
+    uint32_t scan_epoch[dogm_b200::kMaxPasses];
     int tiles;
     bool hist0_valid; // pass-0 tile histograms were produced by the prediction kernel for the current keys
 

@@ -243,25 +243,39 @@ __global__ void __launch_bounds__(kBlock) k_rec_to_soa(const PRec* __restrict__ 
 constexpr int kScanWarps = kWideBlock / 32;
 constexpr int kScanBatch = 16;
 
+// integer flavour of publish_f64 / await_f64 (values below 2^63; the top bit carries the launch parity)
+__device__ __forceinline__ void publish_u64(unsigned long long* p, unsigned long long v, uint32_t epoch)
+{
+    const unsigned long long bits = (v & 0x7fffffffffffffffull) | ((unsigned long long)(epoch & 1u) << 63);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(bits) : "memory");
+}
+__device__ __forceinline__ unsigned long long await_u64(const unsigned long long* p, uint32_t epoch)
+{
+    unsigned long long bits;
+    for (;;)
+    {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+        if ((uint32_t)(bits >> 63) == (epoch & 1u))
+            break;
+        __nanosleep(40);
+    }
+    return bits & 0x7fffffffffffffffull;
+}
+
+// CTA j owns the 32 bins [32 j, 32 j + 32): lane = bin, the warps split the tiles.  On exit table[t][b] is the final
+// position of the first key of tile t with digit b: (keys with a smaller digit) + (same digit in earlier tiles).  The
+// first term needs the totals of the CTAs before: every CTA publishes the sum of its 32 bins and adds up the words of
+// its predecessors (at most 64 CTAs, all resident; integers, so the order of the additions does not matter).
 __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__ table, int tiles, int bins,
-                                                          uint32_t* __restrict__ bin_tot, uint4* __restrict__ zero_ptr,
-                                                          size_t zero_count)
+                                                          unsigned long long* chain, uint32_t epoch)
 {
     pdl_prologue(K_HIST_SCAN * 2 + (bins > 1024 ? 0 : 1));
     __shared__ uint32_t s_part[kScanWarps][32];
+    __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bin = blockIdx.x * 32 + lane;
     const int per = (tiles + kScanWarps - 1) / kScanWarps;
     const int t0 = min(warp * per, tiles), t1 = min(t0 + per, tiles);
-
-    // side job: clear this CTA's share of the next table
-    if (zero_ptr)
-    {
-        const size_t share = (zero_count + gridDim.x - 1) / gridDim.x;
-        const size_t z0 = min((size_t)blockIdx.x * share, zero_count), z1 = min(z0 + share, zero_count);
-        for (size_t z = z0 + threadIdx.x; z < z1; z += kWideBlock)
-            zero_ptr[z] = make_uint4(0u, 0u, 0u, 0u);
-    }
 
     // the common case (at most 16 tiles per warp, i.e. up to 2e6 particles): one batch of loads, kept in registers
     uint32_t v[kScanBatch];
@@ -299,6 +313,30 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
             run += p;
         total += p;
     }
+    // exclusive scan of the 32 bin totals inside the warp, CTA total to the chain
+    uint32_t incl = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    if (threadIdx.x == 31)
+        publish_u64(chain + blockIdx.x, incl, epoch);
+    if (warp == 0)
+    {
+        uint32_t before = 0;
+        for (int j = lane; j < (int)blockIdx.x; j += 32)
+            before += (uint32_t)await_u64(chain + j, epoch);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            before += __shfl_xor_sync(0xffffffffu, before, d);
+        if (lane == 0)
+            s_base = before;
+    }
+    __syncthreads();
+    run += s_base + (incl - total);
     if (single)
     {
 #pragma unroll
@@ -325,8 +363,6 @@ __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__
                 }
         }
     }
-    if (warp == 0)
-        bin_tot[bin] = total; // the exclusive scan over the bins is done by every scatter CTA (cheap, no serial tail here)
 }
 
 // =========================================================================================================
@@ -344,12 +380,7 @@ struct ScatterArgs
     int shift;
     uint32_t mask;
     int bins;
-    const uint32_t* table;    // this pass, exclusive over tiles
-    const uint32_t* bin_tot;  // this pass: number of keys per digit (all tiles)
-    uint32_t* next_table;     // next pass histogram (atomics) or nullptr
-    int next_shift;
-    uint32_t next_mask;
-    int next_bins;
+    const uint32_t* table; // this pass: final position of the first key per (tile, digit), from k_hist_scan
 };
 
 template <bool FIRST>
@@ -357,8 +388,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 {
     pdl_prologue(K_SCATTER * 2 + (FIRST ? 0 : 1));
     extern __shared__ __align__(16) unsigned char s_raw[];
-    uint32_t* s_binoff = (uint32_t*)s_raw;                       // [bins]
-    unsigned short* s_cnt = (unsigned short*)(s_binoff + a.bins); // [warps][bins]
+    unsigned short* s_cnt = (unsigned short*)s_raw; // [warps][bins]
 
     const int* __restrict__ key_in = a.key_in;
     const int2* __restrict__ pair_in = a.pair_in;
@@ -388,22 +418,49 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     unsigned short* my_cnt = s_cnt + warp * a.bins;
     uint32_t rank2[kRoundsPerWarp / 2]; // ranks inside the warp's 512 items, two per register
 
+    // lanes with the same digit, for all 16 rounds first: the MATCH results are independent of each other and of the
+    // counters, so their latencies overlap instead of adding up round by round
+    uint32_t peers[kRoundsPerWarp];
 #pragma unroll
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
-        const int i = warp_base + r * 32 + lane;
-        const bool valid = i < a.n;
+        const bool valid = warp_base + r * 32 + lane < a.n;
         const uint32_t digit = valid ? (((uint32_t)keys[r] >> a.shift) & a.mask) : 0xffffffffu;
-        const unsigned peers = __match_any_sync(full, digit);
-        const int leader = __ffs(peers) - 1;
+        if (!FIRST)
+        {
+            peers[r] = __match_any_sync(full, digit);
+        }
+        else
+        {
+            // MATCH.ANY takes time in proportion to the number of distinct digits in the warp: close to 32 in the first
+            // pass, where neighbouring particles have just been scattered by the process noise (31 us against 22 us
+            // at 2e6 particles), few in the later passes, whose input is grouped by cell already (10 us against 19 us).
+            // One ballot per digit bit costs the same for any input.
+            uint32_t p = __ballot_sync(full, valid);
+#pragma unroll
+            for (int b = 0; b < kMaxDigitBits; b++)
+            {
+                const bool bit = (digit >> b) & 1u;
+                const uint32_t m = __ballot_sync(full, bit);
+                p &= bit ? m : ~m;
+            }
+            peers[r] = p;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const bool valid = warp_base + r * 32 + lane < a.n;
+        const uint32_t digit = ((uint32_t)keys[r] >> a.shift) & a.mask;
+        // every lane reads its digit's counter, the first lane of each group then advances it
         uint32_t old = 0;
-        if (valid && lane == leader)
+        if (valid)
         {
             old = my_cnt[digit];
-            my_cnt[digit] = (unsigned short)(old + __popc(peers));
+            if ((peers[r] & lt) == 0)
+                my_cnt[digit] = (unsigned short)(old + __popc(peers[r]));
         }
-        old = __shfl_sync(full, old, leader);
-        const uint32_t rk = old + __popc(peers & lt);
+        const uint32_t rk = old + __popc(peers[r] & lt);
         if (r & 1)
             rank2[r >> 1] |= rk << 16;
         else
@@ -412,83 +469,62 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     }
     __syncthreads();
 
-    // exclusive prefix over the warps of the tile, and the global offset of every bin for this tile:
-    // (keys with a smaller digit) + (same digit in earlier tiles).  Thread t owns the contiguous bins
-    // [t * per, (t + 1) * per): its share of the exclusive scan over the bin totals is a block scan of per-thread sums.
+    // per bin: exclusive prefix over the warps of the tile; thread t owns the bins t, t + 256, ... (conflict-free)
+    for (int b = threadIdx.x; b < a.bins; b += kBlock)
     {
-        __shared__ uint32_t s_wtot[kWarpsPerBlock];
-        const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins;
-        const uint32_t* __restrict__ tot = a.bin_tot;
-        const int per = a.bins / kBlock > 0 ? a.bins / kBlock : 1; // bins is a power of two >= 32
-        const int b0 = threadIdx.x * per;
-        uint32_t local = 0;
-        if (b0 < a.bins)
-            for (int k = 0; k < per; k++)
-                local += tot[b0 + k];
-        uint32_t incl = local;
+        uint32_t run = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
+        for (int w = 0; w < kWarpsPerBlock; w++)
         {
-            const uint32_t t = __shfl_up_sync(full, incl, d);
-            if (lane >= d)
-                incl += t;
+            const uint32_t c = s_cnt[w * a.bins + b];
+            s_cnt[w * a.bins + b] = (unsigned short)run;
+            run += c;
         }
-        if (lane == 31)
-            s_wtot[warp] = incl;
-        __syncthreads();
-        uint32_t base = incl - local;
-        for (int w = 0; w < warp; w++)
-            base += s_wtot[w];
-        if (b0 < a.bins)
-            for (int k = 0; k < per; k++)
-            {
-                const int b = b0 + k;
-                uint32_t run = 0;
-#pragma unroll
-                for (int w = 0; w < kWarpsPerBlock; w++)
-                {
-                    const uint32_t c = s_cnt[w * a.bins + b];
-                    s_cnt[w * a.bins + b] = (unsigned short)run;
-                    run += c;
-                }
-                s_binoff[b] = base + row[b];
-                base += tot[b];
-            }
     }
     __syncthreads();
 
-    // store phase: the (key, slot) inputs are read again (L1 / L2 hits) instead of being kept in registers
+    // store phase: the inputs are read again (L1 / L2 hits) instead of being kept in registers across the ranking;
+    // all loads of a batch of 8 are issued before the first store (the stores could alias them for the compiler)
+    const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins; // final position of this tile's first key per bin
 #pragma unroll
-    for (int r = 0; r < kRoundsPerWarp; r++)
+    for (int half = 0; half < 2; half++)
     {
-        const int i = warp_base + r * 32 + lane;
-        if (i < a.n)
+        int key[8], slot[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
         {
-            int key, slot;
-            if (FIRST)
+            const int i = warp_base + (half * 8 + q) * 32 + lane;
+            key[q] = 0;
+            slot[q] = i;
+            if (i < a.n)
             {
-                key = key_in[i];
-                slot = i;
+                if (FIRST)
+                {
+                    key[q] = __ldg(key_in + i);
+                }
+                else
+                {
+                    const int2 p = __ldg(pair_in + i);
+                    key[q] = p.x;
+                    slot[q] = p.y;
+                }
             }
-            else
-            {
-                const int2 p = pair_in[i];
-                key = p.x;
-                slot = p.y;
-            }
-            const uint32_t digit = ((uint32_t)key >> a.shift) & a.mask;
+        }
+        uint32_t dest[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int r = half * 8 + q;
+            const uint32_t digit = ((uint32_t)key[q] >> a.shift) & a.mask;
             const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
-            const uint32_t dest = s_binoff[digit] + my_cnt[digit] + rk;
-            pair_out[dest] = make_int2(key, slot);
-#ifndef DOGM_ABLATE_NEXT_ATOMICS
-            if (a.next_table)
-#else
-            if (false)
-#endif
-            {
-                const uint32_t nd = ((uint32_t)key >> a.next_shift) & a.next_mask;
-                atomicAdd(&a.next_table[(size_t)(dest / kTileItems) * a.next_bins + nd], 1u);
-            }
+            dest[q] = __ldg(row + digit) + my_cnt[digit] + rk;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+        {
+            const int i = warp_base + (half * 8 + q) * 32 + lane;
+            if (i < a.n)
+                pair_out[dest[q]] = make_int2(key[q], slot[q]);
         }
     }
 }
@@ -1358,8 +1394,8 @@ int run_assignment(dogm_handle* h)
         }
         {
             LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
-            launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[p], h->tiles, bins, h->bin_tot[p],
-                           (uint4*)nullptr, (size_t)0);
+            launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[p], h->tiles, bins,
+                           (unsigned long long*)h->bin_base[p], ++h->scan_epoch[p]);
         }
         ScatterArgs a;
         a.key_in = h->key0;
@@ -1370,13 +1406,7 @@ int run_assignment(dogm_handle* h)
         a.mask = (uint32_t)(bins - 1);
         a.bins = bins;
         a.table = h->hist[p];
-        a.bin_tot = h->bin_tot[p];
-        const bool has_next = p + 1 < h->passes;
-        a.next_table = nullptr; // the next pass counts its own digits (k_pair_tile_hist)
-        a.next_shift = has_next ? h->digit_shift[p + 1] : 0;
-        a.next_mask = has_next ? (uint32_t)(h->digit_bins[p + 1] - 1) : 0u;
-        a.next_bins = has_next ? h->digit_bins[p + 1] : 0;
-        const size_t smem = (size_t)bins * sizeof(uint32_t) + (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
+        const size_t smem = (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
             LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
             if (p == 0)
@@ -1436,7 +1466,7 @@ int chain_blocks_per_sm()
 int configure_kernels()
 {
     const int max_bins = 1 << kMaxDigitBits;
-    const int smem = max_bins * (int)sizeof(uint32_t) + max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
+    const int smem = max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
     int e = (int)cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e)
         return e;
