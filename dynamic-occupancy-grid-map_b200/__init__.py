@@ -178,6 +178,7 @@ _SYMBOLS = [
     ("dogm_get_launch_count", C.c_uint64, [_P]),
     ("dogm_kernel_timing_enable", C.c_int, [_P, C.c_int]),
     ("dogm_trace_arm", C.c_int, [_P, C.c_int]),
+    ("dogm_debug_read", C.c_int, [_P, C.c_char_p, _P, C.c_size_t]),
     ("dogm_trace_read", C.c_int, [_P, C.POINTER(C.c_uint64), C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     ("dogm_kernel_timing_read", C.c_int, [_P, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int)]),
     ("dogm_timer_start", C.c_int, [_P]),
@@ -499,6 +500,10 @@ class DOGM:
         ms = C.c_float(0)
         _check(self._lib.dogm_timer_elapsed_ms(self._h, C.byref(ms)), "dogm_timer_elapsed_ms")
         return float(ms.value)
+
+    def debug_read(self, name: str, out: np.ndarray) -> np.ndarray:
+        _check(self._lib.dogm_debug_read(self._h, name.encode(), _ptr(out), out.nbytes), "dogm_debug_read")
+        return out
 
     def trace_arm(self, enable: bool = True) -> None:
         _check(self._lib.dogm_trace_arm(self._h, 1 if enable else 0), "dogm_trace_arm")

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 using namespace dogm_b200;
@@ -214,7 +215,10 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     e |= alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int));
     e |= alloc_zero((void**)&h->cdf, (N + B) * sizeof(double));
     e |= alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double));
-    e |= alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 1) * sizeof(double));
+    e |= alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 3) * sizeof(double));
+    e |= alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
+    if (!e)
+        e |= (int)cudaMemset(h->res_start, 0x7f, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
     e |= alloc_zero((void**)&h->chain_flags, (2 * (size_t)h->n_cdf_tiles + 2) * sizeof(uint32_t));
     {
         const char* sk = getenv("DOGM_B200_SKIP");
@@ -283,6 +287,7 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->tile_sum);
     cudaFree(h->tile_off);
     cudaFree(h->chain_flags);
+    cudaFree(h->res_start);
     if (h->trace_buf)
     {
         trace_bind_particles(nullptr);
@@ -909,6 +914,29 @@ static void drain_timed(dogm_handle* h)
         h->event_pool.push_back(t.e1);
     }
     h->timed.clear();
+}
+
+extern "C" int dogm_debug_read(dogm_handle* h, const char* name, void* out_host, size_t bytes)
+{
+    if (!h || !name || !out_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    const void* src = nullptr;
+    size_t have = 0;
+    if (!strcmp(name, "res_start"))
+    {
+        src = h->res_start;
+        have = (size_t)div_up(h->N > 0 ? h->N : 1, kBlock) * sizeof(int);
+    }
+    else if (!strcmp(name, "weight_total"))
+    {
+        src = &h->scal->weight_total;
+        have = sizeof(double);
+    }
+    if (!src || bytes > have)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    DOGM_CHECK(cudaMemcpy(out_host, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 extern "C" int dogm_trace_arm(dogm_handle* h, int enable)

@@ -231,6 +231,7 @@ struct dogm_handle
     double* cdf;      // N + B
     double* tile_sum; // per CDF tile
     double* tile_off; // prefix of the tile groups before (k_cdf_chain)
+    int* res_start;        // [ceil(N / 256)] CDF position of the first offset of every resampling CTA (k_cdf_chain -> k_resample)
     uint32_t* chain_flags; // [tiles] tile flags | [tiles + 1] group flags | ticket
     uint32_t chain_epoch, chain_ticket_base;
     int chain_capacity; // CTAs of k_cdf_chain the device holds at once

@@ -870,6 +870,12 @@ __device__ __forceinline__ float joint_entry(const CdfArgs& a, int i)
     return i < a.n ? a.bw[i - a.N] : 0.0f;
 }
 
+__device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_t slot, uint32_t cycle)
+{
+    const Philox4 p = philox4x32_10(slot, STAGE_RESAMPLE, cycle, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u01_half_open(p.x);
+}
+
 // One kernel, one pass: a tile is 4096 consecutive entries (warp w owns entries [512 w, 512 w + 512) and reads them in
 // 16 coalesced rounds, entry = 512 w + 32 r + lane, which stay in registers).  Tiles are handed out by an atomic
 // ticket, so every tile with a lower number is running or done when a CTA waits for it; a tile publishes its total,
@@ -891,7 +897,53 @@ struct ChainArgs
     uint32_t epoch;
     int tiles;
     double* total_out;
+    // resampling support: where the first offset of every block of 256 output slots falls in the CDF
+    int* res_start;        // [ceil(N / 256)] atomicMin targets, or null (tiles not co-resident / injected offsets)
+    double* total_word;    // published total (the last tile's prefix + sum)
+    int res_blocks;
+    int systematic;        // the offsets share one fraction u0 (otherwise the block boundary itself is used, u = 0)
+    int noise_injected;
+    const float* resample_u;
+    uint64_t seed;
+    uint32_t cycle;
 };
+
+// the k-th block of 256 output slots starts at this offset (same expression as resample_offset for slot 256 k)
+__device__ __forceinline__ double res_boundary(long long k, double u, double step)
+{
+    return ((double)(k * 256) + u) * step;
+}
+
+// smallest k with res_boundary(k) > x (res_blocks if none)
+__device__ __noinline__ long long first_block_behind(double x, double step, double u, double inv, int res_blocks)
+{
+    if (!(x < __longlong_as_double(0x7ff0000000000000ll)))
+        return res_blocks;
+    long long k = (long long)ceil(x * inv - u * (1.0 / 256.0));
+    k = k < 0 ? 0 : (k > res_blocks ? res_blocks : k);
+    while (k < res_blocks && res_boundary(k, u, step) <= x)
+        k++;
+    while (k > 0 && res_boundary(k - 1, u, step) > x)
+        k--;
+    return k;
+}
+
+// entry j covers the offsets (prev, cur]: every block whose first offset lies there has lower_bound j
+__device__ __noinline__ void claim_block_starts(int* res_start, int res_blocks, double prev, double cur, double step,
+                                                   double u, double inv, int j)
+{
+    if (!(cur > prev))
+        return;
+    long long k = (long long)floor(cur * inv - u * (1.0 / 256.0));
+    k = k < res_blocks ? k : res_blocks - 1;
+    k = k < 0 ? 0 : k;
+    while (k + 1 < res_blocks && res_boundary(k + 1, u, step) <= cur)
+        k++;
+    while (k >= 0 && res_boundary(k, u, step) > cur)
+        k--;
+    for (; k >= 0 && res_boundary(k, u, step) > prev; k--)
+        atomicMin(res_start + k, j);
+}
 
 // A published sum travels as one 64-bit word: the sums are non-negative, so the sign bit carries the parity of the
 // launch epoch.  Every launch publishes every word exactly once, hence a word whose sign bit differs from the epoch's
@@ -921,6 +973,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
     pdl_prologue(K_CDF_CHAIN * 2);
     __shared__ double s_w[kWarpsPerBlock];
     __shared__ double s_red[kWarpsPerBlock];
+    __shared__ double s_total;
     __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;)
@@ -933,18 +986,18 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         if (t >= (uint32_t)a.tiles)
             return;
         const int w0 = (int)t * kCdfTile + warp * kChainWarpSpan;
-        // the entries are fetched in two batches of 8: all (cell, weight) loads of a batch are issued before the
+        // the entries are fetched in four batches of 4: all (cell, weight) loads of a batch are issued before the
         // first dependent coefficient load, all coefficient loads before the first use
         float e[kChainRounds];
 #pragma unroll
-        for (int half = 0; half < 2; half++)
+        for (int part = 0; part < 4; part++)
         {
-            int cell[8];
-            float w[8];
+            int cell[4];
+            float w[4];
 #pragma unroll
-            for (int r = 0; r < 8; r++)
+            for (int r = 0; r < 4; r++)
             {
-                const int i = w0 + (half * 8 + r) * 32 + lane;
+                const int i = w0 + (part * 4 + r) * 32 + lane;
                 cell[r] = -1;
                 if (FUSED)
                 {
@@ -959,19 +1012,19 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
             }
             if (FUSED)
             {
-                float4 cf[8];
+                float4 cf[4];
 #pragma unroll
-                for (int r = 0; r < 8; r++)
+                for (int r = 0; r < 4; r++)
                     cf[r] = cell[r] >= 0 ? __ldg(a.c.coef + cell[r]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-                    e[half * 8 + r] = cell[r] >= 0 ? persistent_weight(cf[r], w[r]) : w[r];
+                for (int r = 0; r < 4; r++)
+                    e[part * 4 + r] = cell[r] >= 0 ? persistent_weight(cf[r], w[r]) : w[r];
             }
             else
             {
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-                    e[half * 8 + r] = w[r];
+                for (int r = 0; r < 4; r++)
+                    e[part * 4 + r] = w[r];
             }
         }
         // the warp's total, accumulated exactly as the scan below accumulates its carry
@@ -1020,6 +1073,13 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         { // last tile of its group: publish the prefix the next group starts from
             publish_f64(a.group_base + group + 1, off + tot, a.epoch);
         }
+        if (threadIdx.x == 0 && t + 1 == (uint32_t)a.tiles)
+        { // last tile: the total of the joint weights
+            *a.total_out = off + tot;
+            if (a.res_start)
+                publish_f64(a.total_word, off + tot, a.epoch);
+        }
+        const double tile_off = off;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; w++)
             if (w < warp)
@@ -1037,16 +1097,77 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                     v += u;
             }
             const int i = w0 + r * 32 + lane;
+            const double val = off + (carry + v);
             if (i < a.c.n)
             {
-                const double val = off + (carry + v);
                 __stcs(a.cdf + i, val);
                 if (FUSED && i < a.c.N)
                     a.c.wa_out[i] = e[r];
-                if (i == a.c.n - 1)
-                    *a.total_out = val;
             }
             carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        // third phase (resampling support): which CDF entry is the lower_bound of the first offset of every block of 256
+        // output slots.  Needs the total, which the last tile has published long before this tile finished writing.
+        if (a.res_start)
+        {
+            if (threadIdx.x == 0)
+                s_total = await_f64(a.total_word, a.epoch);
+            __syncthreads();
+            const double total = s_total;
+#ifdef DOGM_AB_NO_PHASE3
+            if (total < -1.0)
+#else
+            if (total > 0.0)
+#endif
+            {
+                const double step = total / (double)a.c.N;
+                const double inv = 1.0 / (256.0 * step);
+                double u = 0.0;
+                if (a.systematic)
+                    u = (double)(a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle));
+                const double kInfD = __longlong_as_double(0x7ff0000000000000ll);
+                // the stored value of the entry before the warp's first: exact inside a tile; the first entry of a
+                // tile only knows it to a rounding, so it reaches back a little (a claim too many is harmless:
+                // atomicMin keeps the true one, which the tile before makes, and k_resample verifies what it reads)
+                double last = off;
+                if (w0 == 0)
+                    last = -1.0;
+                else if (warp == 0)
+                    last = tile_off - 1e-9 * fabs(tile_off);
+                // k_next: the first block whose boundary lies behind `last`; a round of 32 entries is looked at closely
+                // only when that boundary is not behind its last entry (one comparison per round otherwise)
+                long long k_next = first_block_behind(last, step, u, inv, a.res_blocks);
+                double next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
+                for (int half = 0; half < 2; half++)
+                {
+                    double vals[8]; // the tile's own entries, read back in batches (all loads of a batch in flight together)
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                    {
+                        const int i = w0 + (half * 8 + q) * 32 + lane;
+                        vals[q] = i < a.c.n ? __ldcg(a.cdf + i) : kInfD;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                    {
+                        const int r = half * 8 + q;
+                        const int i = w0 + r * 32 + lane;
+                        const double val = vals[q];
+                        const double hi = __shfl_sync(0xffffffffu, val, 31);
+                        if (w0 + r * 32 < a.c.n && next_off <= hi)
+                        {
+                            double prev = __shfl_up_sync(0xffffffffu, val, 1);
+                            if (lane == 0)
+                                prev = last;
+                            if (i < a.c.n)
+                                claim_block_starts(a.res_start, a.res_blocks, prev, val, step, u, inv, i);
+                            k_next = first_block_behind(hi, step, u, inv, a.res_blocks);
+                            next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
+                        }
+                        last = hi;
+                    }
+                }
+            }
         }
     }
 }
@@ -1114,18 +1235,13 @@ struct ResampleArgs
     ParticleSet dst;   // next population
     int* ancestors;
     const DeviceScalars* scal;
+    int* res_start;     // block starts claimed by k_cdf_chain (consumed and reset here), or null
     int mode;           // DOGM_RESAMPLE_*
     int noise_injected; // offsets come from resample_u
     const float* resample_u;
     uint64_t seed;
     uint32_t cycle;
 };
-
-__device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_t slot, uint32_t cycle)
-{
-    const Philox4 p = philox4x32_10(slot, STAGE_RESAMPLE, cycle, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return u01_half_open(p.x);
-}
 
 // One CTA resamples 256 consecutive outputs.  Their offsets ascend, so all ancestors lie in a short window of the
 // CDF behind the ancestor of the CTA's first offset: thread 0 finds that one by binary search in global memory,
@@ -1167,6 +1283,25 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     __shared__ float s_u0, s_jm;
     const int i = blockIdx.x * kBlock + threadIdx.x;
     const bool valid = i < a.N;
+    // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
+    // res_start: every thread reads it and fetches its two window entries straight away, while thread 0 prepares the
+    // scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
+    int lo0 = 0x7f7f7f7f;
+    if (a.res_start)
+        lo0 = __ldcg(a.res_start + blockIdx.x);
+    const bool claimed = lo0 >= 0 && lo0 < a.n_cdf;
+    const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+    double w0 = kInf, w1 = kInf, before = -1.0;
+    if (claimed)
+    {
+        const int j0 = lo0 + (int)threadIdx.x, j1 = j0 + kBlock;
+        if (j0 < a.n_cdf)
+            w0 = __ldcg(a.cdf + j0);
+        if (j1 < a.n_cdf)
+            w1 = __ldcg(a.cdf + j1);
+        if (threadIdx.x == 0 && lo0 > 0)
+            before = __ldcg(a.cdf + lo0 - 1);
+    }
     if (threadIdx.x == 0)
     {
         const double total = a.scal->weight_total;
@@ -1178,27 +1313,42 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         s_step = step;
         s_u0 = u0;
         s_jm = jm;
-        s_first = resample_offset(a, blockIdx.x * kBlock, jm, u0, step); // the CTA's first (smallest) offset
+        // a lower limit of the CTA's offsets: its first offset (systematic, injected) or the block boundary (stratified)
+        s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)(blockIdx.x * kBlock) * step
+                                                     : resample_offset(a, blockIdx.x * kBlock, jm, u0, step);
     }
+    s_cdf[threadIdx.x] = w0;
+    s_cdf[threadIdx.x + kBlock] = w1;
     __syncthreads();
     const float joint_max = s_jm;
     const double r_first = s_first;
     const double r = resample_offset(a, valid ? i : a.N - 1, joint_max, s_u0, s_step);
-    // lower_bound of the first offset by a 256-ary search: every thread probes one CDF entry per round
-    int lo0 = 0, hi0 = a.n_cdf;
-    while (lo0 < hi0)
+    bool ok = claimed;
+    if (threadIdx.x == 0 && claimed)
     {
-        const int stride = (hi0 - lo0 + kBlock - 1) / kBlock;
-        const int q = lo0 + threadIdx.x * stride;
-        const int cnt = __syncthreads_count(q < hi0 && a.cdf[q] < r_first); // monotone: the first cnt probes are below
-        const int nlo = cnt > 0 ? lo0 + (cnt - 1) * stride + 1 : lo0;
-        const long long qn = (long long)lo0 + (long long)cnt * stride;
-        hi0 = qn < hi0 ? (int)qn : hi0;
-        lo0 = nlo;
+        ok = (lo0 == 0 || before < r_first) && w0 >= r_first;
+        a.res_start[blockIdx.x] = 0x7f7f7f7f; // unclaimed again for the next cycle
     }
-    for (int j = threadIdx.x; j < kResWindow; j += kBlock)
-        s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
-    __syncthreads();
+    const bool have = __syncthreads_and(ok);
+    if (!have)
+    { // no valid claim: 256-ary search, every thread probes one CDF entry per round
+        lo0 = 0;
+        int hi0 = a.n_cdf;
+        while (lo0 < hi0)
+        {
+            const int stride = (hi0 - lo0 + kBlock - 1) / kBlock;
+            const int q = lo0 + threadIdx.x * stride;
+            const int cnt = __syncthreads_count(q < hi0 && a.cdf[q] < r_first); // monotone: the first cnt probes are below
+            const int nlo = cnt > 0 ? lo0 + (cnt - 1) * stride + 1 : lo0;
+            const long long qn = (long long)lo0 + (long long)cnt * stride;
+            hi0 = qn < hi0 ? (int)qn : hi0;
+            lo0 = nlo;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < kResWindow; j += kBlock)
+            s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
+        __syncthreads();
+    }
     if (!valid)
         return;
     int anc;
@@ -1501,6 +1651,18 @@ int run_resampling(dogm_handle* h)
         ch.epoch = ++h->chain_epoch;
         ch.tiles = h->n_cdf_tiles;
         ch.total_out = &h->scal->weight_total;
+        const bool resident = h->n_cdf_tiles <= h->chain_capacity;
+        ch.res_start = (resident && h->opts.resample_mode != DOGM_RESAMPLE_INJECTED) ? h->res_start : nullptr;
+#ifdef DOGM_AB_NO_CLAIMS
+        ch.res_start = nullptr;
+#endif
+        ch.total_word = h->tile_off + (h->n_cdf_tiles / kChainGroup + 1);
+        ch.res_blocks = div_up(N, kBlock);
+        ch.systematic = h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC ? 1 : 0;
+        ch.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
+        ch.resample_u = h->resample_u;
+        ch.seed = h->opts.seed;
+        ch.cycle = h->cycle;
         const int grid = h->n_cdf_tiles < h->chain_capacity ? h->n_cdf_tiles : h->chain_capacity;
         h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
         LaunchScope ls(h, K_CDF_CHAIN, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
@@ -1520,6 +1682,7 @@ int run_resampling(dogm_handle* h)
     a.dst = h->pa;
     a.ancestors = h->ancestors;
     a.scal = h->scal;
+    a.res_start = h->opts.resample_mode != DOGM_RESAMPLE_INJECTED ? h->res_start : nullptr;
     a.mode = h->opts.resample_mode;
     a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
     a.resample_u = h->resample_u;

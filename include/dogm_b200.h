@@ -301,6 +301,8 @@ int dogm_kernel_timing_enable(dogm_handle* h, int enable);
  * names, "#2" = second pass of the same kernel) of the launches since the last read and re-arms.  The difference of
  * two consecutive stamps is the earlier kernel's share of the cycle.  One handle per process at a time. */
 int dogm_trace_arm(dogm_handle* h, int enable);
+/* Developer read-out of an internal buffer by name ("res_start", "weight_total"); synchronises. */
+int dogm_debug_read(dogm_handle* h, const char* name, void* out_host, size_t bytes);
 int dogm_trace_read(dogm_handle* h, uint64_t* out_start_ns, char* out_names, int capacity, int* out_count);
 int dogm_kernel_timing_read(dogm_handle* h, dogm_kernel_time* out, int capacity, int* out_count);
 
