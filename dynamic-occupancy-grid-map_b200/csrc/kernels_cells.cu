@@ -41,7 +41,10 @@ struct CellArgs
     int shift_active, x_move, y_move;
 };
 
-__global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
+#ifndef DOGM_CELL_MINBLOCKS
+#define DOGM_CELL_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(kCellBlock, DOGM_CELL_MINBLOCKS) k_cell(CellArgs a)
 {
     pdl_prologue(K_CELL * 2);
     __shared__ double s_scan[kWarpsPerBlock];
@@ -56,30 +59,9 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
     dogm_dynamic_cell dyn_rec;
     if (valid)
     {
+        // all loads that do not depend on the cell being occupied go out together, ahead of the first store
         const int start = a.cell_start[c];
-        if (start >= 0)
-            a.cell_start[c] = -1;
-        const bool occupied = start >= 0;
-        int end = -1;
-        CellSums cs;
-        cs.s0 = cs.s1 = cs.s2 = cs.s3 = cs.s4 = cs.s5 = 0.0f;
-        if (occupied)
-        {
-            end = a.cell_end[c];
-            const float4* sp = reinterpret_cast<const float4*>(a.sums + c);
-            const float4 lo = sp[0], hi = sp[1];
-            cs.s0 = lo.x;
-            cs.s1 = lo.y;
-            cs.s2 = lo.z;
-            cs.s3 = lo.w;
-            cs.s4 = hi.x;
-            cs.s5 = hi.y;
-        }
-        const float4 zq = *reinterpret_cast<const float4*>(a.meas + c);
-        if (a.meas_copy)
-            *reinterpret_cast<float4*>(a.meas_copy + c) = zq;
-        const float z_free = zq.x, z_occ = zq.y, lik = zq.z, p_A = zq.w;
-
+        const float4 zq = __ldg(reinterpret_cast<const float4*>(a.meas + c));
         // ego-motion compensation of the grid (updatePose dogm.cu:175-193, moveMapKernel
         // ego_motion_compensation.cu:25-43): of all cell fields only free_mass survives into the next cycle,
         // so the shift is a shifted read of the previous free masses; vacated cells read 0 (dogm.cu:185)
@@ -88,12 +70,32 @@ __global__ void __launch_bounds__(kCellBlock) k_cell(CellArgs a)
         {
             const int x = c % a.gs, y = c / a.gs;
             const int nx = x + a.x_move, ny = y + a.y_move;
-            free_prev = (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs) ? a.free_cur[nx + a.gs * ny] : 0.0f;
+            free_prev = (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs) ? __ldg(a.free_cur + nx + a.gs * ny) : 0.0f;
         }
         else
         {
-            free_prev = a.free_cur[c];
+            free_prev = __ldg(a.free_cur + c);
         }
+        const bool occupied = start >= 0;
+        int end = -1;
+        CellSums cs;
+        cs.s0 = cs.s1 = cs.s2 = cs.s3 = cs.s4 = cs.s5 = 0.0f;
+        if (occupied)
+        {
+            end = __ldg(a.cell_end + c);
+            const float4* sp = reinterpret_cast<const float4*>(a.sums + c);
+            const float4 lo = __ldg(sp), hi = __ldg(sp + 1);
+            cs.s0 = lo.x;
+            cs.s1 = lo.y;
+            cs.s2 = lo.z;
+            cs.s3 = lo.w;
+            cs.s4 = hi.x;
+            cs.s5 = hi.y;
+            a.cell_start[c] = -1;
+        }
+        if (a.meas_copy)
+            *reinterpret_cast<float4*>(a.meas_copy + c) = zq;
+        const float z_free = zq.x, z_occ = zq.y, lik = zq.z, p_A = zq.w;
 
         // gridCellPredictionUpdateKernel, mass_update.cu:61-93
         float m_occ_pred = occupied ? cs.s0 : 0.0f;

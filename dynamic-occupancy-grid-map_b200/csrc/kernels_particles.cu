@@ -604,7 +604,10 @@ constexpr int kSegPerLane = kSegChunk / 32; // 8 consecutive sorted positions pe
 // joined across lanes by ONE segmented warp scan per 256 particles.  Pieces that cross the chunk border go to the
 // lead / trail records of the chunk and are joined by k_segfix.  Fixed order: serial inside a lane, Kogge-Stone
 // across lanes, chunk order across chunks.
-__global__ void __launch_bounds__(kBlock) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
+#ifndef DOGM_SEGSUM_MINBLOCKS
+#define DOGM_SEGSUM_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kBlock, DOGM_SEGSUM_MINBLOCKS) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
                                                    int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
                                                    SegPiece* trail, int* flags, float* __restrict__ sw)
 {
