@@ -371,6 +371,22 @@ def run_ours(args, dist):
         cycle_resident(True)
     ktimes = d.kernel_timing_read()
     d.kernel_timing_enable(False)
+    # the same cycle without events between the kernels (they break the programmatic launch chain): start stamps taken
+    # by the kernels themselves; the gap between two stamps is the earlier kernel's share of the free-running cycle
+    d.trace_arm(True)
+    gaps, order = {}, []
+    for _ in range(9):
+        cycle_resident(True)
+        d.synchronize()
+        d.trace_read()
+        cycle_resident(True)
+        d.extract_dynamic_cells(0.7, 4.0, capacity=16)  # one unchained kernel: its stamp closes the last gap
+        tr = d.trace_read()
+        order = [k for k, _ in tr]
+        for (k0, t0), (_, t1) in zip(tr[:-1], tr[1:]):
+            gaps.setdefault(k0, []).append((t1 - t0) * 1e-3)
+    d.trace_arm(False)
+    timeline_us = {k: float(np.median(gaps[k])) for k in order[:-1]}
     kernels = {k: v for k, v in ktimes.items() if k not in ("memset", "k_misc")}
     sum_ms = sum(v["total_ms"] for v in ktimes.values())
     peak, peak_src = measured_peak()
@@ -398,6 +414,9 @@ def run_ours(args, dist):
             "formula": "240*N + 37*B + 308*C (SURVEY.md 8d, shifting cycle)",
         },
         "kernels_ms_per_cycle": {k: v["total_ms"] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["total_ms"])},
+        "timeline_us": timeline_us,
+        "timeline_note": "start-to-start gaps of the chained kernels inside one free-running cycle (dogm_trace_*); "
+                         "kernels_ms_per_cycle brackets every launch with CUDA events, which serialises the chain",
     }
 
     result = {

@@ -36,7 +36,8 @@ def main():
         x, y = bench.pose_at(step)
         d.update_grid(ptr, float(x), float(y), 0.0, bench.DT, device=True)
         step += 1
-    skip = d.launch_count() + args.warm  # + one k_meas_grid per generate_grid (not counted by the DOGM handle)
+    # generate_grid launches k_meas_polar + k_meas_apply per call and k_meas_geom once (not counted by the DOGM handle)
+    skip = d.launch_count() + 2 * args.warm + 1
     if args.print_skip:
         print(skip)
         return
@@ -45,7 +46,7 @@ def main():
         x, y = bench.pose_at(step)
         d.update_grid(ptr, float(x), float(y), 0.0, bench.DT, device=True)
         step += 1
-    print("profiled cycles done; launches before them:", skip, "per cycle:", (d.launch_count() - (skip - args.warm)) // args.cycles)
+    print("profiled cycles done; launches before them:", skip, "per cycle:", (d.launch_count() - (skip - 2 * args.warm - 1)) // args.cycles)
 
 
 if __name__ == "__main__":
