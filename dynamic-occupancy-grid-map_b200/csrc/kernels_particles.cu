@@ -970,6 +970,20 @@ __device__ __forceinline__ double await_f64(const double* p, uint32_t epoch)
     return __longlong_as_double((long long)(bits & 0x7fffffffffffffffull));
 }
 
+// as await_f64, but gives up after `polls` attempts (about 50 ns each) and returns -1
+__device__ __forceinline__ double await_f64_bounded(const double* p, uint32_t epoch, int polls)
+{
+    for (int it = 0; it < polls; it++)
+    {
+        unsigned long long bits;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+        if ((uint32_t)(bits >> 63) == (epoch & 1u))
+            return __longlong_as_double((long long)(bits & 0x7fffffffffffffffull));
+        __nanosleep(40);
+    }
+    return -1.0;
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
 {
@@ -1113,15 +1127,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         // output slots.  Needs the total, which the last tile has published long before this tile finished writing.
         if (a.res_start)
         {
+            // The wait is bounded: a tile that holds its SM slot for ever while later tiles of this or another stream's
+            // launch wait for one could dead-lock the device.  Without the total the tile just makes no claims
+            // (k_resample searches for the blocks nobody claimed).
             if (threadIdx.x == 0)
-                s_total = await_f64(a.total_word, a.epoch);
+                s_total = await_f64_bounded(a.total_word, a.epoch, 4096);
             __syncthreads();
             const double total = s_total;
-#ifdef DOGM_AB_NO_PHASE3
-            if (total < -1.0)
-#else
             if (total > 0.0)
-#endif
             {
                 const double step = total / (double)a.c.N;
                 const double inv = 1.0 / (256.0 * step);
