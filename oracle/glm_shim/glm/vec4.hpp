@@ -16,12 +16,34 @@
 
 namespace glm
 {
-struct vec2
+struct vec2 // used by the demo's simulator and evaluator only (host code)
 {
     float x, y;
     vec2() = default;
-    GLM_SHIM_FN vec2(float a, float b) : x(a), y(b) {}
+    template <typename A, typename B>
+    GLM_SHIM_FN vec2(A a, B b) : x(static_cast<float>(a)), y(static_cast<float>(b))
+    {
+    }
+    GLM_SHIM_FN float& operator[](int i) { return (&x)[i]; }
+    GLM_SHIM_FN const float& operator[](int i) const { return (&x)[i]; }
+    GLM_SHIM_FN vec2& operator+=(const vec2& o)
+    {
+        x += o.x;
+        y += o.y;
+        return *this;
+    }
+    GLM_SHIM_FN vec2& operator-=(const vec2& o)
+    {
+        x -= o.x;
+        y -= o.y;
+        return *this;
+    }
 };
+GLM_SHIM_FN vec2 operator+(const vec2& a, const vec2& b) { return vec2(a.x + b.x, a.y + b.y); }
+GLM_SHIM_FN vec2 operator-(const vec2& a, const vec2& b) { return vec2(a.x - b.x, a.y - b.y); }
+GLM_SHIM_FN vec2 operator*(const vec2& a, float s) { return vec2(a.x * s, a.y * s); }
+GLM_SHIM_FN vec2 operator*(float s, const vec2& a) { return vec2(s * a.x, s * a.y); }
+GLM_SHIM_FN bool operator==(const vec2& a, const vec2& b) { return a.x == b.x && a.y == b.y; }
 
 struct vec4
 {
