@@ -2,9 +2,14 @@
 // of include/dogm/dogm.h (plain asserts: gtest is not in this image).  Built and run by tests/test_cpp_facade.py.
 #include "dogm/dogm.h"
 #include "mapping/laser_to_meas_grid.h"
+#include "metrics.h"
+#include "precision_evaluator.h"
+#include "simulator.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <memory>
 #include <vector>
 
 #define CHECK(cond)                                                                                                    \
@@ -135,6 +140,77 @@ static int test_demo_flow()
     return 0;
 }
 
+static int test_demo_main()
+{ // demo/main.cpp:22-103 with the reference's class names: Simulator -> LaserMeasurementGrid -> DOGM -> dynamic cells ->
+  // PrecisionEvaluator (MAE, RMSE); computeCellsWithVelocity (OpenCV) is replaced by DOGM::extractDynamicCells
+    dogm::DOGM::Params grid_params;
+    grid_params.size = 50.0f;
+    grid_params.resolution = 0.2f;
+    grid_params.particle_count = 3 * static_cast<int>(10e4);
+    grid_params.new_born_particle_count = 3 * static_cast<int>(10e3);
+    grid_params.persistence_prob = 0.99f;
+    grid_params.stddev_process_noise_position = 0.1f;
+    grid_params.stddev_process_noise_velocity = 1.0f;
+    grid_params.birth_prob = 0.02f;
+    grid_params.stddev_velocity = 30.0f;
+    grid_params.init_max_velocity = 30.0f;
+    grid_params.freespace_discount = 0.01f;
+
+    LaserMeasurementGrid::Params laser_params;
+    laser_params.fov = 120.0f;
+    laser_params.max_range = 50.0f;
+    laser_params.resolution = grid_params.resolution;
+    laser_params.stddev_range = 0.5f;
+    LaserMeasurementGrid grid_generator(laser_params, grid_params.size, grid_params.resolution);
+
+    const int sensor_horizontal_scan_points = 100;
+    const int num_simulation_steps = 14;
+    const float simulation_step_period = 0.1f;
+    const glm::vec2 ego_velocity{0.0f, 4.0f};
+    const float minimum_occupancy_threshold = 0.7f;
+    const float minimum_velocity_threshold = 4.0f;
+
+    dogm::DOGM grid_map(grid_params);
+    Simulator simulator(sensor_horizontal_scan_points, laser_params.fov, grid_params.size, ego_velocity);
+    simulator.addVehicle(Vehicle(3.5, glm::vec2(10, 30), glm::vec2(15, 0)));
+    simulator.addVehicle(Vehicle(3.0, glm::vec2(10, 20), glm::vec2(0, 5)));
+    simulator.addVehicle(Vehicle(4.0, glm::vec2(35, 35), glm::vec2(0, -10)));
+    simulator.addVehicle(Vehicle(1.8, glm::vec2(45, 15), glm::vec2(0, 0)));
+
+    SimulationData sim_data = simulator.update(num_simulation_steps, simulation_step_period);
+    PrecisionEvaluator precision_evaluator{sim_data, grid_params.resolution, grid_params.size};
+    precision_evaluator.registerMetric("Mean absolute error (MAE)", std::unique_ptr<Metric>(new MAE()));
+    precision_evaluator.registerMetric("Root mean squared error (RMSE)", std::unique_ptr<Metric>(new RMSE()));
+
+    grid_map.setDynamicCellFilter(minimum_occupancy_threshold, minimum_velocity_threshold);
+    for (int step = 0; step < num_simulation_steps; ++step)
+    {
+        dogm::MeasurementCell* meas_grid = grid_generator.generateGrid(sim_data[step].measurements);
+        grid_map.updateGrid(meas_grid, sim_data[step].ego_pose.x, sim_data[step].ego_pose.y, 0.0f, simulation_step_period, true);
+        CHECK(grid_map.last_error == 0);
+        std::vector<dogm_dynamic_cell> dynamic = grid_map.extractDynamicCells(minimum_occupancy_threshold, minimum_velocity_threshold);
+        std::sort(dynamic.begin(), dynamic.end(), [](const dogm_dynamic_cell& a, const dogm_dynamic_cell& b) { return a.cell_idx < b.cell_idx; });
+        std::vector<Point<dogm::GridCell>> cells_with_velocity;
+        for (const dogm_dynamic_cell& c : dynamic)
+        {
+            Point<dogm::GridCell> point;
+            point.x = static_cast<float>(c.cell_idx % grid_map.getGridSize());
+            point.y = static_cast<float>(c.cell_idx / grid_map.getGridSize());
+            point.data = dogm::GridCell();
+            point.data.mean_x_vel = c.mean_x_vel;
+            point.data.mean_y_vel = c.mean_y_vel;
+            point.cluster_id = UNCLASSIFIED;
+            cells_with_velocity.push_back(point);
+        }
+        precision_evaluator.evaluateAndStoreStep(step, cells_with_velocity);
+    }
+    precision_evaluator.printSummary();
+    const PointWithVelocity mae = precision_evaluator.errorStatistic("Mean absolute error (MAE)");
+    CHECK(precision_evaluator.detections("Mean absolute error (MAE)") >= 28);
+    CHECK(mae.x < 1.5f && mae.y < 1.5f && mae.v_x < 4.0f && mae.v_y < 4.0f);
+    return 0;
+}
+
 int main()
 {
     if (dogm_device_count() < 1)
@@ -145,6 +221,7 @@ int main()
     int rc = test_ego_motion_compensation();
     rc |= test_predict();
     rc |= test_demo_flow();
+    rc |= test_demo_main();
     std::printf(rc == 0 ? "dogm_spec_b200: all passed\n" : "dogm_spec_b200: FAILED\n");
     return rc;
 }
