@@ -887,6 +887,7 @@ __device__ __forceinline__ float resample_fraction_philox(uint64_t seed, uint32_
 // addition is fixed by the tile number alone, so the CDF is identical from run to run.
 constexpr int kChainRounds = kCdfTile / kBlock; // 16
 constexpr int kChainWarpSpan = kCdfTile / kWarpsPerBlock; // 512
+constexpr int kQuadRounds = kChainWarpSpan / 128;          // 4 rounds of 32 lanes x 4 consecutive entries
 constexpr int kChainGroup = 256;                // tiles per group
 
 struct ChainArgs
@@ -1003,61 +1004,97 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         if (t >= (uint32_t)a.tiles)
             return;
         const int w0 = (int)t * kCdfTile + warp * kChainWarpSpan;
-        // the entries are fetched in four batches of 4: all (cell, weight) loads of a batch are issued before the
-        // first dependent coefficient load, all coefficient loads before the first use
+        // Entry layout: in round r (0..3) lane l holds the four consecutive entries w0 + 128 r + 4 l + (0..3), so every
+        // load and store is a 16-byte vector and the prefix needs one warp scan per 128 entries (the four entries of a
+        // lane are chained serially).  Two rounds are fetched per batch: all (cell, weight) loads of a batch are issued
+        // before the first dependent coefficient load, all coefficient loads before the first use.
         float e[kChainRounds];
 #pragma unroll
-        for (int part = 0; part < 4; part++)
+        for (int half = 0; half < 2; half++)
         {
-            int cell[4];
-            float w[4];
+            int cell[8];
+            float w[8];
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int rr = 0; rr < 2; rr++)
             {
-                const int i = w0 + (part * 4 + r) * 32 + lane;
-                cell[r] = -1;
-                if (FUSED)
+                const int i = w0 + (half * 2 + rr) * 128 + lane * 4;
+                int* cl = cell + rr * 4;
+                float* ww = w + rr * 4;
+                if (i + 3 < a.c.N)
                 {
-                    if (i < a.c.N)
-                        cell[r] = __ldg(&a.c.spair[i].x);
-                    w[r] = i < a.c.N ? __ldg(a.c.sw + i) : (i < a.c.n ? __ldg(a.c.bw + (i - a.c.N)) : 0.0f);
+                    if (FUSED)
+                    {
+                        const int4* pp = reinterpret_cast<const int4*>(a.c.spair + i);
+                        const int4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+                        const float4 sv = __ldg(reinterpret_cast<const float4*>(a.c.sw + i));
+                        cl[0] = p0.x, cl[1] = p0.z, cl[2] = p1.x, cl[3] = p1.z;
+                        ww[0] = sv.x, ww[1] = sv.y, ww[2] = sv.z, ww[3] = sv.w;
+                    }
+                    else
+                    {
+                        const float4 sv = *reinterpret_cast<const float4*>(a.c.wa + i);
+                        cl[0] = cl[1] = cl[2] = cl[3] = -1;
+                        ww[0] = sv.x, ww[1] = sv.y, ww[2] = sv.z, ww[3] = sv.w;
+                    }
                 }
                 else
                 {
-                    w[r] = i < a.c.N ? a.c.wa[i] : (i < a.c.n ? __ldg(a.c.bw + (i - a.c.N)) : 0.0f);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                    {
+                        const int k = i + q;
+                        cl[q] = -1;
+                        if (FUSED)
+                        {
+                            if (k < a.c.N)
+                                cl[q] = __ldg(&a.c.spair[k].x);
+                            ww[q] = k < a.c.N ? __ldg(a.c.sw + k) : (k < a.c.n ? __ldg(a.c.bw + (k - a.c.N)) : 0.0f);
+                        }
+                        else
+                        {
+                            ww[q] = k < a.c.N ? a.c.wa[k] : (k < a.c.n ? __ldg(a.c.bw + (k - a.c.N)) : 0.0f);
+                        }
+                    }
                 }
             }
             if (FUSED)
             {
-                float4 cf[4];
+                float4 cf[8];
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    cf[r] = cell[r] >= 0 ? __ldg(a.c.coef + cell[r]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int k = 0; k < 8; k++)
+                    cf[k] = cell[k] >= 0 ? __ldg(a.c.coef + cell[k]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    e[part * 4 + r] = cell[r] >= 0 ? persistent_weight(cf[r], w[r]) : w[r];
+                for (int k = 0; k < 8; k++)
+                    e[half * 8 + k] = cell[k] >= 0 ? persistent_weight(cf[k], w[k]) : w[k];
             }
             else
             {
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    e[part * 4 + r] = w[r];
+                for (int k = 0; k < 8; k++)
+                    e[half * 8 + k] = w[k];
             }
         }
-        // the warp's total, accumulated exactly as the scan below accumulates its carry
+        // per round: the prefix in front of this lane's four entries (one warp scan of the lane totals), kept for the
+        // write phase; the warp's total is the running carry
+        double base[kQuadRounds];
         double carry = 0.0;
 #pragma unroll
-        for (int r = 0; r < kChainRounds; r++)
+        for (int r = 0; r < kQuadRounds; r++)
         {
-            double v = (double)e[r];
+            const double lane_total = (((double)e[4 * r] + (double)e[4 * r + 1]) + (double)e[4 * r + 2]) + (double)e[4 * r + 3];
+            double incl = lane_total;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
             {
-                const double u = __shfl_up_sync(0xffffffffu, v, d);
+                const double u = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d)
-                    v += u;
+                    incl += u;
             }
-            carry += __shfl_sync(0xffffffffu, v, 31);
+            double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0)
+                excl = 0.0;
+            base[r] = carry + excl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
         if (lane == 0)
             s_w[warp] = carry;
@@ -1096,32 +1133,44 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
             if (a.res_start)
                 publish_f64(a.total_word, off + tot, a.epoch);
         }
-        const double tile_off = off;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; w++)
             if (w < warp)
                 off += s_w[w];
-        carry = 0.0;
 #pragma unroll
-        for (int r = 0; r < kChainRounds; r++)
+        for (int r = 0; r < kQuadRounds; r++)
         {
-            double v = (double)e[r];
+            const int i = w0 + r * 128 + lane * 4;
+            const double s0 = (double)e[4 * r], s1 = s0 + (double)e[4 * r + 1], s2 = s1 + (double)e[4 * r + 2],
+                         s3 = s2 + (double)e[4 * r + 3];
+            const double v0 = off + (base[r] + s0), v1 = off + (base[r] + s1), v2 = off + (base[r] + s2), v3 = off + (base[r] + s3);
+            if (i + 3 < a.c.n)
+            {
+                double2* out = reinterpret_cast<double2*>(a.cdf + i);
+                __stcs(out, make_double2(v0, v1));
+                __stcs(out + 1, make_double2(v2, v3));
+            }
+            else
+            {
+                if (i < a.c.n)
+                    __stcs(a.cdf + i, v0);
+                if (i + 1 < a.c.n)
+                    __stcs(a.cdf + i + 1, v1);
+                if (i + 2 < a.c.n)
+                    __stcs(a.cdf + i + 2, v2);
+            }
+            if (FUSED)
+            {
+                if (i + 3 < a.c.N)
+                    *reinterpret_cast<float4*>(a.c.wa_out + i) = make_float4(e[4 * r], e[4 * r + 1], e[4 * r + 2], e[4 * r + 3]);
+                else
+                {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-            {
-                const double u = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d)
-                    v += u;
+                    for (int q = 0; q < 3; q++)
+                        if (i + q < a.c.N)
+                            a.c.wa_out[i + q] = e[4 * r + q];
+                }
             }
-            const int i = w0 + r * 32 + lane;
-            const double val = off + (carry + v);
-            if (i < a.c.n)
-            {
-                __stcs(a.cdf + i, val);
-                if (FUSED && i < a.c.N)
-                    a.c.wa_out[i] = e[r];
-            }
-            carry += __shfl_sync(0xffffffffu, v, 31);
         }
         // third phase (resampling support): which CDF entry is the lower_bound of the first offset of every block of 256
         // output slots.  Needs the total, which the last tile has published long before this tile finished writing.
@@ -1142,46 +1191,42 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                 if (a.systematic)
                     u = (double)(a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle));
                 const double kInfD = __longlong_as_double(0x7ff0000000000000ll);
-                // the stored value of the entry before the warp's first: exact inside a tile; the first entry of a
-                // tile only knows it to a rounding, so it reaches back a little (a claim too many is harmless:
-                // atomicMin keeps the true one, which the tile before makes, and k_resample verifies what it reads)
-                double last = off;
-                if (w0 == 0)
-                    last = -1.0;
-                else if (warp == 0)
-                    last = tile_off - 1e-9 * fabs(tile_off);
-                // k_next: the first block whose boundary lies behind `last`; a round of 32 entries is looked at closely
+                // the stored value of the entry before the warp's first is only known to a rounding here, so the warp
+                // reaches back a little (a claim too many is harmless: atomicMin keeps the true one, which the warp
+                // before makes, and k_resample verifies what it reads)
+                double last = w0 == 0 ? -1.0 : off - 1e-9 * fabs(off);
+                // k_next: the first block whose boundary lies behind `last`; a round of 128 entries is looked at closely
                 // only when that boundary is not behind its last entry (one comparison per round otherwise)
                 long long k_next = first_block_behind(last, step, u, inv, a.res_blocks);
                 double next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
-                for (int half = 0; half < 2; half++)
+#pragma unroll
+                for (int r = 0; r < kQuadRounds; r++)
                 {
-                    double vals[8]; // the tile's own entries, read back in batches (all loads of a batch in flight together)
+                    const int i = w0 + r * 128 + lane * 4;
+                    const double s0 = (double)e[4 * r], s1 = s0 + (double)e[4 * r + 1], s2 = s1 + (double)e[4 * r + 2],
+                                 s3 = s2 + (double)e[4 * r + 3];
+                    double v[4] = {off + (base[r] + s0), off + (base[r] + s1), off + (base[r] + s2), off + (base[r] + s3)};
 #pragma unroll
-                    for (int q = 0; q < 8; q++)
+                    for (int q = 0; q < 4; q++)
+                        if (i + q >= a.c.n)
+                            v[q] = kInfD;
+                    const double hi = __shfl_sync(0xffffffffu, v[3], 31);
+                    if (w0 + r * 128 < a.c.n && next_off <= hi)
                     {
-                        const int i = w0 + (half * 8 + q) * 32 + lane;
-                        vals[q] = i < a.c.n ? __ldcg(a.cdf + i) : kInfD;
-                    }
+                        double prev = __shfl_up_sync(0xffffffffu, v[3], 1);
+                        if (lane == 0)
+                            prev = last;
 #pragma unroll
-                    for (int q = 0; q < 8; q++)
-                    {
-                        const int r = half * 8 + q;
-                        const int i = w0 + r * 32 + lane;
-                        const double val = vals[q];
-                        const double hi = __shfl_sync(0xffffffffu, val, 31);
-                        if (w0 + r * 32 < a.c.n && next_off <= hi)
+                        for (int q = 0; q < 4; q++)
                         {
-                            double prev = __shfl_up_sync(0xffffffffu, val, 1);
-                            if (lane == 0)
-                                prev = last;
-                            if (i < a.c.n)
-                                claim_block_starts(a.res_start, a.res_blocks, prev, val, step, u, inv, i);
-                            k_next = first_block_behind(hi, step, u, inv, a.res_blocks);
-                            next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
+                            if (i + q < a.c.n)
+                                claim_block_starts(a.res_start, a.res_blocks, prev, v[q], step, u, inv, i + q);
+                            prev = v[q];
                         }
-                        last = hi;
+                        k_next = first_block_behind(hi, step, u, inv, a.res_blocks);
+                        next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
                     }
+                    last = hi;
                 }
             }
         }
