@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
     pdl_prologue(K_CDF_CHAIN * 2);
     __shared__ double s_w[kWarpsPerBlock];
     __shared__ double s_red[kWarpsPerBlock];
-    __shared__ double s_total;
+    __shared__ double s_total, s_step, s_inv, s_u;
     __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (;;)
@@ -1180,16 +1180,22 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
             // launch wait for one could dead-lock the device.  Without the total the tile just makes no claims
             // (k_resample searches for the blocks nobody claimed).
             if (threadIdx.x == 0)
-                s_total = await_f64_bounded(a.total_word, a.epoch, 4096);
+            { // the scalars every thread needs are prepared once (two double divisions and a Philox block)
+                const double total = await_f64_bounded(a.total_word, a.epoch, 4096);
+                s_total = total;
+                if (total > 0.0)
+                {
+                    const double step = total / (double)a.c.N;
+                    s_step = step;
+                    s_inv = 1.0 / (256.0 * step);
+                    s_u = a.systematic ? (double)(a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle)) : 0.0;
+                }
+            }
             __syncthreads();
             const double total = s_total;
             if (total > 0.0)
             {
-                const double step = total / (double)a.c.N;
-                const double inv = 1.0 / (256.0 * step);
-                double u = 0.0;
-                if (a.systematic)
-                    u = (double)(a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle));
+                const double step = s_step, inv = s_inv, u = s_u;
                 const double kInfD = __longlong_as_double(0x7ff0000000000000ll);
                 // the stored value of the entry before the warp's first is only known to a rounding here, so the warp
                 // reaches back a little (a claim too many is harmless: atomicMin keeps the true one, which the warp
