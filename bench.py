@@ -103,6 +103,11 @@ def pose_at(step):
 # clocks sampling (B200_PROFILING.md recipe), running during the timed region
 # ----------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region.  Sampled in-process through NVML (nvidia-ml-py): spawning
+    nvidia-smi five times a second holds driver locks long enough to slow a loop that calls cudaMalloc / cudaFree every
+    cycle - the reference's - by an order of magnitude (measured: 12 ms vs 140-180 ms per cycle), which would flatter the
+    comparison.  nvidia-smi (the recipe's query, once a second) is the fall-back when NVML is not importable."""
+
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -112,17 +117,50 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        self._handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible:
+                entry = visible.split(",")[gpu_index].strip()
+                phys = int(entry) if entry.isdigit() else None
+            if phys is None:
+                self._handle = pynvml.nvmlDeviceGetHandleByUUID(entry.encode() if hasattr(entry, "encode") else entry)
+            else:
+                self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._handle
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if mask & bit else "Not Active"  # noqa: E731
+        # bit values of nvmlClocksEventReason*: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), "0", flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.2 if self._nvml is not None else 1.0)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -147,7 +185,8 @@ class ClockSampler:
                 continue
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -520,11 +559,14 @@ def run_reference(args, dist):
             x, y = pose_at(step)
             r.update_grid(ring[step % len(ring)], float(x), float(y), 0.0, DT, device=True)
             step += 1
+        per_step = []
         with ClockSampler(dist.local_rank) as clocks:
             t0 = time.perf_counter()
             for _ in range(K):
                 x, y = pose_at(step)
+                ts = time.perf_counter()
                 r.update_grid(ring[step % len(ring)], float(x), float(y), 0.0, DT, device=True)
+                per_step.append(time.perf_counter() - ts)
                 step += 1
             t = time.perf_counter() - t0
         for ptr in ring:
@@ -537,7 +579,12 @@ def run_reference(args, dist):
             "config": {"workload": f"{args.config}: same grid, particle counts, parameters and scene as the CUDA arm; the reference's "
                                    "own updateGrid (cuRAND XORWOW noise, thrust sort/scan) built unmodified for sm_100 (oracle/_ref)",
                        "note": "the reference has no CPU implementation of this path; its CUDA build is the baseline "
-                               "(BASELINE.json north_star); rank 0 only"},
+                               "(BASELINE.json north_star); rank 0 only",
+                       "ms_per_step_median": float(np.median(per_step)) * 1e3,
+                       "ms_per_step_min": float(np.min(per_step)) * 1e3,
+                       "ms_per_step_max": float(np.max(per_step)) * 1e3,
+                       "spread_note": "value is K / total time as the contract asks; the reference allocates and frees ~26 "
+                                      "device buffers per cycle, so single cycles occasionally take 10-50x the median"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                              "sample": f"{K} updateGrid cycles after {W} warm-up cycles; single host thread driving one B200"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
