@@ -455,11 +455,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
         // every lane reads its digit's counter, the first lane of each group then advances it
         uint32_t old = 0;
         if (valid)
-        {
             old = my_cnt[digit];
-            if ((peers[r] & lt) == 0)
-                my_cnt[digit] = (unsigned short)(old + __popc(peers[r]));
-        }
+        __syncwarp(); // all reads of this round before the group leaders' writes
+        if (valid && (peers[r] & lt) == 0)
+            my_cnt[digit] = (unsigned short)(old + __popc(peers[r]));
         const uint32_t rk = old + __popc(peers[r] & lt);
         if (r & 1)
             rank2[r >> 1] |= rk << 16;
