@@ -1309,12 +1309,13 @@ struct ResampleArgs
     uint32_t cycle;
 };
 
-// One CTA resamples 256 consecutive outputs.  Their offsets ascend, so all ancestors lie in a short window of the
-// CDF behind the ancestor of the CTA's first offset: thread 0 finds that one by binary search in global memory,
-// the window is staged in shared memory with coalesced loads and every thread searches it there.  Offsets beyond
-// the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
+// One CTA resamples 1024 consecutive output slots, four per thread.  Their offsets ascend, so all ancestors lie in a short
+// window of the CDF behind the ancestor of the CTA's first offset: k_cdf_chain has left that position in res_start (else a
+// cooperative search finds it), 2048 CDF entries are staged in shared memory with coalesced loads and every thread
+// searches there; the four slot loads and then the four record gathers of a thread are in flight together.  Offsets
+// beyond the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
 // to a search in global memory, so the result is lower_bound on the whole CDF in every case.
-constexpr int kResWindow = 512;
+constexpr int kResWindow = 2048;
 
 __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
@@ -1341,33 +1342,34 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
     return ((double)i + (double)u) * step;
 }
 
+constexpr int kResPer = 4;                     // output slots per thread
+constexpr int kResOutputs = kBlock * kResPer;  // output slots per CTA
+
 __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
 {
     pdl_prologue(K_RESAMPLE * 2);
     __shared__ double s_cdf[kResWindow];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = i < a.N;
+    const int out0 = blockIdx.x * kResOutputs;
     // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
-    // res_start: every thread reads it and fetches its two window entries straight away, while thread 0 prepares the
-    // scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
+    // res_start (one entry per 256 output slots): every thread reads it and fetches its window entries straight away,
+    // while thread 0 prepares the scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
     int lo0 = 0x7f7f7f7f;
     if (a.res_start)
-        lo0 = __ldcg(a.res_start + blockIdx.x);
+        lo0 = __ldcg(a.res_start + blockIdx.x * kResPer);
     const bool claimed = lo0 >= 0 && lo0 < a.n_cdf;
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-    double w0 = kInf, w1 = kInf, before = -1.0;
-    if (claimed)
+    double win[kResWindow / kBlock];
+    double before = -1.0;
+#pragma unroll
+    for (int k = 0; k < kResWindow / kBlock; k++)
     {
-        const int j0 = lo0 + (int)threadIdx.x, j1 = j0 + kBlock;
-        if (j0 < a.n_cdf)
-            w0 = __ldcg(a.cdf + j0);
-        if (j1 < a.n_cdf)
-            w1 = __ldcg(a.cdf + j1);
-        if (threadIdx.x == 0 && lo0 > 0)
-            before = __ldcg(a.cdf + lo0 - 1);
+        const long long j = (long long)lo0 + k * kBlock + (int)threadIdx.x;
+        win[k] = (claimed && j < a.n_cdf) ? __ldcg(a.cdf + j) : kInf;
     }
+    if (claimed && threadIdx.x == 0 && lo0 > 0)
+        before = __ldcg(a.cdf + lo0 - 1);
     if (threadIdx.x == 0)
     {
         const double total = a.scal->weight_total;
@@ -1380,20 +1382,22 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         s_u0 = u0;
         s_jm = jm;
         // a lower limit of the CTA's offsets: its first offset (systematic, injected) or the block boundary (stratified)
-        s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)(blockIdx.x * kBlock) * step
-                                                     : resample_offset(a, blockIdx.x * kBlock, jm, u0, step);
+        s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)out0 * step : resample_offset(a, out0, jm, u0, step);
     }
-    s_cdf[threadIdx.x] = w0;
-    s_cdf[threadIdx.x + kBlock] = w1;
+#pragma unroll
+    for (int k = 0; k < kResWindow / kBlock; k++)
+        s_cdf[k * kBlock + threadIdx.x] = win[k];
     __syncthreads();
     const float joint_max = s_jm;
     const double r_first = s_first;
-    const double r = resample_offset(a, valid ? i : a.N - 1, joint_max, s_u0, s_step);
     bool ok = claimed;
-    if (threadIdx.x == 0 && claimed)
-    {
-        ok = (lo0 == 0 || before < r_first) && w0 >= r_first;
-        a.res_start[blockIdx.x] = 0x7f7f7f7f; // unclaimed again for the next cycle
+    if (claimed && threadIdx.x == 0)
+        ok = (lo0 == 0 || before < r_first) && win[0] >= r_first;
+    if (a.res_start && threadIdx.x < kResPer)
+    { // unclaimed again for the next cycle
+        const int blk = blockIdx.x * kResPer + (int)threadIdx.x;
+        if (blk * kBlock < a.N)
+            a.res_start[blk] = 0x7f7f7f7f;
     }
     const bool have = __syncthreads_and(ok);
     if (!have)
@@ -1412,53 +1416,79 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         }
         __syncthreads();
         for (int j = threadIdx.x; j < kResWindow; j += kBlock)
-            s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : __longlong_as_double(0x7ff0000000000000ll);
+            s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : kInf;
         __syncthreads();
     }
-    if (!valid)
-        return;
-    int anc;
-    if (r < r_first)
-        anc = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
-    else if (r <= s_cdf[kResWindow - 1])
+    // ancestors of this thread's four output slots (out0 + 256 j + thread): search in the window, or in global memory for
+    // offsets outside of it (long runs of zero weights, caller-supplied fractions that do not ascend)
+    const double w_last = s_cdf[kResWindow - 1];
+    int anc[kResPer];
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
     {
-        int l = 0, h = kResWindow;
-        while (l < h)
+        const int i = out0 + j * kBlock + (int)threadIdx.x;
+        const double r = resample_offset(a, i < a.N ? i : a.N - 1, joint_max, s_u0, s_step);
+        int an;
+        if (r < r_first)
+            an = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
+        else if (r <= w_last)
         {
-            const int mid = l + ((h - l) >> 1);
-            if (s_cdf[mid] < r)
-                l = mid + 1;
-            else
-                h = mid;
+            int l = 0, h = kResWindow;
+            while (l < h)
+            {
+                const int mid = l + ((h - l) >> 1);
+                if (s_cdf[mid] < r)
+                    l = mid + 1;
+                else
+                    h = mid;
+            }
+            an = lo0 + l;
         }
-        anc = lo0 + l;
+        else
+            an = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
+        anc[j] = an < a.n_cdf ? an : a.n_cdf - 1;
     }
-    else
-        anc = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
-    anc = anc < a.n_cdf ? anc : a.n_cdf - 1;
-    a.ancestors[i] = anc;
-    float4 s;
-    int cell;
-    uint8_t as;
-    if (anc < a.N)
+    // gather: all slot loads first, then all record loads
+    int slot[kResPer];
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
+        slot[j] = anc[j] < a.N ? __ldg(&a.spair[anc[j]].y) : -1;
+    float4 st[kResPer];
+    int cell[kResPer];
+    uint32_t as[kResPer];
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
     {
-        const float4* p = reinterpret_cast<const float4*>(a.rec + a.spair[anc].y);
-        const float4 rlo = p[0], rhi = p[1];
-        s = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
-        cell = __float_as_int(rlo.z);
-        as = (uint8_t)__float_as_uint(rlo.w);
+        if (slot[j] >= 0)
+        {
+            const float4* p = reinterpret_cast<const float4*>(a.rec + slot[j]);
+            const float4 rlo = __ldg(p), rhi = __ldg(p + 1);
+            st[j] = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
+            cell[j] = __float_as_int(rlo.z);
+            as[j] = __float_as_uint(rlo.w);
+        }
+        else
+        {
+            const int b = anc[j] - a.N;
+            st[j] = a.birth.state[b];
+            cell[j] = a.birth.idx[b];
+            as[j] = a.birth.assoc[b];
+        }
     }
-    else
+    const float w_new = __fdiv_rn(joint_max, (float)a.N);
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
     {
-        const int b = anc - a.N;
-        s = a.birth.state[b];
-        cell = a.birth.idx[b];
-        as = a.birth.assoc[b];
+        const int i = out0 + j * kBlock + (int)threadIdx.x;
+        if (i < a.N)
+        {
+            a.ancestors[i] = anc[j];
+            a.dst.state[i] = st[j];
+            a.dst.idx[i] = cell[j];
+            a.dst.assoc[i] = (uint8_t)as[j];
+            a.dst.weight[i] = w_new;
+        }
     }
-    a.dst.state[i] = s;
-    a.dst.idx[i] = cell;
-    a.dst.assoc[i] = as;
-    a.dst.weight[i] = __fdiv_rn(joint_max, (float)a.N);
 }
 
 // ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
@@ -1756,7 +1786,7 @@ int run_resampling(dogm_handle* h)
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
-        launch_chained(h->stream, k_resample, div_up(N, kBlock), kBlock, 0, a);
+        launch_chained(h->stream, k_resample, div_up(N, kResOutputs), kBlock, 0, a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;
