@@ -409,6 +409,32 @@ def run_ours(args, dist):
             cycle_full()
         t_full = dist.max(time.perf_counter() - t0)
 
+    # ---- SURVEY.md 8(d) protocol extras: the blocking call (what a reference user times, demo/main.cpp:88-92) per cycle,
+    #      and cycles without an ego-motion shift (the pose stops changing, so update_pose never arms a shift)
+    k_blk = max(10, min(K, 50))
+    blk = []
+    for _ in range(k_blk):
+        x, y = pose_at(step)
+        tb = time.perf_counter()
+        d.update_grid(ring_ptrs[step % ring], float(x), float(y), 0.0, DT, device=True, sync=True)
+        blk.append((time.perf_counter() - tb) * 1e3)
+        step += 1
+    x_hold, y_hold = pose_at(step - 1)  # the pose of the last cycle: `step` itself does not advance while the ego vehicle rests
+    for k in range(3):
+        d.update_grid(ring_ptrs[(step + k) % ring], float(x_hold), float(y_hold), 0.0, DT, device=True, sync=True)
+    d.timer_start()
+    for k in range(k_blk):
+        d.update_grid(ring_ptrs[(step + 3 + k) % ring], float(x_hold), float(y_hold), 0.0, DT, device=True, sync=False)
+    d.timer_stop()
+    ms_stationary = d.timer_elapsed_ms() / k_blk
+    d.synchronize()
+    protocol = {
+        "blocking_update_grid_ms": {"median": float(np.median(blk)), "p10": float(np.percentile(blk, 10)),
+                                    "p90": float(np.percentile(blk, 90)), "cycles": k_blk},
+        "stationary_cycle_ms": ms_stationary,
+        "stationary_algorithmic_bytes": 208.0 * cfg["n"] + 37.0 * cfg["b"] + 180.0 * C,
+    }
+
     # ---- independent sensor streams on one GPU (BASELINE.json configs[3]: 64 streams over 8 GPUs = 8 per GPU): extra handles
     #      on their own CUDA streams fill the latency-bound gaps of a single cycle; reported next to the headline value
     streams_info = None
@@ -536,6 +562,7 @@ def run_ours(args, dist):
         },
         "gpu_launches": int(launches),
         "concurrent_streams": streams_info,
+        "protocol": protocol,
         "roofline": roofline,
         "clocks": clocks.summary(),
     }
