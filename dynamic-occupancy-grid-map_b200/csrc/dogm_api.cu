@@ -195,19 +195,15 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     e |= alloc_zero((void**)&h->cell_prefix, C * sizeof(double));
     e |= alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double));
     e |= alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double));
-    e |= alloc_zero((void**)&h->slot_end, C * sizeof(int));
-    e |= alloc_zero((void**)&h->blk_slot_end, (size_t)h->n_cell_blocks * sizeof(int));
     for (int p = 0; p < kMaxPasses; p++)
     {
         h->hist[p] = nullptr;
-        h->bin_tot[p] = nullptr;
         h->bin_base[p] = nullptr;
         h->scan_epoch[p] = 0;
     }
     for (int p = 0; p < h->passes; p++)
     {
         e |= alloc_zero((void**)&h->hist[p], (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t));
-        e |= alloc_zero((void**)&h->bin_tot[p], (size_t)h->digit_bins[p] * sizeof(uint32_t));
         e |= alloc_zero((void**)&h->bin_base[p], (size_t)h->digit_bins[p] * sizeof(uint32_t));
     }
     e |= alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece));
@@ -219,7 +215,7 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     e |= alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
     if (!e)
         e |= (int)cudaMemset(h->res_start, 0x7f, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
-    e |= alloc_zero((void**)&h->chain_flags, (2 * (size_t)h->n_cdf_tiles + 2) * sizeof(uint32_t));
+    e |= alloc_zero((void**)&h->chain_flags, 4 * sizeof(uint32_t));
     {
         const char* sk = getenv("DOGM_B200_SKIP");
         h->skip_mask = sk ? (unsigned)strtoul(sk, nullptr, 0) : 0u;
@@ -272,12 +268,9 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->cell_prefix);
     cudaFree(h->blk_sum);
     cudaFree(h->blk_off);
-    cudaFree(h->slot_end);
-    cudaFree(h->blk_slot_end);
     for (int p = 0; p < kMaxPasses; p++)
     {
         cudaFree(h->hist[p]);
-        cudaFree(h->bin_tot[p]);
         cudaFree(h->bin_base[p]);
     }
     cudaFree(h->seg_lead);

@@ -114,7 +114,6 @@ struct DeviceScalars // device-resident scalars: nothing is read back by the hos
 {
     double born_total;   // sum of born masses (normaliser of the birth / init slot distribution)
     double weight_total; // last entry of the joint weight CDF
-    unsigned int ticket[4];
 };
 
 struct CycleShift // ego-motion compensation of this cycle (dogm.cu:175-178)
@@ -141,7 +140,7 @@ enum KernelId : int
     K_MEAS_POLAR,
     K_BIRTH_PARTICLES,
     K_CDF_CHAIN,
-    K_CDF_SPARE,
+    K_UNUSED,
     K_RESAMPLE,
     K_INIT_MASSES,
     K_INIT_PARTICLES,
@@ -154,7 +153,7 @@ enum KernelId : int
 static const char* const kKernelNames[K_COUNT] = {
     "k_predict",       "k_tile_hist",       "k_hist_scan",  "k_scatter",   "k_segsum",      "k_segfix",
     "k_cell",          "k_blocksum_scan",   "k_weights",    "k_meas_polar", "k_birth_particles", "k_cdf_chain",
-    "k_cdf_spare",     "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
+    "k_unused",       "k_resample",        "k_init_masses", "k_init_particles", "k_meas_grid", "k_misc",
     "memset"};
 
 struct TimedLaunch
@@ -206,8 +205,6 @@ struct dogm_handle
     double* cell_prefix; // block-local inclusive prefix (double) of the born / initial masses, per cell
     double* blk_sum;   // born-mass sum per 256-cell block
     double* blk_off;   // exclusive prefix of blk_sum
-    int* slot_end;     // exclusive end slot per cell of the last birth / init distribution
-    int* blk_slot_end; // slot_end of the last cell of every 256-cell block
     int n_cell_blocks;
 
     // counting sort
@@ -215,7 +212,6 @@ struct dogm_handle
     int digit_shift[dogm_b200::kMaxPasses];
     int digit_bins[dogm_b200::kMaxPasses];
     uint32_t* hist[dogm_b200::kMaxPasses];     // [tiles][bins] per pass
-    uint32_t* bin_tot[dogm_b200::kMaxPasses];  // [bins]
     uint32_t* bin_base[dogm_b200::kMaxPasses]; // chain words of k_hist_scan (bins / 32 x u64)
     uint32_t scan_epoch[dogm_b200::kMaxPasses];
     int tiles;
@@ -232,7 +228,7 @@ struct dogm_handle
     double* tile_sum; // per CDF tile
     double* tile_off; // prefix of the tile groups before (k_cdf_chain)
     int* res_start;        // [ceil(N / 256)] CDF position of the first offset of every resampling CTA (k_cdf_chain -> k_resample)
-    uint32_t* chain_flags; // [tiles] tile flags | [tiles + 1] group flags | ticket
+    uint32_t* chain_flags; // the tile ticket of k_cdf_chain
     uint32_t chain_epoch, chain_ticket_base;
     int chain_capacity; // CTAs of k_cdf_chain the device holds at once
     unsigned skip_mask;  // DOGM_B200_SKIP (developer ablation)

@@ -7,8 +7,9 @@
 //   src/kernel/update_persistent_particles.cu:49-87, src/dogm.cu:386-423, src/kernel/resampling.cu:17-68.
 //
 // Data layout inside a cycle: the public population lives in the reference's ParticlesSoA block (`pa`); prediction
-// turns it into 32-byte records (PRec: one DRAM sector per particle) which the sort passes move, the segmented
-// reduction reads and the resampling gather fetches; resampling writes the next population back into `pa`.
+// turns it into 32-byte records (PRec: one DRAM sector per particle) that stay in slot order; the sort passes move
+// (cell, slot) pairs only, the segmented reduction and the resampling gather fetch the records through the sorted
+// permutation; resampling writes the next population back into `pa`.
 //
 // All float arithmetic that feeds an index (cell index, birth slot, ancestor) is written with explicit
 // round-to-nearest intrinsics and the file is compiled with -fmad=false, so the operation order below IS the
