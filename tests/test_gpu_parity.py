@@ -358,3 +358,47 @@ def test_concurrent_handles_do_not_interfere(gpu):
     for row in dev:
         for ptr in row:
             gpu.device_free(ptr)
+
+
+@pytest.mark.timeout(120)
+def test_degenerate_inputs_terminate(gpu, orc):
+    """Inputs the demo never produces must not hang or crash the cycle (every inter-CTA wait inside the kernels is on
+    words that are published unconditionally): an all-zero measurement grid (no born mass: the birth normaliser is 0),
+    a grid without any free or occupied evidence after the particles have died out, a huge time step that throws every
+    particle out of the grid (total weight 0), and NaN / negative ranges in a scan."""
+    n, b = 40_000, 4_000
+    p = make_params(gpu, 20.0, 0.25, n, b)
+    gs = 80
+    zero = np.zeros(gs * gs, gpu.MEAS_CELL_DTYPE)
+    zero["likelihood"] = 1.0
+    zero["p_A"] = 1.0
+    d = gpu.DOGM(p)
+    for c in range(4):
+        d.update_grid(zero, 0.0, 0.3 * c, 0.0, 0.1, device=False)
+    cells = d.get_grid_cells()
+    assert np.all(cells["occ_mass"][np.isfinite(cells["occ_mass"])] <= 1.0 + 1e-5)
+    d.close()
+
+    d = gpu.DOGM(p)
+    rng = np.random.default_rng(8)
+    meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, gs, rng)
+    for c in range(3):
+        d.update_grid(meas, 0.0, 0.0, 0.0, 0.1, device=False)
+    d.update_grid(meas, 0.0, 0.0, 0.0, 1.0e6, device=False)  # every persistent particle leaves the grid
+    d.update_grid(meas, 0.0, 0.0, 0.0, 0.1, device=False)
+    pa = d.get_particles()
+    assert np.all(np.isfinite(pa.weight)) and np.all(pa.grid_cell_idx >= 0) and np.all(pa.grid_cell_idx < gs * gs)
+    for c in range(3):  # and the filter recovers from the birth particles
+        d.update_grid(meas, 0.0, 0.0, 0.0, 0.1, device=False)
+    assert float(d.get_grid_cells()["occ_mass"].sum()) > 1.0
+    d.close()
+
+    gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(20.0, 0.25, 120.0, 0.5), 20.0, 0.25)
+    z = np.array([np.nan, -1.0, 0.0, np.inf, 5.0, 1e9, -np.inf] * 6, np.float32)
+    grid = gen.generate_grid_host(z)
+    assert np.all(np.isfinite(grid["occ_mass"])) and np.all(np.isfinite(grid["free_mass"]))
+    d = gpu.DOGM(p)
+    for c in range(3):
+        d.update_grid(grid, 0.0, 0.0, 0.0, 0.1, device=False)
+    d.close()
+    gen.close()
