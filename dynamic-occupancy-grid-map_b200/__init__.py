@@ -171,6 +171,7 @@ _SYMBOLS = [
     ("dogm_meas_generate", C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
     ("dogm_meas_generate_into", C.c_int, [_P, _P, _P, C.c_int]),
     ("dogm_meas_polar_grid", C.c_int, [_P, _P, C.c_int, _P]),
+    ("dogm_meas_generate_fused", C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P), _P]),
     ("dogm_meas_get_grid_size", C.c_int, [_P]),
     ("dogm_extract_dynamic_cells", C.c_int, [_P, C.c_float, C.c_float, _P, C.c_int, C.POINTER(C.c_int)]),
     ("dogm_set_dynamic_cell_filter", C.c_int, [_P, C.c_float, C.c_float, C.c_int]),
@@ -572,6 +573,20 @@ class LaserMeasurementGrid:
         out = np.empty(self.grid_size * self.grid_size, dtype=MEAS_CELL_DTYPE)
         _check(self._lib.dogm_memcpy_d2h(_ptr(out), C.c_void_p(ptr), out.nbytes), "dogm_memcpy_d2h")
         return out
+
+    def generate_grid_fused(self, scans, want_polar: bool = False):
+        """Several scans [S, K] fused in the polar grid; returns the device pointer of the measurement grid (and the fused
+        polar grid [H, K, 2] when asked)."""
+        scans = np.ascontiguousarray(scans, dtype=np.float32)
+        assert scans.ndim == 2
+        H = int(np.float32(self.params.max_range) / np.float32(self.params.resolution))
+        polar = np.empty((H, scans.shape[1], 2), dtype=np.float32) if want_polar else None
+        out = C.c_void_p()
+        _check(
+            self._lib.dogm_meas_generate_fused(self._m, _ptr(scans), scans.shape[0], scans.shape[1], C.byref(out), _ptr(polar)),
+            "dogm_meas_generate_fused",
+        )
+        return (out.value, polar) if want_polar else out.value
 
     def polar_grid(self, measurements) -> np.ndarray:
         beams = np.ascontiguousarray(measurements, dtype=np.float32)

@@ -174,6 +174,25 @@ __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
     out[t] = polar_cell(a, a.beams[b], i);
 }
 
+// one more scan into the polar table: Dempster-Shafer combination of the table (prior) with the clamped inverse sensor model
+// of the scan; the result is not clamped again (fusePolarGridTextureKernel + combine_masses, measurement_grid.cu:13-31,91-113)
+__global__ void __launch_bounds__(kBlock) k_meas_polar_fuse(MeasArgs a, float2* table)
+{
+    pdl_prologue(K_MEAS_POLAR * 2 + 1);
+    const int t = blockIdx.x * kBlock + threadIdx.x;
+    if (t >= a.K * a.H)
+        return;
+    const int b = t % a.K, i = t / a.K;
+    const float2 meas = polar_cell(a, a.beams[b], i);
+    const float2 prior = table[t];
+    const float occ = prior.x, fre = prior.y;
+    const float unknown_pred = 1.0f - occ - fre;
+    const float meas_unknown = 1.0f - meas.x - meas.y;
+    const float K = fre * meas.x + occ * meas.y;
+    table[t] = make_float2((occ * meas_unknown + unknown_pred * meas.x + occ * meas.x) / (1.0f - K),
+                           (fre * meas_unknown + unknown_pred * meas.y + fre * meas.y) / (1.0f - K));
+}
+
 static MeasArgs make_args(const dogm_meas_handle* m, int K, dogm_meas_cell* out)
 {
     MeasArgs a;
@@ -211,12 +230,11 @@ static int upload_beams(dogm_meas_handle* m, const float* beams_host, int K, cud
     return 0;
 }
 
-// polar table of this scan + cartesian resampling; rebuilds the geometry when the beam count changes
-static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStream_t stream, dogm_handle* timing)
+// grows the polar table / rebuilds the cached geometry when the beam count changes
+static int prepare_scan(dogm_meas_handle* m, int K, cudaStream_t stream)
 {
     const long long C = (long long)m->gs * m->gs;
     const size_t texels = (size_t)K * m->H;
-    const MeasArgs a = make_args(m, K, out);
     if (texels > m->polar_capacity)
     {
         cudaStreamSynchronize(stream);
@@ -228,17 +246,38 @@ static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStre
     }
     if (m->geom_beams != K)
     {
+        const MeasArgs a = make_args(m, K, nullptr);
         launch_chained(stream, k_meas_geom, div_up(C, kBlock), kBlock, 0, a, m->d_geom);
         DOGM_CHECK(cudaGetLastError());
         m->geom_beams = K;
     }
+    return 0;
+}
+
+// polar table of the scan in d_beams (first = overwrite, otherwise fuse into the table)
+static int launch_polar(dogm_meas_handle* m, int K, bool first, cudaStream_t stream, dogm_handle* timing)
+{
+    const size_t texels = (size_t)K * m->H;
+    const MeasArgs a = make_args(m, K, nullptr);
     if (timing)
     {
         LaunchScope ls(timing, K_MEAS_POLAR, 8.0 * (double)texels);
-        launch_chained(stream, k_meas_polar, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
+        if (first)
+            launch_chained(stream, k_meas_polar, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
+        else
+            launch_chained(stream, k_meas_polar_fuse, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
     }
-    else
+    else if (first)
         launch_chained(stream, k_meas_polar, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
+    else
+        launch_chained(stream, k_meas_polar_fuse, div_up((long long)texels, kBlock), kBlock, 0, a, m->d_polar);
+    return (int)cudaGetLastError();
+}
+
+// cartesian resampling of the polar table
+static int launch_apply(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStream_t stream, dogm_handle* timing)
+{
+    const long long C = (long long)m->gs * m->gs;
     if (timing)
     {
         LaunchScope ls(timing, K_MEAS_GRID, 32.0 * (double)C);
@@ -246,8 +285,15 @@ static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStre
     }
     else
         launch_chained(stream, k_meas_apply, div_up(C, kBlock), kBlock, 0, m->d_geom, m->d_polar, K, m->H, (int)C, out);
-    DOGM_CHECK(cudaGetLastError());
-    return 0;
+    return (int)cudaGetLastError();
+}
+
+static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStream_t stream, dogm_handle* timing)
+{
+    int e = prepare_scan(m, K, stream);
+    e = e ? e : launch_polar(m, K, true, stream, timing);
+    e = e ? e : launch_apply(m, K, out, stream, timing);
+    return e;
 }
 
 int trace_bind_meas(unsigned long long* p)
@@ -350,6 +396,33 @@ extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, cons
     if (e)
         return e;
     return launch_scan(m, num_beams, h->meas, h->stream, h);
+}
+
+extern "C" int dogm_meas_generate_fused(dogm_meas_handle* m, const float* scans_host, int num_scans, int num_beams,
+                                        dogm_meas_cell** out_device, float* out_polar_host)
+{
+    if (!m || !scans_host || num_scans < 1 || num_beams < 1)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    for (int s = 0; s < num_scans; s++)
+    {
+        // the staging buffer is reused per scan: wait for the previous scan's copy before overwriting it
+        DOGM_CHECK(cudaStreamSynchronize(m->stream));
+        int e = upload_beams(m, scans_host + (size_t)s * num_beams, num_beams, m->stream);
+        e = e ? e : (s == 0 ? prepare_scan(m, num_beams, m->stream) : 0);
+        e = e ? e : launch_polar(m, num_beams, s == 0, m->stream, nullptr);
+        if (e)
+            return e;
+    }
+    int e = launch_apply(m, num_beams, m->d_grid, m->stream, nullptr);
+    if (e)
+        return e;
+    if (out_polar_host)
+        DOGM_CHECK(cudaMemcpyAsync(out_polar_host, m->d_polar, (size_t)num_beams * m->H * sizeof(float2), cudaMemcpyDeviceToHost,
+                                   m->stream));
+    DOGM_CHECK(cudaStreamSynchronize(m->stream));
+    if (out_device)
+        *out_device = m->d_grid;
+    return 0;
 }
 
 extern "C" int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, float* out_host)

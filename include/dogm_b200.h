@@ -252,6 +252,12 @@ int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_host, int n
 /* Same, stream-ordered on the stream of `h` and written straight into h's measurement buffer; the following
  * dogm_update_grid(h, NULL, ...) then consumes it without the 16*C-byte copy of dogm.cu:207-208. */
 int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, const float* beam_ranges_host, int num_beams);
+/* Several scans of the same sensor geometry fused in the polar grid before the polar->cartesian step
+ * (createPolarGridTextureKernel for the first scan, fusePolarGridTextureKernel + combine_masses for the others,
+ * measurement_grid.cu:13-31,72-113; the reference ships the fusion kernel but never calls it).  scans_host is
+ * [num_scans][num_beams]; out_polar_host (optional) receives the fused polar grid, [H][num_beams] pairs (occ, free). */
+int dogm_meas_generate_fused(dogm_meas_handle* m, const float* scans_host, int num_scans, int num_beams,
+                             dogm_meas_cell** out_device, float* out_polar_host);
 /* The polar inverse-sensor-model grid alone (createPolarGridTextureKernel, measurement_grid.cu:72-89):
  * out_host[(range_bin * num_beams + beam) * 2 + {0: occ, 1: free}], range bins = int(max_range / resolution). */
 int dogm_meas_polar_grid(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, float* out_host);

@@ -28,6 +28,19 @@ class LaserMeasurementGrid
         dogm_meas_generate(handle, measurements.data(), static_cast<int>(measurements.size()), &out);
         return out;
     }
+    // several scans of the same sensor geometry (equal sizes), fused in the polar grid (the reference's unused
+    // fusePolarGridTextureKernel, measurement_grid.cu:91-113)
+    dogm::MeasurementCell* generateGridFused(const std::vector<std::vector<float>>& scans)
+    {
+        dogm::MeasurementCell* out = nullptr;
+        if (scans.empty())
+            return out;
+        std::vector<float> flat;
+        for (const auto& s : scans)
+            flat.insert(flat.end(), s.begin(), s.end());
+        dogm_meas_generate_fused(handle, flat.data(), static_cast<int>(scans.size()), static_cast<int>(scans[0].size()), &out, nullptr);
+        return out;
+    }
     // straight into a DOGM's measurement buffer; follow with updateGrid(nullptr, ...)
     void generateGridInto(::dogm_handle* dogm, const std::vector<float>& measurements)
     {

@@ -153,6 +153,10 @@ int oracle_meas_polar_height(const oracle_laser_params* p);
 void oracle_meas_polar_grid(const oracle_laser_params* p, const float* beams, int num_beams, float* out /* H*K*2 */);
 void oracle_meas_generate(const oracle_laser_params* p, float grid_length, float resolution, const float* beams,
                           int num_beams, oracle_meas_cell* out /* gs*gs */);
+/* multi-scan fusion in the polar grid (fusePolarGridTextureKernel + combine_masses, measurement_grid.cu:13-31,91-113) */
+void oracle_meas_polar_fuse(const oracle_laser_params* p, float* table /* H*K*2, in place */, const float* beams, int num_beams);
+void oracle_meas_generate_fused(const oracle_laser_params* p, float grid_length, float resolution, const float* scans,
+                                int num_scans, int num_beams, float* table /* H*K*2 scratch */, oracle_meas_cell* out);
 
 /* computeCellsWithVelocity, demo/utils/image_creation.cpp:19-66; returns the count, fills up to capacity records of
  * 8 floats {cell_idx (as int bits), occupancy, mean_x, mean_y, var_x, var_y, covar, mahalanobis} */

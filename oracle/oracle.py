@@ -148,6 +148,8 @@ def load_library() -> C.CDLL:
     lib.oracle_meas_polar_height.restype = C.c_int
     lib.oracle_meas_polar_height.argtypes = [C.POINTER(LaserParams)]
     lib.oracle_meas_polar_grid.argtypes = [C.POINTER(LaserParams), VP, C.c_int, VP]
+    lib.oracle_meas_polar_fuse.argtypes = [C.POINTER(LaserParams), VP, VP, C.c_int]
+    lib.oracle_meas_generate_fused.argtypes = [C.POINTER(LaserParams), C.c_float, C.c_float, VP, C.c_int, C.c_int, VP, VP]
     lib.oracle_meas_generate.argtypes = [C.POINTER(LaserParams), C.c_float, C.c_float, VP, C.c_int, VP]
     lib.oracle_extract_dynamic_cells.restype = C.c_int
     lib.oracle_extract_dynamic_cells.argtypes = [VP, C.c_int, C.c_float, C.c_float, VP, C.c_int]
@@ -344,6 +346,28 @@ def meas_generate(laser: LaserParams, grid_length: float, resolution: float, bea
     gs = lib.oracle_meas_grid_size(grid_length, resolution)
     out = np.empty(gs * gs, dtype=MEAS_CELL_DTYPE)
     lib.oracle_meas_generate(C.byref(laser), grid_length, resolution, beams.ctypes.data, beams.size, out.ctypes.data)
+    return out
+
+
+def meas_polar_fused(laser: LaserParams, scans) -> np.ndarray:
+    """polar grid [H, K, 2] after fusing all scans [S, K] (createPolarGridTextureKernel, then fusePolarGridTextureKernel)"""
+    lib = load_library()
+    scans = np.ascontiguousarray(scans, np.float32)
+    table = meas_polar_grid(laser, scans[0])
+    for s in range(1, scans.shape[0]):
+        lib.oracle_meas_polar_fuse(C.byref(laser), table.ctypes.data, scans[s].ctypes.data, scans.shape[1])
+    return table
+
+
+def meas_generate_fused(laser: LaserParams, grid_length: float, resolution: float, scans) -> np.ndarray:
+    lib = load_library()
+    scans = np.ascontiguousarray(scans, np.float32)
+    H = lib.oracle_meas_polar_height(C.byref(laser))
+    gs = int(np.float32(grid_length) / np.float32(resolution))
+    table = np.empty((H, scans.shape[1], 2), np.float32)
+    out = np.empty(gs * gs, dtype=MEAS_CELL_DTYPE)
+    lib.oracle_meas_generate_fused(C.byref(laser), grid_length, resolution, scans.ctypes.data, scans.shape[0], scans.shape[1],
+                                   table.ctypes.data, out.ctypes.data)
     return out
 
 

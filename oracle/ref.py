@@ -77,6 +77,8 @@ def load_library() -> C.CDLL:
     lib.ref_device_free.argtypes = [VP]
     lib.ref_memcpy_h2d.argtypes = [VP, VP, C.c_size_t]
     lib.ref_polar_grid.argtypes = [VP, C.c_int, C.c_int, C.c_float, C.c_float, VP]
+    if hasattr(lib, "ref_polar_fused"):
+        lib.ref_polar_fused.argtypes = [VP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, VP]
     assert lib.ref_sizeof_particle() == 28 and lib.ref_sizeof_grid_cell() == 64
     _lib = lib
     return lib
@@ -262,6 +264,18 @@ def device_upload(arr: np.ndarray) -> int:
 
 def device_free(ptr: int) -> None:
     load_library().ref_device_free(C.c_void_p(ptr))
+
+
+def polar_fused(scans, height: int, resolution: float, stddev_range: float) -> np.ndarray:
+    """the reference's polar grid after createPolarGridTextureKernel(scan 0) and fusePolarGridTextureKernel(scans 1..)"""
+    lib = load_library()
+    scans = np.ascontiguousarray(scans, dtype=np.float32)
+    out = np.empty((height, scans.shape[1], 2), dtype=np.float32)
+    rc = lib.ref_polar_fused(C.c_void_p(scans.ctypes.data), scans.shape[0], scans.shape[1], height, resolution, stddev_range,
+                             C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"ref_polar_fused failed: {rc}")
+    return out
 
 
 def polar_grid(beams, height: int, resolution: float, stddev_range: float) -> np.ndarray:

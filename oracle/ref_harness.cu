@@ -373,4 +373,39 @@ int ref_polar_grid(const float* beams, int width, int height, float resolution, 
     return (int)cudaGetLastError();
 }
 
+// ---- multi-scan fusion: createPolarGridTextureKernel for the first scan, fusePolarGridTextureKernel for the others ----
+int ref_polar_fused(const float* scans, int num_scans, int width, int height, float resolution, float stddev_range, float* out)
+{
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float2>();
+    cudaArray_t arr = nullptr;
+    if (cudaMallocArray(&arr, &desc, width, height, cudaArraySurfaceLoadStore) != cudaSuccess)
+        return -1;
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaSurfaceObject_t surf = 0;
+    if (cudaCreateSurfaceObject(&surf, &res) != cudaSuccess)
+        return -2;
+    float* d_beams = nullptr;
+    cudaMalloc(&d_beams, (size_t)width * sizeof(float));
+    dim3 dim_block(32, 32);
+    dim3 grid_dim(divUp(width, dim_block.x), divUp(height, dim_block.y));
+    for (int s = 0; s < num_scans; s++)
+    {
+        cudaMemcpy(d_beams, scans + (size_t)s * width, (size_t)width * sizeof(float), cudaMemcpyHostToDevice);
+        if (s == 0)
+            createPolarGridTextureKernel<<<grid_dim, dim_block>>>(surf, d_beams, width, height, resolution, stddev_range);
+        else
+            fusePolarGridTextureKernel<<<grid_dim, dim_block>>>(surf, d_beams, width, height, resolution, stddev_range);
+        cudaDeviceSynchronize();
+    }
+    cudaMemcpy2DFromArray(out, (size_t)width * sizeof(float2), arr, 0, 0, (size_t)width * sizeof(float2), height,
+                          cudaMemcpyDeviceToHost);
+    cudaDestroySurfaceObject(surf);
+    cudaFreeArray(arr);
+    cudaFree(d_beams);
+    return (int)cudaGetLastError();
+}
+
 } // extern "C"

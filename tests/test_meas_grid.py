@@ -126,3 +126,48 @@ def test_generate_into_feeds_update_grid(gpu):
     e.update_grid(ptr, 0.0, 0.0, 0.0, 0.1, device=True)
     assert np.array_equal(d.get_grid_cells().view(np.uint8), e.get_grid_cells().view(np.uint8))
     assert np.array_equal(d.get_particles().block, e.get_particles().block)
+
+
+def test_oracle_fusion_properties(orc):
+    """combine_masses (measurement_grid.cu:13-31): fusing a scan without information changes nothing much, fusing the same
+    evidence twice sharpens it, masses stay in [0, 1] and their sum stays <= 1."""
+    laser = orc.LaserParams(50.0, 0.2, 120.0, 0.5)
+    rng = np.random.default_rng(45)
+    a = demo_beams(rng, 100, 50.0)
+    once = orc.meas_polar_fused(laser, a[None, :])
+    assert np.array_equal(once, orc.meas_polar_grid(laser, a))
+    twice = orc.meas_polar_fused(laser, np.stack([a, a]))
+    assert np.all(twice >= -1e-6) and np.all(twice.sum(axis=2) <= 1.0 + 1e-5)
+    occ_cells = once[..., 0] > 0.5
+    assert occ_cells.any() and np.all(twice[..., 0][occ_cells] >= once[..., 0][occ_cells] - 1e-6)
+    free_cells = once[..., 1] > 0.2
+    assert np.all(twice[..., 1][free_cells] >= once[..., 1][free_cells] - 1e-6)
+    grid = orc.meas_generate_fused(laser, 50.0, 0.2, np.stack([a, a]))
+    assert grid.size == 250 * 250 and np.all(grid["likelihood"] == 1.0)
+
+
+@pytest.mark.gpu
+def test_cuda_fused_scans_match_oracle_and_reference_kernel(gpu, orc):
+    """dogm_meas_generate_fused: the fused polar grid against the C restatement and against the reference's own
+    createPolarGridTextureKernel + fusePolarGridTextureKernel run on a CUDA surface; the cartesian grid against the oracle."""
+    rng = np.random.default_rng(46)
+    gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(50.0, 0.2, 120.0, 0.5), 50.0, 0.2)
+    laser = orc.LaserParams(50.0, 0.2, 120.0, 0.5)
+    scans = np.stack([demo_beams(rng, 100, 50.0) for _ in range(3)])
+    ptr, polar = gen.generate_grid_fused(scans, want_polar=True)
+    pe = orc.meas_polar_fused(laser, scans)
+    assert polar.shape == pe.shape and (np.abs(polar - pe) > 2e-5).sum() <= 6
+    got = np.empty(250 * 250, gpu.MEAS_CELL_DTYPE)
+    gpu.memcpy_d2h(got, ptr)
+    exp = orc.meas_generate_fused(laser, 50.0, 0.2, scans)
+    for f in ("occ_mass", "free_mass"):
+        assert (np.abs(got[f] - exp[f]) > 5e-5).mean() < 3e-4, f
+    # one scan through the fused entry equals the plain entry
+    one = np.empty(250 * 250, gpu.MEAS_CELL_DTYPE)
+    gpu.memcpy_d2h(one, gen.generate_grid_fused(scans[:1]))
+    assert np.array_equal(one.view(np.uint8), gen.generate_grid_host(scans[0]).view(np.uint8))
+    ref = load_ref()
+    if ref.available() and hasattr(ref.load_library(), "ref_polar_fused"):
+        theirs = ref.polar_fused(scans, 250, 0.2, 0.5)
+        assert (np.abs(polar - theirs) > 2e-6).sum() <= 6  # same device, same expf; FMA contraction on their side only
+    gen.close()
