@@ -85,6 +85,20 @@ class Params(C.Structure):
 GridParams = Params  # the name used by BASELINE.json's north_star
 
 
+class BandConfig(C.Structure):
+    """dogm_band_config (include/dogm_b200.h, band mode)"""
+
+    _fields_ = [
+        ("row0", C.c_int),
+        ("rows", C.c_int),
+        ("particle_capacity", C.c_int),
+        ("birth_capacity", C.c_int),
+        ("exchange_capacity", C.c_int),
+        ("halo_rows", C.c_int),
+        ("seed_salt", C.c_uint64),
+    ]
+
+
 class LaserSensorParams(C.Structure):
     """== LaserMeasurementGrid::Params (laser_to_meas_grid.h:16-22)."""
 
@@ -191,6 +205,18 @@ _SYMBOLS = [
     ("dogm_device_free", C.c_int, [_P]),
     ("dogm_memcpy_h2d", C.c_int, [_P, _P, C.c_size_t]),
     ("dogm_memcpy_d2h", C.c_int, [_P, _P, C.c_size_t]),
+    ("dogm_memcpy_d2d", C.c_int, [_P, _P, C.c_size_t]),
+    ("dogm_create_band", C.c_int, [C.POINTER(Params), C.POINTER(BandConfig), C.POINTER(_P)]),
+    ("dogm_band_buffer", _P, [_P, C.c_int]),
+    ("dogm_band_counts", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("dogm_band_init_masses", C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_double)]),
+    ("dogm_band_init_particles", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int)]),
+    ("dogm_band_predict", C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("dogm_band_append", C.c_int, [_P, C.c_int, C.c_int]),
+    ("dogm_band_update", C.c_int, [_P, _P, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]),
+    ("dogm_band_birth", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_double)]),
+    ("dogm_band_resample", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int)]),
+    ("dogm_band_get_particles", C.c_int, [_P, _P, _P, _P, _P]),
     ("dogm_device_count", C.c_int, []),
     ("dogm_set_device", C.c_int, [C.c_int]),
     ("dogm_b200_version", C.c_char_p, []),
@@ -595,6 +621,166 @@ class LaserMeasurementGrid:
         _check(self._lib.dogm_meas_polar_grid(self._m, _ptr(beams), beams.size, _ptr(out)), "dogm_meas_polar_grid")
         return out
 
+
+
+# ----------------------------------------------------------------------------------------------------------
+# band mode: one grid over several handles (one per band of rows; one GPU or several GPUs of this process)
+# ----------------------------------------------------------------------------------------------------------
+BAND_SEND_LO, BAND_SEND_HI, BAND_RECV_LO, BAND_RECV_HI, BAND_HALO_LO, BAND_HALO_HI, BAND_EDGE_LO, BAND_EDGE_HI = range(8)
+
+
+class BandedDOGM:
+    """The orchestrator of include/dogm_b200.h's band mode for the bands of ONE process: it drives the phases of a cycle on
+    every band handle and moves, between the phases, the particles that crossed a band edge (SEND -> RECV boxes), the
+    halo rows of an ego-motion shift and the prefix sums of the two global normalisers (born mass, joint weight).
+    `devices[r]` puts band r on that GPU (copies between bands are then peer copies); by default all bands share the
+    current GPU.  A multi-process driver does the same with NCCL (bench.py --bands)."""
+
+    def __init__(self, params: Params, n_bands: int, devices=None, seed: int = 123456, slack: float = 1.75, halo_rows: int = 64,
+                 resample_mode: int = RESAMPLE_SYSTEMATIC):
+        self._lib = load_library()
+        self.params = params
+        self.G = int(np.float32(params.size) / np.float32(params.resolution))
+        self.R = n_bands
+        base, extra = divmod(self.G, n_bands)
+        self.rows = [base + (1 if r < extra else 0) for r in range(n_bands)]
+        self.row0 = [sum(self.rows[:r]) for r in range(n_bands)]
+        self.devices = list(devices) if devices is not None else [None] * n_bands
+        n, b = params.particle_count, params.new_born_particle_count
+        self.n_cap = n if n_bands == 1 else min(n, int(n / n_bands * slack) + 8192)
+        self.b_cap = b if n_bands == 1 else min(b, int(b / n_bands * slack * 2) + 8192)
+        self.x_cap = 0 if n_bands == 1 else max(8192, self.n_cap // 4)
+        self.halo_rows = 0 if n_bands == 1 else min(halo_rows, min(self.rows))
+        self.h = []
+        for r in range(n_bands):
+            self._on(r)
+            cfg = BandConfig(self.row0[r], self.rows[r], self.n_cap, self.b_cap, self.x_cap, self.halo_rows,
+                             (r * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+            hp = C.c_void_p()
+            _check(self._lib.dogm_create_band(C.byref(params), C.byref(cfg), C.byref(hp)), "dogm_create_band")
+            opts = Options(seed, resample_mode, NOISE_PHILOX)
+            _check(self._lib.dogm_set_options(hp, C.byref(opts)), "dogm_set_options")
+            self.h.append(hp)
+        self.first = True
+        self.last_counts = []
+
+    def _on(self, r):
+        if self.devices[r] is not None:
+            set_device(self.devices[r])
+
+    def close(self):
+        for r, hp in enumerate(self.h):
+            self._on(r)
+            self._lib.dogm_destroy(hp)
+        self.h = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buf(self, r, which):
+        return self._lib.dogm_band_buffer(self.h[r], which)
+
+    @staticmethod
+    def _prefix(values):
+        """sequential running sum (the bands must see bit-identical prefixes: before[r + 1] = before[r] + values[r])"""
+        before, acc = [], 0.0
+        for v in values:
+            before.append(acc)
+            acc = acc + float(v)
+        return before, acc
+
+    def update_grid(self, meas_band_ptrs, new_x, new_y, new_yaw, dt):
+        """meas_band_ptrs[r]: device address (on band r's GPU) of the rows of the measurement grid that band r owns"""
+        lib, R = self._lib, self.R
+        if self.first:
+            masses = []
+            for r in range(R):
+                self._on(r)
+                m = C.c_double(0.0)
+                _check(lib.dogm_band_init_masses(self.h[r], C.c_void_p(meas_band_ptrs[r]), 1, C.byref(m)), "dogm_band_init_masses")
+                masses.append(m.value)
+            before, total = self._prefix(masses)
+            for r in range(R):
+                self._on(r)
+                _check(lib.dogm_band_init_particles(self.h[r], before[r], total, None), "dogm_band_init_particles")
+            self.first = False
+        lo, hi = [], []
+        for r in range(R):
+            self._on(r)
+            a, b = C.c_int(0), C.c_int(0)
+            _check(lib.dogm_band_predict(self.h[r], new_x, new_y, new_yaw, dt, C.byref(a), C.byref(b)), "dogm_band_predict")
+            lo.append(a.value)
+            hi.append(b.value)
+        for r in range(R):  # band r receives what its neighbours sent towards it
+            self._on(r)
+            n_lo = hi[r - 1] if r > 0 else 0
+            n_hi = lo[r + 1] if r + 1 < R else 0
+            if n_lo:
+                _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_RECV_LO), self._buf(r - 1, BAND_SEND_HI), n_lo * 32), "dogm_memcpy_d2d")
+            if n_hi:
+                _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_RECV_HI), self._buf(r + 1, BAND_SEND_LO), n_hi * 32), "dogm_memcpy_d2d")
+            _check(lib.dogm_band_append(self.h[r], n_lo, n_hi), "dogm_band_append")
+        self.last_migration = (lo, hi)
+        if self.halo_rows:
+            nbytes = self.halo_rows * self.G * 4
+            for r in range(R):  # the neighbours' edge rows of the PREVIOUS free masses, before any band updates its cells
+                self._on(r)
+                if r > 0:
+                    _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_LO), self._buf(r - 1, BAND_EDGE_HI), nbytes), "dogm_memcpy_d2d")
+                if r + 1 < R:
+                    _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_HI), self._buf(r + 1, BAND_EDGE_LO), nbytes), "dogm_memcpy_d2d")
+        born = []
+        for r in range(R):
+            self._on(r)
+            v = C.c_double(0.0)
+            _check(lib.dogm_band_update(self.h[r], C.c_void_p(meas_band_ptrs[r]), 1, dt, 1 if self.halo_rows else 0, C.byref(v)),
+                   "dogm_band_update")
+            born.append(v.value)
+        before, total = self._prefix(born)
+        weight = []
+        for r in range(R):
+            self._on(r)
+            v = C.c_double(0.0)
+            _check(lib.dogm_band_birth(self.h[r], before[r], total, C.byref(v)), "dogm_band_birth")
+            weight.append(v.value)
+        before, total = self._prefix(weight)
+        counts = []
+        for r in range(R):
+            self._on(r)
+            n = C.c_int(0)
+            _check(lib.dogm_band_resample(self.h[r], before[r], total, C.byref(n)), "dogm_band_resample")
+            counts.append(n.value)
+        self.last_counts = counts
+        self.last_totals = {"born": sum(born), "weight": total}
+        return counts
+
+    def band_handle(self, r):
+        return self.h[r]
+
+    def get_particles(self, r):
+        """(state [n, 4], cell index inside the band [n], weight [n], associated [n]) of band r"""
+        self._on(r)
+        n = C.c_int(0)
+        _check(self._lib.dogm_band_counts(self.h[r], C.byref(n), None), "dogm_band_counts")
+        state = np.empty((n.value, 4), np.float32)
+        idx = np.empty(n.value, np.int32)
+        w = np.empty(n.value, np.float32)
+        a = np.empty(n.value, np.uint8)
+        _check(self._lib.dogm_band_get_particles(self.h[r], _ptr(state), _ptr(idx), _ptr(w), _ptr(a)), "dogm_band_get_particles")
+        return state, idx, w, a
+
+    def get_grid_cells(self):
+        """the grid cells of all bands, stacked in row order (start_idx / end_idx refer to the band's own particle list)"""
+        parts = []
+        for r in range(self.R):
+            self._on(r)
+            out = np.empty(self.rows[r] * self.G, dtype=GRID_CELL_DTYPE)
+            _check(self._lib.dogm_get_grid_cells(self.h[r], _ptr(out)), "dogm_get_grid_cells")
+            parts.append(out)
+        return np.concatenate(parts)
 
 def device_count() -> int:
     return load_library().dogm_device_count()

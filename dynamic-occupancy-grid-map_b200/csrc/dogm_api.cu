@@ -2,6 +2,7 @@
 // One stream, every buffer allocated once in dogm_create, no allocation / host read-back inside a cycle
 // (the reference does ~26 cudaMalloc/cudaFree pairs and 3 blocking scalar copies per cycle).
 #include "dogm_internal.cuh"
+#include "philox.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -98,7 +99,7 @@ static int copy_in(void* dst_device, const void* src, size_t bytes, int on_devic
 // ---------------------------------------------------------------------------------------------------------
 // life cycle
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
+static int create_impl(const dogm_params* params, const dogm_band_config* band, dogm_handle** out)
 {
     if (!params || !out)
         return DOGM_ERR_INVALID_ARGUMENT;
@@ -106,9 +107,15 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     if (!(params->resolution > 0.0f) || params->particle_count < 0 || params->new_born_particle_count < 0)
         return DOGM_ERR_INVALID_ARGUMENT;
     const int gs = (int)(params->size / params->resolution); // dogm.cu:34
-    if (gs <= 0 || (long long)gs * gs > (1ll << 30))
+    const int rows = band ? band->rows : gs;
+    if (gs <= 0 || rows <= 0 || (long long)gs * rows > (1ll << 30))
         return DOGM_ERR_INVALID_ARGUMENT;
-    if ((long long)params->particle_count + params->new_born_particle_count >= (1ll << 31))
+    if (band && (band->row0 < 0 || band->row0 + band->rows > gs || band->particle_capacity < 0 || band->birth_capacity < 0 ||
+                 band->exchange_capacity < 0 || band->halo_rows < 0))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    const long long n_cap = band ? band->particle_capacity : params->particle_count;
+    const long long b_cap = band ? band->birth_capacity : params->new_born_particle_count;
+    if (n_cap + b_cap >= (1ll << 31) || (long long)params->particle_count + params->new_born_particle_count >= (1ll << 31))
         return DOGM_ERR_INVALID_ARGUMENT;
 
     int device = 0;
@@ -125,9 +132,29 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
     h->opts.resample_mode = DOGM_RESAMPLE_SYSTEMATIC;
     h->opts.noise_mode = DOGM_NOISE_PHILOX;
     h->gs = gs;
-    h->C = gs * gs;
-    h->N = params->particle_count;
-    h->B = params->new_born_particle_count;
+    h->C = gs * rows;
+    // sized for the capacities; without bands these are the particle counts themselves
+    h->N = (int)n_cap;
+    h->B = (int)b_cap;
+    h->band.enabled = band ? 1 : 0;
+    h->band.G = gs;
+    h->band.row0 = band ? band->row0 : 0;
+    h->band.rows = rows;
+    h->band.n_cap = (int)n_cap;
+    h->band.b_cap = (int)b_cap;
+    h->band.n_glob = params->particle_count;
+    h->band.b_glob = params->new_born_particle_count;
+    h->band.salt = band ? band->seed_salt : 0ull;
+    h->band.born_base = 0.0;
+    h->band.birth_slot_base = 0;
+    h->band.cdf_base = 0.0;
+    h->band.out_base = 0;
+    h->band.n_out = 0;
+    h->band.send[0] = h->band.send[1] = h->band.recv[0] = h->band.recv[1] = nullptr;
+    h->band.send_count = nullptr;
+    h->band.send_cap = band ? band->exchange_capacity : 0;
+    h->band.halo[0] = h->band.halo[1] = nullptr;
+    h->band.halo_rows = band ? band->halo_rows : 0;
     h->device = device;
     h->sm_count = sm_count;
     h->first_pose_received = false;
@@ -231,6 +258,21 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
         dogm_destroy(h);
         return e;
     }
+    if (band)
+    {
+        for (int d = 0; d < 2; d++)
+        {
+            e |= alloc_zero((void**)&h->band.send[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec));
+            e |= alloc_zero((void**)&h->band.recv[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec));
+            e |= alloc_zero((void**)&h->band.halo[d], (size_t)(h->band.halo_rows ? h->band.halo_rows : 1) * gs * sizeof(float));
+        }
+        e |= alloc_zero((void**)&h->band.send_count, 2 * sizeof(int));
+        if (e)
+        {
+            dogm_destroy(h);
+            return e;
+        }
+    }
     e = run_init_grid(h); // DOGM::initialize, dogm.cu:95-113
     if (e == 0)
         e = (int)cudaStreamSynchronize(h->stream);
@@ -239,9 +281,29 @@ extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
         dogm_destroy(h);
         return e;
     }
+    if (band)
+        set_particle_counts(h, 0, 0); // a band starts empty: the first cycle hands it its share of the particles
     *out = h;
     return 0;
 }
+
+extern "C" int dogm_create(const dogm_params* params, dogm_handle** out)
+{
+    return create_impl(params, nullptr, out);
+}
+
+namespace dogm_b200
+{
+// band mode: the counts of this cycle and everything derived from them (the buffers are sized for the capacities)
+void set_particle_counts(dogm_handle* h, int n, int b)
+{
+    h->N = n;
+    h->B = b;
+    h->tiles = div_up(n > 0 ? n : 1, kTileItems);
+    h->n_chunks = div_up(n > 0 ? n : 1, kSegChunk);
+    h->n_cdf_tiles = div_up((long long)n + b > 0 ? (long long)n + b : 1, kCdfTile);
+}
+} // namespace dogm_b200
 
 extern "C" void dogm_destroy(dogm_handle* h)
 {
@@ -281,6 +343,13 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->tile_off);
     cudaFree(h->chain_flags);
     cudaFree(h->res_start);
+    for (int d = 0; d < 2; d++)
+    {
+        cudaFree(h->band.send[d]);
+        cudaFree(h->band.recv[d]);
+        cudaFree(h->band.halo[d]);
+    }
+    cudaFree(h->band.send_count);
     if (h->trace_buf)
     {
         trace_bind_particles(nullptr);
@@ -887,6 +956,274 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// band mode (include/dogm_b200.h, "Band mode"): the cycle in phases, the orchestrator moves data between the bands
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int dogm_create_band(const dogm_params* params, const dogm_band_config* band, dogm_handle** out)
+{
+    if (!band)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    return create_impl(params, band, out);
+}
+
+#define BAND_PROLOGUE()                                                                                                \
+    if (!h || !h->band.enabled)                                                                                        \
+        return DOGM_ERR_INVALID_ARGUMENT;                                                                              \
+    if (h->opts.noise_mode != DOGM_NOISE_PHILOX || h->opts.resample_mode == DOGM_RESAMPLE_INJECTED)                    \
+        return DOGM_ERR_UNSUPPORTED;                                                                                   \
+    int e = 0;
+
+extern "C" void* dogm_band_buffer(dogm_handle* h, int which)
+{
+    if (!h || !h->band.enabled)
+        return nullptr;
+    switch (which)
+    {
+    case DOGM_BAND_SEND_LO: return h->band.send[0];
+    case DOGM_BAND_SEND_HI: return h->band.send[1];
+    case DOGM_BAND_RECV_LO: return h->band.recv[0];
+    case DOGM_BAND_RECV_HI: return h->band.recv[1];
+    case DOGM_BAND_HALO_LO: return h->band.halo[0];
+    case DOGM_BAND_HALO_HI: return h->band.halo[1];
+    case DOGM_BAND_EDGE_LO: return h->free_cur;
+    case DOGM_BAND_EDGE_HI: return h->free_cur + (size_t)(h->band.rows - h->band.halo_rows) * h->gs;
+    default: return nullptr;
+    }
+}
+
+extern "C" int dogm_band_counts(dogm_handle* h, int* particles, int* birth_particles)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (particles)
+        *particles = h->N;
+    if (birth_particles)
+        *birth_particles = h->B;
+    return 0;
+}
+
+// first and one-past-last slot of a band in a slot numbering that spans all bands: slots are handed out in proportion
+// to mass, slot end of a prefix = int(float(prefix) * scale) exactly as the kernels evaluate it per cell
+static void band_slot_range(double before, double local, double total, int count_glob, int* first, int* past)
+{
+    if (!(total > 0.0))
+    {
+        *first = *past = 0;
+        return;
+    }
+    const float scale = (float)count_glob / (float)total;
+    *first = (int)((float)before * scale);
+    *past = (int)((float)(before + local) * scale);
+    if (*past < *first)
+        *past = *first;
+}
+
+extern "C" int dogm_band_init_masses(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, double* mass_local)
+{
+    BAND_PROLOGUE();
+    if (!mass_local)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (measurement_band && measurement_band != h->meas)
+        DOGM_CHECK((cudaError_t)copy_in(h->meas, measurement_band, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
+    e = run_init_masses(h);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    DOGM_CHECK(cudaMemcpy(&h->band.born_local, &h->scal->born_total, sizeof(double), cudaMemcpyDeviceToHost));
+    *mass_local = h->band.born_local;
+    return 0;
+}
+
+extern "C" int dogm_band_init_particles(dogm_handle* h, double mass_before, double mass_total, int* particles)
+{
+    BAND_PROLOGUE();
+    int first, past;
+    band_slot_range(mass_before, h->band.born_local, mass_total, h->band.n_glob, &first, &past);
+    int n = past - first;
+    if (n > h->band.n_cap)
+        return DOGM_ERR_INVALID_ARGUMENT; // the band's share does not fit its capacity
+    h->band.born_base = mass_before;
+    h->band.birth_slot_base = first;
+    DOGM_CHECK(cudaMemcpy(&h->scal->born_total, &mass_total, sizeof(double), cudaMemcpyHostToDevice));
+    set_particle_counts(h, n, 0);
+    e = run_init_fill(h);
+    h->first_measurement_received = true;
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    if (particles)
+        *particles = n;
+    return 0;
+}
+
+extern "C" int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float new_yaw, float dt, int* send_lo, int* send_hi)
+{
+    BAND_PROLOGUE();
+    update_pose(h, new_x, new_y, new_yaw);
+    DOGM_CHECK(cudaMemsetAsync(h->band.send_count, 0, 2 * sizeof(int), h->stream));
+    e = run_predict(h, dt);
+    if (e)
+        return e;
+    h->shift_particles_pending = false;
+    int counts[2] = {0, 0};
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    DOGM_CHECK(cudaMemcpy(counts, h->band.send_count, sizeof(counts), cudaMemcpyDeviceToHost));
+    if (counts[0] > h->band.send_cap || counts[1] > h->band.send_cap)
+        return DOGM_ERR_INVALID_ARGUMENT; // more particles crossed an edge than the exchange boxes hold
+    if (send_lo)
+        *send_lo = counts[0];
+    if (send_hi)
+        *send_hi = counts[1];
+    return 0;
+}
+
+extern "C" int dogm_band_append(dogm_handle* h, int recv_lo, int recv_hi)
+{
+    BAND_PROLOGUE();
+    if (recv_lo < 0 || recv_hi < 0 || recv_lo > h->band.send_cap || recv_hi > h->band.send_cap)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (h->N == 0 && recv_lo + recv_hi > 0)
+    { // nothing was predicted here: the records are the band's whole population
+        h->pa_current = false;
+        h->rec_valid = true;
+        h->sorted_valid = false;
+    }
+    e = run_band_append(h, recv_lo, recv_hi);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, float dt, int halo_valid,
+                                double* born_local)
+{
+    BAND_PROLOGUE();
+    if (!born_local)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    h->meas_src = nullptr;
+    if (measurement_band && measurement_band != h->meas)
+    {
+        if (on_device)
+            h->meas_src = measurement_band; // the cell kernel copies it on the way
+        else
+            DOGM_CHECK((cudaError_t)copy_in(h->meas, measurement_band, (size_t)h->C * sizeof(dogm_meas_cell), 0, h->stream));
+    }
+    h->band.halo_valid = halo_valid ? 1 : 0;
+    if ((e = run_assignment(h)))
+        return e;
+    if ((e = run_occupancy_update(h, dt)))
+        return e;
+    if ((e = run_persistent_weights(h, true)))
+        return e;
+    if ((e = run_born_scan(h)))
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    DOGM_CHECK(cudaMemcpy(&h->band.born_local, &h->scal->born_total, sizeof(double), cudaMemcpyDeviceToHost));
+    *born_local = h->band.born_local;
+    return 0;
+}
+
+extern "C" int dogm_band_birth(dogm_handle* h, double born_before, double born_total, double* weight_local)
+{
+    BAND_PROLOGUE();
+    if (!weight_local)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    int first, past;
+    band_slot_range(born_before, h->band.born_local, born_total, h->band.b_glob, &first, &past);
+    int b = past - first;
+    if (b > h->band.b_cap)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    h->band.born_base = born_before;
+    h->band.birth_slot_base = first;
+    DOGM_CHECK(cudaMemcpy(&h->scal->born_total, &born_total, sizeof(double), cudaMemcpyHostToDevice));
+    set_particle_counts(h, h->N, b);
+    if ((e = run_birth_fill(h)))
+        return e;
+    if ((e = run_cdf(h)))
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    h->band.weight_local = 0.0;
+    if (h->N + h->B > 0)
+        DOGM_CHECK(cudaMemcpy(&h->band.weight_local, &h->scal->weight_total, sizeof(double), cudaMemcpyDeviceToHost));
+    *weight_local = h->band.weight_local;
+    return 0;
+}
+
+extern "C" int dogm_band_resample(dogm_handle* h, double weight_before, double weight_total, int* particles_out)
+{
+    BAND_PROLOGUE();
+    const long long n_glob = h->band.n_glob;
+    long long i_lo = 0, i_hi = 0;
+    if (weight_total > 0.0 && n_glob > 0 && h->band.weight_local > 0.0)
+    {
+        const double step = weight_total / (double)n_glob;
+        const bool systematic = h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC;
+        const uint32_t s_lo = (uint32_t)h->opts.seed, s_hi = (uint32_t)(h->opts.seed >> 32);
+        const float u0 = systematic ? u01_half_open(philox4x32_10(0u, STAGE_RESAMPLE, h->cycle, 0u, s_lo, s_hi).x) : 0.0f;
+        // the offset of output slot i, the expression of resample_offset (kernels_particles.cu)
+        auto offset = [&](long long i) {
+            const float u = systematic ? u0 : u01_half_open(philox4x32_10((uint32_t)i, STAGE_RESAMPLE, h->cycle, 0u, s_lo, s_hi).x);
+            return ((double)i + (double)u) * step;
+        };
+        // smallest slot whose offset exceeds x (offsets ascend with the slot number)
+        auto first_behind = [&](double x) {
+            long long lo = 0, hi = n_glob;
+            while (lo < hi)
+            {
+                const long long mid = lo + ((hi - lo) >> 1);
+                if (offset(mid) > x)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            return lo;
+        };
+        const double upto = weight_before + h->band.weight_local; // == the next band's weight_before (same addition)
+        i_lo = weight_before > 0.0 ? first_behind(weight_before) : 0;
+        i_hi = upto >= weight_total ? n_glob : first_behind(upto);
+        if (i_hi < i_lo)
+            i_hi = i_lo;
+    }
+    const long long n_out = i_hi - i_lo;
+    if (n_out > h->band.n_cap)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    h->band.cdf_base = weight_before;
+    h->band.out_base = i_lo;
+    h->band.n_out = (int)n_out;
+    DOGM_CHECK(cudaMemcpy(&h->scal->weight_total, &weight_total, sizeof(double), cudaMemcpyHostToDevice));
+    e = run_resample_gather(h);
+    if (e)
+        return e;
+    set_particle_counts(h, (int)n_out, h->B);
+    h->cycle++;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    if (particles_out)
+        *particles_out = (int)n_out;
+    return 0;
+}
+
+extern "C" int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated)
+{
+    BAND_PROLOGUE();
+    e = ensure_soa(h);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)h->N;
+    if (n == 0)
+        return 0;
+    if (state_xyvv)
+        DOGM_CHECK(cudaMemcpy(state_xyvv, h->pa.state, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (cell_idx)
+        DOGM_CHECK(cudaMemcpy(cell_idx, h->pa.idx, n * sizeof(int), cudaMemcpyDeviceToHost));
+    if (weight)
+        DOGM_CHECK(cudaMemcpy(weight, h->pa.weight, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (associated)
+        DOGM_CHECK(cudaMemcpy(associated, h->pa.assoc, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // instrumentation
 // ---------------------------------------------------------------------------------------------------------
 extern "C" void* dogm_get_stream(dogm_handle* h) { return h ? (void*)h->stream : nullptr; }
@@ -1080,6 +1417,11 @@ extern "C" int dogm_device_free(void* p)
 extern "C" int dogm_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes)
 {
     DOGM_CHECK(cudaMemcpy(dst_device, src_host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int dogm_memcpy_d2d(void* dst_device, const void* src_device, size_t bytes)
+{ // unified addressing: also a peer copy when the two buffers live on different GPUs of this process
+    DOGM_CHECK(cudaMemcpy(dst_device, src_device, bytes, cudaMemcpyDefault));
     return 0;
 }
 extern "C" int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes)

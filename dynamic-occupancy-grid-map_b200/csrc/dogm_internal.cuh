@@ -171,7 +171,34 @@ struct dogm_handle
 {
     dogm_params params;
     dogm_options opts;
-    int gs, C, N, B;
+    int gs, C, N, B;              // row length, cells, current persistent / birth particle counts
+    // Band mode (dogm_create_band): this handle owns the rows [row0, row0 + rows) of a G x G grid and the particles that
+    // lie there; particle counts vary from cycle to cycle within the capacities; an orchestrator exchanges the
+    // particles that cross a band edge and the global normalisers.  Without bands: G = rows = gs, row0 = 0, the
+    // capacities are the counts, the bases are 0 - every formula below then reduces to the single-grid one.
+    struct Band
+    {
+        int enabled;
+        int G, row0, rows;
+        int n_cap, b_cap;          // buffer capacities (particles)
+        int n_glob, b_glob;        // particle counts of the whole grid (Params)
+        uint64_t salt;             // added to the seed for per-particle noise (ranks must not share their streams)
+        // set per cycle by the orchestrator
+        double born_base;          // born mass of the bands before this one
+        int birth_slot_base;       // global number of this band's first birth slot
+        double cdf_base;           // joint weight of the bands before this one
+        long long out_base;        // global number of this band's first resampled particle
+        int n_out;                 // resampled particles of this band
+        // migration and halo buffers
+        dogm_b200::PRec* send[2];  // particles leaving through the lower / upper edge (records with global coordinates)
+        dogm_b200::PRec* recv[2];
+        int* send_count;           // device, 2 counters
+        int send_cap;
+        float* halo[2];            // rows of the neighbours' previous free masses needed by an ego-motion shift in y
+        int halo_rows;
+        int halo_valid;            // the orchestrator filled the halo rows for this cycle
+        double born_local, weight_local; // host copies of this band's normaliser shares
+    } band;
     int device;
     int sm_count;
     cudaStream_t stream;
@@ -355,7 +382,15 @@ int run_assignment(dogm_handle* h);
 int run_occupancy_update(dogm_handle* h, float dt);
 int run_persistent_weights(dogm_handle* h, bool defer);
 int run_birth(dogm_handle* h);
+int run_init_masses(dogm_handle* h); // first-cycle masses + their block scan
+int run_init_fill(dogm_handle* h);   // first-cycle particles
+int run_born_scan(dogm_handle* h);   // block offsets and total of the born masses
+int run_birth_fill(dogm_handle* h);  // birth particles
 int run_resampling(dogm_handle* h);
+int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of run_resampling)
+int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
+int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi);
+void set_particle_counts(dogm_handle* h, int n, int b); // band mode: current counts and everything derived from them
 int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells
 int run_init_grid(dogm_handle* h);         // initGridCellsKernel
 int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out);

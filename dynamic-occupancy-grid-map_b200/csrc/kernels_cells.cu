@@ -39,6 +39,11 @@ struct CellArgs
     float dyn_min_occ, dyn_min_vel;
     float p_B, alpha;
     int shift_active, x_move, y_move;
+    // band mode: this handle holds rows [row0, row0 + rows) of a grid of gs rows; rows that an ego-motion shift pulls in
+    // from a neighbour band are read from the halo copies (halo_lo: the halo_rows rows below row0, halo_hi: above)
+    int row0, rows, halo_rows;
+    const float* halo_lo;
+    const float* halo_hi;
 };
 
 #ifndef DOGM_CELL_MINBLOCKS
@@ -68,9 +73,19 @@ __global__ void __launch_bounds__(kCellBlock, DOGM_CELL_MINBLOCKS) k_cell(CellAr
         float free_prev;
         if (a.shift_active)
         {
-            const int x = c % a.gs, y = c / a.gs;
+            const int x = c % a.gs, y = c / a.gs + a.row0;
             const int nx = x + a.x_move, ny = y + a.y_move;
-            free_prev = (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs) ? __ldg(a.free_cur + nx + a.gs * ny) : 0.0f;
+            free_prev = 0.0f;
+            if (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs)
+            {
+                const int nl = ny - a.row0; // row inside this band
+                if (nl >= 0 && nl < a.rows)
+                    free_prev = __ldg(a.free_cur + nx + a.gs * nl);
+                else if (nl < 0 && a.halo_lo && -nl <= a.halo_rows)
+                    free_prev = __ldg(a.halo_lo + nx + a.gs * (a.halo_rows + nl));
+                else if (nl >= a.rows && a.halo_hi && nl - a.rows < a.halo_rows)
+                    free_prev = __ldg(a.halo_hi + nx + a.gs * (nl - a.rows));
+            }
         }
         else
         {
@@ -222,22 +237,26 @@ struct SlotView
     const double* prefix;
     int n_blocks, C;
     float scale; // (float)count / (float)total
+    // band mode: mass of the bands in front of this one and the global number of this band's first slot (0, 0 otherwise)
+    double base_off;
+    int slot_base;
 };
 
 __device__ __forceinline__ int slot_end_of_block(const SlotView& v, int b)
 {
-    return __float2int_rz((float)(v.blk_off[b] + v.blk_sum[b]) * v.scale);
+    return __float2int_rz((float)((v.base_off + v.blk_off[b]) + v.blk_sum[b]) * v.scale) - v.slot_base;
 }
 __device__ __forceinline__ int slot_end_of_cell(const SlotView& v, int c)
 {
-    return __float2int_rz((float)(v.blk_off[c / kCellBlock] + v.prefix[c]) * v.scale);
+    return __float2int_rz((float)((v.base_off + v.blk_off[c / kCellBlock]) + v.prefix[c]) * v.scale) - v.slot_base;
 }
 __device__ __forceinline__ int slot_start_of_cell(const SlotView& v, int c)
 {
     if (c == 0)
         return 0;
     // the cell in front of the first cell of a block ends where that block's offset puts it
-    return (c % kCellBlock) ? slot_end_of_cell(v, c - 1) : __float2int_rz((float)v.blk_off[c / kCellBlock] * v.scale);
+    return (c % kCellBlock) ? slot_end_of_cell(v, c - 1)
+                            : __float2int_rz((float)(v.base_off + v.blk_off[c / kCellBlock]) * v.scale) - v.slot_base;
 }
 
 // owner cell of slot s: first cell j whose end slot exceeds s (two-level search: 256-cell blocks, then cells)
@@ -288,6 +307,8 @@ __device__ __forceinline__ BirthWeights birth_weights_of_cell(const SlotView& v,
 struct BirthArgs
 {
     int B, gs;
+    int B_glob;    // birth particles of the whole grid (the slot scale); == B without bands
+    int cell_base; // number of this band's first cell in the whole grid (0 without bands)
     SlotView slots;
     const DeviceScalars* scal;
     const float* born_masses;
@@ -310,7 +331,7 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     if (s >= a.B)
         return;
     SlotView v = a.slots;
-    v.scale = (float)a.B / (float)a.scal->born_total;
+    v.scale = (float)a.B_glob / (float)a.scal->born_total;
     int j = find_slot_owner(v, s);
     bool assoc = false;
     float weight;
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
         vel = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
     }
     const float x = (float)(j % a.gs) + 0.5f;
-    const float y = (float)j / (float)a.gs + 0.5f; // float division, init_new_particles.cu:173
+    const float y = (float)(j + a.cell_base) / (float)a.gs + 0.5f; // float division, init_new_particles.cu:173
     a.birth.idx[s] = j;
     a.birth.assoc[s] = assoc ? 1 : 0;
     a.birth.weight[s] = weight;
@@ -372,6 +393,8 @@ __global__ void __launch_bounds__(kCellBlock) k_init_masses(const dogm_meas_cell
 struct InitArgs
 {
     int N, gs;
+    int N_glob;    // particles of the whole grid (slot scale and initial weight); == N without bands
+    int row0;      // first row of this band (0 without bands)
     SlotView slots;
     const DeviceScalars* scal;
     ParticleSet p;
@@ -389,7 +412,7 @@ __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
     if (i >= a.N)
         return;
     SlotView sv = a.slots;
-    sv.scale = (float)a.N / (float)a.scal->born_total;
+    sv.scale = (float)a.N_glob / (float)a.scal->born_total;
     int j = find_slot_owner(sv, i);
     if (j < 0)
         j = a.p.idx[i];
@@ -404,9 +427,9 @@ __global__ void __launch_bounds__(kBlock) k_init_particles(InitArgs a)
         v = make_float2(lo + span * (1.0f - u01_open_low(r.x)), lo + span * (1.0f - u01_open_low(r.y)));
     }
     const float x = (float)(j % a.gs) + 0.5f;
-    const float y = (float)(j / a.gs) + 0.5f; // integer division, init_new_particles.cu:115
+    const float y = (float)(j / a.gs + a.row0) + 0.5f; // integer division, init_new_particles.cu:115
     a.p.idx[i] = j;
-    a.p.weight[i] = 1.0f / (float)a.N;
+    a.p.weight[i] = 1.0f / (float)a.N_glob;
     a.p.state[i] = make_float4(x, y, v.x, v.y);
 }
 
@@ -497,31 +520,38 @@ static SlotView make_slot_view(dogm_handle* h)
     v.n_blocks = h->n_cell_blocks;
     v.C = h->C;
     v.scale = 0.0f;
+    v.base_off = h->band.enabled ? h->band.born_base : 0.0;
+    v.slot_base = h->band.enabled ? h->band.birth_slot_base : 0;
     return v;
 }
 
-int run_init_particles(dogm_handle* h)
+// first-cycle initialisation in two steps, so that a band orchestrator can put the global normaliser in between
+int run_init_masses(dogm_handle* h)
 {
     {
         LaunchScope ls(h, K_INIT_MASSES, 8.0 * h->C);
         launch_chained(h->stream, k_init_masses, h->n_cell_blocks, kCellBlock, 0, h->meas, h->born_masses, h->C, h->blk_sum,
                                                                       h->cell_prefix);
     }
-    int e = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
-    if (e)
-        return e;
+    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
+}
+
+int run_init_fill(dogm_handle* h)
+{
     if (h->N <= 0)
         return 0;
     InitArgs a;
     a.N = h->N;
     a.gs = h->gs;
+    a.N_glob = h->band.enabled ? h->band.n_glob : h->N;
+    a.row0 = h->band.row0;
     a.slots = make_slot_view(h);
     a.scal = h->scal;
     a.p = h->pa;
     a.init_velocity = h->init_velocity;
     a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
     a.init_max_velocity = h->params.init_max_velocity;
-    a.seed = h->opts.seed;
+    a.seed = h->opts.seed + h->band.salt;
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_INIT_PARTICLES, 24.0 * h->N);
@@ -532,6 +562,12 @@ int run_init_particles(dogm_handle* h)
     h->rec_valid = false;
     h->sorted_valid = false;
     return (int)cudaGetLastError();
+}
+
+int run_init_particles(dogm_handle* h)
+{
+    int e = run_init_masses(h);
+    return e ? e : run_init_fill(h);
 }
 
 int run_occupancy_update(dogm_handle* h, float dt)
@@ -556,6 +592,11 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.shift_active = (h->shift_grid_pending && h->shift.active) ? 1 : 0;
     a.x_move = h->shift.x_move;
     a.y_move = h->shift.y_move;
+    a.row0 = h->band.row0;
+    a.rows = h->band.rows;
+    a.halo_rows = h->band.halo_rows;
+    a.halo_lo = h->band.halo_valid ? h->band.halo[0] : nullptr;
+    a.halo_hi = h->band.halo_valid ? h->band.halo[1] : nullptr;
     a.dyn_out = nullptr;
     a.dyn_count = h->dyn_count;
     a.dyn_capacity = h->dyn_filter_capacity;
@@ -582,16 +623,26 @@ int run_occupancy_update(dogm_handle* h, float dt)
     return (int)cudaGetLastError();
 }
 
+int run_born_scan(dogm_handle* h)
+{
+    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
+}
+
 int run_birth(dogm_handle* h)
 {
-    int e = run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
-    if (e)
-        return e;
+    int e = run_born_scan(h);
+    return e ? e : run_birth_fill(h);
+}
+
+int run_birth_fill(dogm_handle* h)
+{
     if (h->B <= 0)
         return 0;
     BirthArgs a;
     a.B = h->B;
     a.gs = h->gs;
+    a.B_glob = h->band.enabled ? h->band.b_glob : h->B;
+    a.cell_base = h->band.row0 * h->gs;
     a.slots = make_slot_view(h);
     a.scal = h->scal;
     a.born_masses = h->born_masses;
@@ -601,7 +652,7 @@ int run_birth(dogm_handle* h)
     a.noise = h->birth_noise;
     a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
     a.stddev_velocity = h->params.stddev_velocity;
-    a.seed = h->opts.seed;
+    a.seed = h->opts.seed + h->band.salt;
     a.cycle = h->cycle;
     {
         LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B);

@@ -43,7 +43,12 @@ struct PredictArgs
     PRec* out;
     int* key_out;
     int n;
-    int gs;
+    int gs;            // row length of the (band of the) grid = cells per side of the whole grid
+    int row0, rows;    // rows of the whole grid this handle owns (0, gs without bands)
+    PRec* send_lo;     // band mode: records of the particles that leave through the lower / upper edge
+    PRec* send_hi;
+    int* send_count;
+    int send_cap;
     float dt, p_S, sigma_pos, sigma_vel;
     int shift_active, x_move, y_move;
     const float4* noise;
@@ -113,7 +118,24 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
             if ((x > hi || x < 0.0f) || (y > hi || y < 0.0f))
                 w = 0.0f;
             const int px = min(max(__float2int_rz(x), 0), a.gs - 1);
-            const int py = min(max(__float2int_rz(y), 0), a.gs - 1);
+            int py = min(max(__float2int_rz(y), 0), a.gs - 1) - a.row0;
+            if (py < 0 || py >= a.rows)
+            { // band mode only: the particle now lies in a neighbour's band; it goes into the outbox with its weight
+              // and stays behind as a weightless ghost in the edge row until resampling drops it
+                if (w > 0.0f)
+                {
+                    const int dir = py < 0 ? 0 : 1;
+                    const int at = atomicAdd(a.send_count + dir, 1);
+                    if (at < a.send_cap)
+                    {
+                        float4* so = reinterpret_cast<float4*>((dir ? a.send_hi : a.send_lo) + at);
+                        so[0] = rec_lo(x, y, 0, as);
+                        so[1] = rec_hi(vx, vy, w);
+                    }
+                }
+                w = 0.0f;
+                py = py < 0 ? 0 : a.rows - 1;
+            }
             const int cell = px + a.gs * py;
             float4* o = reinterpret_cast<float4*>(out + i);
             o[0] = rec_lo(x, y, cell, as);
@@ -1295,7 +1317,11 @@ struct ResampleArgs
 {
     const double* cdf;
     int n_cdf;
-    int N;
+    int N;              // persistent entries of the CDF (the entries behind are birth particles)
+    int N_out;          // output slots of this handle (== N without bands)
+    int N_glob;         // output slots of the whole grid: step = total / N_glob, new weight = total / N_glob
+    long long out_base; // global number of this handle's first output slot (0 without bands)
+    double cdf_base;    // joint weight in front of this handle's CDF (0 without bands)
     const PRec* rec;    // persistent particles (records in slot order)
     const int2* spair;  // sorted (cell, slot) pairs: position p of the sorted set is record spair[p].y
     ParticleSet birth;  // birth particles
@@ -1337,10 +1363,11 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
 {
     if (a.mode == DOGM_RESAMPLE_INJECTED)
         return (double)__fmul_rn(joint_max, a.resample_u[i]);
+    const long long gi = a.out_base + i; // slot number in the whole grid
     float u = u0;
     if (a.mode == DOGM_RESAMPLE_STRATIFIED)
-        u = a.noise_injected ? a.resample_u[i] : resample_fraction_philox(a.seed, (uint32_t)i, a.cycle);
-    return ((double)i + (double)u) * step;
+        u = a.noise_injected ? a.resample_u[i] : resample_fraction_philox(a.seed, (uint32_t)gi, a.cycle);
+    return ((double)gi + (double)u) * step - a.cdf_base;
 }
 
 constexpr int kResPer = 4;                     // output slots per thread
@@ -1378,12 +1405,13 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         float u0 = 0.0f;
         if (a.mode == DOGM_RESAMPLE_SYSTEMATIC)
             u0 = a.noise_injected ? a.resample_u[0] : resample_fraction_philox(a.seed, 0u, a.cycle);
-        const double step = total / (double)a.N;
+        const double step = total / (double)a.N_glob;
         s_step = step;
         s_u0 = u0;
         s_jm = jm;
         // a lower limit of the CTA's offsets: its first offset (systematic, injected) or the block boundary (stratified)
-        s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)out0 * step : resample_offset(a, out0, jm, u0, step);
+        s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)(a.out_base + out0) * step - a.cdf_base
+                                                     : resample_offset(a, out0, jm, u0, step);
     }
 #pragma unroll
     for (int k = 0; k < kResWindow / kBlock; k++)
@@ -1397,7 +1425,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     if (a.res_start && threadIdx.x < kResPer)
     { // unclaimed again for the next cycle
         const int blk = blockIdx.x * kResPer + (int)threadIdx.x;
-        if (blk * kBlock < a.N)
+        if (blk * kBlock < a.N_out)
             a.res_start[blk] = 0x7f7f7f7f;
     }
     const bool have = __syncthreads_and(ok);
@@ -1428,7 +1456,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     for (int j = 0; j < kResPer; j++)
     {
         const int i = out0 + j * kBlock + (int)threadIdx.x;
-        const double r = resample_offset(a, i < a.N ? i : a.N - 1, joint_max, s_u0, s_step);
+        const double r = resample_offset(a, i < a.N_out ? i : a.N_out - 1, joint_max, s_u0, s_step);
         int an;
         if (r < r_first)
             an = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
@@ -1476,12 +1504,12 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             as[j] = a.birth.assoc[b];
         }
     }
-    const float w_new = __fdiv_rn(joint_max, (float)a.N);
+    const float w_new = __fdiv_rn(joint_max, (float)a.N_glob);
 #pragma unroll
     for (int j = 0; j < kResPer; j++)
     {
         const int i = out0 + j * kBlock + (int)threadIdx.x;
-        if (i < a.N)
+        if (i < a.N_out)
         {
             a.ancestors[i] = anc[j];
             a.dst.state[i] = st[j];
@@ -1576,6 +1604,12 @@ int run_predict(dogm_handle* h, float dt)
     a.key_out = h->key0;
     a.n = h->N;
     a.gs = h->gs;
+    a.row0 = h->band.row0;
+    a.rows = h->band.rows;
+    a.send_lo = h->band.send[0];
+    a.send_hi = h->band.send[1];
+    a.send_count = h->band.send_count;
+    a.send_cap = h->band.send_cap;
     a.dt = dt;
     a.p_S = h->params.persistence_prob;
     a.sigma_pos = h->params.stddev_process_noise_position;
@@ -1584,7 +1618,7 @@ int run_predict(dogm_handle* h, float dt)
     a.x_move = h->shift.x_move;
     a.y_move = h->shift.y_move;
     a.noise = h->predict_noise;
-    a.seed = h->opts.seed;
+    a.seed = h->opts.seed + h->band.salt;
     a.cycle = h->cycle;
     a.hist = h->hist[0];
     a.bins = h->digit_bins[0];
@@ -1720,13 +1754,13 @@ int configure_kernels()
     return (int)cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
-int run_resampling(dogm_handle* h)
+int run_cdf(dogm_handle* h)
 {
     const int N = h->N, n = h->N + h->B;
-    if (N <= 0)
+    if (n <= 0)
         return 0;
-    if (!h->sorted_valid)
-        return DOGM_ERR_NOT_INITIALIZED; // resampling gathers from the sorted records of dogm_particle_assignment
+    if (N > 0 && !h->sorted_valid)
+        return DOGM_ERR_NOT_INITIALIZED; // the CDF reads the sorted weights of dogm_particle_assignment
     CdfArgs ca;
     ca.wa = h->weight_array;
     ca.wa_out = h->weight_array;
@@ -1737,31 +1771,38 @@ int run_resampling(dogm_handle* h)
     ca.N = N;
     ca.n = n;
     const bool fused = h->weights_deferred;
-    {
-        ChainArgs ch;
-        ch.c = ca;
-        ch.cdf = h->cdf;
-        ch.tile_sum = h->tile_sum;
-        ch.group_base = h->tile_off;
-        ch.ticket = h->chain_flags;
-        ch.ticket_base = h->chain_ticket_base;
-        ch.epoch = ++h->chain_epoch;
-        ch.tiles = h->n_cdf_tiles;
-        ch.total_out = &h->scal->weight_total;
-        const bool resident = h->n_cdf_tiles <= h->chain_capacity;
-        ch.res_start = (resident && h->opts.resample_mode != DOGM_RESAMPLE_INJECTED) ? h->res_start : nullptr;
+    ChainArgs ch;
+    ch.c = ca;
+    ch.cdf = h->cdf;
+    ch.tile_sum = h->tile_sum;
+    ch.group_base = h->tile_off;
+    ch.ticket = h->chain_flags;
+    ch.ticket_base = h->chain_ticket_base;
+    ch.epoch = ++h->chain_epoch;
+    ch.tiles = h->n_cdf_tiles;
+    ch.total_out = &h->scal->weight_total;
+    const bool resident = h->n_cdf_tiles <= h->chain_capacity;
+    ch.res_start = (resident && h->opts.resample_mode != DOGM_RESAMPLE_INJECTED && !h->band.enabled) ? h->res_start : nullptr;
 #ifdef DOGM_AB_NO_CLAIMS
-        ch.res_start = nullptr;
+    ch.res_start = nullptr;
 #endif
-        ch.total_word = h->tile_off + (h->n_cdf_tiles / kChainGroup + 1);
-        ch.res_blocks = div_up(N, kBlock);
-        ch.systematic = h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC ? 1 : 0;
-        ch.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
-        ch.resample_u = h->resample_u;
-        ch.seed = h->opts.seed;
-        ch.cycle = h->cycle;
-        const int grid = h->n_cdf_tiles < h->chain_capacity ? h->n_cdf_tiles : h->chain_capacity;
-        h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
+    if (h->band.enabled)
+    { // the number of tiles changes from cycle to cycle, so the parity of the published words cannot alternate: the
+      // words are cleared and every launch publishes with parity 1
+        cudaMemsetAsync(h->tile_sum, 0, (size_t)h->n_cdf_tiles * sizeof(double), h->stream);
+        cudaMemsetAsync(h->tile_off, 0, ((size_t)h->n_cdf_tiles + 3) * sizeof(double), h->stream);
+        ch.epoch = 1u;
+    }
+    ch.total_word = h->tile_off + (h->n_cdf_tiles / kChainGroup + 1);
+    ch.res_blocks = div_up(N > 0 ? N : 1, kBlock);
+    ch.systematic = h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC ? 1 : 0;
+    ch.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
+    ch.resample_u = h->resample_u;
+    ch.seed = h->opts.seed;
+    ch.cycle = h->cycle;
+    const int grid = h->n_cdf_tiles < h->chain_capacity ? h->n_cdf_tiles : h->chain_capacity;
+    h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
+    {
         LaunchScope ls(h, K_CDF_CHAIN, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
         if (fused)
             launch_chained(h->stream, k_cdf_chain<true>, grid, kBlock, 0, ch);
@@ -1769,31 +1810,91 @@ int run_resampling(dogm_handle* h)
             launch_chained(h->stream, k_cdf_chain<false>, grid, kBlock, 0, ch);
     }
     h->weights_deferred = false;
+    return (int)cudaGetLastError();
+}
+
+int run_resample_gather(dogm_handle* h)
+{
+    const int N = h->N, n = h->N + h->B;
+    const int n_out = h->band.enabled ? h->band.n_out : N;
     ResampleArgs a;
     a.cdf = h->cdf;
     a.n_cdf = n;
     a.N = N;
+    a.N_out = n_out;
+    a.N_glob = h->band.enabled ? h->band.n_glob : N;
+    a.out_base = h->band.enabled ? h->band.out_base : 0ll;
+    a.cdf_base = h->band.enabled ? h->band.cdf_base : 0.0;
     a.rec = h->rec;
     a.spair = h->spair;
     a.birth = h->birth;
     a.dst = h->pa;
     a.ancestors = h->ancestors;
     a.scal = h->scal;
-    a.res_start = h->opts.resample_mode != DOGM_RESAMPLE_INJECTED ? h->res_start : nullptr;
+    a.res_start = (h->opts.resample_mode != DOGM_RESAMPLE_INJECTED && !h->band.enabled) ? h->res_start : nullptr;
     a.mode = h->opts.resample_mode;
     a.noise_injected = (h->opts.noise_mode == DOGM_NOISE_INJECTED) ? 1 : 0;
     a.resample_u = h->resample_u;
     a.seed = h->opts.seed;
     a.cycle = h->cycle;
+    if (n_out > 0 && n > 0)
     {
-        LaunchScope ls(h, K_RESAMPLE, 69.0 * N);
-        launch_chained(h->stream, k_resample, div_up(N, kResOutputs), kBlock, 0, a);
+        LaunchScope ls(h, K_RESAMPLE, 69.0 * n_out);
+        launch_chained(h->stream, k_resample, div_up(n_out, kResOutputs), kBlock, 0, a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;
     h->rec_valid = false;
     h->sorted_valid = false;
     h->hist0_valid = false;
+    return (int)cudaGetLastError();
+}
+
+int run_resampling(dogm_handle* h)
+{
+    if (h->N <= 0)
+        return 0;
+    if (!h->sorted_valid)
+        return DOGM_ERR_NOT_INITIALIZED; // resampling gathers from the sorted records of dogm_particle_assignment
+    int e = run_cdf(h);
+    return e ? e : run_resample_gather(h);
+}
+
+// band mode: the particles that arrived from the neighbours (records with global coordinates in the two inboxes) become
+// the tail of this cycle's record list
+__global__ void __launch_bounds__(kBlock) k_band_append(const PRec* __restrict__ in_lo, int n_lo, const PRec* __restrict__ in_hi,
+                                                        int n_hi, PRec* __restrict__ rec, int* __restrict__ key0, int n_cur,
+                                                        int gs, int row0, int rows)
+{
+    pdl_prologue(K_MISC * 2);
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n_lo + n_hi)
+        return;
+    const float4* src = reinterpret_cast<const float4*>(k < n_lo ? in_lo + k : in_hi + (k - n_lo));
+    const float4 lo = src[0], hi = src[1];
+    const int px = min(max(__float2int_rz(lo.x), 0), gs - 1);
+    const int py = min(max(__float2int_rz(lo.y) - row0, 0), rows - 1); // (it does lie in this band: the sender checked)
+    const int cell = px + gs * py;
+    float4* o = reinterpret_cast<float4*>(rec + n_cur + k);
+    o[0] = rec_lo(lo.x, lo.y, cell, __float_as_uint(lo.w));
+    o[1] = hi;
+    key0[n_cur + k] = cell;
+}
+
+int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi)
+{
+    const int add = n_from_lo + n_from_hi;
+    if (add <= 0)
+        return 0;
+    if (h->N + add > h->band.n_cap)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    {
+        LaunchScope ls(h, K_MISC, 68.0 * add);
+        launch_chained(h->stream, k_band_append, div_up(add, kBlock), kBlock, 0, h->band.recv[0], n_from_lo, h->band.recv[1], n_from_hi,
+                       h->rec, h->key0, h->N, h->gs, h->band.row0, h->band.rows);
+    }
+    set_particle_counts(h, h->N + add, h->B);
+    h->hist0_valid = false; // the histogram of the first sort pass has to include the new records
     return (int)cudaGetLastError();
 }
 

@@ -138,6 +138,70 @@ int dogm_statistical_moments(dogm_handle* h);                  /* dogm.cu:350-38
 int dogm_resampling(dogm_handle* h);                           /* dogm.cu:386-423, plus the publish of dogm.cu:128 */
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Band mode: one large grid shared by several handles (one per GPU), each owning a band of rows
+ *
+ * The reference runs on one device (dogm.cu:39-43).  Here a G x G grid can be split into bands of whole rows
+ * (row-major idx = x + G * y makes a band a contiguous range of cells): a band handle holds the cells of its rows and
+ * the particles that currently lie there.  One cycle is driven in phases by an orchestrator, which moves three things
+ * between the bands (device-to-device copies inside a process, NVLink peer copies or NCCL between processes):
+ *   1. the particles that crossed a band edge during prediction (32-byte records, dogm_band_buffer SEND -> RECV),
+ *   2. per band one double per normaliser: born mass (birth slots are handed out over the whole grid) and joint
+ *      weight (resampling draws over the whole grid); every band gets the sum of the bands in front of it and the total,
+ *   3. |y_move| rows of the previous free masses next to a band edge when the ego-motion shift moves the grid in y.
+ * Everything else (sort, per-cell sums, occupancy update, weights, moments, CDF, gather) is local to a band.
+ * Particle coordinates stay global; particle counts per band vary from cycle to cycle within the capacities.
+ * With a single band covering the whole grid the phases reproduce dogm_update_grid bit for bit.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dogm_band_config
+{
+    int row0;               /* first row of the band */
+    int rows;               /* number of rows */
+    int particle_capacity;  /* persistent particles the band can hold (its share plus head-room for drift) */
+    int birth_capacity;     /* birth particles the band can hold */
+    int exchange_capacity;  /* particles per edge and cycle that may leave / arrive */
+    int halo_rows;          /* largest |y_move| of an ego-motion shift */
+    uint64_t seed_salt;     /* added to the seed for per-particle noise: bands must not share their noise streams */
+} dogm_band_config;
+
+#define DOGM_BAND_SEND_LO 0 /* records leaving through the lower edge (towards smaller rows) */
+#define DOGM_BAND_SEND_HI 1
+#define DOGM_BAND_RECV_LO 2 /* records arriving through the lower edge */
+#define DOGM_BAND_RECV_HI 3
+#define DOGM_BAND_HALO_LO 4 /* halo_rows rows below the band: filled from the lower neighbour's DOGM_BAND_EDGE_HI */
+#define DOGM_BAND_HALO_HI 5
+#define DOGM_BAND_EDGE_LO 6 /* the band's own first halo_rows rows of the previous free masses */
+#define DOGM_BAND_EDGE_HI 7 /* its last halo_rows rows */
+
+/* params describe the WHOLE grid (size, resolution, particle counts of all bands together) */
+int dogm_create_band(const dogm_params* params, const dogm_band_config* band, dogm_handle** out);
+/* device address of an exchange buffer (see the DOGM_BAND_* names); sizes: exchange_capacity * 32 bytes for the particle
+ * boxes, halo_rows * G * 4 bytes for the row buffers */
+void* dogm_band_buffer(dogm_handle* h, int which);
+/* current persistent / birth particle counts of the band */
+int dogm_band_counts(dogm_handle* h, int* particles, int* birth_particles);
+/* first cycle, step 1: takes the band's measurement grid (rows * G cells), returns the band's initial mass
+ * (initializeParticles, dogm.cu:217-241: copyMassesKernel + scan) */
+int dogm_band_init_masses(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, double* mass_local);
+/* first cycle, step 2: the band creates its share of the particles (initParticlesKernel1/2); mass_before = sum of
+ * the masses of the bands in front of this one */
+int dogm_band_init_particles(dogm_handle* h, double mass_before, double mass_total, int* particles);
+/* every cycle, step 1: ego-motion bookkeeping (updatePose) + prediction; fills the SEND boxes and returns their counts */
+int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float new_yaw, float dt, int* send_lo, int* send_hi);
+/* step 2: the records the orchestrator put into the RECV boxes join the band's particles */
+int dogm_band_append(dogm_handle* h, int recv_lo, int recv_hi);
+/* step 3: assignment, occupancy update (with the halo rows when halo_valid), persistent weights; returns the band's born
+ * mass.  measurement_band may be NULL after the first cycle's dogm_band_init_masses (keeps that grid). */
+int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, float dt, int halo_valid,
+                     double* born_local);
+/* step 4: birth particles of the band's cells (their slots are numbered over the whole grid) and the band's joint weight
+ * CDF; returns the band's joint weight */
+int dogm_band_birth(dogm_handle* h, double born_before, double born_total, double* weight_local);
+/* step 5: the band draws the output slots whose offsets fall into its part of the global CDF; returns how many */
+int dogm_band_resample(dogm_handle* h, double weight_before, double weight_total, int* particles_out);
+/* read-out of the band's current particles (n = dogm_band_counts): any pointer may be NULL */
+int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Read-out (blocking device-to-host copies, dogm.cu:133-159, dogm.h:111-139)
  * ---------------------------------------------------------------------------------------------------------- */
 int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host);        /* getGridCells: grid_cell_count * 64 B */
@@ -324,6 +388,7 @@ int dogm_device_alloc(void** out, size_t bytes);
 int dogm_device_free(void* p);
 int dogm_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
 int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
+int dogm_memcpy_d2d(void* dst_device, const void* src_device, size_t bytes); /* same GPU or peer GPU of this process */
 int dogm_device_count(void);
 int dogm_set_device(int device);
 const char* dogm_b200_version(void);

@@ -1,0 +1,127 @@
+"""Band mode (include/dogm_b200.h): one grid over several handles, each owning a band of rows, driven in phases by
+BandedDOGM (all bands on one GPU here; the exchange steps are the ones a multi-GPU run does over NVLink).
+  * one band covering the whole grid reproduces dogm_update_grid bit for bit (same phases, same kernels);
+  * with several bands: every particle lies in its band, the global particle count and the total weight are what the
+    single-grid run has, the per-band counts follow the mass, and the maps agree statistically with the single-grid run
+    (the bands draw other random numbers, so not bit for bit)."""
+import numpy as np
+import pytest
+
+from conftest import make_params
+
+pytestmark = pytest.mark.gpu
+
+SIZE, RES, N, B = 60.0, 0.2, 400_000, 40_000  # 300 x 300 cells
+
+
+def scans(gpu, steps, seed=3):
+    gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(SIZE, RES, 120.0, 0.5), SIZE, RES)
+    rng = np.random.default_rng(seed)
+    out = []
+    z = np.full(120, np.inf, np.float32)
+    hit = rng.uniform(size=120) < 0.6
+    z[hit] = rng.uniform(6.0, 55.0, size=int(hit.sum())).astype(np.float32)
+    for s in range(steps):
+        z = z.copy()
+        z[hit] = np.clip(z[hit] + rng.normal(0, 0.3, int(hit.sum())), 3.0, 58.0).astype(np.float32)
+        out.append(gen.generate_grid_host(z))
+    gen.close()
+    return out
+
+
+def run_plain(gpu, grids, poses, seed=77):
+    d = gpu.DOGM(make_params(gpu, SIZE, RES, N, B))
+    d.set_options(seed=seed, resample_mode=gpu.RESAMPLE_SYSTEMATIC, noise_mode=gpu.NOISE_PHILOX)
+    for g, (x, y) in zip(grids, poses):
+        d.update_grid(g, x, y, 0.0, 0.1, device=False)
+    return d
+
+
+def run_banded(gpu, grids, poses, bands, seed=77):
+    bd = gpu.BandedDOGM(make_params(gpu, SIZE, RES, N, B), bands, seed=seed)
+    dev = gpu.device_alloc(grids[0].nbytes)
+    history = []
+    for g, (x, y) in zip(grids, poses):
+        gpu.memcpy_h2d(dev, g)
+        ptrs = [dev + bd.row0[r] * bd.G * 16 for r in range(bands)]
+        history.append(bd.update_grid(ptrs, x, y, 0.0, 0.1))
+    gpu.device_free(dev)
+    return bd, history
+
+
+def poses(steps, vy=4.0, vx=0.0):
+    return [(np.float32(vx * 0.1 * (s + 1)), np.float32(vy * 0.1 * (s + 1))) for s in range(steps)]
+
+
+def test_one_band_reproduces_the_single_grid_cycle(gpu):
+    grids, ps = scans(gpu, 6), poses(6)
+    plain = run_plain(gpu, grids, ps)
+    bd, hist = run_banded(gpu, grids, ps, 1)
+    assert all(h == [N] for h in hist)
+    state, idx, w, a = bd.get_particles(0)
+    ref = plain.get_particles()
+    assert np.array_equal(state.view(np.uint32), ref.state.view(np.uint32))
+    assert np.array_equal(idx, ref.grid_cell_idx) and np.array_equal(w.view(np.uint32), ref.weight.view(np.uint32))
+    assert np.array_equal(bd.get_grid_cells().view(np.uint8), plain.get_grid_cells().view(np.uint8))
+    bd.close()
+    plain.close()
+
+
+@pytest.mark.parametrize("bands,vx,vy", [(2, 0.0, 4.0), (3, 3.0, 0.0), (4, -2.0, 6.0)])
+def test_bands_conserve_and_agree_with_the_single_grid(gpu, bands, vx, vy):
+    steps = 8
+    grids, ps = scans(gpu, steps), poses(steps, vy, vx)
+    plain = run_plain(gpu, grids, ps)
+    bd, hist = run_banded(gpu, grids, ps, bands)
+    G = bd.G
+    # every cycle hands out exactly the global number of particles, or one fewer per band edge through float rounding
+    for counts in hist:
+        assert N - bands <= sum(counts) <= N
+    total_w, n_seen = 0.0, 0
+    for r in range(bands):
+        state, idx, w, _ = bd.get_particles(r)
+        n_seen += len(w)
+        total_w += float(w.astype(np.float64).sum())
+        # the resampled particles are copies of particles (or birth particles) that were in the band
+        assert np.all(idx >= 0) and np.all(idx < bd.rows[r] * G)
+        rows = state[:, 1].astype(np.int32)
+        inside = (state[:, 1] >= 0) & (state[:, 1] <= G - 1)
+        # (birth particles sit at y = cell / float(G) + 0.5, init_new_particles.cu:173, i.e. up to half a cell above
+        #  their cell's row: those of a band's last row may already lie in the next band and move there next cycle)
+        assert np.all((rows[inside] >= bd.row0[r]) & (rows[inside] <= bd.row0[r] + bd.rows[r]))
+        assert np.unique(w).size == 1  # weight = joint total / N of the whole grid
+    assert n_seen == sum(hist[-1])
+    pw = plain.get_particles().weight.astype(np.float64).sum()
+    assert abs(total_w - pw) <= 0.02 * pw
+    # particles did cross band edges (the test would be vacuous otherwise)
+    lo, hi = bd.last_migration
+    assert sum(lo) + sum(hi) > 0
+    # the maps agree statistically: occupied mass in 10 x 10 blocks
+    cb, cp = bd.get_grid_cells(), plain.get_grid_cells()
+    assert cb.size == cp.size == G * G
+
+    def blocks(cells, field):
+        v = cells[field].astype(np.float64).reshape(G, G)
+        return v.reshape(G // 10, 10, G // 10, 10).sum(axis=(1, 3))
+
+    # yardstick: the same single-grid run with another seed (two independent realisations of the same filter)
+    other = run_plain(gpu, grids, ps, seed=78)
+    co = other.get_grid_cells()
+    other.close()
+    ob, op, oo = blocks(cb, "occ_mass"), blocks(cp, "occ_mass"), blocks(co, "occ_mass")
+    big = op > 2.0
+    rel = np.abs(ob[big] - op[big]) / op[big]
+    rel_seed = np.abs(oo[big] - op[big]) / op[big]
+    print("blocks", int(big.sum()), "banded vs single: median", np.median(rel), "p90", np.percentile(rel, 90),
+          "| seed vs seed: median", np.median(rel_seed), "p90", np.percentile(rel_seed, 90))
+    assert big.sum() > 20
+    assert np.median(rel) < 1.5 * np.median(rel_seed) + 0.005 and np.percentile(rel, 90) < 1.5 * np.percentile(rel_seed, 90) + 0.01
+    fb, fp = blocks(cb, "free_mass"), blocks(cp, "free_mass")
+    assert np.allclose(fb, fp, rtol=0.02, atol=0.3)
+    # the velocity estimate of well-populated cells agrees too
+    sel = (cp["occ_mass"] > 0.6) & (cb["occ_mass"] > 0.6)
+    assert sel.sum() > 50
+    dv = np.abs(cb["mean_y_vel"][sel] - cp["mean_y_vel"][sel])
+    assert np.median(dv) < 6.0  # cells / s, i.e. 1.2 m/s
+    bd.close()
+    plain.close()
