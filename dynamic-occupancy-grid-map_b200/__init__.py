@@ -629,21 +629,40 @@ class LaserMeasurementGrid:
 BAND_SEND_LO, BAND_SEND_HI, BAND_RECV_LO, BAND_RECV_HI, BAND_HALO_LO, BAND_HALO_HI, BAND_EDGE_LO, BAND_EDGE_HI = range(8)
 
 
+def balanced_rows(row_load, n_bands: int, min_rows: int = 64):
+    """Splits the rows of a grid into n_bands bands of about equal load.  row_load[y] is a non-negative estimate of the
+    work in row y, e.g. the occupied mass of a measurement grid per row plus a floor for the cell work."""
+    load = np.asarray(row_load, np.float64)
+    G = load.size
+    cum = np.concatenate([[0.0], np.cumsum(load)])
+    cuts = [0]
+    for r in range(1, n_bands):
+        target = cum[-1] * r / n_bands
+        cut = int(np.searchsorted(cum, target))
+        cut = max(cut, cuts[-1] + min_rows)
+        cut = min(cut, G - (n_bands - r) * min_rows)
+        cuts.append(cut)
+    cuts.append(G)
+    return [cuts[i + 1] - cuts[i] for i in range(n_bands)]
+
+
 class BandedDOGM:
     """The orchestrator of include/dogm_b200.h's band mode for the bands of ONE process: it drives the phases of a cycle on
     every band handle and moves, between the phases, the particles that crossed a band edge (SEND -> RECV boxes), the
     halo rows of an ego-motion shift and the prefix sums of the two global normalisers (born mass, joint weight).
-    `devices[r]` puts band r on that GPU (copies between bands are then peer copies); by default all bands share the
-    current GPU.  A multi-process driver does the same with NCCL (bench.py --bands)."""
+    `devices[r]` puts band r on that GPU: the bands then work concurrently (one host thread per band, the C calls
+    release the GIL) and the copies between bands are NVLink peer copies.  By default all bands share the current GPU."""
 
     def __init__(self, params: Params, n_bands: int, devices=None, seed: int = 123456, slack: float = 1.75, halo_rows: int = 64,
-                 resample_mode: int = RESAMPLE_SYSTEMATIC):
+                 resample_mode: int = RESAMPLE_SYSTEMATIC, rows=None):
+        """rows: rows per band (default: equal shares; see balanced_rows for a split by expected particle load)"""
         self._lib = load_library()
         self.params = params
         self.G = int(np.float32(params.size) / np.float32(params.resolution))
         self.R = n_bands
         base, extra = divmod(self.G, n_bands)
-        self.rows = [base + (1 if r < extra else 0) for r in range(n_bands)]
+        self.rows = list(rows) if rows is not None else [base + (1 if r < extra else 0) for r in range(n_bands)]
+        assert len(self.rows) == n_bands and sum(self.rows) == self.G and min(self.rows) > 0
         self.row0 = [sum(self.rows[:r]) for r in range(n_bands)]
         self.devices = list(devices) if devices is not None else [None] * n_bands
         n, b = params.particle_count, params.new_born_particle_count
@@ -651,28 +670,50 @@ class BandedDOGM:
         self.b_cap = b if n_bands == 1 else min(b, int(b / n_bands * slack * 2) + 8192)
         self.x_cap = 0 if n_bands == 1 else max(8192, self.n_cap // 4)
         self.halo_rows = 0 if n_bands == 1 else min(halo_rows, min(self.rows))
-        self.h = []
-        for r in range(n_bands):
-            self._on(r)
+        self.pool = None
+        if devices is not None and len(set(self.devices)) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self.pool = ThreadPoolExecutor(max_workers=n_bands)
+        self.h = [None] * n_bands
+
+        def create(r):
             cfg = BandConfig(self.row0[r], self.rows[r], self.n_cap, self.b_cap, self.x_cap, self.halo_rows,
                              (r * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
             hp = C.c_void_p()
             _check(self._lib.dogm_create_band(C.byref(params), C.byref(cfg), C.byref(hp)), "dogm_create_band")
             opts = Options(seed, resample_mode, NOISE_PHILOX)
             _check(self._lib.dogm_set_options(hp, C.byref(opts)), "dogm_set_options")
-            self.h.append(hp)
+            self.h[r] = hp
+
+        self._each(create)
         self.first = True
         self.last_counts = []
+        self.last_migration = ([], [])
+        self.last_totals = {}
 
     def _on(self, r):
         if self.devices[r] is not None:
             set_device(self.devices[r])
 
+    def _each(self, fn):
+        """fn(r) for every band, concurrently when the bands live on different GPUs; returns the results in band order"""
+
+        def run(r):
+            self._on(r)  # the current device is a per-thread setting
+            return fn(r)
+
+        if self.pool is not None:
+            return list(self.pool.map(run, range(self.R)))
+        return [run(r) for r in range(self.R)]
+
     def close(self):
-        for r, hp in enumerate(self.h):
-            self._on(r)
-            self._lib.dogm_destroy(hp)
+        if self.h and any(self.h):
+            self._each(lambda r: self._lib.dogm_destroy(self.h[r]) if self.h[r] else None)
         self.h = []
+        if self.pool is not None:
+            self.pool.shutdown()
+            self.pool = None
 
     def __del__(self):
         try:
@@ -696,26 +737,28 @@ class BandedDOGM:
         """meas_band_ptrs[r]: device address (on band r's GPU) of the rows of the measurement grid that band r owns"""
         lib, R = self._lib, self.R
         if self.first:
-            masses = []
-            for r in range(R):
-                self._on(r)
+            def masses(r):
                 m = C.c_double(0.0)
                 _check(lib.dogm_band_init_masses(self.h[r], C.c_void_p(meas_band_ptrs[r]), 1, C.byref(m)), "dogm_band_init_masses")
-                masses.append(m.value)
-            before, total = self._prefix(masses)
-            for r in range(R):
-                self._on(r)
-                _check(lib.dogm_band_init_particles(self.h[r], before[r], total, None), "dogm_band_init_particles")
+                return m.value
+
+            before, total = self._prefix(self._each(masses))
+            self._each(lambda r: _check(lib.dogm_band_init_particles(self.h[r], before[r], total, None), "dogm_band_init_particles"))
             self.first = False
-        lo, hi = [], []
-        for r in range(R):
-            self._on(r)
+
+        def predict(r):
             a, b = C.c_int(0), C.c_int(0)
             _check(lib.dogm_band_predict(self.h[r], new_x, new_y, new_yaw, dt, C.byref(a), C.byref(b)), "dogm_band_predict")
-            lo.append(a.value)
-            hi.append(b.value)
-        for r in range(R):  # band r receives what its neighbours sent towards it
-            self._on(r)
+            return a.value, b.value
+
+        import time as _time
+
+        t_phase = [_time.perf_counter()]
+        sent = self._each(predict)
+        t_phase.append(_time.perf_counter())
+        lo, hi = [s[0] for s in sent], [s[1] for s in sent]
+
+        def receive(r):  # band r takes what its neighbours sent towards it, and their edge rows of the PREVIOUS free masses
             n_lo = hi[r - 1] if r > 0 else 0
             n_hi = lo[r + 1] if r + 1 < R else 0
             if n_lo:
@@ -723,38 +766,47 @@ class BandedDOGM:
             if n_hi:
                 _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_RECV_HI), self._buf(r + 1, BAND_SEND_LO), n_hi * 32), "dogm_memcpy_d2d")
             _check(lib.dogm_band_append(self.h[r], n_lo, n_hi), "dogm_band_append")
-        self.last_migration = (lo, hi)
-        if self.halo_rows:
-            nbytes = self.halo_rows * self.G * 4
-            for r in range(R):  # the neighbours' edge rows of the PREVIOUS free masses, before any band updates its cells
-                self._on(r)
+            if self.halo_rows:
+                nbytes = self.halo_rows * self.G * 4
                 if r > 0:
                     _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_LO), self._buf(r - 1, BAND_EDGE_HI), nbytes), "dogm_memcpy_d2d")
                 if r + 1 < R:
                     _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_HI), self._buf(r + 1, BAND_EDGE_LO), nbytes), "dogm_memcpy_d2d")
-        born = []
-        for r in range(R):
-            self._on(r)
+
+        self._each(receive)  # (all bands finish this before any of them updates its cells: _each is a barrier)
+        t_phase.append(_time.perf_counter())
+        self.last_migration = (lo, hi)
+
+        def update(r):
             v = C.c_double(0.0)
             _check(lib.dogm_band_update(self.h[r], C.c_void_p(meas_band_ptrs[r]), 1, dt, 1 if self.halo_rows else 0, C.byref(v)),
                    "dogm_band_update")
-            born.append(v.value)
-        before, total = self._prefix(born)
-        weight = []
-        for r in range(R):
-            self._on(r)
+            return v.value
+
+        born = self._each(update)
+        t_phase.append(_time.perf_counter())
+        before_b, total_b = self._prefix(born)
+
+        def birth(r):
             v = C.c_double(0.0)
-            _check(lib.dogm_band_birth(self.h[r], before[r], total, C.byref(v)), "dogm_band_birth")
-            weight.append(v.value)
-        before, total = self._prefix(weight)
-        counts = []
-        for r in range(R):
-            self._on(r)
+            _check(lib.dogm_band_birth(self.h[r], before_b[r], total_b, C.byref(v)), "dogm_band_birth")
+            return v.value
+
+        weight = self._each(birth)
+        t_phase.append(_time.perf_counter())
+        before_w, total_w = self._prefix(weight)
+
+        def resample(r):
             n = C.c_int(0)
-            _check(lib.dogm_band_resample(self.h[r], before[r], total, C.byref(n)), "dogm_band_resample")
-            counts.append(n.value)
+            _check(lib.dogm_band_resample(self.h[r], before_w[r], total_w, C.byref(n)), "dogm_band_resample")
+            return n.value
+
+        counts = self._each(resample)
+        t_phase.append(_time.perf_counter())
+        # host wall clock per phase [ms]: predict, exchange + append, update, birth + CDF, resample
+        self.last_phase_ms = [1e3 * (b - a) for a, b in zip(t_phase[:-1], t_phase[1:])]
         self.last_counts = counts
-        self.last_totals = {"born": sum(born), "weight": total}
+        self.last_totals = {"born": total_b, "weight": total_w}
         return counts
 
     def band_handle(self, r):
@@ -781,6 +833,7 @@ class BandedDOGM:
             _check(self._lib.dogm_get_grid_cells(self.h[r], _ptr(out)), "dogm_get_grid_cells")
             parts.append(out)
         return np.concatenate(parts)
+
 
 def device_count() -> int:
     return load_library().dogm_device_count()
