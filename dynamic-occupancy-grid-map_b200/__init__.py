@@ -217,6 +217,9 @@ _SYMBOLS = [
     ("dogm_band_birth", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     ("dogm_band_resample", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int)]),
     ("dogm_band_get_particles", C.c_int, [_P, _P, _P, _P, _P]),
+    ("dogm_band_slot_range", C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("dogm_band_output_range", C.c_int, [C.c_uint64, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     ("dogm_device_count", C.c_int, []),
     ("dogm_set_device", C.c_int, [C.c_int]),
     ("dogm_b200_version", C.c_char_p, []),

@@ -1017,6 +1017,58 @@ static void band_slot_range(double before, double local, double total, int count
         *past = *first;
 }
 
+// Pure host arithmetic of the band mode, exported so that an orchestrator (and a CPU test) can check that the parts of
+// consecutive bands tile the slot ranges without gap or overlap.
+extern "C" int dogm_band_slot_range(double mass_before, double mass_local, double mass_total, int slots_total, int* first,
+                                    int* past)
+{
+    if (!first || !past)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    band_slot_range(mass_before, mass_local, mass_total, slots_total, first, past);
+    return 0;
+}
+
+extern "C" int dogm_band_output_range(uint64_t seed, uint32_t cycle, int resample_mode, long long n_glob, double weight_before,
+                                      double weight_local, double weight_total, long long* first, long long* past)
+{
+    if (!first || !past)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    long long i_lo = 0, i_hi = 0;
+    if (weight_total > 0.0 && n_glob > 0 && weight_local > 0.0)
+    {
+        const double step = weight_total / (double)n_glob;
+        const bool systematic = resample_mode == DOGM_RESAMPLE_SYSTEMATIC;
+        const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+        const float u0 = systematic ? u01_half_open(philox4x32_10(0u, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x) : 0.0f;
+        // the offset of output slot i, the expression of resample_offset (kernels_particles.cu)
+        auto offset = [&](long long i) {
+            const float u = systematic ? u0 : u01_half_open(philox4x32_10((uint32_t)i, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x);
+            return ((double)i + (double)u) * step;
+        };
+        // smallest slot whose offset exceeds x (offsets ascend with the slot number)
+        auto first_behind = [&](double x) {
+            long long lo = 0, hi = n_glob;
+            while (lo < hi)
+            {
+                const long long mid = lo + ((hi - lo) >> 1);
+                if (offset(mid) > x)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            return lo;
+        };
+        const double upto = weight_before + weight_local; // == the next band's weight_before (same addition)
+        i_lo = weight_before > 0.0 ? first_behind(weight_before) : 0;
+        i_hi = upto >= weight_total ? n_glob : first_behind(upto);
+        if (i_hi < i_lo)
+            i_hi = i_lo;
+    }
+    *first = i_lo;
+    *past = i_hi;
+    return 0;
+}
+
 extern "C" int dogm_band_init_masses(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, double* mass_local)
 {
     BAND_PROLOGUE();
@@ -1152,38 +1204,9 @@ extern "C" int dogm_band_birth(dogm_handle* h, double born_before, double born_t
 extern "C" int dogm_band_resample(dogm_handle* h, double weight_before, double weight_total, int* particles_out)
 {
     BAND_PROLOGUE();
-    const long long n_glob = h->band.n_glob;
     long long i_lo = 0, i_hi = 0;
-    if (weight_total > 0.0 && n_glob > 0 && h->band.weight_local > 0.0)
-    {
-        const double step = weight_total / (double)n_glob;
-        const bool systematic = h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC;
-        const uint32_t s_lo = (uint32_t)h->opts.seed, s_hi = (uint32_t)(h->opts.seed >> 32);
-        const float u0 = systematic ? u01_half_open(philox4x32_10(0u, STAGE_RESAMPLE, h->cycle, 0u, s_lo, s_hi).x) : 0.0f;
-        // the offset of output slot i, the expression of resample_offset (kernels_particles.cu)
-        auto offset = [&](long long i) {
-            const float u = systematic ? u0 : u01_half_open(philox4x32_10((uint32_t)i, STAGE_RESAMPLE, h->cycle, 0u, s_lo, s_hi).x);
-            return ((double)i + (double)u) * step;
-        };
-        // smallest slot whose offset exceeds x (offsets ascend with the slot number)
-        auto first_behind = [&](double x) {
-            long long lo = 0, hi = n_glob;
-            while (lo < hi)
-            {
-                const long long mid = lo + ((hi - lo) >> 1);
-                if (offset(mid) > x)
-                    hi = mid;
-                else
-                    lo = mid + 1;
-            }
-            return lo;
-        };
-        const double upto = weight_before + h->band.weight_local; // == the next band's weight_before (same addition)
-        i_lo = weight_before > 0.0 ? first_behind(weight_before) : 0;
-        i_hi = upto >= weight_total ? n_glob : first_behind(upto);
-        if (i_hi < i_lo)
-            i_hi = i_lo;
-    }
+    dogm_band_output_range(h->opts.seed, h->cycle, h->opts.resample_mode, h->band.n_glob, weight_before, h->band.weight_local,
+                           weight_total, &i_lo, &i_hi);
     const long long n_out = i_hi - i_lo;
     if (n_out > h->band.n_cap)
         return DOGM_ERR_INVALID_ARGUMENT;

@@ -198,6 +198,12 @@ int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measurement_band, int
 int dogm_band_birth(dogm_handle* h, double born_before, double born_total, double* weight_local);
 /* step 5: the band draws the output slots whose offsets fall into its part of the global CDF; returns how many */
 int dogm_band_resample(dogm_handle* h, double weight_before, double weight_total, int* particles_out);
+/* the host arithmetic of steps 4 and 5 on its own (no device needed): which birth slots / output slots of the whole grid a
+ * band gets, given the mass / weight in front of it, its own share and the total.  Consecutive bands tile [0, total) when
+ * every band's `before` is the running sum before[r + 1] = before[r] + local[r]. */
+int dogm_band_slot_range(double mass_before, double mass_local, double mass_total, int slots_total, int* first, int* past);
+int dogm_band_output_range(uint64_t seed, uint32_t cycle, int resample_mode, long long n_glob, double weight_before,
+                           double weight_local, double weight_total, long long* first, long long* past);
 /* read-out of the band's current particles (n = dogm_band_counts): any pointer may be NULL */
 int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated);
 

@@ -1,0 +1,107 @@
+"""Host arithmetic of the band mode (no GPU): the slot ranges that consecutive bands derive from the shared prefix sums tile
+the global ranges exactly - birth slots [0, int(total * scale)) and output slots [0, N) - for random splits of the mass, for
+systematic and stratified offsets, and when the prefixes are exchanged between two processes (gloo, world size 2)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from _loader import ROOT, load_dogm_b200
+
+
+def ranges(gpu, lib, locals_, n_glob, seed, cycle, mode):
+    before, acc = [], 0.0
+    for v in locals_:
+        before.append(acc)
+        acc = acc + float(v)
+    out = []
+    for b, v in zip(before, locals_):
+        lo, hi = C.c_longlong(0), C.c_longlong(0)
+        assert lib.dogm_band_output_range(seed, cycle, mode, n_glob, b, float(v), acc, C.byref(lo), C.byref(hi)) == 0
+        out.append((lo.value, hi.value))
+    return out, before, acc
+
+
+def test_output_ranges_tile_the_global_slots():
+    gpu = load_dogm_b200()
+    lib = gpu.load_library()
+    rng = np.random.default_rng(0)
+    for case in range(200):
+        R = int(rng.integers(1, 9))
+        n_glob = int(rng.choice([1, 7, 1000, 2_000_000, 200_000_000]))
+        w = rng.uniform(0.0, 1.0, R) ** 4 * rng.choice([1e-3, 1.0, 1e4])
+        if case % 5 == 0:
+            w[rng.integers(0, R)] = 0.0  # an empty band
+        if w.sum() <= 0:
+            w[0] = 1.0
+        for mode in (gpu.RESAMPLE_SYSTEMATIC, gpu.RESAMPLE_STRATIFIED if n_glob <= 2_000_000 else gpu.RESAMPLE_SYSTEMATIC):
+            rs, before, total = ranges(gpu, lib, w, n_glob, 123456 + case, case, mode)
+            assert rs[0][0] == 0
+            nonzero = [r for r, v in zip(rs, w) if v > 0]
+            for (a0, a1), (b0, b1) in zip(nonzero[:-1], nonzero[1:]):
+                assert a1 == b0, (case, rs)
+            assert nonzero[-1][1] == n_glob
+            for (lo, hi), v in zip(rs, w):
+                assert lo <= hi and (v > 0 or lo == hi)
+                # a band's share of the slots follows its share of the weight (systematic: within one slot)
+                assert abs((hi - lo) - v / total * n_glob) <= 1.0 + 1e-9 * n_glob or mode != gpu.RESAMPLE_SYSTEMATIC
+
+
+def test_birth_slot_ranges_tile():
+    gpu = load_dogm_b200()
+    lib = gpu.load_library()
+    rng = np.random.default_rng(1)
+    for case in range(200):
+        R = int(rng.integers(1, 9))
+        m = rng.uniform(0.0, 50.0, R)
+        b_glob = int(rng.choice([0, 1, 333, 200_000, 20_000_000]))
+        before, acc = [], 0.0
+        for v in m:
+            before.append(acc)
+            acc = acc + float(v)
+        prev_past = 0
+        for r in range(R):
+            f, p = C.c_int(0), C.c_int(0)
+            assert lib.dogm_band_slot_range(before[r], float(m[r]), acc, b_glob, C.byref(f), C.byref(p)) == 0
+            assert f.value == prev_past and p.value >= f.value
+            prev_past = p.value
+        assert b_glob - 1 <= prev_past <= b_glob or acc <= 0  # int(float(total) * (B / total)) is B or B - 1
+
+
+WORKER = r"""
+import ctypes as C, os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from _loader import load_dogm_b200
+gpu = load_dogm_b200(); lib = gpu.load_library()
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+local = torch.tensor([3.25 if rank == 0 else 7.5], dtype=torch.float64)
+parts = [torch.zeros(1, dtype=torch.float64) for _ in range(2)]
+dist.all_gather(parts, local)                     # the one exchange of the resampling normaliser: a double per band
+before, acc = [], 0.0
+for p in parts:
+    before.append(acc); acc = acc + float(p[0])
+lo, hi = C.c_longlong(0), C.c_longlong(0)
+lib.dogm_band_output_range(123456, 5, gpu.RESAMPLE_SYSTEMATIC, 1000003, before[rank], float(local[0]), acc, C.byref(lo), C.byref(hi))
+mine = torch.tensor([lo.value, hi.value], dtype=torch.int64)
+both = [torch.zeros(2, dtype=torch.int64) for _ in range(2)]
+dist.all_gather(both, mine)
+if rank == 0:
+    assert both[0][0] == 0 and both[0][1] == both[1][0] and both[1][1] == 1000003, both
+    print("tiling ok", [b.tolist() for b in both])
+dist.destroy_process_group()
+"""
+
+
+def test_two_processes_agree_on_the_partition(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29600 + os.getpid() % 200)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "tiling ok" in outs[0]
