@@ -551,7 +551,7 @@ def run_ours(args, dist):
             "unit": UNIT,
             "h2d_bytes_per_step": 4 * cfg["beams"],
             "d2h_bytes_per_step": float(np.mean(d2h_bytes)),
-            "path": "beams(host, pinned) -> dogm_meas_generate_into -> dogm_update_grid_async -> dogm_extract_dynamic_cells(host, syncs)",
+            "path": "beams(host, pinned) -> dogm_meas_generate_into (polar table; cartesian resampling inside the cell kernel) -> dogm_update_grid_async -> dogm_extract_dynamic_cells (host list; returns when the cell kernel has published it, the rest of the cycle overlaps the next submission)",
             "full_readback": None if t_full is None else {
                 "value": dist.world * k_full / t_full,
                 "unit": UNIT,

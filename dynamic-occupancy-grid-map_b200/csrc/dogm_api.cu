@@ -179,6 +179,13 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->dyn_filter_on = h->dyn_list_valid = false;
     h->dyn_filter_capacity = 0;
     h->dyn_mapped_host = h->dyn_mapped_dev = nullptr;
+    h->lazy_meas.pending = false;
+    h->lazy_meas.geom = nullptr;
+    h->lazy_meas.polar = nullptr;
+    h->lazy_meas.K = h->lazy_meas.H = 0;
+    h->dyn_pub_host = h->dyn_pub_dev = nullptr;
+    h->dyn_pub_seq = 0;
+    h->dyn_pub_armed = h->dyn_pub_pending = false;
     for (int k = 0; k < K_COUNT; k++)
     {
         h->acc_ms[k] = 0.0;
@@ -367,6 +374,8 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->dyn_count);
     if (h->dyn_count_host)
         cudaFreeHost(h->dyn_count_host);
+    if (h->dyn_pub_host)
+        cudaFreeHost(h->dyn_pub_host);
     if (h->dyn_mapped_host)
         cudaFreeHost(h->dyn_mapped_host);
     for (auto& t : h->timed)
@@ -443,6 +452,7 @@ static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float ne
     h->meas_src = nullptr;
     if (meas && meas != h->meas)
     {
+        h->lazy_meas.pending = false; // superseded by the caller's grid
         if (on_device && h->first_measurement_received)
         {
             // the cell kernel reads the caller's buffer and writes the handle's copy on the way: the reference's
@@ -457,6 +467,8 @@ static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float ne
     }
     if (!h->first_measurement_received)
     {
+        if ((e = materialize_meas(h)))
+            return e;
         e = run_init_particles(h);
         if (e)
             return e;
@@ -505,7 +517,9 @@ extern "C" int dogm_synchronize(dogm_handle* h)
 #define STAGE_PROLOGUE()                                                                                               \
     if (!h)                                                                                                            \
         return DOGM_ERR_INVALID_ARGUMENT;                                                                              \
-    int e = 0;
+    int e = materialize_meas(h);                                                                                       \
+    if (e)                                                                                                             \
+        return e;
 #define STAGE_EPILOGUE()                                                                                               \
     if (e)                                                                                                             \
         return e;                                                                                                      \
@@ -622,6 +636,8 @@ extern "C" int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host)
 }
 extern "C" int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_host)
 {
+    if (h && materialize_meas(h))
+        return (int)cudaGetLastError();
     return copy_out(h, out_host, h ? h->meas : nullptr, h ? (size_t)h->C * sizeof(dogm_meas_cell) : 0);
 }
 extern "C" int dogm_get_particles(dogm_handle* h, void* out_block)
@@ -688,6 +704,7 @@ extern "C" int dogm_get_device_ptrs(dogm_handle* h, dogm_device_ptrs* out)
     if (!h || !out)
         return DOGM_ERR_INVALID_ARGUMENT;
     out->grid_cell_array = h->grid;
+    materialize_meas(h);
     ensure_soa(h);
     out->particle_array = h->pa.block;
     out->particle_array_next = h->pa.block; // resampling writes the next population in place (no 28*N-byte publish copy)
@@ -825,6 +842,7 @@ extern "C" int dogm_set_measurement_cells(dogm_handle* h, const dogm_meas_cell* 
 {
     if (!h || !cells)
         return DOGM_ERR_INVALID_ARGUMENT;
+    h->lazy_meas.pending = false;
     DOGM_CHECK((cudaError_t)copy_in(h->meas, cells, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -872,6 +890,9 @@ static int ensure_dyn_counter(dogm_handle* h)
     {
         DOGM_CHECK(cudaMalloc(&h->dyn_count, 2 * sizeof(int))); // [0] fused into the cycle, [1] stand-alone pass
         DOGM_CHECK(cudaMallocHost(&h->dyn_count_host, sizeof(int)));
+        DOGM_CHECK(cudaHostAlloc((void**)&h->dyn_pub_host, 2 * sizeof(int), cudaHostAllocMapped));
+        h->dyn_pub_host[0] = h->dyn_pub_host[1] = 0;
+        DOGM_CHECK(cudaHostGetDevicePointer((void**)&h->dyn_pub_dev, h->dyn_pub_host, 0));
     }
     return 0;
 }
@@ -916,9 +937,34 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
     if (h->dyn_filter_on && h->dyn_list_valid && h->dyn_list_cycle + 1 == h->cycle && min_occupancy == h->dyn_filter_occ &&
         min_velocity == h->dyn_filter_vel)
     {
-        DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        DOGM_CHECK(cudaStreamSynchronize(h->stream));
-        const int found = *h->dyn_count_host;
+        int found = -1;
+        if (h->dyn_pub_pending)
+        { // wait for the publication written behind the cell kernel, not for the end of the cycle
+            volatile int* pub = h->dyn_pub_host;
+            for (unsigned spin = 1; found < 0; spin++)
+            {
+                if (pub[1] == h->dyn_pub_seq)
+                    found = pub[0];
+                else if ((spin & 0x3ffu) == 0)
+                {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q == cudaSuccess)
+                    { // nothing left in flight: the word is final one way or the other
+                        if (pub[1] == h->dyn_pub_seq)
+                            found = pub[0];
+                        break;
+                    }
+                    if (q != cudaErrorNotReady)
+                        return (int)q;
+                }
+            }
+        }
+        if (found < 0)
+        {
+            DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            DOGM_CHECK(cudaStreamSynchronize(h->stream));
+            found = *h->dyn_count_host;
+        }
         if (found <= h->dyn_filter_capacity || capacity <= h->dyn_filter_capacity)
         {
             *out_count = found;

@@ -220,6 +220,16 @@ struct dogm_handle
     float* weight_array;
     float* born_masses;
     const dogm_meas_cell* meas_src; // caller's device measurement grid of the running cycle (copied by the cell kernel)
+    // Measurement grid still to be produced (dogm_meas_generate_into): the polar table of the scan exists, the cartesian
+    // resampling (k_meas_apply) is left to the cell kernel of the next cycle, which writes `meas` on the way - or to
+    // materialize_meas() when somebody wants to see `meas` earlier.  geom / polar belong to the generator handle.
+    struct
+    {
+        bool pending;
+        const float4* geom;
+        const float2* polar;
+        int K, H;
+    } lazy_meas;
     bool ranges_in_soa;             // cell_start / cell_end hold the ranges of the last assignment (not yet consumed)
 
     // per-cell working set
@@ -293,6 +303,14 @@ struct dogm_handle
     uint32_t dyn_list_cycle;
     dogm_dynamic_cell* dyn_mapped_host;
     dogm_dynamic_cell* dyn_mapped_dev;
+    // early publication of that list: the kernel behind the cell kernel (k_blocksum_scan) writes {count, sequence number}
+    // into host-mapped memory, so dogm_extract_dynamic_cells returns as soon as the list exists - the rest of the cycle
+    // (birth particles, CDF, resampling) keeps running while the host consumes the list and enqueues the next scan
+    int* dyn_pub_host; // pinned + mapped, 2 ints
+    int* dyn_pub_dev;
+    int dyn_pub_seq;      // sequence number of the last list whose publication was enqueued
+    bool dyn_pub_armed;   // the cell kernel of the running cycle fills the list; the next born-mass scan publishes it
+    bool dyn_pub_pending; // a publication has been enqueued for the current list
 
     // instrumentation
     bool timer_ready;
@@ -391,9 +409,10 @@ int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of 
 int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
 int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi);
 void set_particle_counts(dogm_handle* h, int n, int b); // band mode: current counts and everything derived from them
+int materialize_meas(dogm_handle* h);      // kernels_meas.cu: runs a pending cartesian resampling into h->meas
 int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells
 int run_init_grid(dogm_handle* h);         // initGridCellsKernel
-int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out);
+int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out, bool publish_dyn = false);
 int configure_kernels();
 int chain_blocks_per_sm();
 int trace_bind_particles(unsigned long long* p);
@@ -408,6 +427,33 @@ int run_extract_dynamic_cells(dogm_handle* h, float min_occ, float min_vel, dogm
 // ---------------------------------------------------------------------------------------------------------
 // device helpers shared by the kernels
 // ---------------------------------------------------------------------------------------------------------
+// Cartesian measurement cell from the polar table of a scan: bilinear sample (GL_LINEAR, mip level 0, GL_CLAMP_TO_BORDER with
+// border 0, texture.cpp:16-29) at the position cached per cell by k_meas_geom; MeasurementCell {free_mass, occ_mass,
+// likelihood, p_A} as in measurement_grid.cu:126-130.  Used by k_meas_apply and by the cell kernel's fused variant.
+constexpr int kNoTexel = -(1 << 30);
+__device__ __forceinline__ float2 polar_fetch(const float2* __restrict__ table, int K, int H, int bi, int ri)
+{
+    if (bi < 0 || bi >= K || ri < 0 || ri >= H)
+        return make_float2(0.0f, 0.0f);
+    return __ldg(table + (size_t)ri * K + bi);
+}
+__device__ __forceinline__ float4 meas_cell_from_polar(const float4 g, const float2* __restrict__ table, int K, int H)
+{
+    const int i0 = __float_as_int(g.x), j0 = __float_as_int(g.y);
+    float occ_out = 0.0f, free_out = 0.0f;
+    if (i0 != kNoTexel)
+    {
+        const float wu = g.z, wv = g.w;
+        const float2 t00 = polar_fetch(table, K, H, i0, j0), t10 = polar_fetch(table, K, H, i0 + 1, j0);
+        const float2 t01 = polar_fetch(table, K, H, i0, j0 + 1), t11 = polar_fetch(table, K, H, i0 + 1, j0 + 1);
+        const float ob = t00.x + wu * (t10.x - t00.x), ot = t01.x + wu * (t11.x - t01.x);
+        const float fb = t00.y + wu * (t10.y - t00.y), ft = t01.y + wu * (t11.y - t01.y);
+        occ_out = ob + wv * (ot - ob);
+        free_out = fb + wv * (ft - fb);
+    }
+    return make_float4(free_out, occ_out, 1.0f, 1.0f);
+}
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m;

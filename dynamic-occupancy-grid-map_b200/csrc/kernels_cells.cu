@@ -44,12 +44,21 @@ struct CellArgs
     int row0, rows, halo_rows;
     const float* halo_lo;
     const float* halo_hi;
+    // kLazyMeas: the measurement cell is sampled from the polar table of the scan here (dogm_meas_generate_into) instead of
+    // being read from `meas`; `meas_copy` receives it
+    const float4* geom;
+    const float2* polar;
+    int polar_K, polar_H;
 };
 
 #ifndef DOGM_CELL_MINBLOCKS
 #define DOGM_CELL_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(kCellBlock, DOGM_CELL_MINBLOCKS) k_cell(CellArgs a)
+#ifndef DOGM_CELL_MINBLOCKS_LAZY
+#define DOGM_CELL_MINBLOCKS_LAZY 6
+#endif
+template <bool kLazyMeas>
+__global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LAZY : DOGM_CELL_MINBLOCKS) k_cell(CellArgs a)
 {
     pdl_prologue(K_CELL * 2);
     __shared__ double s_scan[kWarpsPerBlock];
@@ -66,7 +75,11 @@ __global__ void __launch_bounds__(kCellBlock, DOGM_CELL_MINBLOCKS) k_cell(CellAr
     {
         // all loads that do not depend on the cell being occupied go out together, ahead of the first store
         const int start = a.cell_start[c];
-        const float4 zq = __ldg(reinterpret_cast<const float4*>(a.meas + c));
+        float4 zq;
+        if constexpr (kLazyMeas)
+            zq = meas_cell_from_polar(__ldcs(a.geom + c), a.polar, a.polar_K, a.polar_H);
+        else
+            zq = __ldg(reinterpret_cast<const float4*>(a.meas + c));
         // ego-motion compensation of the grid (updatePose dogm.cu:175-193, moveMapKernel
         // ego_motion_compensation.cu:25-43): of all cell fields only free_mass survives into the next cycle,
         // so the shift is a shifted read of the previous free masses; vacated cells read 0 (dogm.cu:185)
@@ -609,10 +622,29 @@ int run_occupancy_update(dogm_handle* h, float dt)
             cudaMemsetAsync(h->dyn_count, 0, sizeof(int), h->stream);
         h->dyn_list_cycle = h->cycle;
         h->dyn_list_valid = true;
+        h->dyn_pub_armed = true;
+        h->dyn_pub_pending = false;
     }
+    a.geom = nullptr;
+    a.polar = nullptr;
+    a.polar_K = a.polar_H = 0;
+    const bool lazy = h->lazy_meas.pending && !h->meas_src;
+    if (lazy)
+    {
+        a.geom = h->lazy_meas.geom;
+        a.polar = h->lazy_meas.polar;
+        a.polar_K = h->lazy_meas.K;
+        a.polar_H = h->lazy_meas.H;
+        a.meas = nullptr;
+        a.meas_copy = h->meas;
+    }
+    h->lazy_meas.pending = false; // consumed, or superseded by the caller's grid
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
-        launch_chained(h->stream, k_cell, h->n_cell_blocks, kCellBlock, 0, a);
+        if (lazy)
+            launch_chained(h->stream, k_cell<true>, h->n_cell_blocks, kCellBlock, 0, a);
+        else
+            launch_chained(h->stream, k_cell<false>, h->n_cell_blocks, kCellBlock, 0, a);
     }
     h->shift_grid_pending = false;
     h->meas_src = nullptr;
@@ -625,7 +657,7 @@ int run_occupancy_update(dogm_handle* h, float dt)
 
 int run_born_scan(dogm_handle* h)
 {
-    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total);
+    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total, true);
 }
 
 int run_birth(dogm_handle* h)

@@ -80,8 +80,6 @@ __device__ __forceinline__ float2 polar_cell(const MeasArgs& a, float zk, int i)
     return make_float2(fmaxf(eps, fminf(1.0f - eps, occ_m)), fmaxf(eps, fminf(1.0f - eps, free_m)));
 }
 
-constexpr int kNoTexel = -(1 << 30);
-
 // Scan-independent part of the lookup: which fan triangle the cell centre falls into and where the rasteriser's
 // interpolated texture coordinate lands in the K x H polar texture.
 __global__ void __launch_bounds__(kBlock) k_meas_geom(MeasArgs a, float4* geom)
@@ -132,13 +130,6 @@ __global__ void __launch_bounds__(kBlock) k_meas_geom(MeasArgs a, float4* geom)
     geom[c] = g;
 }
 
-__device__ __forceinline__ float2 polar_fetch(const float2* __restrict__ table, int K, int H, int bi, int ri)
-{
-    if (bi < 0 || bi >= K || ri < 0 || ri >= H) // GL_CLAMP_TO_BORDER, border R = G = 0 (texture.cpp:16-29)
-        return make_float2(0.0f, 0.0f);
-    return __ldg(table + (size_t)ri * K + bi);
-}
-
 // Per scan: bilinear sample (GL_LINEAR, mip level 0) of the polar table at the precomputed position.
 __global__ void __launch_bounds__(kBlock)
     k_meas_apply(const float4* __restrict__ geom, const float2* __restrict__ table, int K, int H, int C, dogm_meas_cell* out)
@@ -148,20 +139,7 @@ __global__ void __launch_bounds__(kBlock)
     if (c >= C)
         return;
     const float4 g = __ldcs(geom + c);
-    const int i0 = __float_as_int(g.x), j0 = __float_as_int(g.y);
-    float occ_out = 0.0f, free_out = 0.0f;
-    if (i0 != kNoTexel)
-    {
-        const float wu = g.z, wv = g.w;
-        const float2 t00 = polar_fetch(table, K, H, i0, j0), t10 = polar_fetch(table, K, H, i0 + 1, j0);
-        const float2 t01 = polar_fetch(table, K, H, i0, j0 + 1), t11 = polar_fetch(table, K, H, i0 + 1, j0 + 1);
-        const float ob = t00.x + wu * (t10.x - t00.x), ot = t01.x + wu * (t11.x - t01.x);
-        const float fb = t00.y + wu * (t10.y - t00.y), ft = t01.y + wu * (t11.y - t01.y);
-        occ_out = ob + wv * (ot - ob);
-        free_out = fb + wv * (ft - fb);
-    }
-    // MeasurementCell {free_mass, occ_mass, likelihood, p_A}, measurement_grid.cu:126-130
-    __stcs(reinterpret_cast<float4*>(out + c), make_float4(free_out, occ_out, 1.0f, 1.0f));
+    __stcs(reinterpret_cast<float4*>(out + c), meas_cell_from_polar(g, table, K, H));
 }
 
 __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
@@ -172,6 +150,23 @@ __global__ void __launch_bounds__(kBlock) k_meas_polar(MeasArgs a, float2* out)
         return;
     const int b = t % a.K, i = t / a.K;
     out[t] = polar_cell(a, a.beams[b], i);
+}
+
+// Same table, the scan passed by value in the kernel parameters: no host-to-device copy node in front of the launch, so the
+// programmatic launch chain of the stream runs on from the previous cycle (dogm_meas_generate_into, up to kBeamsByValue beams)
+constexpr int kBeamsByValue = 960;
+struct BeamBlock
+{
+    float z[kBeamsByValue];
+};
+__global__ void __launch_bounds__(kBlock) k_meas_polar_byvalue(MeasArgs a, float2* out, const __grid_constant__ BeamBlock scan)
+{
+    pdl_prologue(K_MEAS_POLAR * 2);
+    const int t = blockIdx.x * kBlock + threadIdx.x;
+    if (t >= a.K * a.H)
+        return;
+    const int b = t % a.K, i = t / a.K;
+    out[t] = polar_cell(a, scan.z[b], i);
 }
 
 // one more scan into the polar table: Dempster-Shafer combination of the table (prior) with the clamped inverse sensor model
@@ -296,6 +291,17 @@ static int launch_scan(dogm_meas_handle* m, int K, dogm_meas_cell* out, cudaStre
     return e;
 }
 
+int materialize_meas(dogm_handle* h)
+{
+    if (!h->lazy_meas.pending)
+        return 0;
+    h->lazy_meas.pending = false;
+    LaunchScope ls(h, K_MEAS_GRID, 32.0 * (double)h->C);
+    launch_chained(h->stream, k_meas_apply, div_up(h->C, kBlock), kBlock, 0, h->lazy_meas.geom, h->lazy_meas.polar, h->lazy_meas.K,
+                   h->lazy_meas.H, h->C, h->meas);
+    return (int)cudaGetLastError();
+}
+
 int trace_bind_meas(unsigned long long* p)
 {
     return (int)cudaMemcpyToSymbol(c_trace, &p, sizeof(p));
@@ -390,12 +396,40 @@ extern "C" int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_
 
 extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, const float* beam_ranges_host, int num_beams)
 {
-    if (!m || !h || m->gs != h->gs)
+    if (!m || !h || m->gs != h->gs || num_beams <= 0 || !beam_ranges_host)
         return DOGM_ERR_INVALID_ARGUMENT;
-    int e = upload_beams(m, beam_ranges_host, num_beams, h->stream);
+    if (h->band.enabled)
+        return DOGM_ERR_UNSUPPORTED; // a band holds some rows of the grid only: generate the grid, hand the band its rows
+    const int K = num_beams;
+    int e = 0;
+    if (K <= kBeamsByValue)
+    {
+        if ((e = prepare_scan(m, K, h->stream)))
+            return e;
+        BeamBlock scan;
+        memcpy(scan.z, beam_ranges_host, (size_t)K * sizeof(float));
+        const MeasArgs a = make_args(m, K, nullptr);
+        LaunchScope ls(h, K_MEAS_POLAR, 8.0 * (double)K * m->H);
+        launch_chained(h->stream, k_meas_polar_byvalue, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);
+        e = (int)cudaGetLastError();
+    }
+    else
+    {
+        e = upload_beams(m, beam_ranges_host, K, h->stream);
+        e = e ? e : prepare_scan(m, K, h->stream);
+        e = e ? e : launch_polar(m, K, true, h->stream, h);
+    }
     if (e)
         return e;
-    return launch_scan(m, num_beams, h->meas, h->stream, h);
+    // the cartesian resampling is left to the cell kernel of the next cycle (run_occupancy_update), or to materialize_meas()
+    h->lazy_meas.pending = true;
+    h->lazy_meas.geom = m->d_geom;
+    h->lazy_meas.polar = m->d_polar;
+    h->lazy_meas.K = K;
+    h->lazy_meas.H = m->H;
+    if (!h->first_measurement_received)
+        return materialize_meas(h); // the first cycle distributes the particles over this grid before any cell kernel runs
+    return 0;
 }
 
 extern "C" int dogm_meas_generate_fused(dogm_meas_handle* m, const float* scans_host, int num_scans, int num_beams,

@@ -1263,9 +1263,17 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
 
 // exclusive scan of up to a few 10^5 block sums by one CTA (thread-serial chunks + one block scan)
 __global__ void __launch_bounds__(1024) k_blocksum_scan(const double* __restrict__ in, double* __restrict__ out_excl,
-                                                        int n, double* total_out)
+                                                        int n, double* total_out, const int* pub_count, int* pub_host,
+                                                        int pub_seq)
 {
     pdl_prologue(K_BLOCKSUM_SCAN * 2);
+    if (pub_host && threadIdx.x == 0)
+    { // the cell kernel in front has completed: its dynamic-cell list (host-mapped) is final; tell the waiting host
+        const int found = __ldcg(pub_count);
+        *reinterpret_cast<volatile int*>(pub_host) = found;
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(pub_host + 1) = pub_seq;
+    }
     __shared__ double s_warp[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (n + 1023) / 1024;
@@ -1728,10 +1736,21 @@ int run_persistent_weights(dogm_handle* h, bool defer)
     return (int)cudaGetLastError();
 }
 
-int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out)
+int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out, bool publish_dyn)
 {
+    const int* pub_count = nullptr;
+    int* pub_host = nullptr;
+    int pub_seq = 0;
+    if (publish_dyn && h->dyn_pub_armed && h->dyn_pub_dev)
+    {
+        pub_count = h->dyn_count;
+        pub_host = h->dyn_pub_dev;
+        pub_seq = ++h->dyn_pub_seq;
+        h->dyn_pub_armed = false;
+        h->dyn_pub_pending = true;
+    }
     LaunchScope ls(h, K_BLOCKSUM_SCAN, 16.0 * n);
-    launch_chained(h->stream, k_blocksum_scan, 1, 1024, 0, in, out_excl, n, total_out);
+    launch_chained(h->stream, k_blocksum_scan, 1, 1024, 0, in, out_excl, n, total_out, pub_count, pub_host, pub_seq);
     return (int)cudaGetLastError();
 }
 

@@ -319,8 +319,12 @@ void dogm_meas_destroy(dogm_meas_handle* m);
 /* generateGrid(measurements), laser_to_meas_grid.cu:25-70: host beam ranges (inf = no return) -> device
  * MeasurementCell[grid_size^2] owned by the generator.  Synchronous like the reference (:67). */
 int dogm_meas_generate(dogm_meas_handle* m, const float* beam_ranges_host, int num_beams, dogm_meas_cell** out_device);
-/* Same, stream-ordered on the stream of `h` and written straight into h's measurement buffer; the following
- * dogm_update_grid(h, NULL, ...) then consumes it without the 16*C-byte copy of dogm.cu:207-208. */
+/* Same scan for the next cycle of `h`, stream-ordered on the stream of `h`: the polar table of the scan is built now (up to 960
+ * beams travel in the kernel parameters: no copy node), the cartesian resampling is done by the per-cell kernel of the following
+ * dogm_update_grid(h, NULL, ...), which writes h's measurement buffer on the way - no measurement-grid pass and no 16*C-byte
+ * copy (dogm.cu:207-208) of its own.  Whoever looks at the measurement buffer earlier (dogm_get_measurement_cells,
+ * dogm_get_device_ptrs, a stage call, the first cycle's particle initialisation) gets it produced then.  `m` has to stay alive
+ * until that update has been enqueued; a measurement grid passed to the update supersedes the scan.  Not for band handles. */
 int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, const float* beam_ranges_host, int num_beams);
 /* Several scans of the same sensor geometry fused in the polar grid before the polar->cartesian step
  * (createPolarGridTextureKernel for the first scan, fusePolarGridTextureKernel + combine_masses for the others,
@@ -353,7 +357,10 @@ int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_ve
                                int capacity, int* out_count);
 /* Registers the filter ahead of time (capacity 0 switches it off): every following cycle then compacts the matching
  * cells inside its per-cell kernel, straight into pinned host memory, and dogm_extract_dynamic_cells with the same
- * thresholds returns that list with one 4-byte copy instead of a pass over all 64*C bytes of grid cells. */
+ * thresholds returns that list instead of running a pass over all 64*C bytes of grid cells.  After dogm_update_grid_async it
+ * returns as soon as the list exists - the kernel behind the per-cell kernel writes {count, sequence number} into host-mapped
+ * memory the call spins on - while birth, CDF and resampling of that cycle are still running: the caller consumes the list and
+ * enqueues the next scan in the meantime, so the stream never runs dry.  (Every other getter still synchronises.) */
 int dogm_set_dynamic_cell_filter(dogm_handle* h, float min_occupancy, float min_velocity, int capacity);
 
 /* ------------------------------------------------------------------------------------------------------------

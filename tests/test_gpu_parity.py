@@ -321,6 +321,47 @@ def test_dynamic_cell_filter_fused_into_cycle(gpu, orc):
     assert count4 == n4
 
 
+def test_dynamic_cell_list_published_before_cycle_end(gpu, orc):
+    """With a registered filter dogm_extract_dynamic_cells does not wait for the end of the cycle: the kernel behind the cell
+    kernel publishes {count, sequence number} into host-mapped memory.  Asynchronous cycles (device-resident measurement
+    grids, the next cycle enqueued straight after the read-out) give the same lists as the stand-alone pass over the
+    published grid cells, and the final state equals that of a handle driven with blocking calls."""
+    n, b = 200000, 20000
+    p = make_params(gpu, 40.0, 0.2, n, b)
+    d = gpu.DOGM(p)
+    ref = gpu.DOGM(p)
+    d.set_dynamic_cell_filter(0.6, 0.5, 8192)
+    grids = []
+    for c in range(5):
+        meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, d.grid_size, np.random.default_rng(50 + c))
+        ptr = gpu.device_alloc(meas.nbytes)
+        gpu.memcpy_h2d(ptr, meas)
+        grids.append(ptr)
+    lists = []
+    for c in range(5):
+        d.update_grid(grids[c], 0.5 * c, 0.3 * c, 0.0, 0.1, device=True, sync=False)
+        got, count = d.extract_dynamic_cells(0.6, 0.5, capacity=8192)  # returns while the cycle is still running
+        lists.append((np.sort(got["cell_idx"]).copy(), count))
+    for c in range(5):
+        ref.update_grid(grids[c], 0.5 * c, 0.3 * c, 0.0, 0.1, device=True)
+        rec, n_exp = orc.extract_dynamic_cells(ref.get_grid_cells().view(orc.GRID_CELL_DTYPE), 0.6, 0.5)
+        assert lists[c][1] == n_exp
+        assert np.array_equal(lists[c][0], np.sort(rec[:, 0].copy().view(np.int32)))
+    assert lists[-1][1] > 0
+    assert np.array_equal(d.get_grid_cells(), ref.get_grid_cells())
+    assert np.array_equal(d.get_particles().block, ref.get_particles().block)
+    # the stage API stops after the occupancy update: nothing publishes the list, the read-out falls back to a stream sync
+    d.update_pose(3.0, 2.0, 0.0)
+    d.particle_prediction(0.1)
+    d.particle_assignment()
+    d.grid_cell_occupancy_update(0.1)
+    got, count = d.extract_dynamic_cells(0.6, 0.5, capacity=8192)
+    rec, n_exp = orc.extract_dynamic_cells(d.get_grid_cells().view(orc.GRID_CELL_DTYPE), 0.6, 0.5)
+    assert count == n_exp and np.array_equal(np.sort(got["cell_idx"]), np.sort(rec[:, 0].copy().view(np.int32)))
+    for ptr in grids:
+        gpu.device_free(ptr)
+
+
 def test_concurrent_handles_do_not_interfere(gpu):
     """Independent sensor streams on one GPU (BASELINE.json configs[3]): handles driven interleaved and asynchronously on
     their own CUDA streams end in exactly the state each reaches when run alone (the kernels' inter-CTA waits - chained

@@ -126,6 +126,50 @@ def test_generate_into_feeds_update_grid(gpu):
     e.update_grid(ptr, 0.0, 0.0, 0.0, 0.1, device=True)
     assert np.array_equal(d.get_grid_cells().view(np.uint8), e.get_grid_cells().view(np.uint8))
     assert np.array_equal(d.get_particles().block, e.get_particles().block)
+    # later cycles: the cartesian resampling runs inside the cycle's cell kernel (no measurement-grid pass of its own);
+    # the handle's measurement grid, the map and the particles equal those of the two-step path, with grid shifts
+    for c in range(1, 5):
+        beams = demo_beams(rng)
+        host = gen.generate_grid_host(beams)
+        ptr = gen.generate_grid(beams)
+        e.update_grid(ptr, 0.3 * c, 0.5 * c, 0.0, 0.1, device=True)
+        gen.generate_grid_into(d, beams)
+        if c == 2:  # looking at the grid before the cycle forces it into existence; the cycle then takes the plain path
+            assert np.array_equal(d.get_measurement_cells().view(np.uint8), host.view(np.uint8))
+        d.update_grid(None, 0.3 * c, 0.5 * c, 0.0, 0.1, sync=(c != 3))
+        assert np.array_equal(d.get_measurement_cells().view(np.uint8), host.view(np.uint8)), c
+        assert np.array_equal(d.get_grid_cells().view(np.uint8), e.get_grid_cells().view(np.uint8)), c
+        assert np.array_equal(d.get_particles().block, e.get_particles().block), c
+    # a scan that is generated but superseded by a caller-supplied grid is dropped
+    other = demo_beams(rng)
+    gen.generate_grid_into(d, other)
+    beams = demo_beams(rng)
+    host = gen.generate_grid_host(beams)
+    ptr = gen.generate_grid(beams)
+    d.update_grid(ptr, 1.5, 2.5, 0.0, 0.1, device=True)
+    e.update_grid(ptr, 1.5, 2.5, 0.0, 0.1, device=True)
+    assert np.array_equal(d.get_measurement_cells().view(np.uint8), host.view(np.uint8))
+    assert np.array_equal(d.get_grid_cells().view(np.uint8), e.get_grid_cells().view(np.uint8))
+    d.update_grid(None, 1.5, 2.5, 0.0, 0.1)  # and does not come back
+    assert np.array_equal(d.get_measurement_cells().view(np.uint8), host.view(np.uint8))
+
+
+@pytest.mark.gpu
+def test_generate_into_many_beams(gpu):
+    """More beams than travel in the kernel parameters (960): the scan goes through the device copy; same grid either way."""
+    from conftest import make_params
+
+    rng = np.random.default_rng(45)
+    p = make_params(gpu, 30.0, 0.1, 20000, 2000)
+    d = gpu.DOGM(p)
+    gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(30.0, 0.1, 120.0, 0.5), 30.0, 0.1)
+    for k in (1200, 960, 961, 7):
+        for c in range(2):
+            beams = demo_beams(rng, k, 30.0)
+            host = gen.generate_grid_host(beams)
+            gen.generate_grid_into(d, beams)
+            d.update_grid(None, 0.0, 0.2 * c, 0.0, 0.1)
+            assert np.array_equal(d.get_measurement_cells().view(np.uint8), host.view(np.uint8)), (k, c)
 
 
 def test_oracle_fusion_properties(orc):
