@@ -1331,6 +1331,11 @@ extern "C" int dogm_debug_read(dogm_handle* h, const char* name, void* out_host,
         src = &h->scal->weight_total;
         have = sizeof(double);
     }
+    if (!strcmp(name, "phase_chain") || !strcmp(name, "phase_resample"))
+    {
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+        return debug_phase_read(!strcmp(name, "phase_resample"), out_host, bytes);
+    }
     if (!src || bytes > have)
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK(cudaStreamSynchronize(h->stream));

@@ -415,6 +415,7 @@ int run_init_grid(dogm_handle* h);         // initGridCellsKernel
 int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n, double* total_out, bool publish_dyn = false);
 int configure_kernels();
 int chain_blocks_per_sm();
+int debug_phase_read(int which, void* out_host, size_t bytes); // -DDOGM_PHASE_TRACE builds only
 int trace_bind_particles(unsigned long long* p);
 int trace_bind_cells(unsigned long long* p);
 int trace_bind_meas(unsigned long long* p);                   // opt-in shared memory sizes

@@ -911,6 +911,7 @@ constexpr int kChainRounds = kCdfTile / kBlock; // 16
 constexpr int kChainWarpSpan = kCdfTile / kWarpsPerBlock; // 512
 constexpr int kQuadRounds = kChainWarpSpan / 128;          // 4 rounds of 32 lanes x 4 consecutive entries
 constexpr int kChainGroup = 256;                // tiles per group
+constexpr int kChainFlat = 4;                   // up to kChainFlat * 256 tiles every tile sums all the totals in front of it
 
 struct ChainArgs
 {
@@ -927,6 +928,7 @@ struct ChainArgs
     int* res_start;        // [ceil(N / 256)] atomicMin targets, or null (tiles not co-resident / injected offsets)
     double* total_word;    // published total (the last tile's prefix + sum)
     int res_blocks;
+    int flat;              // tiles <= kChainFlat * 256: no groups
     int systematic;        // the offsets share one fraction u0 (otherwise the block boundary itself is used, u = 0)
     int noise_injected;
     const float* resample_u;
@@ -954,22 +956,24 @@ __device__ __noinline__ long long first_block_behind(double x, double step, doub
     return k;
 }
 
-// entry j covers the offsets (prev, cur]: every block whose first offset lies there has lower_bound j
-__device__ __noinline__ void claim_block_starts(int* res_start, int res_blocks, double prev, double cur, double step,
-                                                   double u, double inv, int j)
+// Developer build (-DDOGM_PHASE_TRACE, tools/build_variant.sh): thread 0 of every CTA of k_cdf_chain / k_resample stamps
+// %globaltimer at its phase boundaries; dogm_debug_read("phase_chain" / "phase_resample") returns the stamps.
+#ifdef DOGM_PHASE_TRACE
+constexpr int kPhaseCtas = 4096, kPhaseSlots = 8;
+__device__ unsigned long long g_phase[2][kPhaseCtas][kPhaseSlots];
+__device__ __forceinline__ void phase_stamp(int which, unsigned cta, int slot, unsigned dep)
 {
-    if (!(cur > prev))
-        return;
-    long long k = (long long)floor(cur * inv - u * (1.0 / 256.0));
-    k = k < res_blocks ? k : res_blocks - 1;
-    k = k < 0 ? 0 : k;
-    while (k + 1 < res_blocks && res_boundary(k + 1, u, step) <= cur)
-        k++;
-    while (k >= 0 && res_boundary(k, u, step) > cur)
-        k--;
-    for (; k >= 0 && res_boundary(k, u, step) > prev; k--)
-        atomicMin(res_start + k, j);
+    if (threadIdx.x == 0 && cta < (unsigned)kPhaseCtas)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer; // %1" : "=l"(t) : "r"(dep) : "memory");
+        g_phase[which][cta][slot] = t;
+    }
 }
+#define PHASE_STAMP(which, cta, slot, dep) phase_stamp(which, cta, slot, (unsigned)(dep))
+#else
+#define PHASE_STAMP(which, cta, slot, dep)
+#endif
 
 // A published sum travels as one 64-bit word: the sums are non-negative, so the sign bit carries the parity of the
 // launch epoch.  Every launch publishes every word exactly once, hence a word whose sign bit differs from the epoch's
@@ -1025,6 +1029,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         const uint32_t t = s_tile;
         if (t >= (uint32_t)a.tiles)
             return;
+        PHASE_STAMP(0, t, 0, t);
         const int w0 = (int)t * kCdfTile + warp * kChainWarpSpan;
         // Entry layout: in round r (0..3) lane l holds the four consecutive entries w0 + 128 r + 4 l + (0..3), so every
         // load and store is a 16-byte vector and the prefix needs one warp scan per 128 entries (the four entries of a
@@ -1118,20 +1123,53 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
             base[r] = carry + excl;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
+        PHASE_STAMP(0, t, 1, __float_as_uint(e[15]));
         if (lane == 0)
             s_w[warp] = carry;
         __syncthreads();
+        PHASE_STAMP(0, t, 2, 0);
         double tot = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; w++)
             tot += s_w[w];
         if (threadIdx.x == 0)
             publish_f64(a.tile_sum + t, tot, a.epoch);
-        // totals of the tiles before this one inside its group, in a fixed order
+        // totals of the tiles before this one, in a fixed order
         const uint32_t group = t / kChainGroup, first = group * kChainGroup;
-        // (a group has at most 256 tiles: one word per thread, all polls in flight together)
         double part = 0.0;
-        if (first + threadIdx.x < t)
+        if (a.flat)
+        { // up to kChainFlat * 256 tiles: every tile adds up all the words in front of it (kChainFlat per thread, all polls in
+          // flight together) - no tile waits for another tile's prefix, only for the totals, which need no look-back
+            unsigned long long bits[kChainFlat];
+            unsigned need = 0;
+#pragma unroll
+            for (int k = 0; k < kChainFlat; k++)
+                if ((uint32_t)(k * kBlock) + threadIdx.x < t)
+                    need |= 1u << k;
+            unsigned todo = need;
+            while (todo)
+            {
+#pragma unroll
+                for (int k = 0; k < kChainFlat; k++)
+                    if (todo & (1u << k))
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];"
+                                     : "=l"(bits[k])
+                                     : "l"(a.tile_sum + k * kBlock + threadIdx.x)
+                                     : "memory");
+#pragma unroll
+                for (int k = 0; k < kChainFlat; k++)
+                    if ((todo & (1u << k)) && (uint32_t)(bits[k] >> 63) == (a.epoch & 1u))
+                        todo &= ~(1u << k);
+                if (todo)
+                    __nanosleep(40);
+            }
+#pragma unroll
+            for (int k = 0; k < kChainFlat; k++)
+                if (need & (1u << k))
+                    part += __longlong_as_double((long long)(bits[k] & 0x7fffffffffffffffull));
+        }
+        // (a group has at most 256 tiles: one word per thread, all polls in flight together)
+        else if (first + threadIdx.x < t)
             part = await_f64(a.tile_sum + first + threadIdx.x, a.epoch);
         else if (group > 0 && first + threadIdx.x == t)
             part = await_f64(a.group_base + group, a.epoch); // prefix of the groups before
@@ -1141,11 +1179,12 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
         if (lane == 0)
             s_red[warp] = part;
         __syncthreads();
+        PHASE_STAMP(0, t, 3, 0);
         double off = 0.0;
 #pragma unroll
         for (int w = 0; w < kWarpsPerBlock; w++)
             off += s_red[w];
-        if (threadIdx.x == 0 && (t + 1) % kChainGroup == 0 && t + 1 < (uint32_t)a.tiles)
+        if (!a.flat && threadIdx.x == 0 && (t + 1) % kChainGroup == 0 && t + 1 < (uint32_t)a.tiles)
         { // last tile of its group: publish the prefix the next group starts from
             publish_f64(a.group_base + group + 1, off + tot, a.epoch);
         }
@@ -1194,6 +1233,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                 }
             }
         }
+        PHASE_STAMP(0, t, 4, 0);
         // third phase (resampling support): which CDF entry is the lower_bound of the first offset of every block of 256
         // output slots.  Needs the total, which the last tile has published long before this tile finished writing.
         if (a.res_start)
@@ -1214,6 +1254,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                 }
             }
             __syncthreads();
+            PHASE_STAMP(0, t, 5, 0);
             const double total = s_total;
             if (total > 0.0)
             {
@@ -1222,9 +1263,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                 // the stored value of the entry before the warp's first is only known to a rounding here, so the warp
                 // reaches back a little (a claim too many is harmless: atomicMin keeps the true one, which the warp
                 // before makes, and k_resample verifies what it reads)
-                double last = w0 == 0 ? -1.0 : off - 1e-9 * fabs(off);
-                // k_next: the first block whose boundary lies behind `last`; a round of 128 entries is looked at closely
-                // only when that boundary is not behind its last entry (one comparison per round otherwise)
+                const double last = w0 == 0 ? -1.0 : off - 1e-9 * fabs(off);
+                // k_next: the first block whose boundary lies behind `last`.  A round of 128 entries is looked at closely only
+                // when that boundary is not behind its last entry: the lower_bound of the boundary is then the number of
+                // entries of the round below it (four ballots), claimed by one lane
                 long long k_next = first_block_behind(last, step, u, inv, a.res_blocks);
                 double next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
 #pragma unroll
@@ -1234,30 +1276,30 @@ __global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
                     const double s0 = (double)e[4 * r], s1 = s0 + (double)e[4 * r + 1], s2 = s1 + (double)e[4 * r + 2],
                                  s3 = s2 + (double)e[4 * r + 3];
                     double v[4] = {off + (base[r] + s0), off + (base[r] + s1), off + (base[r] + s2), off + (base[r] + s3)};
+                    // (entries behind the end carry weight 0: v[3] of lane 31 is the last valid entry's value)
+                    const double hi = __shfl_sync(0xffffffffu, v[3], 31);
 #pragma unroll
                     for (int q = 0; q < 4; q++)
                         if (i + q >= a.c.n)
                             v[q] = kInfD;
-                    const double hi = __shfl_sync(0xffffffffu, v[3], 31);
-                    if (w0 + r * 128 < a.c.n && next_off <= hi)
+                    if (w0 + r * 128 < a.c.n)
                     {
-                        double prev = __shfl_up_sync(0xffffffffu, v[3], 1);
-                        if (lane == 0)
-                            prev = last;
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        while (k_next < a.res_blocks && next_off <= hi)
                         {
-                            if (i + q < a.c.n)
-                                claim_block_starts(a.res_start, a.res_blocks, prev, v[q], step, u, inv, i + q);
-                            prev = v[q];
+                            const int below = __popc(__ballot_sync(0xffffffffu, v[0] < next_off)) +
+                                              __popc(__ballot_sync(0xffffffffu, v[1] < next_off)) +
+                                              __popc(__ballot_sync(0xffffffffu, v[2] < next_off)) +
+                                              __popc(__ballot_sync(0xffffffffu, v[3] < next_off));
+                            if (lane == 0)
+                                atomicMin(a.res_start + k_next, w0 + r * 128 + below);
+                            k_next++;
+                            next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
                         }
-                        k_next = first_block_behind(hi, step, u, inv, a.res_blocks);
-                        next_off = k_next < a.res_blocks ? res_boundary(k_next, u, step) : kInfD;
                     }
-                    last = hi;
                 }
             }
         }
+        PHASE_STAMP(0, t, 6, 0);
     }
 }
 
@@ -1388,6 +1430,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
     const int out0 = blockIdx.x * kResOutputs;
+    PHASE_STAMP(1, blockIdx.x, 0, 0);
     // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
     // res_start (one entry per 256 output slots): every thread reads it and fetches its window entries straight away,
     // while thread 0 prepares the scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
@@ -1425,6 +1468,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     for (int k = 0; k < kResWindow / kBlock; k++)
         s_cdf[k * kBlock + threadIdx.x] = win[k];
     __syncthreads();
+    PHASE_STAMP(1, blockIdx.x, 1, 0);
     const float joint_max = s_jm;
     const double r_first = s_first;
     bool ok = claimed;
@@ -1458,6 +1502,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
     }
     // ancestors of this thread's four output slots (out0 + 256 j + thread): search in the window, or in global memory for
     // offsets outside of it (long runs of zero weights, caller-supplied fractions that do not ascend)
+    PHASE_STAMP(1, blockIdx.x, 2, 0);
     const double w_last = s_cdf[kResWindow - 1];
     int anc[kResPer];
 #pragma unroll
@@ -1485,11 +1530,13 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             an = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
         anc[j] = an < a.n_cdf ? an : a.n_cdf - 1;
     }
+    PHASE_STAMP(1, blockIdx.x, 3, anc[kResPer - 1]);
     // gather: all slot loads first, then all record loads
     int slot[kResPer];
 #pragma unroll
     for (int j = 0; j < kResPer; j++)
         slot[j] = anc[j] < a.N ? __ldg(&a.spair[anc[j]].y) : -1;
+    PHASE_STAMP(1, blockIdx.x, 4, slot[kResPer - 1]);
     float4 st[kResPer];
     int cell[kResPer];
     uint32_t as[kResPer];
@@ -1512,6 +1559,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             as[j] = a.birth.assoc[b];
         }
     }
+    PHASE_STAMP(1, blockIdx.x, 5, __float_as_uint(st[kResPer - 1].w) ^ __float_as_uint(st[0].x));
     const float w_new = __fdiv_rn(joint_max, (float)a.N_glob);
 #pragma unroll
     for (int j = 0; j < kResPer; j++)
@@ -1526,6 +1574,7 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             a.dst.weight[i] = w_new;
         }
     }
+    PHASE_STAMP(1, blockIdx.x, 6, 0);
 }
 
 // ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
@@ -1754,6 +1803,18 @@ int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n,
     return (int)cudaGetLastError();
 }
 
+int debug_phase_read(int which, void* out_host, size_t bytes)
+{
+#ifdef DOGM_PHASE_TRACE
+    if (which < 0 || which > 1 || bytes > sizeof(g_phase[0]))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    return (int)cudaMemcpyFromSymbol(out_host, g_phase, bytes, (size_t)which * sizeof(g_phase[0]), cudaMemcpyDeviceToHost);
+#else
+    (void)which, (void)out_host, (void)bytes;
+    return DOGM_ERR_UNSUPPORTED;
+#endif
+}
+
 int chain_blocks_per_sm()
 {
     int a = 0, b = 0;
@@ -1799,6 +1860,7 @@ int run_cdf(dogm_handle* h)
     ch.ticket_base = h->chain_ticket_base;
     ch.epoch = ++h->chain_epoch;
     ch.tiles = h->n_cdf_tiles;
+    ch.flat = h->n_cdf_tiles <= kChainFlat * kBlock ? 1 : 0;
     ch.total_out = &h->scal->weight_total;
     const bool resident = h->n_cdf_tiles <= h->chain_capacity;
     ch.res_start = (resident && h->opts.resample_mode != DOGM_RESAMPLE_INJECTED && !h->band.enabled) ? h->res_start : nullptr;
