@@ -1393,6 +1393,7 @@ struct ResampleArgs
 // beyond the window (long runs of zero weights) or out of order (caller-supplied fractions that do not ascend) fall back
 // to a search in global memory, so the result is lower_bound on the whole CDF in every case.
 constexpr int kResWindow = 2048;
+constexpr int kResSlides = 6; // further windows a CTA looks at before its open offsets are searched in global memory
 
 __device__ __forceinline__ int lower_bound_f64(const double* __restrict__ cdf, int lo, int hi, double r)
 {
@@ -1423,20 +1424,26 @@ __device__ __forceinline__ double resample_offset(const ResampleArgs& a, int i, 
 constexpr int kResPer = 4;                     // output slots per thread
 constexpr int kResOutputs = kBlock * kResPer;  // output slots per CTA
 
-__global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
+#ifndef DOGM_RES_MINBLOCKS
+#define DOGM_RES_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(ResampleArgs a)
 {
     pdl_prologue(K_RESAMPLE * 2);
     __shared__ double s_cdf[kResWindow];
+    __shared__ __align__(16) int s_anc[kResOutputs];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
-    const int out0 = blockIdx.x * kResOutputs;
+    // the CTAs at the end of the CDF (birth particles: several window slides) take longest: they go first
+    const int blk = (int)(gridDim.x - 1 - blockIdx.x);
+    const int out0 = blk * kResOutputs;
     PHASE_STAMP(1, blockIdx.x, 0, 0);
     // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
     // res_start (one entry per 256 output slots): every thread reads it and fetches its window entries straight away,
     // while thread 0 prepares the scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
     int lo0 = 0x7f7f7f7f;
     if (a.res_start)
-        lo0 = __ldcg(a.res_start + blockIdx.x * kResPer);
+        lo0 = __ldcg(a.res_start + blk * kResPer);
     const bool claimed = lo0 >= 0 && lo0 < a.n_cdf;
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
     double win[kResWindow / kBlock];
@@ -1476,9 +1483,9 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
         ok = (lo0 == 0 || before < r_first) && win[0] >= r_first;
     if (a.res_start && threadIdx.x < kResPer)
     { // unclaimed again for the next cycle
-        const int blk = blockIdx.x * kResPer + (int)threadIdx.x;
-        if (blk * kBlock < a.N_out)
-            a.res_start[blk] = 0x7f7f7f7f;
+        const int claim = blk * kResPer + (int)threadIdx.x;
+        if (claim * kBlock < a.N_out)
+            a.res_start[claim] = 0x7f7f7f7f;
     }
     const bool have = __syncthreads_and(ok);
     if (!have)
@@ -1500,36 +1507,107 @@ __global__ void __launch_bounds__(kBlock) k_resample(ResampleArgs a)
             s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : kInf;
         __syncthreads();
     }
-    // ancestors of this thread's four output slots (out0 + 256 j + thread): search in the window, or in global memory for
-    // offsets outside of it (long runs of zero weights, caller-supplied fractions that do not ascend)
+    // Ancestors of this thread's four CONSECUTIVE output slots out0 + 4 thread + (0..3): the first by binary search in the
+    // window; offsets ascend, so each of the others starts where the one before ended and is normally found within a probe or
+    // two.  Where the CDF is dense in entries (the birth particles at its end: many entries of little weight) the CTA's offsets
+    // reach beyond the window: the CTA then slides the window on, up to kResSlides times, and the offsets still open are
+    // searched there.  Offsets in front of the window (caller-supplied fractions that do not ascend) or still open after the
+    // last slide (very long runs of zero weights) are searched in global memory, so that the result is lower_bound on the
+    // whole CDF in every case.
+    const int ibase = out0 + kResPer * (int)threadIdx.x;
     PHASE_STAMP(1, blockIdx.x, 2, 0);
-    const double w_last = s_cdf[kResWindow - 1];
+    double r[kResPer];
     int anc[kResPer];
+    unsigned open = 0; // bit j: output j has no ancestor yet
 #pragma unroll
     for (int j = 0; j < kResPer; j++)
     {
-        const int i = out0 + j * kBlock + (int)threadIdx.x;
-        const double r = resample_offset(a, i < a.N_out ? i : a.N_out - 1, joint_max, s_u0, s_step);
-        int an;
-        if (r < r_first)
-            an = lower_bound_f64(a.cdf, 0, a.n_cdf, r);
-        else if (r <= w_last)
+        const int i = ibase + j;
+        r[j] = resample_offset(a, i < a.N_out ? i : a.N_out - 1, joint_max, s_u0, s_step);
+        anc[j] = 0;
+        if (r[j] < r_first)
+            anc[j] = lower_bound_f64(a.cdf, 0, a.n_cdf, r[j]);
+        else
+            open |= 1u << j;
+    }
+    for (int slide = 0;; slide++)
+    {
+        const double w_last = s_cdf[kResWindow - 1];
+        int l_prev = 0;
+        double r_prev = 0.0;
+        bool chained = false; // the output before this one was resolved in this window (l_prev / r_prev are valid)
+#pragma unroll
+        for (int j = 0; j < kResPer; j++)
         {
+            if (!(open & (1u << j)) || !(r[j] <= w_last))
+            {
+                chained = false;
+                continue;
+            }
+            // every entry in front of the window is below r[j]
             int l = 0, h = kResWindow;
+            if (chained && r[j] >= r_prev)
+            { // lower_bound(r) >= lower_bound(r_prev): two probes forward, then a search bounded by a short gallop
+                l = l_prev;
+                h = l;
+                if (s_cdf[l] < r[j])
+                {
+                    l += 1; // l < kResWindow: s_cdf[l_prev] < r <= w_last
+                    h = l;
+                    if (s_cdf[l] < r[j])
+                    {
+                        l += 1;
+                        h = min(l + 14, kResWindow);
+                        if (s_cdf[h - 1] < r[j])
+                        {
+                            l = h;
+                            h = kResWindow;
+                        }
+                    }
+                }
+            }
             while (l < h)
             {
                 const int mid = l + ((h - l) >> 1);
-                if (s_cdf[mid] < r)
+                if (s_cdf[mid] < r[j])
                     l = mid + 1;
                 else
                     h = mid;
             }
-            an = lo0 + l;
+            anc[j] = lo0 + l;
+            open &= ~(1u << j);
+            l_prev = l;
+            r_prev = r[j];
+            chained = true;
         }
-        else
-            an = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r);
-        anc[j] = an < a.n_cdf ? an : a.n_cdf - 1;
+        if (!__syncthreads_or(open != 0)) // (also: nobody reads this window any more)
+            break;
+        if (slide == kResSlides || lo0 + kResWindow >= a.n_cdf)
+        { // (the second condition cannot hold with open offsets: the entries behind the end are +inf; kept as a guard)
+#pragma unroll
+            for (int j = 0; j < kResPer; j++)
+                if (open & (1u << j))
+                    anc[j] = lower_bound_f64(a.cdf, min(lo0 + kResWindow, a.n_cdf), a.n_cdf, r[j]);
+            break;
+        }
+        lo0 += kResWindow;
+#pragma unroll
+        for (int k = 0; k < kResWindow / kBlock; k++)
+        {
+            const long long e = (long long)lo0 + k * kBlock + (int)threadIdx.x;
+            s_cdf[k * kBlock + threadIdx.x] = e < a.n_cdf ? __ldcg(a.cdf + e) : kInf;
+        }
+        __syncthreads();
     }
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
+        anc[j] = anc[j] < a.n_cdf ? anc[j] : a.n_cdf - 1;
+    // from here on thread t handles the output slots out0 + 256 j + t (every global load and store of a warp is contiguous)
+    *reinterpret_cast<int4*>(s_anc + kResPer * threadIdx.x) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kResPer; j++)
+        anc[j] = s_anc[j * kBlock + threadIdx.x];
     PHASE_STAMP(1, blockIdx.x, 3, anc[kResPer - 1]);
     // gather: all slot loads first, then all record loads
     int slot[kResPer];
