@@ -151,7 +151,8 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->band.out_base = 0;
     h->band.n_out = 0;
     h->band.send[0] = h->band.send[1] = h->band.recv[0] = h->band.recv[1] = nullptr;
-    h->band.send_count = nullptr;
+    h->band.mig = nullptr;
+    h->band.out_cnt[0] = h->band.out_cnt[1] = h->band.out_off[0] = h->band.out_off[1] = h->band.out_total = nullptr;
     h->band.send_cap = band ? band->exchange_capacity : 0;
     h->band.halo[0] = h->band.halo[1] = nullptr;
     h->band.halo_rows = band ? band->halo_rows : 0;
@@ -273,7 +274,14 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
             e |= alloc_zero((void**)&h->band.recv[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec));
             e |= alloc_zero((void**)&h->band.halo[d], (size_t)(h->band.halo_rows ? h->band.halo_rows : 1) * gs * sizeof(float));
         }
-        e |= alloc_zero((void**)&h->band.send_count, 2 * sizeof(int));
+        const size_t out_tiles = (size_t)div_up(h->band.n_cap > 0 ? h->band.n_cap : 1, kTileItems);
+        e |= alloc_zero((void**)&h->band.mig, (size_t)(h->band.n_cap > 0 ? h->band.n_cap : 1) + 16);
+        for (int d = 0; d < 2; d++)
+        {
+            e |= alloc_zero((void**)&h->band.out_cnt[d], out_tiles * sizeof(double));
+            e |= alloc_zero((void**)&h->band.out_off[d], out_tiles * sizeof(double));
+        }
+        e |= alloc_zero((void**)&h->band.out_total, 2 * sizeof(double));
         if (e)
         {
             dogm_destroy(h);
@@ -356,7 +364,13 @@ extern "C" void dogm_destroy(dogm_handle* h)
         cudaFree(h->band.recv[d]);
         cudaFree(h->band.halo[d]);
     }
-    cudaFree(h->band.send_count);
+    cudaFree(h->band.mig);
+    for (int d = 0; d < 2; d++)
+    {
+        cudaFree(h->band.out_cnt[d]);
+        cudaFree(h->band.out_off[d]);
+    }
+    cudaFree(h->band.out_total);
     if (h->trace_buf)
     {
         trace_bind_particles(nullptr);
@@ -1157,14 +1171,23 @@ extern "C" int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float
 {
     BAND_PROLOGUE();
     update_pose(h, new_x, new_y, new_yaw);
-    DOGM_CHECK(cudaMemsetAsync(h->band.send_count, 0, 2 * sizeof(int), h->stream));
     e = run_predict(h, dt);
     if (e)
         return e;
     h->shift_particles_pending = false;
     int counts[2] = {0, 0};
-    DOGM_CHECK(cudaStreamSynchronize(h->stream));
-    DOGM_CHECK(cudaMemcpy(counts, h->band.send_count, sizeof(counts), cudaMemcpyDeviceToHost));
+    if (h->N > 0)
+    {
+        if ((e = run_band_outbox(h)))
+            return e;
+        double totals[2] = {0.0, 0.0};
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+        DOGM_CHECK(cudaMemcpy(totals, h->band.out_total, sizeof(totals), cudaMemcpyDeviceToHost));
+        counts[0] = (int)totals[0];
+        counts[1] = (int)totals[1];
+    }
+    else
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
     if (counts[0] > h->band.send_cap || counts[1] > h->band.send_cap)
         return DOGM_ERR_INVALID_ARGUMENT; // more particles crossed an edge than the exchange boxes hold
     if (send_lo)

@@ -192,7 +192,10 @@ struct dogm_handle
         // migration and halo buffers
         dogm_b200::PRec* send[2];  // particles leaving through the lower / upper edge (records with global coordinates)
         dogm_b200::PRec* recv[2];
-        int* send_count;           // device, 2 counters
+        uint8_t* mig;              // per slot: leaves through the lower (1) / upper (2) edge (k_predict -> k_outbox_*)
+        double* out_cnt[2];        // per tile of 4096 slots: particles leaving through either edge
+        double* out_off[2];        // their exclusive prefix
+        double* out_total;         // device, 2 totals
         int send_cap;
         float* halo[2];            // rows of the neighbours' previous free masses needed by an ego-motion shift in y
         int halo_rows;
@@ -407,6 +410,7 @@ int run_birth_fill(dogm_handle* h);  // birth particles
 int run_resampling(dogm_handle* h);
 int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of run_resampling)
 int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
+int run_band_outbox(dogm_handle* h); // compacts the particles k_predict flagged into the send boxes, in slot order
 int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi);
 void set_particle_counts(dogm_handle* h, int n, int b); // band mode: current counts and everything derived from them
 int materialize_meas(dogm_handle* h);      // kernels_meas.cu: runs a pending cartesian resampling into h->meas

@@ -45,10 +45,7 @@ struct PredictArgs
     int n;
     int gs;            // row length of the (band of the) grid = cells per side of the whole grid
     int row0, rows;    // rows of the whole grid this handle owns (0, gs without bands)
-    PRec* send_lo;     // band mode: records of the particles that leave through the lower / upper edge
-    PRec* send_hi;
-    int* send_count;
-    int send_cap;
+    uint8_t* mig;      // band mode: per slot 0 = stays, 1 / 2 = leaves through the lower / upper edge (k_outbox_* compact them)
     float dt, p_S, sigma_pos, sigma_vel;
     int shift_active, x_move, y_move;
     const float4* noise;
@@ -119,27 +116,27 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
                 w = 0.0f;
             const int px = min(max(__float2int_rz(x), 0), a.gs - 1);
             int py = min(max(__float2int_rz(y), 0), a.gs - 1) - a.row0;
+            float w_leaving = 0.0f;
+            uint8_t leaves = 0;
             if (py < 0 || py >= a.rows)
-            { // band mode only: the particle now lies in a neighbour's band; it goes into the outbox with its weight
-              // and stays behind as a weightless ghost in the edge row until resampling drops it
+            { // band mode only: the particle now lies in a neighbour's band.  It stays behind as a weightless ghost in the
+              // edge row until resampling drops it; its weight rides in the record's spare word and the slot is flagged, so
+              // that k_outbox_write can copy it into the outbox IN SLOT ORDER (the order of an atomic append would change
+              // from run to run, and with it the neighbour's particle order)
                 if (w > 0.0f)
                 {
-                    const int dir = py < 0 ? 0 : 1;
-                    const int at = atomicAdd(a.send_count + dir, 1);
-                    if (at < a.send_cap)
-                    {
-                        float4* so = reinterpret_cast<float4*>((dir ? a.send_hi : a.send_lo) + at);
-                        so[0] = rec_lo(x, y, 0, as);
-                        so[1] = rec_hi(vx, vy, w);
-                    }
+                    leaves = py < 0 ? 1 : 2;
+                    w_leaving = w;
                 }
                 w = 0.0f;
                 py = py < 0 ? 0 : a.rows - 1;
             }
+            if (a.mig)
+                a.mig[i] = leaves;
             const int cell = px + a.gs * py;
             float4* o = reinterpret_cast<float4*>(out + i);
             o[0] = rec_lo(x, y, cell, as);
-            o[1] = rec_hi(vx, vy, w);
+            o[1] = make_float4(vx, vy, w, w_leaving);
             key_out[i] = cell;
             atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
         }
@@ -1741,10 +1738,7 @@ int run_predict(dogm_handle* h, float dt)
     a.gs = h->gs;
     a.row0 = h->band.row0;
     a.rows = h->band.rows;
-    a.send_lo = h->band.send[0];
-    a.send_hi = h->band.send[1];
-    a.send_count = h->band.send_count;
-    a.send_cap = h->band.send_cap;
+    a.mig = h->band.enabled ? h->band.mig : nullptr;
     a.dt = dt;
     a.p_S = h->params.persistence_prob;
     a.sigma_pos = h->params.stddev_process_noise_position;
@@ -2021,6 +2015,101 @@ int run_resampling(dogm_handle* h)
 
 // band mode: the particles that arrived from the neighbours (records with global coordinates in the two inboxes) become
 // the tail of this cycle's record list
+// Band mode, outbox: the slots k_predict flagged are compacted into the two send boxes in slot order.
+//   k_outbox_count: per tile of 4096 slots the number of particles leaving through either edge (as doubles: the tile
+//                   offsets come from the same single-CTA scan the born masses use)
+//   k_outbox_write: rank inside the tile (block scan in slot order) + tile offset -> position in the box
+constexpr int kOutboxPer = kTileItems / kBlock; // 16 consecutive slots per thread
+__device__ __forceinline__ unsigned long long outbox_thread_counts(const uint8_t* __restrict__ mig, int n, int i0, uint8_t* f)
+{
+    unsigned long long c = 0;
+    if (i0 + kOutboxPer <= n)
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(mig + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < kOutboxPer; k++)
+            f[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < kOutboxPer; k++)
+            f[k] = i0 + k < n ? mig[i0 + k] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kOutboxPer; k++)
+        c += f[k] == 1 ? 1ull : (f[k] == 2 ? (1ull << 32) : 0ull);
+    return c; // low word: lower edge, high word: upper edge
+}
+
+__global__ void __launch_bounds__(kBlock) k_outbox_count(const uint8_t* __restrict__ mig, int n, double* cnt_lo, double* cnt_hi)
+{
+    pdl_prologue(K_MISC * 2);
+    __shared__ unsigned long long s_w[kWarpsPerBlock];
+    uint8_t f[kOutboxPer];
+    unsigned long long c = outbox_thread_counts(mig, n, blockIdx.x * kTileItems + threadIdx.x * kOutboxPer, f);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0)
+        s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long t = 0;
+        for (int w = 0; w < kWarpsPerBlock; w++)
+            t += s_w[w];
+        cnt_lo[blockIdx.x] = (double)(uint32_t)t;
+        cnt_hi[blockIdx.x] = (double)(uint32_t)(t >> 32);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_outbox_write(const uint8_t* __restrict__ mig, const PRec* __restrict__ rec, int n,
+                                                         const double* __restrict__ off_lo, const double* __restrict__ off_hi,
+                                                         PRec* send_lo, PRec* send_hi, int send_cap)
+{
+    pdl_prologue(K_MISC * 2 + 1);
+    __shared__ unsigned long long s_w[kWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * kTileItems + threadIdx.x * kOutboxPer;
+    uint8_t f[kOutboxPer];
+    const unsigned long long mine = outbox_thread_counts(mig, n, i0, f);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    if (lane == 31)
+        s_w[warp] = incl;
+    __syncthreads();
+    if (mine == 0)
+        return;
+    unsigned long long before = incl - mine;
+    for (int w = 0; w < warp; w++)
+        before += s_w[w];
+    long long at_lo = (long long)off_lo[blockIdx.x] + (long long)(uint32_t)before;
+    long long at_hi = (long long)off_hi[blockIdx.x] + (long long)(uint32_t)(before >> 32);
+#pragma unroll
+    for (int k = 0; k < kOutboxPer; k++)
+    {
+        if (f[k] == 0)
+            continue;
+        const long long at = f[k] == 1 ? at_lo++ : at_hi++;
+        if (at < send_cap)
+        {
+            const float4* src = reinterpret_cast<const float4*>(rec + i0 + k);
+            const float4 lo = src[0], hi = src[1];
+            float4* so = reinterpret_cast<float4*>((f[k] == 1 ? send_lo : send_hi) + at);
+            so[0] = rec_lo(lo.x, lo.y, 0, __float_as_uint(lo.w));
+            so[1] = rec_hi(hi.x, hi.y, hi.w); // the weight the ghost gave up
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_band_append(const PRec* __restrict__ in_lo, int n_lo, const PRec* __restrict__ in_hi,
                                                         int n_hi, PRec* __restrict__ rec, int* __restrict__ key0, int n_cur,
                                                         int gs, int row0, int rows)
@@ -2038,6 +2127,27 @@ __global__ void __launch_bounds__(kBlock) k_band_append(const PRec* __restrict__
     o[0] = rec_lo(lo.x, lo.y, cell, __float_as_uint(lo.w));
     o[1] = hi;
     key0[n_cur + k] = cell;
+}
+
+int run_band_outbox(dogm_handle* h)
+{
+    const int n = h->N;
+    const int tiles = div_up(n > 0 ? n : 1, kTileItems);
+    {
+        LaunchScope ls(h, K_MISC, 1.0 * n);
+        launch_chained(h->stream, k_outbox_count, tiles, kBlock, 0, h->band.mig, n, h->band.out_cnt[0], h->band.out_cnt[1]);
+    }
+    int e = (int)cudaGetLastError();
+    e = e ? e : run_blocksum_scan(h, h->band.out_cnt[0], h->band.out_off[0], tiles, h->band.out_total);
+    e = e ? e : run_blocksum_scan(h, h->band.out_cnt[1], h->band.out_off[1], tiles, h->band.out_total + 1);
+    if (e)
+        return e;
+    {
+        LaunchScope ls(h, K_MISC, 1.0 * n);
+        launch_chained(h->stream, k_outbox_write, tiles, kBlock, 0, h->band.mig, h->rec, n, h->band.out_off[0], h->band.out_off[1],
+                       h->band.send[0], h->band.send[1], h->band.send_cap);
+    }
+    return (int)cudaGetLastError();
 }
 
 int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi)
