@@ -159,14 +159,30 @@ struct BeamBlock
 {
     float z[kBeamsByValue];
 };
+// Nothing this kernel reads comes from the kernels in front of it in the stream (the scan is in its parameters; the last
+// reader of the table, the cell kernel of the cycle before, finished several kernels ago), so it does its work first and waits
+// for its predecessor only before it exits: its CTAs run in the tail of the previous cycle's resampling kernel, and completion
+// still is transitive along the stream (this kernel ends after its predecessor has).
+// (kEarly = false: the plain order, for a scan that replaces one no cycle has consumed yet - two early kernels could overlap.)
+template <bool kEarly>
 __global__ void __launch_bounds__(kBlock) k_meas_polar_byvalue(MeasArgs a, float2* out, const __grid_constant__ BeamBlock scan)
 {
-    pdl_prologue(K_MEAS_POLAR * 2);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!kEarly)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     const int t = blockIdx.x * kBlock + threadIdx.x;
-    if (t >= a.K * a.H)
-        return;
-    const int b = t % a.K, i = t / a.K;
-    out[t] = polar_cell(a, scan.z[b], i);
+    if (t < a.K * a.H)
+    {
+        const int b = t % a.K, i = t / a.K;
+        out[t] = polar_cell(a, scan.z[b], i);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0 && c_trace)
+    {
+        unsigned long long ts;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+        atomicMin(c_trace + K_MEAS_POLAR * 2, ts);
+    }
 }
 
 // one more scan into the polar table: Dempster-Shafer combination of the table (prior) with the clamped inverse sensor model
@@ -410,7 +426,10 @@ extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, cons
         memcpy(scan.z, beam_ranges_host, (size_t)K * sizeof(float));
         const MeasArgs a = make_args(m, K, nullptr);
         LaunchScope ls(h, K_MEAS_POLAR, 8.0 * (double)K * m->H);
-        launch_chained(h->stream, k_meas_polar_byvalue, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);
+        if (h->lazy_meas.pending)
+            launch_chained(h->stream, k_meas_polar_byvalue<false>, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);
+        else
+            launch_chained(h->stream, k_meas_polar_byvalue<true>, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);
         e = (int)cudaGetLastError();
     }
     else
