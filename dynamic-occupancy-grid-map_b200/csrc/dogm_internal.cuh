@@ -306,13 +306,13 @@ struct dogm_handle
     uint32_t dyn_list_cycle;
     dogm_dynamic_cell* dyn_mapped_host;
     dogm_dynamic_cell* dyn_mapped_dev;
-    // early publication of that list: the kernel behind the cell kernel (k_blocksum_scan) writes {count, sequence number}
+    // early publication of that list: a kernel behind the cell kernel (k_birth_particles) writes {count, sequence number}
     // into host-mapped memory, so dogm_extract_dynamic_cells returns as soon as the list exists - the rest of the cycle
     // (birth particles, CDF, resampling) keeps running while the host consumes the list and enqueues the next scan
     int* dyn_pub_host; // pinned + mapped, 2 ints
     int* dyn_pub_dev;
     int dyn_pub_seq;      // sequence number of the last list whose publication was enqueued
-    bool dyn_pub_armed;   // the cell kernel of the running cycle fills the list; the next born-mass scan publishes it
+    bool dyn_pub_armed;   // the cell kernel of the running cycle fills the list; the birth kernel behind it publishes it
     bool dyn_pub_pending; // a publication has been enqueued for the current list
 
     // instrumentation

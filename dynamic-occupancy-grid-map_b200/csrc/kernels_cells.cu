@@ -55,7 +55,7 @@ struct CellArgs
 #define DOGM_CELL_MINBLOCKS 8
 #endif
 #ifndef DOGM_CELL_MINBLOCKS_LAZY
-#define DOGM_CELL_MINBLOCKS_LAZY 6
+#define DOGM_CELL_MINBLOCKS_LAZY 8
 #endif
 template <bool kLazyMeas>
 __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LAZY : DOGM_CELL_MINBLOCKS) k_cell(CellArgs a)
@@ -212,7 +212,11 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
             {
                 const int at = base + __popc(m & lanemask_lt());
                 if (at < a.dyn_capacity)
-                    a.dyn_out[at] = dyn_rec;
+                { // two 16-byte stores (the buffer may be host-mapped: every store instruction is a PCIe write)
+                    float4* o = reinterpret_cast<float4*>(a.dyn_out + at);
+                    o[0] = make_float4(__int_as_float(dyn_rec.cell_idx), dyn_rec.occupancy, dyn_rec.mean_x_vel, dyn_rec.mean_y_vel);
+                    o[1] = make_float4(dyn_rec.var_x_vel, dyn_rec.var_y_vel, dyn_rec.covar_xy_vel, dyn_rec.mahalanobis);
+                }
             }
         }
     }
@@ -333,6 +337,11 @@ struct BirthArgs
     float stddev_velocity;
     uint64_t seed;
     uint32_t cycle;
+    // early publication of the dynamic-cell list (see dogm_handle::dyn_pub_host): written by one thread of this kernel, where
+    // the system-wide fence hides behind the other CTAs' work (in the single-CTA scan in front it would delay the whole cycle)
+    const int* pub_count;
+    int* pub_host;
+    int pub_seq;
 };
 
 // initBirthParticlesKernel (init.cu:46-67) + initNewParticlesKernel1 (init_new_particles.cu:126-155, with the
@@ -341,6 +350,13 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 {
     pdl_prologue(K_BIRTH_PARTICLES * 2);
     const int s = blockIdx.x * kBlock + threadIdx.x;
+    if (a.pub_host && s == 0)
+    {
+        const int found = __ldcg(a.pub_count);
+        *reinterpret_cast<volatile int*>(a.pub_host) = found;
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(a.pub_host + 1) = a.pub_seq;
+    }
     if (s >= a.B)
         return;
     SlotView v = a.slots;
@@ -657,7 +673,8 @@ int run_occupancy_update(dogm_handle* h, float dt)
 
 int run_born_scan(dogm_handle* h)
 {
-    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total, true);
+    // (the dynamic-cell list is published by the birth kernel behind this scan; without birth particles, by the scan itself)
+    return run_blocksum_scan(h, h->blk_sum, h->blk_off, h->n_cell_blocks, &h->scal->born_total, h->B <= 0);
 }
 
 int run_birth(dogm_handle* h)
@@ -686,6 +703,17 @@ int run_birth_fill(dogm_handle* h)
     a.stddev_velocity = h->params.stddev_velocity;
     a.seed = h->opts.seed + h->band.salt;
     a.cycle = h->cycle;
+    a.pub_count = nullptr;
+    a.pub_host = nullptr;
+    a.pub_seq = 0;
+    if (h->dyn_pub_armed && h->dyn_pub_dev)
+    {
+        a.pub_count = h->dyn_count;
+        a.pub_host = h->dyn_pub_dev;
+        a.pub_seq = ++h->dyn_pub_seq;
+        h->dyn_pub_armed = false;
+        h->dyn_pub_pending = true;
+    }
     {
         LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B);
         launch_chained(h->stream, k_birth_particles, div_up(h->B, kBlock), kBlock, 0, a);

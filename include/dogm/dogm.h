@@ -81,6 +81,13 @@ class DOGM
     void resampling() { stage(dogm_resampling(handle)); }
 
     // extras of this implementation
+    // the cycle without the device synchronisation of dogm.cu:130: returns once the kernels are enqueued.  Pair it with
+    // setDynamicCellFilter + extractDynamicCells (which returns as soon as the cycle has produced its list) or synchronize().
+    void updateGridAsync(MeasurementCell* measurement_grid, float new_x, float new_y, float new_yaw, float dt, bool device = true)
+    {
+        last_error = dogm_update_grid_async(handle, measurement_grid, new_x, new_y, new_yaw, dt, device ? 1 : 0);
+    }
+    void synchronize() { last_error = dogm_synchronize(handle); }
     std::vector<::dogm_dynamic_cell> extractDynamicCells(float min_occupancy, float min_velocity, int capacity = 1 << 16)
     {
         std::vector<::dogm_dynamic_cell> out(static_cast<size_t>(capacity));

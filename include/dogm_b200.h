@@ -358,7 +358,7 @@ int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, float min_ve
 /* Registers the filter ahead of time (capacity 0 switches it off): every following cycle then compacts the matching
  * cells inside its per-cell kernel, straight into pinned host memory, and dogm_extract_dynamic_cells with the same
  * thresholds returns that list instead of running a pass over all 64*C bytes of grid cells.  After dogm_update_grid_async it
- * returns as soon as the list exists - the kernel behind the per-cell kernel writes {count, sequence number} into host-mapped
+ * returns as soon as the list exists - a kernel behind the per-cell kernel writes {count, sequence number} into host-mapped
  * memory the call spins on - while birth, CDF and resampling of that cycle are still running: the caller consumes the list and
  * enqueues the next scan in the meantime, so the stream never runs dry.  (Every other getter still synchronises.) */
 int dogm_set_dynamic_cell_filter(dogm_handle* h, float min_occupancy, float min_velocity, int capacity);

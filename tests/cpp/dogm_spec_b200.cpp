@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 #include <vector>
 
@@ -211,6 +212,63 @@ static int test_demo_main()
     return 0;
 }
 
+static int test_streaming_loop()
+{ // generateGridInto + updateGridAsync + extractDynamicCells (returns from the middle of the cycle) gives, scan
+  // after scan, the list the blocking demo loop gives
+    dogm::DOGM::Params grid_params;
+    grid_params.size = 50.0f;
+    grid_params.resolution = 0.2f;
+    grid_params.particle_count = 200000;
+    grid_params.new_born_particle_count = 20000;
+    grid_params.persistence_prob = 0.99f;
+    grid_params.stddev_process_noise_position = 0.1f;
+    grid_params.stddev_process_noise_velocity = 1.0f;
+    grid_params.birth_prob = 0.02f;
+    grid_params.stddev_velocity = 30.0f;
+    grid_params.init_max_velocity = 30.0f;
+    grid_params.freespace_discount = 0.01f;
+    LaserMeasurementGrid::Params laser_params;
+    laser_params.fov = 120.0f;
+    laser_params.max_range = 50.0f;
+    laser_params.resolution = grid_params.resolution;
+    laser_params.stddev_range = 0.5f;
+    LaserMeasurementGrid grid_generator(laser_params, grid_params.size, grid_params.resolution);
+    Simulator simulator(100, laser_params.fov, grid_params.size, glm::vec2{0.0f, 4.0f});
+    simulator.addVehicle(Vehicle(3.5, glm::vec2(10, 30), glm::vec2(15, 0)));
+    simulator.addVehicle(Vehicle(4.0, glm::vec2(35, 35), glm::vec2(0, -10)));
+    SimulationData sim_data = simulator.update(10, 0.1f);
+
+    dogm::DOGM blocking(grid_params), streaming(grid_params);
+    blocking.setDynamicCellFilter(0.7f, 4.0f);
+    streaming.setDynamicCellFilter(0.7f, 4.0f);
+    size_t total = 0;
+    for (int step = 0; step < 10; ++step)
+    {
+        dogm::MeasurementCell* meas_grid = grid_generator.generateGrid(sim_data[step].measurements);
+        blocking.updateGrid(meas_grid, sim_data[step].ego_pose.x, sim_data[step].ego_pose.y, 0.0f, 0.1f, true);
+        std::vector<dogm_dynamic_cell> a = blocking.extractDynamicCells(0.7f, 4.0f);
+
+        grid_generator.generateGridInto(streaming.native(), sim_data[step].measurements);
+        streaming.updateGridAsync(nullptr, sim_data[step].ego_pose.x, sim_data[step].ego_pose.y, 0.0f, 0.1f);
+        CHECK(streaming.last_error == 0);
+        std::vector<dogm_dynamic_cell> b = streaming.extractDynamicCells(0.7f, 4.0f);
+        CHECK(streaming.last_error == 0);
+
+        auto by_cell = [](const dogm_dynamic_cell& x, const dogm_dynamic_cell& y) { return x.cell_idx < y.cell_idx; };
+        std::sort(a.begin(), a.end(), by_cell);
+        std::sort(b.begin(), b.end(), by_cell);
+        CHECK(a.size() == b.size());
+        for (size_t k = 0; k < a.size(); k++)
+            CHECK(a[k].cell_idx == b[k].cell_idx && a[k].mean_x_vel == b[k].mean_x_vel && a[k].occupancy == b[k].occupancy);
+        total += a.size();
+    }
+    CHECK(total > 0);
+    streaming.synchronize();
+    const std::vector<dogm::GridCell> ga = blocking.getGridCells(), gb = streaming.getGridCells();
+    CHECK(std::memcmp(ga.data(), gb.data(), ga.size() * sizeof(dogm::GridCell)) == 0);
+    return 0;
+}
+
 int main()
 {
     if (dogm_device_count() < 1)
@@ -222,6 +280,7 @@ int main()
     rc |= test_predict();
     rc |= test_demo_flow();
     rc |= test_demo_main();
+    rc |= test_streaming_loop();
     std::printf(rc == 0 ? "dogm_spec_b200: all passed\n" : "dogm_spec_b200: FAILED\n");
     return rc;
 }
