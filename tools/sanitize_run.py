@@ -21,6 +21,13 @@ for (size, res, n, b) in [(20.0, 0.25, 20000, 2000), (13.0, 0.5, 5001, 333)]:
             d.update_grid(ptr, 0.3 * c, 0.45 * c, 0.0, 0.1, device=True)
             d.extract_dynamic_cells(0.6, 0.5, capacity=4096)
             d.extract_dynamic_cells(0.5, 0.25)
+    # streaming loop: scan resampled inside the cell kernel, list published from the middle of the cycle
+    for c in range(3):
+        z = np.where(rng.uniform(size=37) < 0.6, rng.uniform(2, size * 0.9, 37), np.inf).astype(np.float32)
+        gen.generate_grid_into(d, z)
+        d.update_grid(None, 1.2 + 0.3 * c, 1.8 + 0.45 * c, 0.0, 0.1, sync=False)
+        d.extract_dynamic_cells(0.6, 0.5, capacity=4096)
+    d.synchronize()
     d.update_measurement_grid(gen.generate_grid_host(z))
     d.update_pose(2.0, 3.0, 0.0)
     d.particle_prediction(0.1); d.get_particles()
@@ -30,4 +37,19 @@ for (size, res, n, b) in [(20.0, 0.25, 20000, 2000), (13.0, 0.5, 5001, 333)]:
     d.get_grid_cells(); d.get_measurement_cells(); d.get_birth_particles(); d.get_weight_array(); d.get_joint_weight_accum()
     d.get_resampled_indices(); d.export_philox_noise(3)
     gen.close(); d.close()
+# band mode: two and three bands on one GPU (outbox compaction, append, halo rows, global normalisers)
+size, res, n, b = 24.0, 0.25, 30000, 3000
+gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(size, res, 120.0, 0.5), size, res)
+rng = np.random.default_rng(2)
+for bands in (2, 3):
+    bd = gpu.BandedDOGM(make_params(gpu, size, res, n, b), bands, seed=5, halo_rows=8)
+    dev = gpu.device_alloc(bd.G * bd.G * 16)
+    for c in range(4):
+        z = np.where(rng.uniform(size=48) < 0.6, rng.uniform(2, size * 0.9, 48), np.inf).astype(np.float32)
+        gpu.memcpy_h2d(dev, gen.generate_grid_host(z))
+        bd.update_grid([dev + bd.row0[r] * bd.G * 16 for r in range(bands)], 0.2 * c, 0.6 * c, 0.0, 0.1)
+    bd.get_grid_cells()
+    bd.close()
+    gpu.device_free(dev)
+gen.close()
 print("sanitize run done")
