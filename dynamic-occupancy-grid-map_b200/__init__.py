@@ -129,6 +129,10 @@ class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("total_ms", C.c_double), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_double)]
 
 
+class BandCycleInfo(C.Structure):
+    _fields_ = [("born_total", C.c_double), ("weight_total", C.c_double), ("migrated", C.c_longlong), ("phase_ms", C.c_float * 5)]
+
+
 class DogmError(RuntimeError):
     pass
 
@@ -213,6 +217,12 @@ _SYMBOLS = [
     ("dogm_band_init_particles", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int)]),
     ("dogm_band_predict", C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("dogm_band_append", C.c_int, [_P, C.c_int, C.c_int]),
+    ("dogm_band_receive", C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, _P]),
+    ("dogm_enable_peer_access", C.c_int, [C.c_int, C.c_int]),
+    ("dogm_band_group_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    ("dogm_band_group_destroy", None, [_P]),
+    ("dogm_band_group_update", C.c_int, [_P, C.POINTER(C.c_void_p), C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int),
+                                        C.c_void_p]),
     ("dogm_band_update", C.c_int, [_P, _P, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]),
     ("dogm_band_birth", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     ("dogm_band_resample", C.c_int, [_P, C.c_double, C.c_double, C.POINTER(C.c_int)]),
@@ -657,7 +667,7 @@ class BandedDOGM:
     release the GIL) and the copies between bands are NVLink peer copies.  By default all bands share the current GPU."""
 
     def __init__(self, params: Params, n_bands: int, devices=None, seed: int = 123456, slack: float = 1.75, halo_rows: int = 64,
-                 resample_mode: int = RESAMPLE_SYSTEMATIC, rows=None):
+                 resample_mode: int = RESAMPLE_SYSTEMATIC, rows=None, native: bool = True):
         """rows: rows per band (default: equal shares; see balanced_rows for a split by expected particle load)"""
         self._lib = load_library()
         self.params = params
@@ -690,10 +700,24 @@ class BandedDOGM:
             self.h[r] = hp
 
         self._each(create)
+        # neighbouring bands on different GPUs talk over NVLink: without peer access every copy would be staged through the host
+        self.peer_access = []
+        for r in range(n_bands - 1):
+            a, b = self.devices[r], self.devices[r + 1]
+            if a is not None and b is not None and a != b:
+                ok = self._lib.dogm_enable_peer_access(a, b) == 0 and self._lib.dogm_enable_peer_access(b, a) == 0
+                self.peer_access.append(bool(ok))
         self.first = True
         self.last_counts = []
         self.last_migration = ([], [])
         self.last_totals = {}
+        # the native orchestrator (one host thread per band inside the library); `native=False` keeps the phases in Python
+        self.group = None
+        if native:
+            arr = (C.c_void_p * n_bands)(*[h.value for h in self.h])
+            g = C.c_void_p()
+            _check(self._lib.dogm_band_group_create(arr, n_bands, C.byref(g)), "dogm_band_group_create")
+            self.group = g
 
     def _on(self, r):
         if self.devices[r] is not None:
@@ -711,6 +735,9 @@ class BandedDOGM:
         return [run(r) for r in range(self.R)]
 
     def close(self):
+        if getattr(self, "group", None) is not None:
+            self._lib.dogm_band_group_destroy(self.group)
+            self.group = None
         if self.h and any(self.h):
             self._each(lambda r: self._lib.dogm_destroy(self.h[r]) if self.h[r] else None)
         self.h = []
@@ -739,6 +766,18 @@ class BandedDOGM:
     def update_grid(self, meas_band_ptrs, new_x, new_y, new_yaw, dt):
         """meas_band_ptrs[r]: device address (on band r's GPU) of the rows of the measurement grid that band r owns"""
         lib, R = self._lib, self.R
+        if self.group is not None:
+            ptrs = (C.c_void_p * R)(*[int(p) for p in meas_band_ptrs])
+            counts = (C.c_int * R)()
+            info = BandCycleInfo()
+            _check(lib.dogm_band_group_update(self.group, ptrs, new_x, new_y, new_yaw, dt, counts, C.addressof(info)),
+                   "dogm_band_group_update")
+            self.first = False
+            self.last_phase_ms = [float(v) for v in info.phase_ms]
+            self.last_counts = [int(c) for c in counts]
+            self.last_migration = ([int(info.migrated)], [0])
+            self.last_totals = {"born": info.born_total, "weight": info.weight_total}
+            return self.last_counts
         if self.first:
             def masses(r):
                 m = C.c_double(0.0)
@@ -764,17 +803,12 @@ class BandedDOGM:
         def receive(r):  # band r takes what its neighbours sent towards it, and their edge rows of the PREVIOUS free masses
             n_lo = hi[r - 1] if r > 0 else 0
             n_hi = lo[r + 1] if r + 1 < R else 0
-            if n_lo:
-                _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_RECV_LO), self._buf(r - 1, BAND_SEND_HI), n_lo * 32), "dogm_memcpy_d2d")
-            if n_hi:
-                _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_RECV_HI), self._buf(r + 1, BAND_SEND_LO), n_hi * 32), "dogm_memcpy_d2d")
-            _check(lib.dogm_band_append(self.h[r], n_lo, n_hi), "dogm_band_append")
-            if self.halo_rows:
-                nbytes = self.halo_rows * self.G * 4
-                if r > 0:
-                    _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_LO), self._buf(r - 1, BAND_EDGE_HI), nbytes), "dogm_memcpy_d2d")
-                if r + 1 < R:
-                    _check(lib.dogm_memcpy_d2d(self._buf(r, BAND_HALO_HI), self._buf(r + 1, BAND_EDGE_LO), nbytes), "dogm_memcpy_d2d")
+            box_lo = self._buf(r - 1, BAND_SEND_HI) if n_lo else None
+            box_hi = self._buf(r + 1, BAND_SEND_LO) if n_hi else None
+            edge_lo = self._buf(r - 1, BAND_EDGE_HI) if (self.halo_rows and r > 0) else None
+            edge_hi = self._buf(r + 1, BAND_EDGE_LO) if (self.halo_rows and r + 1 < R) else None
+            self._on(r)
+            _check(lib.dogm_band_receive(self.h[r], box_lo, n_lo, box_hi, n_hi, edge_lo, edge_hi), "dogm_band_receive")
 
         self._each(receive)  # (all bands finish this before any of them updates its cells: _each is a barrier)
         t_phase.append(_time.perf_counter())

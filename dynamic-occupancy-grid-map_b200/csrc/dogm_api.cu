@@ -1215,6 +1215,41 @@ extern "C" int dogm_band_append(dogm_handle* h, int recv_lo, int recv_hi)
     return 0;
 }
 
+// The exchange step of a band in one call: the neighbours' outboxes and edge rows are copied on the band's own stream
+// (direct NVLink copies once dogm_enable_peer_access has been called for the two devices, staged through the host otherwise),
+// the received particles are appended, one synchronisation at the end.
+extern "C" int dogm_band_receive(dogm_handle* h, const void* outbox_of_lower_neighbour, int recv_lo,
+                                 const void* outbox_of_upper_neighbour, int recv_hi, const void* edge_rows_of_lower_neighbour,
+                                 const void* edge_rows_of_upper_neighbour)
+{
+    BAND_PROLOGUE();
+    if (recv_lo < 0 || recv_hi < 0 || recv_lo > h->band.send_cap || recv_hi > h->band.send_cap ||
+        (recv_lo > 0 && !outbox_of_lower_neighbour) || (recv_hi > 0 && !outbox_of_upper_neighbour))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (recv_lo > 0)
+        DOGM_CHECK(cudaMemcpyAsync(h->band.recv[0], outbox_of_lower_neighbour, (size_t)recv_lo * sizeof(PRec), cudaMemcpyDefault,
+                                   h->stream));
+    if (recv_hi > 0)
+        DOGM_CHECK(cudaMemcpyAsync(h->band.recv[1], outbox_of_upper_neighbour, (size_t)recv_hi * sizeof(PRec), cudaMemcpyDefault,
+                                   h->stream));
+    const size_t halo_bytes = (size_t)h->band.halo_rows * h->gs * sizeof(float);
+    if (halo_bytes && edge_rows_of_lower_neighbour)
+        DOGM_CHECK(cudaMemcpyAsync(h->band.halo[0], edge_rows_of_lower_neighbour, halo_bytes, cudaMemcpyDefault, h->stream));
+    if (halo_bytes && edge_rows_of_upper_neighbour)
+        DOGM_CHECK(cudaMemcpyAsync(h->band.halo[1], edge_rows_of_upper_neighbour, halo_bytes, cudaMemcpyDefault, h->stream));
+    if (h->N == 0 && recv_lo + recv_hi > 0)
+    { // nothing was predicted here: the records are the band's whole population
+        h->pa_current = false;
+        h->rec_valid = true;
+        h->sorted_valid = false;
+    }
+    e = run_band_append(h, recv_lo, recv_hi);
+    if (e)
+        return e;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, float dt, int halo_valid,
                                 double* born_local)
 {
@@ -1524,6 +1559,27 @@ extern "C" int dogm_memcpy_d2d(void* dst_device, const void* src_device, size_t 
 extern "C" int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes)
 {
     DOGM_CHECK(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int dogm_enable_peer_access(int device, int peer_device)
+{ // lets `device` read and write `peer_device`'s memory directly (NVLink / NVSwitch); copies between the two then bypass the host
+    if (device == peer_device)
+        return 0;
+    int can = 0;
+    DOGM_CHECK(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can)
+        return DOGM_ERR_UNSUPPORTED;
+    int prev = 0;
+    DOGM_CHECK(cudaGetDevice(&prev));
+    DOGM_CHECK(cudaSetDevice(device));
+    cudaError_t pe = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (pe == cudaErrorPeerAccessAlreadyEnabled)
+    {
+        cudaGetLastError();
+        pe = cudaSuccess;
+    }
+    cudaSetDevice(prev);
+    DOGM_CHECK(pe);
     return 0;
 }
 extern "C" int dogm_device_count(void)

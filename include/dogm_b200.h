@@ -189,6 +189,12 @@ int dogm_band_init_particles(dogm_handle* h, double mass_before, double mass_tot
 int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float new_yaw, float dt, int* send_lo, int* send_hi);
 /* step 2: the records the orchestrator put into the RECV boxes join the band's particles */
 int dogm_band_append(dogm_handle* h, int recv_lo, int recv_hi);
+/* The whole exchange step in one call: copies `recv_lo` records from the lower neighbour's DOGM_BAND_SEND_HI box and `recv_hi`
+ * from the upper neighbour's DOGM_BAND_SEND_LO box into this band's inboxes, the neighbours' edge rows (DOGM_BAND_EDGE_HI of the
+ * lower, DOGM_BAND_EDGE_LO of the upper neighbour; NULL = none) into its halo rows, and appends the records - all on the band's
+ * stream, one synchronisation.  The source addresses may lie on another GPU of this process (see dogm_enable_peer_access). */
+int dogm_band_receive(dogm_handle* h, const void* outbox_of_lower_neighbour, int recv_lo, const void* outbox_of_upper_neighbour,
+                      int recv_hi, const void* edge_rows_of_lower_neighbour, const void* edge_rows_of_upper_neighbour);
 /* step 3: assignment, occupancy update (with the halo rows when halo_valid), persistent weights; returns the band's born
  * mass.  measurement_band may be NULL after the first cycle's dogm_band_init_masses (keeps that grid). */
 int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measurement_band, int on_device, float dt, int halo_valid,
@@ -205,6 +211,26 @@ int dogm_band_slot_range(double mass_before, double mass_local, double mass_tota
 int dogm_band_output_range(uint64_t seed, uint32_t cycle, int resample_mode, long long n_glob, double weight_before,
                            double weight_local, double weight_total, long long* first, long long* past);
 /* read-out of the band's current particles (n = dogm_band_counts): any pointer may be NULL */
+/* Band group: the native in-process orchestrator of the phases above for the GPUs of one box.  One persistent host thread per
+ * band (bound to the band's GPU) runs the phases, the threads meet at a barrier where the bands depend on each other, the
+ * normaliser shares are added up in band order, records and halo rows move by direct GPU-to-GPU copies (peer access is enabled
+ * between neighbouring bands' GPUs).  The group borrows the handles (destroy the group first). */
+typedef struct dogm_band_group dogm_band_group;
+typedef struct dogm_band_cycle_info
+{
+    double born_total;   /* born mass of the whole grid in this cycle */
+    double weight_total; /* joint weight of the whole grid before resampling */
+    long long migrated;  /* particles that changed band */
+    float phase_ms[5];   /* host wall clock: predict, exchange + append, update, birth + CDF, resample */
+} dogm_band_cycle_info;
+int dogm_band_group_create(dogm_handle* const* bands, int n_bands, dogm_band_group** out);
+void dogm_band_group_destroy(dogm_band_group* g);
+/* One cycle of the whole grid.  measurement_bands[r]: the rows of the measurement grid band r owns, on band r's GPU (required in
+ * the first cycle; NULL entries later keep the previous grid).  particles_out[r] (may be NULL): band r's particle count after
+ * resampling.  Blocking: returns when every band has finished the cycle. */
+int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* const* measurement_bands, float new_x, float new_y,
+                           float new_yaw, float dt, int* particles_out, dogm_band_cycle_info* info);
+
 int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -403,6 +429,8 @@ int dogm_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes);
 int dogm_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes);
 int dogm_memcpy_d2d(void* dst_device, const void* src_device, size_t bytes); /* same GPU or peer GPU of this process */
 int dogm_device_count(void);
+/* peer access from `device` to `peer_device` (NVLink / NVSwitch): device-to-device copies between them then bypass the host */
+int dogm_enable_peer_access(int device, int peer_device);
 int dogm_set_device(int device);
 const char* dogm_b200_version(void);
 

@@ -37,8 +37,8 @@ def run_plain(gpu, grids, poses, seed=77):
     return d
 
 
-def run_banded(gpu, grids, poses, bands, seed=77):
-    bd = gpu.BandedDOGM(make_params(gpu, SIZE, RES, N, B), bands, seed=seed)
+def run_banded(gpu, grids, poses, bands, seed=77, native=True):
+    bd = gpu.BandedDOGM(make_params(gpu, SIZE, RES, N, B), bands, seed=seed, native=native)
     dev = gpu.device_alloc(grids[0].nbytes)
     history = []
     for g, (x, y) in zip(grids, poses):
@@ -145,3 +145,21 @@ def test_bands_are_deterministic(gpu, bands):
         for a, b in zip(p0[r], p1[r]):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
     assert np.array_equal(g0.view(np.uint8), g1.view(np.uint8))
+
+
+def test_native_band_group_equals_the_phase_calls(gpu):
+    """dogm_band_group_* (host threads inside the library) runs the same phases as the dogm_band_* calls driven from Python:
+    bit-identical particles and maps."""
+    grids, ps = scans(gpu, 6), poses(6, vy=5.0, vx=-1.0)
+    out = []
+    for native in (True, False):
+        bd, hist = run_banded(gpu, grids, ps, 3, native=native)
+        assert (bd.group is not None) == native
+        parts = [tuple(np.ascontiguousarray(a).copy() for a in bd.get_particles(r)) for r in range(3)]
+        out.append((hist, parts, bd.get_grid_cells().copy(), dict(bd.last_totals)))
+        bd.close()
+    assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
+    for r in range(3):
+        for a, b in zip(out[0][1][r], out[1][1][r]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
+    assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))

@@ -20,7 +20,7 @@ cfg = bench.CONFIGS[name]
 ndev = gpu.device_count()
 params = gpu.Params(cfg["size"], cfg["resolution"], cfg["n"], cfg["b"], *bench.DEMO_PARAMS)
 laser = gpu.LaserSensorParams(cfg["size"], cfg["resolution"], bench.FOV, bench.STDDEV_RANGE)
-beams = bench.make_beams(cfg, 4, seed=1234)
+beams = bench.make_beams(cfg, int(os.environ.get("BAND_SCANS", "4")), seed=1234)
 gpu.set_device(0)
 gen = gpu.LaserMeasurementGrid(laser, cfg["size"], cfg["resolution"])
 grids = [gen.generate_grid_host(b) for b in beams]  # full grids on the host; every band gets its rows
@@ -29,7 +29,8 @@ gen.close()
 # leaves a row histogram of its particles, which sets the band edges of the multi-band runs (every row also costs its cells)
 G = int(np.sqrt(grids[0].size))
 row_load = None
-for R in [r for r in (1, 2, 4, 8) if r <= ndev]:
+want = [int(v) for v in os.environ.get("BAND_COUNTS", "1,2,4,8").split(",")]  # the 1-band run also measures the row loads
+for R in [r for r in want if r <= ndev]:
     rows = gpu.balanced_rows(row_load, R) if (row_load is not None and R > 1) else None
     bd = gpu.BandedDOGM(params, R, devices=list(range(R)), seed=123456, rows=rows, slack=2.5)
     meas = []  # per band: its rows of every scan, resident on the band's GPU
@@ -61,7 +62,7 @@ for R in [r for r in (1, 2, 4, 8) if r <= ndev]:
     lo, hi = bd.last_migration
     print(f"{name}: {R} band(s) on {R} GPU(s), rows {bd.rows}: {1e3 * t:8.3f} ms/cycle, {1.0 / t:8.1f} cycles/s; particles per band {counts}, "
           f"migrated last cycle {sum(lo) + sum(hi)}; phases [predict, exchange, update, birth+cdf, resample] ms "
-          f"{[round(v, 2) for v in bd.last_phase_ms]}")
+          f"{[round(v, 2) for v in bd.last_phase_ms]}; peer access {bd.peer_access}")
     if row_load is None:
         hist = np.zeros(G, np.float64)
         for r in range(R):

@@ -7,7 +7,7 @@ SRC=$ROOT/dynamic-occupancy-grid-map_b200/csrc
 OUT=$ROOT/build_ab
 mkdir -p $OUT/obj_$NAME
 FLAGS="-O3 -std=c++17 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart static $*"
-for f in dogm_api kernels_particles kernels_cells kernels_meas; do
+for f in dogm_api kernels_particles kernels_cells kernels_meas band_group; do
   nvcc $FLAGS -c $SRC/$f.cu -o $OUT/obj_$NAME/$f.o &
 done
 wait
