@@ -152,6 +152,7 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->band.n_out = 0;
     h->band.send[0] = h->band.send[1] = h->band.recv[0] = h->band.recv[1] = nullptr;
     h->band.mig = nullptr;
+    h->band.pin = nullptr;
     h->band.out_cnt[0] = h->band.out_cnt[1] = h->band.out_off[0] = h->band.out_off[1] = h->band.out_total = nullptr;
     h->band.send_cap = band ? band->exchange_capacity : 0;
     h->band.halo[0] = h->band.halo[1] = nullptr;
@@ -282,6 +283,7 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
             e |= alloc_zero((void**)&h->band.out_off[d], out_tiles * sizeof(double));
         }
         e |= alloc_zero((void**)&h->band.out_total, 2 * sizeof(double));
+        e |= (int)cudaMallocHost((void**)&h->band.pin, 8 * sizeof(double));
         if (e)
         {
             dogm_destroy(h);
@@ -371,6 +373,8 @@ extern "C" void dogm_destroy(dogm_handle* h)
         cudaFree(h->band.out_off[d]);
     }
     cudaFree(h->band.out_total);
+    if (h->band.pin)
+        cudaFreeHost(h->band.pin);
     if (h->trace_buf)
     {
         trace_bind_particles(nullptr);
@@ -1018,6 +1022,17 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
 // ---------------------------------------------------------------------------------------------------------
 // band mode (include/dogm_b200.h, "Band mode"): the cycle in phases, the orchestrator moves data between the bands
 // ---------------------------------------------------------------------------------------------------------
+// band phases end with a scalar for the host: copied into pinned memory on the band's stream, one synchronisation
+static int band_sync_and_fetch(dogm_handle* h, void* dst_host, const void* src_device, size_t bytes)
+{
+    if (dst_host && bytes)
+        DOGM_CHECK(cudaMemcpyAsync(h->band.pin, src_device, bytes, cudaMemcpyDeviceToHost, h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    if (dst_host && bytes)
+        memcpy(dst_host, h->band.pin, bytes);
+    return 0;
+}
+
 extern "C" int dogm_create_band(const dogm_params* params, const dogm_band_config* band, dogm_handle** out)
 {
     if (!band)
@@ -1181,8 +1196,8 @@ extern "C" int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float
         if ((e = run_band_outbox(h)))
             return e;
         double totals[2] = {0.0, 0.0};
-        DOGM_CHECK(cudaStreamSynchronize(h->stream));
-        DOGM_CHECK(cudaMemcpy(totals, h->band.out_total, sizeof(totals), cudaMemcpyDeviceToHost));
+        if ((e = band_sync_and_fetch(h, totals, h->band.out_total, sizeof(totals))))
+            return e;
         counts[0] = (int)totals[0];
         counts[1] = (int)totals[1];
     }
@@ -1273,8 +1288,8 @@ extern "C" int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measuremen
         return e;
     if ((e = run_born_scan(h)))
         return e;
-    DOGM_CHECK(cudaStreamSynchronize(h->stream));
-    DOGM_CHECK(cudaMemcpy(&h->band.born_local, &h->scal->born_total, sizeof(double), cudaMemcpyDeviceToHost));
+    if ((e = band_sync_and_fetch(h, &h->band.born_local, &h->scal->born_total, sizeof(double))))
+        return e;
     *born_local = h->band.born_local;
     return 0;
 }
@@ -1291,16 +1306,16 @@ extern "C" int dogm_band_birth(dogm_handle* h, double born_before, double born_t
         return DOGM_ERR_INVALID_ARGUMENT;
     h->band.born_base = born_before;
     h->band.birth_slot_base = first;
-    DOGM_CHECK(cudaMemcpy(&h->scal->born_total, &born_total, sizeof(double), cudaMemcpyHostToDevice));
+    DOGM_CHECK(cudaMemcpyAsync(&h->scal->born_total, &born_total, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     set_particle_counts(h, h->N, b);
     if ((e = run_birth_fill(h)))
         return e;
     if ((e = run_cdf(h)))
         return e;
-    DOGM_CHECK(cudaStreamSynchronize(h->stream));
     h->band.weight_local = 0.0;
-    if (h->N + h->B > 0)
-        DOGM_CHECK(cudaMemcpy(&h->band.weight_local, &h->scal->weight_total, sizeof(double), cudaMemcpyDeviceToHost));
+    const bool any = h->N + h->B > 0;
+    if ((e = band_sync_and_fetch(h, any ? &h->band.weight_local : nullptr, &h->scal->weight_total, any ? sizeof(double) : 0)))
+        return e;
     *weight_local = h->band.weight_local;
     return 0;
 }
@@ -1317,7 +1332,7 @@ extern "C" int dogm_band_resample(dogm_handle* h, double weight_before, double w
     h->band.cdf_base = weight_before;
     h->band.out_base = i_lo;
     h->band.n_out = (int)n_out;
-    DOGM_CHECK(cudaMemcpy(&h->scal->weight_total, &weight_total, sizeof(double), cudaMemcpyHostToDevice));
+    DOGM_CHECK(cudaMemcpyAsync(&h->scal->weight_total, &weight_total, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     e = run_resample_gather(h);
     if (e)
         return e;

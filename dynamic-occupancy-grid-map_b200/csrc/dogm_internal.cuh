@@ -196,6 +196,7 @@ struct dogm_handle
         double* out_cnt[2];        // per tile of 4096 slots: particles leaving through either edge
         double* out_off[2];        // their exclusive prefix
         double* out_total;         // device, 2 totals
+        double* pin;               // pinned host staging for the scalars a phase hands back (8 doubles)
         int send_cap;
         float* halo[2];            // rows of the neighbours' previous free masses needed by an ego-motion shift in y
         int halo_rows;
