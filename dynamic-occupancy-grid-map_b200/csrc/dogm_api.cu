@@ -2,6 +2,8 @@
 // One stream, every buffer allocated once in dogm_create, no allocation / host read-back inside a cycle
 // (the reference does ~26 cudaMalloc/cudaFree pairs and 3 blocking scalar copies per cycle).
 #include "dogm_internal.cuh"
+
+#include <atomic>
 #include "philox.cuh"
 
 #include <cmath>
@@ -977,6 +979,7 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
                 }
             }
         }
+        std::atomic_thread_fence(std::memory_order_acquire); // the list is read after the sequence number, not before
         if (found < 0)
         {
             DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
