@@ -1407,6 +1407,11 @@ extern "C" int dogm_debug_read(dogm_handle* h, const char* name, void* out_host,
         src = &h->scal->weight_total;
         have = sizeof(double);
     }
+    if (!strcmp(name, "phase_birth"))
+    {
+        DOGM_CHECK(cudaStreamSynchronize(h->stream));
+        return debug_phase_read_cells(out_host, bytes);
+    }
     if (!strcmp(name, "phase_chain") || !strcmp(name, "phase_resample"))
     {
         DOGM_CHECK(cudaStreamSynchronize(h->stream));

@@ -421,6 +421,7 @@ int run_blocksum_scan(dogm_handle* h, const double* in, double* out_excl, int n,
 int configure_kernels();
 int chain_blocks_per_sm();
 int debug_phase_read(int which, void* out_host, size_t bytes); // -DDOGM_PHASE_TRACE builds only
+int debug_phase_read_cells(void* out_host, size_t bytes);
 int trace_bind_particles(unsigned long long* p);
 int trace_bind_cells(unsigned long long* p);
 int trace_bind_meas(unsigned long long* p);                   // opt-in shared memory sizes

@@ -344,6 +344,35 @@ struct BirthArgs
     int pub_seq;
 };
 
+// Developer build (-DDOGM_PHASE_TRACE): phase stamps of k_birth_particles (thread 0 of every CTA), see tools/phase_trace.py
+#ifdef DOGM_PHASE_TRACE
+constexpr int kPhaseCtasC = 4096, kPhaseSlotsC = 8;
+__device__ unsigned long long g_phase_cells[kPhaseCtasC][kPhaseSlotsC];
+__device__ __forceinline__ void phase_stamp_c(unsigned cta, int slot, unsigned dep)
+{
+    if (threadIdx.x == 0 && cta < (unsigned)kPhaseCtasC)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer; // %1" : "=l"(t) : "r"(dep) : "memory");
+        g_phase_cells[cta][slot] = t;
+    }
+}
+#define PHASE_STAMP_C(cta, slot, dep) phase_stamp_c(cta, slot, (unsigned)(dep))
+#else
+#define PHASE_STAMP_C(cta, slot, dep)
+#endif
+int debug_phase_read_cells(void* out_host, size_t bytes)
+{
+#ifdef DOGM_PHASE_TRACE
+    if (bytes > sizeof(g_phase_cells))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    return (int)cudaMemcpyFromSymbol(out_host, g_phase_cells, bytes, 0, cudaMemcpyDeviceToHost);
+#else
+    (void)out_host, (void)bytes;
+    return DOGM_ERR_UNSUPPORTED;
+#endif
+}
+
 // initBirthParticlesKernel (init.cu:46-67) + initNewParticlesKernel1 (init_new_particles.cu:126-155, with the
 // deterministic ownership rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
 __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
@@ -359,9 +388,12 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     }
     if (s >= a.B)
         return;
+    PHASE_STAMP_C(blockIdx.x, 0, 0);
     SlotView v = a.slots;
     v.scale = (float)a.B_glob / (float)a.scal->born_total;
+    PHASE_STAMP_C(blockIdx.x, 1, __float_as_uint(v.scale));
     int j = find_slot_owner(v, s);
+    PHASE_STAMP_C(blockIdx.x, 2, j);
     bool assoc = false;
     float weight;
     if (j >= 0)
@@ -388,12 +420,14 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
         const float4 g = philox_normal4(a.seed, (uint32_t)s, STAGE_BIRTH, a.cycle);
         vel = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
     }
+    PHASE_STAMP_C(blockIdx.x, 3, __float_as_uint(weight) ^ __float_as_uint(vel.x));
     const float x = (float)(j % a.gs) + 0.5f;
     const float y = (float)(j + a.cell_base) / (float)a.gs + 0.5f; // float division, init_new_particles.cu:173
     a.birth.idx[s] = j;
     a.birth.assoc[s] = assoc ? 1 : 0;
     a.birth.weight[s] = weight;
     a.birth.state[s] = make_float4(x, y, vel.x, vel.y);
+    PHASE_STAMP_C(blockIdx.x, 4, 0);
 }
 
 // =========================================================================================================

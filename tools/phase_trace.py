@@ -32,17 +32,20 @@ LABELS = {
     "phase_chain": ["ticket", "entries loaded", "block total", "prefix known", "cdf written", "total known", "claims done"],
     "phase_resample": ["start", "window staged", "claim checked", "ancestors", "slots", "records", "stored"],
 }
-for key, n in (("phase_chain", n_chain), ("phase_resample", n_res)):
+LABELS["phase_birth"] = ["start", "scale known", "owner found", "weights + noise", "stored", "-", "-"]
+for key, n in (("phase_chain", n_chain), ("phase_resample", n_res), ("phase_birth", (cfg["b"] + 255) // 256)):
     buf = np.zeros((4096, 8), np.uint64)
     d.debug_read(key, buf)
     t = buf[: min(n, 4096), :7].astype(np.int64)
+    last = 4 if key == "phase_birth" else 6
+    t[:, last + 1:] = t[:, last:last + 1]
     t0 = t[:, 0].min()
     rel = (t - t0) * 1e-3
     print(f"{key}: {n} CTAs, kernel span {rel.max():.1f} us (first stamp to last)")
     for k, lab in enumerate(LABELS[key]):
         c = rel[:, k]
         print(f"   {lab:16s} min {c.min():7.1f}  p10 {np.percentile(c, 10):7.1f}  median {np.median(c):7.1f}  p90 {np.percentile(c, 90):7.1f}  max {c.max():7.1f}")
-    dur = rel[:, 6] - rel[:, 0]
+    dur = rel[:, last] - rel[:, 0]
     print(f"   per-CTA duration: median {np.median(dur):.1f} us, max {dur.max():.1f} us; CTA start times: median {np.median(rel[:,0]):.1f}, p90 {np.percentile(rel[:,0],90):.1f}, max {rel[:,0].max():.1f}")
     steps = np.diff(rel, axis=1)
     print("   median step durations:", " ".join(f"{LABELS[key][k+1]}={np.median(steps[:,k]):.2f}" for k in range(6)))
