@@ -183,6 +183,7 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->dyn_filter_on = h->dyn_list_valid = false;
     h->dyn_filter_capacity = 0;
     h->dyn_mapped_host = h->dyn_mapped_dev = nullptr;
+    h->cell_kernel_done = true;
     h->lazy_meas.pending = false;
     h->lazy_meas.geom = nullptr;
     h->lazy_meas.polar = nullptr;
@@ -510,7 +511,10 @@ static int update_grid_impl(dogm_handle* h, const dogm_meas_cell* meas, float ne
         return e;
     h->cycle++;
     if (sync)
+    {
         DOGM_CHECK(cudaStreamSynchronize(h->stream));
+        h->cell_kernel_done = true;
+    }
     return 0;
 }
 
@@ -531,6 +535,7 @@ extern "C" int dogm_synchronize(dogm_handle* h)
     if (!h)
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    h->cell_kernel_done = true;
     return 0;
 }
 
@@ -964,7 +969,10 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
             for (unsigned spin = 1; found < 0; spin++)
             {
                 if (pub[1] == h->dyn_pub_seq)
+                {
                     found = pub[0];
+                    h->cell_kernel_done = true; // (the publisher runs behind the cell kernel)
+                }
                 else if ((spin & 0x3ffu) == 0)
                 {
                     const cudaError_t q = cudaStreamQuery(h->stream);
@@ -985,6 +993,7 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
             DOGM_CHECK(cudaMemcpyAsync(h->dyn_count_host, h->dyn_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             DOGM_CHECK(cudaStreamSynchronize(h->stream));
             found = *h->dyn_count_host;
+            h->cell_kernel_done = true;
         }
         if (found <= h->dyn_filter_capacity || capacity <= h->dyn_filter_capacity)
         {

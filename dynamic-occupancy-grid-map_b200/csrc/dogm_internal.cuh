@@ -234,6 +234,10 @@ struct dogm_handle
         const float2* polar;
         int K, H;
     } lazy_meas;
+    // the host has seen the last launched cell kernel complete (a synchronisation, or the published dynamic-cell list): only then
+    // may the next scan's polar-table kernel run ahead of its dependency wait - on a small grid the CTAs of a whole cycle can be
+    // resident at once, each waiting for its predecessor, and an early writer of the table could overtake the cell kernel reading it
+    bool cell_kernel_done;
     bool ranges_in_soa;             // cell_start / cell_end hold the ranges of the last assignment (not yet consumed)
 
     // per-cell working set

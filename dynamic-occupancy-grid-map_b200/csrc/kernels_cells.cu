@@ -689,6 +689,7 @@ int run_occupancy_update(dogm_handle* h, float dt)
         a.meas_copy = h->meas;
     }
     h->lazy_meas.pending = false; // consumed, or superseded by the caller's grid
+    h->cell_kernel_done = false;
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
         if (lazy)

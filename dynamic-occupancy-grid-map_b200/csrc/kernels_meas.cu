@@ -163,7 +163,8 @@ struct BeamBlock
 // reader of the table, the cell kernel of the cycle before, finished several kernels ago), so it does its work first and waits
 // for its predecessor only before it exits: its CTAs run in the tail of the previous cycle's resampling kernel, and completion
 // still is transitive along the stream (this kernel ends after its predecessor has).
-// (kEarly = false: the plain order, for a scan that replaces one no cycle has consumed yet - two early kernels could overlap.)
+// (kEarly = false: the plain order - for a scan that replaces one no cycle has consumed yet (two early kernels could overlap), and
+// whenever the host has not seen the last cell kernel complete: on a small grid a whole cycle's CTAs can be resident at once.)
 template <bool kEarly>
 __global__ void __launch_bounds__(kBlock) k_meas_polar_byvalue(MeasArgs a, float2* out, const __grid_constant__ BeamBlock scan)
 {
@@ -426,7 +427,7 @@ extern "C" int dogm_meas_generate_into(dogm_meas_handle* m, dogm_handle* h, cons
         memcpy(scan.z, beam_ranges_host, (size_t)K * sizeof(float));
         const MeasArgs a = make_args(m, K, nullptr);
         LaunchScope ls(h, K_MEAS_POLAR, 8.0 * (double)K * m->H);
-        if (h->lazy_meas.pending)
+        if (h->lazy_meas.pending || !h->cell_kernel_done)
             launch_chained(h->stream, k_meas_polar_byvalue<false>, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);
         else
             launch_chained(h->stream, k_meas_polar_byvalue<true>, div_up((long long)K * m->H, kBlock), kBlock, 0, a, m->d_polar, scan);

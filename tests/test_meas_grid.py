@@ -215,3 +215,31 @@ def test_cuda_fused_scans_match_oracle_and_reference_kernel(gpu, orc):
         theirs = ref.polar_fused(scans, 250, 0.2, 0.5)
         assert (np.abs(polar - theirs) > 2e-6).sum() <= 6  # same device, same expf; FMA contraction on their side only
     gen.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("readout", [False, True])
+def test_generate_into_back_to_back_on_a_small_grid(gpu, readout):
+    """Scans and cycles enqueued back to back without waiting (a small grid: the CTAs of a whole cycle fit on the device at
+    once, each kernel waiting for the one in front): the polar table of scan c+1 must not overtake the cell kernel of cycle c
+    that still reads the table of scan c.  Same final state as the blocking two-step path."""
+    from conftest import make_params
+
+    rng = np.random.default_rng(46)
+    p = make_params(gpu, 20.0, 0.2, 30000, 3000)
+    d, e = gpu.DOGM(p), gpu.DOGM(p)
+    gen = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(20.0, 0.2, 120.0, 0.5), 20.0, 0.2)
+    gen2 = gpu.LaserMeasurementGrid(gpu.LaserSensorParams(20.0, 0.2, 120.0, 0.5), 20.0, 0.2)
+    scans = [demo_beams(rng, 60, 20.0) for _ in range(25)]
+    if readout:
+        d.set_dynamic_cell_filter(0.6, 0.5, 4096)
+    for c, z in enumerate(scans):
+        gen.generate_grid_into(d, z)
+        d.update_grid(None, 0.1 * c, 0.3 * c, 0.0, 0.1, sync=False)
+        if readout:
+            d.extract_dynamic_cells(0.6, 0.5, capacity=4096)
+    for c, z in enumerate(scans):
+        e.update_grid(gen2.generate_grid(z), 0.1 * c, 0.3 * c, 0.0, 0.1, device=True)
+    assert np.array_equal(d.get_grid_cells().view(np.uint8), e.get_grid_cells().view(np.uint8))
+    assert np.array_equal(d.get_particles().block, e.get_particles().block)
+    assert np.array_equal(d.get_measurement_cells().view(np.uint8), e.get_measurement_cells().view(np.uint8))
