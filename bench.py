@@ -824,8 +824,7 @@ def run_bands(args, dist):
         dist.dist.all_reduce(hist)
         hist = hist.cpu().numpy()
         pilot.close()
-        load = hist / max(hist.sum(), 1.0) * (240.0 * cfg["n"] + 37.0 * cfg["b"]) + 100.0 * G
-        rows = gpu.balanced_rows(load, R)
+        rows = gpu.balanced_rows_by_phase(hist, R)  # edges that balance the phases, not one load figure
     band = Band(rows, slack=2.5)
     counts = 0
     with ClockSampler(dist.local_rank) as clocks:

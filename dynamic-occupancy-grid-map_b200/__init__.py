@@ -221,6 +221,7 @@ _SYMBOLS = [
     ("dogm_enable_peer_access", C.c_int, [C.c_int, C.c_int]),
     ("dogm_band_group_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     ("dogm_band_group_destroy", None, [_P]),
+    ("dogm_band_group_band_times", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("dogm_band_group_update", C.c_int, [_P, C.POINTER(C.c_void_p), C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int),
                                         C.c_void_p]),
     ("dogm_band_update", C.c_int, [_P, _P, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]),
@@ -659,6 +660,73 @@ def balanced_rows(row_load, n_bands: int, min_rows: int = 64):
     return [cuts[i + 1] - cuts[i] for i in range(n_bands)]
 
 
+def balanced_rows_by_phase(particles_per_row, n_bands: int, cost_particle_phases: float = 43.0, cost_particle_update: float = 37.0,
+                           cost_cell_update: float = 25.0, min_rows: int = 64):
+    """Band edges for a cycle that runs in phases with a barrier after each: the particle phases (prediction, birth + CDF,
+    resampling) cost a band `cost_particle_phases` per particle, the update phase (sort, per-cell sums, cell kernel)
+    `cost_particle_update` per particle plus `cost_cell_update` per cell (picoseconds, measured on one B200; only the ratios
+    matter).  A cycle takes  max_b(particle phases) + max_b(update phase):  the edges minimise that sum, which one load figure per
+    row (balanced_rows) cannot - a band of many empty rows is cheap in particles and expensive in cells.
+    For every bound P on the particle phases the smallest feasible bound U on the update phase is found by bisection; feasibility
+    is a greedy sweep (a band takes rows while both bounds hold), exact for contiguous bands."""
+    n_row = np.asarray(particles_per_row, np.float64)
+    G = n_row.size
+    cum_n = np.concatenate([[0.0], np.cumsum(n_row)])
+    cum_u = cost_particle_update * cum_n + cost_cell_update * G * np.arange(G + 1, dtype=np.float64)
+    total_n, total_u = cum_n[-1], cum_u[-1]
+
+    def sweep(P, U):
+        """greedy cuts under the bounds, or None"""
+        cuts = [0]
+        for r in range(n_bands):
+            lo = cuts[-1]
+            left = n_bands - r - 1  # bands still to come: each needs min_rows rows
+            end_p = int(np.searchsorted(cum_n, cum_n[lo] + P, side="right")) - 1
+            end_u = int(np.searchsorted(cum_u, cum_u[lo] + U, side="right")) - 1
+            end = min(end_p, end_u, G - left * min_rows)
+            if end < lo + min_rows:
+                if lo + min_rows > G - left * min_rows:
+                    return None
+                # the minimum band violates a bound: infeasible for these bounds
+                return None
+            cuts.append(end)
+        return cuts if cuts[-1] == G else None
+
+    best = None
+    p_lo = total_n / n_bands
+    for P in np.linspace(p_lo, max(p_lo * 4.0, p_lo + 1.0), 97):
+        lo_u, hi_u = total_u / n_bands, total_u
+        if sweep(P, hi_u) is None:
+            continue
+        for _ in range(40):
+            mid = 0.5 * (lo_u + hi_u)
+            if sweep(P, mid) is None:
+                lo_u = mid
+            else:
+                hi_u = mid
+        cuts = sweep(P, hi_u)
+        n_b = np.diff(cum_n[cuts])
+        u_b = np.diff(cum_u[cuts])
+        t = cost_particle_phases * n_b.max() + u_b.max()
+        if best is None or t < best[0]:
+            best = (t, cuts)
+    if best is None:
+        return balanced_rows(n_row + 1.0, n_bands, min_rows)
+    cuts = best[1]
+    return [cuts[i + 1] - cuts[i] for i in range(n_bands)]
+
+
+def band_cycle_model(particles_per_row, rows, cost_particle_phases: float = 43.0, cost_particle_update: float = 37.0,
+                     cost_cell_update: float = 25.0) -> float:
+    """the modelled cycle time (same units as the costs) of a given split: max over bands per phase, summed"""
+    n_row = np.asarray(particles_per_row, np.float64)
+    G = n_row.size
+    cuts = np.concatenate([[0], np.cumsum(rows)]).astype(int)
+    n_b = np.array([n_row[cuts[i]:cuts[i + 1]].sum() for i in range(len(rows))])
+    u_b = cost_particle_update * n_b + cost_cell_update * G * np.asarray(rows, np.float64)
+    return float(cost_particle_phases * n_b.max() + u_b.max())
+
+
 class BandedDOGM:
     """The orchestrator of include/dogm_b200.h's band mode for the bands of ONE process: it drives the phases of a cycle on
     every band handle and moves, between the phases, the particles that crossed a band edge (SEND -> RECV boxes), the
@@ -777,6 +845,9 @@ class BandedDOGM:
             self.last_counts = [int(c) for c in counts]
             self.last_migration = ([int(info.migrated)], [0])
             self.last_totals = {"born": info.born_total, "weight": info.weight_total}
+            times = (C.c_float * (5 * R))()
+            lib.dogm_band_group_band_times(self.group, times)
+            self.last_band_ms = [[float(times[r * 5 + k]) for k in range(5)] for r in range(R)]
             return self.last_counts
         if self.first:
             def masses(r):

@@ -64,6 +64,7 @@ struct dogm_band_group
     std::atomic<int> error{0};
     double born_total = 0.0, weight_total = 0.0;
     std::chrono::steady_clock::time_point stamp[6];
+    std::vector<float> band_ms; // [band][5]: what each band itself spent in every phase (without the waiting at the barriers)
 };
 
 namespace
@@ -112,12 +113,20 @@ void run_cycle(dogm_band_group* g, int r)
         g->barrier->wait();
     }
     mark(0);
+    auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](int k) {
+        const auto now = std::chrono::steady_clock::now();
+        g->band_ms[(size_t)r * 5 + k] = std::chrono::duration<float, std::milli>(now - t_begin).count();
+    };
+    auto restart = [&]() { t_begin = std::chrono::steady_clock::now(); };
     int a = 0, b = 0;
     if (ok())
         fail(g, dogm_band_predict(h, g->x, g->y, g->yaw, g->dt, &a, &b));
     g->sent_lo[r] = a;
     g->sent_hi[r] = b;
+    lap(0);
     g->barrier->wait();
+    restart();
     mark(1);
     if (ok())
     { // what the neighbours sent towards this band, and their edge rows of the previous free masses
@@ -130,12 +139,15 @@ void run_cycle(dogm_band_group* g, int r)
         const void* edge_hi = (halo && r + 1 < R) ? dogm_band_buffer(g->bands[r + 1], DOGM_BAND_EDGE_LO) : nullptr;
         fail(g, dogm_band_receive(h, box_lo, n_lo, box_hi, n_hi, edge_lo, edge_hi));
     }
+    lap(1);
     g->barrier->wait(); // every band has its halo rows before any band's cell kernel swaps the free masses
     mark(2);
+    restart();
     double v = 0.0;
     if (ok())
         fail(g, dogm_band_update(h, meas, 1, g->dt, h->band.halo_rows > 0 ? 1 : 0, &v));
     g->share[r] = v;
+    lap(2);
     g->barrier->wait();
     mark(3);
     double before, total;
@@ -143,12 +155,15 @@ void run_cycle(dogm_band_group* g, int r)
     if (r == 0)
         g->born_total = total;
     g->barrier->wait(); // (share[] is rewritten next)
+    restart();
     v = 0.0;
     if (ok())
         fail(g, dogm_band_birth(h, before, total, &v));
     g->share[r] = v;
+    lap(3);
     g->barrier->wait();
     mark(4);
+    restart();
     prefix_of(g->share, r, &before, &total);
     if (r == 0)
         g->weight_total = total;
@@ -156,6 +171,7 @@ void run_cycle(dogm_band_group* g, int r)
     if (ok())
         fail(g, dogm_band_resample(h, before, total, &n_out));
     g->counts[r] = n_out;
+    lap(4);
     g->barrier->wait();
     mark(5);
 }
@@ -207,6 +223,7 @@ extern "C" int dogm_band_group_create(dogm_handle* const* bands, int n_bands, do
     g->sent_hi.assign(n_bands, 0);
     g->counts.assign(n_bands, 0);
     g->share.assign(n_bands, 0.0);
+    g->band_ms.assign((size_t)n_bands * 5, 0.0f);
     g->barrier = new SpinBarrier(n_bands);
     for (int r = 0; r < n_bands; r++)
         g->workers.emplace_back(worker_main, g, r);
@@ -267,4 +284,13 @@ extern "C" int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* 
             info->phase_ms[k] = std::chrono::duration<float, std::milli>(g->stamp[k + 1] - g->stamp[k]).count();
     }
     return e;
+}
+
+extern "C" int dogm_band_group_band_times(const dogm_band_group* g, float* out_ms)
+{ // [band][5]: predict, exchange + append, update, birth + CDF, resample - the band's own time in the last cycle
+    if (!g || !out_ms)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    for (size_t k = 0; k < g->band_ms.size(); k++)
+        out_ms[k] = g->band_ms[k];
+    return 0;
 }

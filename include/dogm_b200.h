@@ -231,6 +231,10 @@ void dogm_band_group_destroy(dogm_band_group* g);
 int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* const* measurement_bands, float new_x, float new_y,
                            float new_yaw, float dt, int* particles_out, dogm_band_cycle_info* info);
 
+/* out_ms[band * 5 + phase]: what every band itself spent in the phases of the last cycle (host wall clock, without the waiting
+ * at the barriers) - the input for placing the band edges */
+int dogm_band_group_band_times(const dogm_band_group* g, float* out_ms);
+
 int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -105,3 +105,29 @@ def test_two_processes_agree_on_the_partition(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "tiling ok" in outs[0]
+
+
+def test_band_edges_by_phase():
+    """balanced_rows_by_phase: the split tiles the rows, keeps the minimum band height, and its modelled cycle time (slowest band
+    per phase, summed over the phases) is never worse than that of a split by one load figure per row - clearly better for a
+    scene whose particles sit in a part of the grid (a band of empty rows is cheap in particles, expensive in cells)."""
+    gpu = load_dogm_b200()
+    G = 4096
+    y = np.arange(G, dtype=np.float64)
+    fan = np.exp(-(G - y) / 700.0)
+    fan[:1400] *= 0.02  # far rows: hardly any particles
+    fan = fan / fan.sum() * 2e7
+    uniform = np.full(G, 2e7 / G)
+    for hist in (fan, uniform):
+        for R in (2, 3, 4, 8):
+            rows = gpu.balanced_rows_by_phase(hist, R)
+            assert len(rows) == R and sum(rows) == G and min(rows) >= 64
+            load = hist / hist.sum() * (240.0 * 2e7 + 37.0 * 2e6) + 100.0 * G
+            ref = gpu.balanced_rows(load, R)
+            t_new, t_ref = gpu.band_cycle_model(hist, rows), gpu.band_cycle_model(hist, ref)
+            assert t_new <= t_ref * 1.001, (R, t_new, t_ref)
+    rows8 = gpu.balanced_rows_by_phase(fan, 8)
+    assert gpu.band_cycle_model(fan, rows8) < 0.95 * gpu.band_cycle_model(fan, gpu.balanced_rows(fan / fan.sum() * (240.0 * 2e7 + 37.0 * 2e6) + 100.0 * G, 8))
+    # degenerate: no particles at all -> still a valid split
+    rows0 = gpu.balanced_rows_by_phase(np.zeros(G), 4)
+    assert len(rows0) == 4 and sum(rows0) == G and min(rows0) >= 64

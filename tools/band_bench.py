@@ -29,9 +29,16 @@ gen.close()
 # leaves a row histogram of its particles, which sets the band edges of the multi-band runs (every row also costs its cells)
 G = int(np.sqrt(grids[0].size))
 row_load = None
+row_hist = None
 want = [int(v) for v in os.environ.get("BAND_COUNTS", "1,2,4,8").split(",")]  # the 1-band run also measures the row loads
-for R in [r for r in want if r <= ndev]:
-    rows = gpu.balanced_rows(row_load, R) if (row_load is not None and R > 1) else None
+# BAND_EDGES: "phase" = edges that minimise the sum over the phases of the slowest band (balanced_rows_by_phase),
+#             "load"  = one load figure per row (balanced_rows); both can be listed
+methods = os.environ.get("BAND_EDGES", "phase").split(",")
+runs = [(r, m) for r in want if r <= ndev for m in (methods if r > 1 else methods[:1])]
+for R, method in runs:
+    rows = None
+    if row_load is not None and R > 1:
+        rows = gpu.balanced_rows_by_phase(row_hist, R) if method == "phase" else gpu.balanced_rows(row_load, R)
     bd = gpu.BandedDOGM(params, R, devices=list(range(R)), seed=123456, rows=rows, slack=2.5)
     meas = []  # per band: its rows of every scan, resident on the band's GPU
     for r in range(R):
@@ -60,15 +67,18 @@ for R in [r for r in want if r <= ndev]:
         counts = cycle()
     t = (time.perf_counter() - t0) / K
     lo, hi = bd.last_migration
-    print(f"{name}: {R} band(s) on {R} GPU(s), rows {bd.rows}: {1e3 * t:8.3f} ms/cycle, {1.0 / t:8.1f} cycles/s; particles per band {counts}, "
+    print(f"{name}: {R} band(s) on {R} GPU(s), edges by {method if R > 1 else '-'}, rows {bd.rows}: {1e3 * t:8.3f} ms/cycle, {1.0 / t:8.1f} cycles/s; particles per band {counts}, "
           f"migrated last cycle {sum(lo) + sum(hi)}; phases [predict, exchange, update, birth+cdf, resample] ms "
           f"{[round(v, 2) for v in bd.last_phase_ms]}; peer access {bd.peer_access}")
+    if getattr(bd, "last_band_ms", None):
+        print("    per band [predict, exchange, update, birth+cdf, resample] ms:", [[round(v, 2) for v in row] for row in bd.last_band_ms])
     if row_load is None:
         hist = np.zeros(G, np.float64)
         for r in range(R):
             state = bd.get_particles(r)[0]
             hist += np.bincount(np.clip(state[:, 1].astype(np.int64), 0, G - 1), minlength=G)
             del state
+        row_hist = hist
         row_load = hist / hist.sum() * (240.0 * cfg["n"] + 37.0 * cfg["b"]) + 100.0 * G  # measured: a particle costs about 2.4 cells
     for r in range(R):
         gpu.set_device(r)
