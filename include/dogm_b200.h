@@ -185,7 +185,8 @@ int dogm_band_init_masses(dogm_handle* h, const dogm_meas_cell* measurement_band
 /* first cycle, step 2: the band creates its share of the particles (initParticlesKernel1/2); mass_before = sum of
  * the masses of the bands in front of this one */
 int dogm_band_init_particles(dogm_handle* h, double mass_before, double mass_total, int* particles);
-/* every cycle, step 1: ego-motion bookkeeping (updatePose) + prediction; fills the SEND boxes and returns their counts */
+/* every cycle, step 1: ego-motion bookkeeping (updatePose) + prediction; fills the SEND boxes (in the order of the senders' slots:
+ * runs are bit-reproducible for any number of bands) and returns their counts */
 int dogm_band_predict(dogm_handle* h, float new_x, float new_y, float new_yaw, float dt, int* send_lo, int* send_hi);
 /* step 2: the records the orchestrator put into the RECV boxes join the band's particles */
 int dogm_band_append(dogm_handle* h, int recv_lo, int recv_hi);
