@@ -364,7 +364,7 @@ __device__ __forceinline__ void pdl_prologue(int trace_slot)
 
 // developer ablation switch (DOGM_B200_SKIP=<bit mask of KernelId>, effective from cycle 12 on): LaunchScope arms it for
 // the launch it brackets; results are garbage, only the timing of the remaining kernels is of interest
-inline bool g_skip_next_launch = false;
+inline thread_local bool g_skip_next_launch = false; // (per host thread: band groups launch from several threads)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chained(cudaStream_t stream, void (*kernel)(KArgs...), long long grid, int block, size_t smem,
