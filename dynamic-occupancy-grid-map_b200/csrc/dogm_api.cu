@@ -200,40 +200,56 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     }
     plan_sort(h);
     h->n_cell_blocks = div_up(h->C, kCellBlock);
+    h->n_blk_groups = div_up(h->n_cell_blocks, 256);
+    h->birth_epoch = 0;
     h->n_chunks = div_up(h->N > 0 ? h->N : 1, kSegChunk);
     h->n_cdf_tiles = div_up((long long)h->N + h->B > 0 ? (long long)h->N + h->B : 1, kCdfTile);
 
-    DOGM_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // from here on every failure goes through dogm_destroy(h) (cudaFree / cudaFreeHost accept the null pointers of a
+    // half-built handle); the first error code is the one returned
+    int e = 0;
+    auto keep_first = [&e](int code) {
+        if (e == 0)
+            e = code;
+    };
+    h->stream = nullptr;
+    keep_first(check_cuda(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), __FILE__, __LINE__));
+    if (e)
+    {
+        delete h;
+        return e;
+    }
 
     const size_t C = (size_t)h->C, N = (size_t)h->N, B = (size_t)h->B;
-    void* blk;
-    int e = 0;
-    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N));
+    void* blk = nullptr;
+    keep_first(alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(N)));
     particle_set_assign(h->pa, blk, h->N);
-    e |= alloc_zero((void**)&h->rec, (N ? N : 1) * sizeof(PRec));
-    e |= alloc_zero((void**)&h->key0, (N ? N : 1) * sizeof(int));
-    e |= alloc_zero((void**)&h->pairs[0], (N ? N : 1) * sizeof(int2));
-    e |= alloc_zero((void**)&h->pairs[1], (N ? N : 1) * sizeof(int2));
+    keep_first(alloc_zero((void**)&h->rec, (N ? N : 1) * sizeof(PRec)));
+    keep_first(alloc_zero((void**)&h->key0, (N ? N : 1) * sizeof(int)));
+    keep_first(alloc_zero((void**)&h->pairs[0], (N ? N : 1) * sizeof(int2)));
+    keep_first(alloc_zero((void**)&h->pairs[1], (N ? N : 1) * sizeof(int2)));
     h->spair = h->pairs[0];
-    e |= alloc_zero((void**)&h->sw, (N ? N : 1) * sizeof(float));
+    keep_first(alloc_zero((void**)&h->sw, (N ? N : 1) * sizeof(float)));
     h->pa_current = true;
     h->rec_valid = false;
     h->sorted_valid = false;
-    e |= alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(B));
+    keep_first(alloc_zero(&blk, DOGM_PARTICLE_BLOCK_BYTES(B)));
     particle_set_assign(h->birth, blk, h->B);
-    e |= alloc_zero((void**)&h->grid, C * sizeof(dogm_grid_cell));
-    e |= alloc_zero((void**)&h->meas, C * sizeof(dogm_meas_cell));
-    e |= alloc_zero((void**)&h->weight_array, N * sizeof(float));
-    e |= alloc_zero((void**)&h->born_masses, C * sizeof(float));
-    e |= alloc_zero((void**)&h->free_cur, C * sizeof(float));
-    e |= alloc_zero((void**)&h->free_next, C * sizeof(float));
-    e |= alloc_zero((void**)&h->cell_start, C * sizeof(int));
-    e |= alloc_zero((void**)&h->cell_end, C * sizeof(int));
-    e |= alloc_zero((void**)&h->cell_sums, C * sizeof(CellSums));
-    e |= alloc_zero((void**)&h->cell_coef, C * sizeof(float4));
-    e |= alloc_zero((void**)&h->cell_prefix, C * sizeof(double));
-    e |= alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double));
-    e |= alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double));
+    keep_first(alloc_zero((void**)&h->grid, C * sizeof(dogm_grid_cell)));
+    keep_first(alloc_zero((void**)&h->meas, C * sizeof(dogm_meas_cell)));
+    keep_first(alloc_zero((void**)&h->weight_array, N * sizeof(float)));
+    keep_first(alloc_zero((void**)&h->born_masses, C * sizeof(float)));
+    keep_first(alloc_zero((void**)&h->free_cur, C * sizeof(float)));
+    keep_first(alloc_zero((void**)&h->free_next, C * sizeof(float)));
+    keep_first(alloc_zero((void**)&h->cell_start, C * sizeof(int)));
+    keep_first(alloc_zero((void**)&h->cell_end, C * sizeof(int)));
+    keep_first(alloc_zero((void**)&h->cell_sums, C * sizeof(CellSums)));
+    keep_first(alloc_zero((void**)&h->cell_coef, C * sizeof(float4)));
+    keep_first(alloc_zero((void**)&h->cell_prefix, C * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->grp_word, (size_t)h->n_blk_groups * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->grp_zero, ((size_t)h->n_blk_groups + 1) * sizeof(double)));
     for (int p = 0; p < kMaxPasses; p++)
     {
         h->hist[p] = nullptr;
@@ -242,19 +258,19 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     }
     for (int p = 0; p < h->passes; p++)
     {
-        e |= alloc_zero((void**)&h->hist[p], (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t));
-        e |= alloc_zero((void**)&h->bin_base[p], (size_t)h->digit_bins[p] * sizeof(uint32_t));
+        keep_first(alloc_zero((void**)&h->hist[p], (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t)));
+        keep_first(alloc_zero((void**)&h->bin_base[p], (size_t)h->digit_bins[p] * sizeof(uint32_t)));
     }
-    e |= alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece));
-    e |= alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece));
-    e |= alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int));
-    e |= alloc_zero((void**)&h->cdf, (N + B) * sizeof(double));
-    e |= alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double));
-    e |= alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 3) * sizeof(double));
-    e |= alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
+    keep_first(alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
+    keep_first(alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
+    keep_first(alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int)));
+    keep_first(alloc_zero((void**)&h->cdf, (N + B) * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 3) * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int)));
     if (!e)
-        e |= (int)cudaMemset(h->res_start, 0x7f, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
-    e |= alloc_zero((void**)&h->chain_flags, 4 * sizeof(uint32_t));
+        e = (int)cudaMemset(h->res_start, 0x7f, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int));
+    keep_first(alloc_zero((void**)&h->chain_flags, 4 * sizeof(uint32_t)));
     {
         const char* sk = getenv("DOGM_B200_SKIP");
         h->skip_mask = sk ? (unsigned)strtoul(sk, nullptr, 0) : 0u;
@@ -263,8 +279,8 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->chain_epoch = 0;
     h->chain_ticket_base = 0;
     h->chain_capacity = chain_blocks_per_sm() * sm_count;
-    e |= alloc_zero((void**)&h->ancestors, N * sizeof(int));
-    e |= alloc_zero((void**)&h->scal, sizeof(DeviceScalars));
+    keep_first(alloc_zero((void**)&h->ancestors, N * sizeof(int)));
+    keep_first(alloc_zero((void**)&h->scal, sizeof(DeviceScalars)));
     if (e)
     {
         dogm_destroy(h);
@@ -274,19 +290,19 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     {
         for (int d = 0; d < 2; d++)
         {
-            e |= alloc_zero((void**)&h->band.send[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec));
-            e |= alloc_zero((void**)&h->band.recv[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec));
-            e |= alloc_zero((void**)&h->band.halo[d], (size_t)(h->band.halo_rows ? h->band.halo_rows : 1) * gs * sizeof(float));
+            keep_first(alloc_zero((void**)&h->band.send[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec)));
+            keep_first(alloc_zero((void**)&h->band.recv[d], (size_t)(h->band.send_cap ? h->band.send_cap : 1) * sizeof(PRec)));
+            keep_first(alloc_zero((void**)&h->band.halo[d], (size_t)(h->band.halo_rows ? h->band.halo_rows : 1) * gs * sizeof(float)));
         }
         const size_t out_tiles = (size_t)div_up(h->band.n_cap > 0 ? h->band.n_cap : 1, kTileItems);
-        e |= alloc_zero((void**)&h->band.mig, (size_t)(h->band.n_cap > 0 ? h->band.n_cap : 1) + 16);
+        keep_first(alloc_zero((void**)&h->band.mig, (size_t)(h->band.n_cap > 0 ? h->band.n_cap : 1) + 16));
         for (int d = 0; d < 2; d++)
         {
-            e |= alloc_zero((void**)&h->band.out_cnt[d], out_tiles * sizeof(double));
-            e |= alloc_zero((void**)&h->band.out_off[d], out_tiles * sizeof(double));
+            keep_first(alloc_zero((void**)&h->band.out_cnt[d], out_tiles * sizeof(double)));
+            keep_first(alloc_zero((void**)&h->band.out_off[d], out_tiles * sizeof(double)));
         }
-        e |= alloc_zero((void**)&h->band.out_total, 2 * sizeof(double));
-        e |= (int)cudaMallocHost((void**)&h->band.pin, 8 * sizeof(double));
+        keep_first(alloc_zero((void**)&h->band.out_total, 2 * sizeof(double)));
+        keep_first((int)cudaMallocHost((void**)&h->band.pin, 8 * sizeof(double)));
         if (e)
         {
             dogm_destroy(h);
@@ -350,6 +366,8 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->cell_prefix);
     cudaFree(h->blk_sum);
     cudaFree(h->blk_off);
+    cudaFree(h->grp_word);
+    cudaFree(h->grp_zero);
     for (int p = 0; p < kMaxPasses; p++)
     {
         cudaFree(h->hist[p]);
@@ -437,8 +455,14 @@ static int noise_ready(const dogm_handle* h, bool first_cycle)
 // prediction kernel and the grid shift into the cell kernel
 static void update_pose(dogm_handle* h, float new_x, float new_y, float new_yaw)
 {
-    h->shift.active = 0;
-    h->shift_particles_pending = h->shift_grid_pending = false;
+    // A shift that neither the prediction nor the cell kernel has consumed yet (the stage API allows two pose updates in a
+    // row) is carried over: the reference moves grid and particles inside updatePose, so two calls add up there too.
+    const bool carry = h->shift.active && h->shift_particles_pending && h->shift_grid_pending;
+    const int carry_x = carry ? h->shift.x_move : 0, carry_y = carry ? h->shift.y_move : 0;
+    h->shift.active = carry ? 1 : 0;
+    h->shift.x_move = carry_x;
+    h->shift.y_move = carry_y;
+    h->shift_particles_pending = h->shift_grid_pending = carry;
     if (!h->first_pose_received)
     {
         h->position_x = new_x;
@@ -451,8 +475,8 @@ static void update_pose(dogm_handle* h, float new_x, float new_y, float new_yaw)
     const float y_diff = new_y - h->position_y;
     if (fabsf(x_diff) > h->params.resolution || fabsf(y_diff) > h->params.resolution)
     {
-        h->shift.x_move = -(int)(x_diff / h->params.resolution);
-        h->shift.y_move = -(int)(y_diff / h->params.resolution);
+        h->shift.x_move = carry_x - (int)(x_diff / h->params.resolution);
+        h->shift.y_move = carry_y - (int)(y_diff / h->params.resolution);
         h->shift.active = 1;
         h->shift_particles_pending = h->shift_grid_pending = true;
         h->position_x = new_x;
@@ -970,6 +994,7 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
             {
                 if (pub[1] == h->dyn_pub_seq)
                 {
+                    std::atomic_thread_fence(std::memory_order_acquire); // the count is read after the sequence number
                     found = pub[0];
                     h->cell_kernel_done = true; // (the publisher runs behind the cell kernel)
                 }
@@ -979,7 +1004,10 @@ extern "C" int dogm_extract_dynamic_cells(dogm_handle* h, float min_occupancy, f
                     if (q == cudaSuccess)
                     { // nothing left in flight: the word is final one way or the other
                         if (pub[1] == h->dyn_pub_seq)
+                        {
+                            std::atomic_thread_fence(std::memory_order_acquire);
                             found = pub[0];
+                        }
                         break;
                     }
                     if (q != cudaErrorNotReady)
@@ -1166,8 +1194,8 @@ extern "C" int dogm_band_init_masses(dogm_handle* h, const dogm_meas_cell* measu
     e = run_init_masses(h);
     if (e)
         return e;
-    DOGM_CHECK(cudaStreamSynchronize(h->stream));
-    DOGM_CHECK(cudaMemcpy(&h->band.born_local, &h->scal->born_total, sizeof(double), cudaMemcpyDeviceToHost));
+    if ((e = band_sync_and_fetch(h, &h->band.born_local, &h->scal->born_total, sizeof(double))))
+        return e;
     *mass_local = h->band.born_local;
     return 0;
 }
@@ -1182,7 +1210,8 @@ extern "C" int dogm_band_init_particles(dogm_handle* h, double mass_before, doub
         return DOGM_ERR_INVALID_ARGUMENT; // the band's share does not fit its capacity
     h->band.born_base = mass_before;
     h->band.birth_slot_base = first;
-    DOGM_CHECK(cudaMemcpy(&h->scal->born_total, &mass_total, sizeof(double), cudaMemcpyHostToDevice));
+    h->band.pin[4] = mass_total; // (pinned: the asynchronous copy reads it when the stream gets there)
+    DOGM_CHECK(cudaMemcpyAsync(&h->scal->born_total, &h->band.pin[4], sizeof(double), cudaMemcpyHostToDevice, h->stream));
     set_particle_counts(h, n, 0);
     e = run_init_fill(h);
     h->first_measurement_received = true;
@@ -1292,6 +1321,9 @@ extern "C" int dogm_band_update(dogm_handle* h, const dogm_meas_cell* measuremen
             DOGM_CHECK((cudaError_t)copy_in(h->meas, measurement_band, (size_t)h->C * sizeof(dogm_meas_cell), 0, h->stream));
     }
     h->band.halo_valid = halo_valid ? 1 : 0;
+    if (h->shift_grid_pending && h->shift.active && h->band.rows < h->band.G &&
+        (h->shift.y_move > h->band.halo_rows || -h->shift.y_move > h->band.halo_rows))
+        return DOGM_ERR_INVALID_ARGUMENT; // the shift pulls in more rows of the neighbour than the halo holds
     if ((e = run_assignment(h)))
         return e;
     if ((e = run_occupancy_update(h, dt)))

@@ -249,8 +249,12 @@ struct dogm_handle
     float4* cell_coef; // {likelihood, p_A*mu_A, (1-p_A)*mu_UA, over-unit divisor or 0} for non-empty cells
     double* cell_prefix; // block-local inclusive prefix (double) of the born / initial masses, per cell
     double* blk_sum;   // born-mass sum per 256-cell block
-    double* blk_off;   // exclusive prefix of blk_sum
+    double* blk_off;   // exclusive prefix of blk_sum: inside the block's group of 256 (birth kernel) or complete (k_blocksum_scan)
     int n_cell_blocks;
+    int n_blk_groups;  // groups of 256 blocks
+    double* grp_word;  // [n_blk_groups] group sums published by the scanning CTAs of the birth kernel (parity words)
+    double* grp_zero;  // [n_blk_groups + 1] zeros: the group offsets when blk_off holds complete offsets
+    uint32_t birth_epoch;
 
     // counting sort
     int key_bits, passes;
@@ -411,7 +415,7 @@ int run_birth(dogm_handle* h);
 int run_init_masses(dogm_handle* h); // first-cycle masses + their block scan
 int run_init_fill(dogm_handle* h);   // first-cycle particles
 int run_born_scan(dogm_handle* h);   // block offsets and total of the born masses
-int run_birth_fill(dogm_handle* h);  // birth particles
+int run_birth_fill(dogm_handle* h, bool fused_scan = false); // birth particles (fused_scan: the kernel scans the block sums itself)
 int run_resampling(dogm_handle* h);
 int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of run_resampling)
 int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
@@ -476,6 +480,28 @@ __device__ __forceinline__ unsigned lanemask_le()
     unsigned m;
     asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
     return m;
+}
+
+// A published sum travels as one 64-bit word: the sums are non-negative, so the sign bit carries the parity of the
+// launch epoch.  Every launch publishes every word exactly once, hence a word whose sign bit differs from the epoch's
+// parity still holds the previous launch's value.  One relaxed 64-bit load is both the flag and the payload.
+__device__ __forceinline__ void publish_f64(double* p, double v, uint32_t epoch)
+{
+    const unsigned long long bits =
+        ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull) | ((unsigned long long)(epoch & 1u) << 63);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(bits) : "memory");
+}
+__device__ __forceinline__ double await_f64(const double* p, uint32_t epoch)
+{
+    unsigned long long bits;
+    for (;;)
+    {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
+        if ((uint32_t)(bits >> 63) == (epoch & 1u))
+            break;
+        __nanosleep(40);
+    }
+    return __longlong_as_double((long long)(bits & 0x7fffffffffffffffull));
 }
 
 // inclusive scan of a double over the 256 threads of a CTA, fixed combination order.

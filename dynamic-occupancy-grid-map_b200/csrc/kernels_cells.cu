@@ -243,12 +243,20 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
 
 // =========================================================================================================
 // slot distribution: accumulate + normalize_particle_orders + calc_start_idx/calc_end_idx
-// (init_new_particles.cu:30-43,66-74).  The running sum over all cells is  blk_off[block] + prefix[cell]  (doubles:
-// block-local prefix from the cell kernel, block offsets from one small scan); the exclusive end slot of a cell,
+// (init_new_particles.cu:30-43,66-74).  The running sum over all cells is  grp_off[block / 256] + blk_off[block] +
+// prefix[cell]  (doubles: block-local prefix from the cell kernel; the block sums are scanned in groups of 256 blocks,
+// blk_off being the prefix inside the group and grp_off the sum of the groups in front); the exclusive end slot of a cell,
 // int(float(sum) * (count / total)), is evaluated where it is needed instead of being stored per cell.
+// Two producers of (grp_off, blk_off): the birth kernel itself (run_birth_fill: its first CTAs scan one group each, every CTA
+// then adds up the few group sums in shared memory - no launch between the cell kernel and the birth kernel), or
+// k_blocksum_scan (band mode and the first cycle, where a global normaliser has to leave the device in between): it writes
+// the complete offsets into blk_off, and grp_off points at zeros.
 // =========================================================================================================
+constexpr int kBlkGroup = 256; // 256-cell blocks per scan group
+
 struct SlotView
 {
+    const double* grp_off;
     const double* blk_off;
     const double* blk_sum;
     const double* prefix;
@@ -259,13 +267,17 @@ struct SlotView
     int slot_base;
 };
 
+__device__ __forceinline__ double block_offset(const SlotView& v, int b)
+{ // (blk_off may have been written by other CTAs of the running kernel: read through L2)
+    return v.grp_off[b / kBlkGroup] + __ldcg(v.blk_off + b);
+}
 __device__ __forceinline__ int slot_end_of_block(const SlotView& v, int b)
 {
-    return __float2int_rz((float)((v.base_off + v.blk_off[b]) + v.blk_sum[b]) * v.scale) - v.slot_base;
+    return __float2int_rz((float)((v.base_off + block_offset(v, b)) + v.blk_sum[b]) * v.scale) - v.slot_base;
 }
 __device__ __forceinline__ int slot_end_of_cell(const SlotView& v, int c)
 {
-    return __float2int_rz((float)((v.base_off + v.blk_off[c / kCellBlock]) + v.prefix[c]) * v.scale) - v.slot_base;
+    return __float2int_rz((float)((v.base_off + block_offset(v, c / kCellBlock)) + v.prefix[c]) * v.scale) - v.slot_base;
 }
 __device__ __forceinline__ int slot_start_of_cell(const SlotView& v, int c)
 {
@@ -273,7 +285,7 @@ __device__ __forceinline__ int slot_start_of_cell(const SlotView& v, int c)
         return 0;
     // the cell in front of the first cell of a block ends where that block's offset puts it
     return (c % kCellBlock) ? slot_end_of_cell(v, c - 1)
-                            : __float2int_rz((float)(v.base_off + v.blk_off[c / kCellBlock]) * v.scale) - v.slot_base;
+                            : __float2int_rz((float)(v.base_off + block_offset(v, c / kCellBlock)) * v.scale) - v.slot_base;
 }
 
 // owner cell of slot s: first cell j whose end slot exceeds s (two-level search: 256-cell blocks, then cells)
@@ -342,6 +354,12 @@ struct BirthArgs
     const int* pub_count;
     int* pub_host;
     int pub_seq;
+    // fused scan of the block sums (see SlotView): group g is scanned by CTA g, group sums travel as parity words
+    int n_groups;          // 0: the offsets were produced by k_blocksum_scan
+    double* blk_off_w;     // == slots.blk_off
+    double* grp_word;      // [n_groups]
+    uint32_t epoch;
+    double* total_out;     // DeviceScalars::born_total
 };
 
 // Developer build (-DDOGM_PHASE_TRACE): phase stamps of k_birth_particles (thread 0 of every CTA), see tools/phase_trace.py
@@ -378,6 +396,8 @@ int debug_phase_read_cells(void* out_host, size_t bytes)
 __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
 {
     pdl_prologue(K_BIRTH_PARTICLES * 2);
+    extern __shared__ double s_grp[]; // [n_groups + 1] exclusive prefix of the group sums; the last entry is the total
+    __shared__ double s_scan[kWarpsPerBlock];
     const int s = blockIdx.x * kBlock + threadIdx.x;
     if (a.pub_host && s == 0)
     {
@@ -386,11 +406,82 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
         __threadfence_system();
         *reinterpret_cast<volatile int*>(a.pub_host + 1) = a.pub_seq;
     }
-    if (s >= a.B)
-        return;
+    // the velocity draw does not depend on the slot distribution: it overlaps the ticket and the group scans
+    float2 vel = make_float2(0.0f, 0.0f);
+    if (s < a.B)
+    {
+        if (a.noise_injected)
+            vel = a.noise[s];
+        else
+        {
+            const float4 g = philox_normal4(a.seed, (uint32_t)s, STAGE_BIRTH, a.cycle);
+            vel = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
+        }
+    }
     PHASE_STAMP_C(blockIdx.x, 0, 0);
     SlotView v = a.slots;
-    v.scale = (float)a.B_glob / (float)a.scal->born_total;
+    double born_total;
+    if (a.n_groups > 0)
+    {
+        // The first CTAs of the grid scan one group of 256 block sums each (fixed order inside a group) and publish the group
+        // sum; they wait for nobody and are dispatched before every CTA behind them, so every wait below ends.  Every CTA then
+        // adds up the group sums in group order.
+        for (int g = (int)blockIdx.x; g < a.n_groups; g += (int)gridDim.x)
+        {
+            const int j = g * kBlkGroup + (int)threadIdx.x;
+            const double val = j < v.n_blocks ? v.blk_sum[j] : 0.0;
+            double total;
+            const double incl = block_inclusive_scan_f64(val, s_scan, &total);
+            if (j < v.n_blocks)
+                __stcg(a.blk_off_w + j, incl - val);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+                publish_f64(a.grp_word + g, total, a.epoch);
+        }
+        for (int g = threadIdx.x; g < a.n_groups; g += kBlock)
+            s_grp[g] = await_f64(a.grp_word + g, a.epoch);
+        __threadfence(); // the group's block offsets were written before its word
+        __syncthreads();
+        if (a.n_groups <= kBlock)
+        {
+            const double val = (int)threadIdx.x < a.n_groups ? s_grp[threadIdx.x] : 0.0;
+            double total;
+            const double incl = block_inclusive_scan_f64(val, s_scan, &total);
+            if ((int)threadIdx.x < a.n_groups)
+                s_grp[threadIdx.x] = incl - val;
+            if (threadIdx.x == 0)
+                s_grp[a.n_groups] = total;
+        }
+        else
+        { // very large grids: consecutive groups per thread
+            const int per = (a.n_groups + kBlock - 1) / kBlock;
+            const int g0 = min((int)threadIdx.x * per, a.n_groups), g1 = min(g0 + per, a.n_groups);
+            double local = 0.0;
+            for (int g = g0; g < g1; g++)
+                local += s_grp[g];
+            double total;
+            double run = block_inclusive_scan_f64(local, s_scan, &total) - local;
+            for (int g = g0; g < g1; g++)
+            {
+                const double val = s_grp[g];
+                s_grp[g] = run;
+                run += val;
+            }
+            if (threadIdx.x == 0)
+                s_grp[a.n_groups] = total;
+        }
+        __syncthreads();
+        v.grp_off = s_grp;
+        born_total = s_grp[a.n_groups];
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            *a.total_out = born_total;
+    }
+    else
+        born_total = a.scal->born_total;
+    if (s >= a.B)
+        return;
+    v.scale = (float)a.B_glob / (float)born_total;
     PHASE_STAMP_C(blockIdx.x, 1, __float_as_uint(v.scale));
     int j = find_slot_owner(v, s);
     PHASE_STAMP_C(blockIdx.x, 2, j);
@@ -411,14 +502,6 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     { // a slot no cell owns keeps its previous cell index, as in the reference
         j = a.birth.idx[s];
         weight = birth_weights_of_cell(v, j, a.meas[j].p_A, a.born_masses[j]).w_UA;
-    }
-    float2 vel;
-    if (a.noise_injected)
-        vel = a.noise[s];
-    else
-    {
-        const float4 g = philox_normal4(a.seed, (uint32_t)s, STAGE_BIRTH, a.cycle);
-        vel = make_float2(g.x * a.stddev_velocity, g.y * a.stddev_velocity);
     }
     PHASE_STAMP_C(blockIdx.x, 3, __float_as_uint(weight) ^ __float_as_uint(vel.x));
     const float x = (float)(j % a.gs) + 0.5f;
@@ -577,6 +660,7 @@ __global__ void __launch_bounds__(kBlock) k_extract_dynamic(const dogm_grid_cell
 static SlotView make_slot_view(dogm_handle* h)
 {
     SlotView v;
+    v.grp_off = h->grp_zero;
     v.blk_off = h->blk_off;
     v.blk_sum = h->blk_sum;
     v.prefix = h->cell_prefix;
@@ -714,11 +798,13 @@ int run_born_scan(dogm_handle* h)
 
 int run_birth(dogm_handle* h)
 {
+    if (h->B > 0 && !h->band.enabled)
+        return run_birth_fill(h, true); // the birth kernel scans the block sums itself
     int e = run_born_scan(h);
-    return e ? e : run_birth_fill(h);
+    return e ? e : run_birth_fill(h, false);
 }
 
-int run_birth_fill(dogm_handle* h)
+int run_birth_fill(dogm_handle* h, bool fused_scan)
 {
     if (h->B <= 0)
         return 0;
@@ -749,9 +835,22 @@ int run_birth_fill(dogm_handle* h)
         h->dyn_pub_armed = false;
         h->dyn_pub_pending = true;
     }
+    const int grid = div_up(h->B, kBlock);
+    a.n_groups = 0;
+    a.blk_off_w = h->blk_off;
+    a.grp_word = h->grp_word;
+    a.epoch = 0;
+    a.total_out = &h->scal->born_total;
+    size_t smem = sizeof(double);
+    if (fused_scan)
     {
-        LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B);
-        launch_chained(h->stream, k_birth_particles, div_up(h->B, kBlock), kBlock, 0, a);
+        a.n_groups = h->n_blk_groups;
+        a.epoch = ++h->birth_epoch;
+        smem = ((size_t)h->n_blk_groups + 1) * sizeof(double);
+    }
+    {
+        LaunchScope ls(h, K_BIRTH_PARTICLES, 25.0 * h->B + 16.0 * h->n_cell_blocks);
+        launch_chained(h->stream, k_birth_particles, grid, kBlock, smem, a);
     }
     return (int)cudaGetLastError();
 }

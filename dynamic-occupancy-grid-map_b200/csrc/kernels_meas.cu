@@ -27,7 +27,10 @@ struct dogm_meas_handle
     float* d_beams;
     float2* d_verts; // arc vertices (NDC offsets from the fan centre), wedges + 1 entries
     dogm_meas_cell* d_grid;
-    float* h_beams_pinned;
+    float* h_beams_pinned;      // two staging halves of max_beams floats each, used in turn
+    cudaEvent_t beams_copied[2]; // recorded behind the host-to-device copy out of each half
+    bool beams_event_ready;
+    int beams_half;
     float4* d_geom;  // per cartesian cell: (i0, j0, wu, wv) of its bilinear lookup, i0 = kNoTexel outside the fan
     int geom_beams;  // beam count d_geom was built for (0 = none)
     float2* d_polar; // K x H polar table of the current scan
@@ -228,17 +231,33 @@ static int upload_beams(dogm_meas_handle* m, const float* beams_host, int K, cud
 {
     if (K <= 0 || !beams_host)
         return DOGM_ERR_INVALID_ARGUMENT;
+    if (!m->beams_event_ready)
+    {
+        DOGM_CHECK(cudaEventCreateWithFlags(&m->beams_copied[0], cudaEventDisableTiming));
+        DOGM_CHECK(cudaEventCreateWithFlags(&m->beams_copied[1], cudaEventDisableTiming));
+        m->beams_event_ready = true;
+    }
     if (K > m->max_beams)
     {
         cudaStreamSynchronize(stream);
+        cudaEventSynchronize(m->beams_copied[0]);
+        cudaEventSynchronize(m->beams_copied[1]);
         cudaFree(m->d_beams);
         cudaFreeHost(m->h_beams_pinned);
         m->max_beams = K;
         DOGM_CHECK(cudaMalloc(&m->d_beams, (size_t)K * sizeof(float)));
-        DOGM_CHECK(cudaMallocHost(&m->h_beams_pinned, (size_t)K * sizeof(float)));
+        DOGM_CHECK(cudaMallocHost(&m->h_beams_pinned, 2 * (size_t)K * sizeof(float)));
     }
-    memcpy(m->h_beams_pinned, beams_host, (size_t)K * sizeof(float));
-    DOGM_CHECK(cudaMemcpyAsync(m->d_beams, m->h_beams_pinned, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, stream));
+    // The copy out of the staging memory is asynchronous: in a pipelined loop (generate_into, updateGridAsync, generate_into,
+    // ...) it may still be queued behind the previous cycle when the next scan arrives.  Two halves used in turn, and the
+    // host waits for the copy out of a half (issued two scans ago) before it writes that half again.
+    const int half = m->beams_half;
+    m->beams_half ^= 1;
+    DOGM_CHECK(cudaEventSynchronize(m->beams_copied[half]));
+    float* stage = m->h_beams_pinned + (size_t)half * m->max_beams;
+    memcpy(stage, beams_host, (size_t)K * sizeof(float));
+    DOGM_CHECK(cudaMemcpyAsync(m->d_beams, stage, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, stream));
+    DOGM_CHECK(cudaEventRecord(m->beams_copied[half], stream));
     return 0;
 }
 
@@ -313,6 +332,9 @@ int materialize_meas(dogm_handle* h)
     if (!h->lazy_meas.pending)
         return 0;
     h->lazy_meas.pending = false;
+    // a reader of the polar table is in flight now: the next scan's table kernel must not run ahead of its dependency wait
+    // until the host has seen the stream drain (the flag is only set again where the host observes a synchronisation)
+    h->cell_kernel_done = false;
     LaunchScope ls(h, K_MEAS_GRID, 32.0 * (double)h->C);
     launch_chained(h->stream, k_meas_apply, div_up(h->C, kBlock), kBlock, 0, h->lazy_meas.geom, h->lazy_meas.polar, h->lazy_meas.K,
                    h->lazy_meas.H, h->C, h->meas);
@@ -354,6 +376,8 @@ extern "C" int dogm_meas_create(const dogm_laser_params* params, float grid_leng
     m->max_beams = 0;
     m->d_beams = nullptr;
     m->h_beams_pinned = nullptr;
+    m->beams_event_ready = false;
+    m->beams_half = 0;
     m->d_verts = nullptr;
     m->d_grid = nullptr;
     m->d_geom = nullptr;
@@ -381,6 +405,11 @@ extern "C" void dogm_meas_destroy(dogm_meas_handle* m)
     cudaStreamSynchronize(m->stream);
     cudaFree(m->d_beams);
     cudaFreeHost(m->h_beams_pinned);
+    if (m->beams_event_ready)
+    {
+        cudaEventDestroy(m->beams_copied[0]);
+        cudaEventDestroy(m->beams_copied[1]);
+    }
     cudaFree(m->d_verts);
     cudaFree(m->d_grid);
     cudaFree(m->d_geom);
@@ -459,8 +488,6 @@ extern "C" int dogm_meas_generate_fused(dogm_meas_handle* m, const float* scans_
         return DOGM_ERR_INVALID_ARGUMENT;
     for (int s = 0; s < num_scans; s++)
     {
-        // the staging buffer is reused per scan: wait for the previous scan's copy before overwriting it
-        DOGM_CHECK(cudaStreamSynchronize(m->stream));
         int e = upload_beams(m, scans_host + (size_t)s * num_beams, num_beams, m->stream);
         e = e ? e : (s == 0 ? prepare_scan(m, num_beams, m->stream) : 0);
         e = e ? e : launch_polar(m, num_beams, s == 0, m->stream, nullptr);

@@ -972,28 +972,6 @@ __device__ __forceinline__ void phase_stamp(int which, unsigned cta, int slot, u
 #define PHASE_STAMP(which, cta, slot, dep)
 #endif
 
-// A published sum travels as one 64-bit word: the sums are non-negative, so the sign bit carries the parity of the
-// launch epoch.  Every launch publishes every word exactly once, hence a word whose sign bit differs from the epoch's
-// parity still holds the previous launch's value.  One relaxed 64-bit load is both the flag and the payload.
-__device__ __forceinline__ void publish_f64(double* p, double v, uint32_t epoch)
-{
-    const unsigned long long bits =
-        ((unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull) | ((unsigned long long)(epoch & 1u) << 63);
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(bits) : "memory");
-}
-__device__ __forceinline__ double await_f64(const double* p, uint32_t epoch)
-{
-    unsigned long long bits;
-    for (;;)
-    {
-        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(p) : "memory");
-        if ((uint32_t)(bits >> 63) == (epoch & 1u))
-            break;
-        __nanosleep(40);
-    }
-    return __longlong_as_double((long long)(bits & 0x7fffffffffffffffull));
-}
-
 // as await_f64, but gives up after `polls` attempts (about 50 ns each) and returns -1
 __device__ __forceinline__ double await_f64_bounded(const double* p, uint32_t epoch, int polls)
 {
@@ -2121,11 +2099,17 @@ __global__ void __launch_bounds__(kBlock) k_band_append(const PRec* __restrict__
     const float4* src = reinterpret_cast<const float4*>(k < n_lo ? in_lo + k : in_hi + (k - n_lo));
     const float4 lo = src[0], hi = src[1];
     const int px = min(max(__float2int_rz(lo.x), 0), gs - 1);
-    const int py = min(max(__float2int_rz(lo.y) - row0, 0), rows - 1); // (it does lie in this band: the sender checked)
+    const int py_raw = min(max(__float2int_rz(lo.y), 0), gs - 1) - row0;
+    const int py = min(max(py_raw, 0), rows - 1);
+    // the sender only knows that the particle left ITS band: one that jumped over this whole band (thin bands, a large
+    // ego-motion shift) is kept as a weightless ghost in the edge row instead of adding its weight to a cell it is not in
+    float4 hi2 = hi;
+    if (py_raw != py)
+        hi2.z = 0.0f;
     const int cell = px + gs * py;
     float4* o = reinterpret_cast<float4*>(rec + n_cur + k);
     o[0] = rec_lo(lo.x, lo.y, cell, __float_as_uint(lo.w));
-    o[1] = hi;
+    o[1] = hi2;
     key0[n_cur + k] = cell;
 }
 
