@@ -221,6 +221,13 @@ _SYMBOLS = [
     ("dogm_enable_peer_access", C.c_int, [C.c_int, C.c_int]),
     ("dogm_band_group_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     ("dogm_band_group_destroy", None, [_P]),
+    ("dogm_band_group_set_mode", C.c_int, [_P, C.c_int]),
+    ("dogm_band_group_get_mode", C.c_int, [_P]),
+    ("dogm_band_mailbox", C.c_void_p, [_P]),
+    ("dogm_band_link", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("dogm_band_cycle_enqueue", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
+    ("dogm_band_cycle_finish", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                         C.POINTER(C.c_double)]),
     ("dogm_band_group_band_times", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("dogm_band_group_update", C.c_int, [_P, C.POINTER(C.c_void_p), C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int),
                                         C.c_void_p]),
@@ -735,8 +742,10 @@ class BandedDOGM:
     release the GIL) and the copies between bands are NVLink peer copies.  By default all bands share the current GPU."""
 
     def __init__(self, params: Params, n_bands: int, devices=None, seed: int = 123456, slack: float = 1.75, halo_rows: int = 64,
-                 resample_mode: int = RESAMPLE_SYSTEMATIC, rows=None, native: bool = True):
-        """rows: rows per band (default: equal shares; see balanced_rows for a split by expected particle load)"""
+                 resample_mode: int = RESAMPLE_SYSTEMATIC, rows=None, native: bool = True, device_paced=None):
+        """rows: rows per band (default: equal shares; see balanced_rows for a split by expected particle load)
+        device_paced (native orchestrator only): True / False selects how the group drives a cycle (include/dogm_b200.h,
+        DOGM_BAND_GROUP_*); None keeps the library's choice (device-paced when every band's GPU reaches all the others)"""
         self._lib = load_library()
         self.params = params
         self.G = int(np.float32(params.size) / np.float32(params.resolution))
@@ -786,6 +795,9 @@ class BandedDOGM:
             g = C.c_void_p()
             _check(self._lib.dogm_band_group_create(arr, n_bands, C.byref(g)), "dogm_band_group_create")
             self.group = g
+            if device_paced is not None:
+                _check(self._lib.dogm_band_group_set_mode(g, 1 if device_paced else 0), "dogm_band_group_set_mode")
+            self.device_paced = self._lib.dogm_band_group_get_mode(g) == 1
 
     def _on(self, r):
         if self.devices[r] is not None:

@@ -4,10 +4,16 @@
 // The per-cycle cost of the orchestration itself is a handful of barrier crossings (microseconds), where a scripting-language
 // thread pool needs tens of microseconds per phase and band.
 //
+// Two ways to run a cycle (dogm_band_group_set_mode):
+//   device-paced (default): every band thread enqueues its band's whole cycle (dogm_band_cycle_enqueue) and waits once at the
+//     end; what the bands tell each other - record counts, the records and halo rows themselves, the two normalisers - travels
+//     GPU to GPU inside the streams (peer loads / stores, single-block kernels that wait for the messages), no host barrier;
+//   host-paced: the phase calls, one synchronisation + one barrier per phase (the first cycle's initialisation always).
 // The reference has nothing to compare with (single device, dogm.cu:39-43); the phases are those of DESIGN.md section 8.
 #include "dogm_internal.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -65,6 +71,10 @@ struct dogm_band_group
     double born_total = 0.0, weight_total = 0.0;
     std::chrono::steady_clock::time_point stamp[6];
     std::vector<float> band_ms; // [band][5]: what each band itself spent in every phase (without the waiting at the barriers)
+    int mode = DOGM_BAND_GROUP_HOST_PACED;
+    bool linked = false;               // every band knows every band's mailbox and can reach it
+    bool shared_device = false;        // at least two bands live on the same GPU
+    std::vector<const void*> edge_lo, edge_hi; // the bands' edge rows of the previous free masses at the start of the cycle
 };
 
 namespace
@@ -114,6 +124,46 @@ void run_cycle(dogm_band_group* g, int r)
     }
     mark(0);
     auto t_begin = std::chrono::steady_clock::now();
+    if (g->mode == DOGM_BAND_GROUP_DEVICE_PACED && g->linked)
+    { // the whole cycle in one go; the bands meet inside their streams
+        const bool halo = h->band.halo_rows > 0;
+        const void* box_lo = r > 0 ? dogm_band_buffer(g->bands[r - 1], DOGM_BAND_SEND_HI) : nullptr;
+        const void* box_hi = r + 1 < R ? dogm_band_buffer(g->bands[r + 1], DOGM_BAND_SEND_LO) : nullptr;
+        const void* edge_lo = (halo && r > 0) ? g->edge_hi[r - 1] : nullptr;
+        const void* edge_hi = (halo && r + 1 < R) ? g->edge_lo[r + 1] : nullptr;
+        int e = 0;
+        if (!g->shared_device)
+            e = dogm_band_cycle_enqueue(h, DOGM_BAND_STAGE_ALL, meas, 1, g->x, g->y, g->yaw, g->dt, box_lo, box_hi, edge_lo, edge_hi);
+        else
+        { // bands that share a GPU: stage k of every band is enqueued before stage k + 1 of any (host barrier, no device sync)
+            for (int stage = DOGM_BAND_STAGE_PREDICT; stage <= DOGM_BAND_STAGE_RESAMPLE; stage <<= 1)
+            {
+                if (e == 0)
+                    e = dogm_band_cycle_enqueue(h, stage, meas, 1, g->x, g->y, g->yaw, g->dt, box_lo, box_hi, edge_lo, edge_hi);
+                if (stage != DOGM_BAND_STAGE_RESAMPLE)
+                    g->barrier->wait();
+            }
+        }
+        g->band_ms[(size_t)r * 5 + 0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        int n_out = 0, a = 0, b = 0;
+        double born = 0.0, weight = 0.0;
+        const int e2 = dogm_band_cycle_finish(h, &n_out, &a, &b, &born, &weight); // (also drains the stream after a failed enqueue)
+        fail(g, e ? e : e2);
+        g->counts[r] = n_out;
+        g->sent_lo[r] = a;
+        g->sent_hi[r] = b;
+        if (r == 0)
+        {
+            g->born_total = born;
+            g->weight_total = weight;
+        }
+        for (int k = 1; k < 5; k++)
+            g->band_ms[(size_t)r * 5 + k] = 0.0f;
+        g->band_ms[(size_t)r * 5 + 4] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        for (int k = 1; k <= 5; k++)
+            mark(k);
+        return;
+    }
     auto lap = [&](int k) {
         const auto now = std::chrono::steady_clock::now();
         g->band_ms[(size_t)r * 5 + k] = std::chrono::duration<float, std::milli>(now - t_begin).count();
@@ -224,6 +274,42 @@ extern "C" int dogm_band_group_create(dogm_handle* const* bands, int n_bands, do
     g->counts.assign(n_bands, 0);
     g->share.assign(n_bands, 0.0);
     g->band_ms.assign((size_t)n_bands * 5, 0.0f);
+    g->edge_lo.assign(n_bands, nullptr);
+    g->edge_hi.assign(n_bands, nullptr);
+    // device-paced cycles: every band stores its normaliser shares into every band's mailbox, so every GPU has to reach all
+    // the others; if it cannot (or there are more bands than a mailbox has entries), the group stays host-paced
+    if (n_bands <= dogm_b200::kMaxBands)
+    {
+        bool reach = true;
+        for (int a = 0; a < n_bands && reach; a++)
+            for (int b = 0; b < n_bands && reach; b++)
+                if (g->devices[a] != g->devices[b] && dogm_enable_peer_access(g->devices[a], g->devices[b]) != 0)
+                    reach = false;
+        if (reach)
+        {
+            std::vector<void*> mails(n_bands);
+            for (int r = 0; r < n_bands; r++)
+                mails[r] = dogm_band_mailbox(bands[r]);
+            int prev = 0;
+            cudaGetDevice(&prev);
+            bool ok = true;
+            for (int r = 0; r < n_bands && ok; r++)
+            {
+                cudaSetDevice(g->devices[r]);
+                ok = dogm_band_link(bands[r], r, n_bands, mails.data()) == 0;
+            }
+            cudaSetDevice(prev);
+            g->linked = ok;
+        }
+    }
+    for (int a = 0; a < n_bands; a++)
+        for (int b = a + 1; b < n_bands; b++)
+            if (g->devices[a] == g->devices[b])
+                g->shared_device = true;
+    {
+        const char* env = getenv("DOGM_BAND_HOST_PACED");
+        g->mode = (g->linked && !(env && env[0] == '1')) ? DOGM_BAND_GROUP_DEVICE_PACED : DOGM_BAND_GROUP_HOST_PACED;
+    }
     g->barrier = new SpinBarrier(n_bands);
     for (int r = 0; r < n_bands; r++)
         g->workers.emplace_back(worker_main, g, r);
@@ -259,6 +345,11 @@ extern "C" int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* 
     g->yaw = new_yaw;
     g->dt = dt;
     g->error.store(0);
+    for (int r = 0; r < g->n; r++)
+    { // (the cell kernel of a cycle swaps a band's free-mass buffers: the neighbours must see this cycle's "previous" rows)
+        g->edge_lo[r] = dogm_band_buffer(g->bands[r], DOGM_BAND_EDGE_LO);
+        g->edge_hi[r] = dogm_band_buffer(g->bands[r], DOGM_BAND_EDGE_HI);
+    }
     {
         std::unique_lock<std::mutex> lk(g->m);
         g->finished = 0;
@@ -284,6 +375,21 @@ extern "C" int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* 
             info->phase_ms[k] = std::chrono::duration<float, std::milli>(g->stamp[k + 1] - g->stamp[k]).count();
     }
     return e;
+}
+
+extern "C" int dogm_band_group_set_mode(dogm_band_group* g, int mode)
+{
+    if (!g || (mode != DOGM_BAND_GROUP_HOST_PACED && mode != DOGM_BAND_GROUP_DEVICE_PACED))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (mode == DOGM_BAND_GROUP_DEVICE_PACED && !g->linked)
+        return DOGM_ERR_UNSUPPORTED; // some band's GPU cannot reach another band's memory
+    g->mode = mode;
+    return 0;
+}
+
+extern "C" int dogm_band_group_get_mode(const dogm_band_group* g)
+{
+    return g ? g->mode : DOGM_ERR_INVALID_ARGUMENT;
 }
 
 extern "C" int dogm_band_group_band_times(const dogm_band_group* g, float* out_ms)

@@ -159,6 +159,26 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->band.send_cap = band ? band->exchange_capacity : 0;
     h->band.halo[0] = h->band.halo[1] = nullptr;
     h->band.halo_rows = band ? band->halo_rows : 0;
+    h->band.cnt = nullptr;
+    h->band.cnt_host = nullptr;
+    h->band.mail = nullptr;
+    for (int k = 0; k < kMaxBands; k++)
+        h->band.peer_mail[k] = nullptr;
+    h->band.group_size = 0;
+    h->band.group_rank = 0;
+    h->band.dev_cnt = nullptr;
+    h->band.seq = 0;
+    h->band.n_pred = 0;
+    h->band.est_recv = 65536;
+    h->band.est_birth = band ? band->birth_capacity : 0;
+    h->band.est_out = band ? band->particle_capacity : 0;
+    {
+        // developer / test switch: fixed (deliberately wrong) launch-size estimates, to exercise the kernels' loops
+        const char* ef = getenv("DOGM_B200_BAND_EST");
+        h->band.est_forced = ef ? atoi(ef) : 0;
+        if (h->band.est_forced > 0)
+            h->band.est_recv = h->band.est_birth = h->band.est_out = h->band.est_forced;
+    }
     h->device = device;
     h->sm_count = sm_count;
     h->first_pose_received = false;
@@ -303,6 +323,9 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
         }
         keep_first(alloc_zero((void**)&h->band.out_total, 2 * sizeof(double)));
         keep_first((int)cudaMallocHost((void**)&h->band.pin, 8 * sizeof(double)));
+        keep_first(alloc_zero((void**)&h->band.cnt, sizeof(BandCounts)));
+        keep_first(alloc_zero((void**)&h->band.mail, sizeof(BandMail)));
+        keep_first((int)cudaMallocHost((void**)&h->band.cnt_host, sizeof(BandCounts)));
         if (e)
         {
             dogm_destroy(h);
@@ -396,6 +419,10 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->band.out_total);
     if (h->band.pin)
         cudaFreeHost(h->band.pin);
+    cudaFree(h->band.cnt);
+    cudaFree(h->band.mail);
+    if (h->band.cnt_host)
+        cudaFreeHost(h->band.cnt_host);
     if (h->trace_buf)
     {
         trace_bind_particles(nullptr);
@@ -1116,22 +1143,6 @@ extern "C" int dogm_band_counts(dogm_handle* h, int* particles, int* birth_parti
     return 0;
 }
 
-// first and one-past-last slot of a band in a slot numbering that spans all bands: slots are handed out in proportion
-// to mass, slot end of a prefix = int(float(prefix) * scale) exactly as the kernels evaluate it per cell
-static void band_slot_range(double before, double local, double total, int count_glob, int* first, int* past)
-{
-    if (!(total > 0.0))
-    {
-        *first = *past = 0;
-        return;
-    }
-    const float scale = (float)count_glob / (float)total;
-    *first = (int)((float)before * scale);
-    *past = (int)((float)(before + local) * scale);
-    if (*past < *first)
-        *past = *first;
-}
-
 // Pure host arithmetic of the band mode, exported so that an orchestrator (and a CPU test) can check that the parts of
 // consecutive bands tile the slot ranges without gap or overlap.
 extern "C" int dogm_band_slot_range(double mass_before, double mass_local, double mass_total, int slots_total, int* first,
@@ -1149,36 +1160,8 @@ extern "C" int dogm_band_output_range(uint64_t seed, uint32_t cycle, int resampl
     if (!first || !past)
         return DOGM_ERR_INVALID_ARGUMENT;
     long long i_lo = 0, i_hi = 0;
-    if (weight_total > 0.0 && n_glob > 0 && weight_local > 0.0)
-    {
-        const double step = weight_total / (double)n_glob;
-        const bool systematic = resample_mode == DOGM_RESAMPLE_SYSTEMATIC;
-        const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
-        const float u0 = systematic ? u01_half_open(philox4x32_10(0u, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x) : 0.0f;
-        // the offset of output slot i, the expression of resample_offset (kernels_particles.cu)
-        auto offset = [&](long long i) {
-            const float u = systematic ? u0 : u01_half_open(philox4x32_10((uint32_t)i, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x);
-            return ((double)i + (double)u) * step;
-        };
-        // smallest slot whose offset exceeds x (offsets ascend with the slot number)
-        auto first_behind = [&](double x) {
-            long long lo = 0, hi = n_glob;
-            while (lo < hi)
-            {
-                const long long mid = lo + ((hi - lo) >> 1);
-                if (offset(mid) > x)
-                    hi = mid;
-                else
-                    lo = mid + 1;
-            }
-            return lo;
-        };
-        const double upto = weight_before + weight_local; // == the next band's weight_before (same addition)
-        i_lo = weight_before > 0.0 ? first_behind(weight_before) : 0;
-        i_hi = upto >= weight_total ? n_glob : first_behind(upto);
-        if (i_hi < i_lo)
-            i_hi = i_lo;
-    }
+    band_output_range(seed, cycle, resample_mode == DOGM_RESAMPLE_SYSTEMATIC, n_glob, weight_before, weight_local, weight_total, &i_lo,
+                      &i_hi);
     *first = i_lo;
     *past = i_hi;
     return 0;
@@ -1385,6 +1368,166 @@ extern "C" int dogm_band_resample(dogm_handle* h, double weight_before, double w
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     if (particles_out)
         *particles_out = (int)n_out;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-paced cycle: the whole cycle of a band is enqueued in one go; the particle counts of the cycle and the bands'
+// messages stay on the devices (BandCounts / BandMail, kernels_particles.cu), the host looks once, at the end
+// ---------------------------------------------------------------------------------------------------------
+extern "C" void* dogm_band_mailbox(dogm_handle* h)
+{
+    return (h && h->band.enabled) ? (void*)h->band.mail : nullptr;
+}
+
+extern "C" int dogm_band_link(dogm_handle* h, int rank, int n_bands, void* const* mailboxes)
+{
+    if (!h || !h->band.enabled || !mailboxes || n_bands < 1 || n_bands > kMaxBands || rank < 0 || rank >= n_bands)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (mailboxes[rank] != (void*)h->band.mail)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < kMaxBands; k++)
+        h->band.peer_mail[k] = k < n_bands ? (BandMail*)mailboxes[k] : nullptr;
+    h->band.group_size = n_bands;
+    h->band.group_rank = rank;
+    h->band.seq = 0;
+    DOGM_CHECK(cudaMemsetAsync(h->band.mail, 0, sizeof(BandMail), h->stream));
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_meas_cell* measurement_band, int on_device, float new_x,
+                                       float new_y, float new_yaw, float dt, const void* outbox_of_lower_neighbour,
+                                       const void* outbox_of_upper_neighbour, const void* edge_rows_of_lower_neighbour,
+                                       const void* edge_rows_of_upper_neighbour)
+{
+    BAND_PROLOGUE();
+    if (h->band.group_size < 1 || !h->band.cnt)
+        return DOGM_ERR_NOT_INITIALIZED; // dogm_band_link first
+    if (!h->first_measurement_received)
+        return DOGM_ERR_NOT_INITIALIZED; // the first cycle's initialisation runs through dogm_band_init_*
+    const int R = h->band.group_size, me = h->band.group_rank;
+    if ((me > 0 && !outbox_of_lower_neighbour) || (me + 1 < R && !outbox_of_upper_neighbour))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (stages & DOGM_BAND_STAGE_PREDICT)
+    { // prediction, the records that leave, their counts to the neighbours
+        h->band.seq++;
+        update_pose(h, new_x, new_y, new_yaw);
+        h->band.n_pred = h->N;
+        if ((e = run_predict(h, dt)))
+            return e;
+        h->shift_particles_pending = false;
+        if (h->N > 0 && (e = run_band_outbox(h)))
+            return e;
+        if ((e = run_band_publish_sent(h)))
+            return e;
+    }
+    if (stages & DOGM_BAND_STAGE_UPDATE)
+    { // the neighbours' counts and records; sort, per-cell sums, occupancy update; this band's born mass to all bands
+        const int n_pred = h->band.n_pred;
+        if ((e = run_band_collect_sent(h, n_pred)))
+            return e;
+        const bool halo = h->band.halo_rows > 0;
+        if (R > 1 && (e = run_band_pull(h, n_pred, outbox_of_lower_neighbour, outbox_of_upper_neighbour,
+                                        halo ? (const float*)edge_rows_of_lower_neighbour : nullptr,
+                                        halo ? (const float*)edge_rows_of_upper_neighbour : nullptr)))
+            return e;
+        // from here on the particle count of the band is known on the device only: the host sizes the launches for an upper
+        // bound, the kernels read the counts (h->band.dev_cnt)
+        long long n_ub = R > 1 ? (long long)n_pred + h->band.est_recv : n_pred;
+        if (n_ub > h->band.n_cap)
+            n_ub = h->band.n_cap;
+        h->band.dev_cnt = h->band.cnt;
+        set_particle_counts(h, (int)n_ub, h->band.est_birth > 0 ? h->band.est_birth : 1);
+        if (R > 1)
+            h->hist0_valid = false; // the histogram of the first sort pass has to include the records that arrived
+        h->pa_current = false;
+        h->rec_valid = true;
+        h->sorted_valid = false;
+        h->meas_src = nullptr;
+        if (measurement_band && measurement_band != h->meas)
+        {
+            if (on_device)
+                h->meas_src = measurement_band; // the cell kernel copies it on the way
+            else
+                e = copy_in(h->meas, measurement_band, (size_t)h->C * sizeof(dogm_meas_cell), 0, h->stream);
+        }
+        h->band.halo_valid = (halo && R > 1) ? 1 : 0;
+        if (!e && h->shift_grid_pending && h->shift.active && h->band.rows < h->band.G &&
+            (h->shift.y_move > h->band.halo_rows || -h->shift.y_move > h->band.halo_rows))
+            e = DOGM_ERR_INVALID_ARGUMENT;
+        e = e ? e : run_assignment(h);
+        e = e ? e : run_occupancy_update(h, dt);
+        e = e ? e : run_persistent_weights(h, true);
+        e = e ? e : run_born_scan(h);
+        e = e ? e : run_band_publish_share(h, 0);
+        h->band.dev_cnt = nullptr;
+        if (e)
+            return e; // (the other bands run into the bounded waits of their collectors)
+    }
+    if (stages & DOGM_BAND_STAGE_BIRTH)
+    { // born mass of the whole grid; birth particles; joint CDF; this band's joint weight to all bands
+        h->band.dev_cnt = h->band.cnt;
+        e = run_band_collect_born(h);
+        e = e ? e : run_birth_fill(h);
+        e = e ? e : run_cdf(h);
+        e = e ? e : run_band_publish_share(h, 1);
+        h->band.dev_cnt = nullptr;
+        if (e)
+            return e;
+    }
+    if (stages & DOGM_BAND_STAGE_RESAMPLE)
+    { // joint weight of the whole grid; this band's part of the draw
+        h->band.dev_cnt = h->band.cnt;
+        e = run_band_collect_weight(h);
+        e = e ? e : run_resample_gather(h);
+        h->band.dev_cnt = nullptr;
+        if (e)
+            return e;
+        DOGM_CHECK(cudaMemcpyAsync(h->band.cnt_host, h->band.cnt, sizeof(BandCounts), cudaMemcpyDeviceToHost, h->stream));
+        h->cycle++;
+    }
+    return 0;
+}
+
+extern "C" int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* sent_lo, int* sent_hi, double* born_total,
+                                      double* weight_total)
+{
+    if (!h || !h->band.enabled || !h->band.cnt_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    const BandCounts c = *h->band.cnt_host;
+    set_particle_counts(h, c.n_out, c.B);
+    if (h->band.est_forced <= 0)
+    { // launch sizes of the next cycle: what this one needed plus a margin
+        long long v = ((long long)c.n_lo + c.n_hi) * 5 / 4 + 16384;
+        h->band.est_recv = (int)(v < 2ll * h->band.send_cap ? v : 2ll * h->band.send_cap);
+        v = (long long)c.B * 9 / 8 + 4096;
+        h->band.est_birth = (int)(v < h->band.b_cap ? v : h->band.b_cap);
+        v = (long long)c.n_out * 17 / 16 + 8192;
+        h->band.est_out = (int)(v < h->band.n_cap ? v : h->band.n_cap);
+    }
+    h->band.n_out = c.n_out;
+    h->band.born_local = c.born_local;
+    h->band.weight_local = c.weight_local;
+    h->band.born_base = c.born_base;
+    h->band.birth_slot_base = c.birth_slot_base;
+    h->band.cdf_base = c.cdf_base;
+    h->band.out_base = c.out_base;
+    if (particles_out)
+        *particles_out = c.n_out;
+    if (sent_lo)
+        *sent_lo = c.sent_lo;
+    if (sent_hi)
+        *sent_hi = c.sent_hi;
+    if (born_total)
+        *born_total = c.born_total;
+    if (weight_total)
+        *weight_total = c.weight_total;
+    if (c.err & BAND_ERR_TIMEOUT)
+        return DOGM_ERR_NOT_INITIALIZED; // a message of another band never arrived
+    if (c.err)
+        return DOGM_ERR_INVALID_ARGUMENT; // a capacity of the band configuration was exceeded
     return 0;
 }
 

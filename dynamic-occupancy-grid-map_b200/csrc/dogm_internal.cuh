@@ -116,6 +116,99 @@ struct DeviceScalars // device-resident scalars: nothing is read back by the hos
     double weight_total; // last entry of the joint weight CDF
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// band mode, device-paced cycle: what the bands tell each other travels GPU to GPU (peer stores into the receiver's
+// mailbox), what a band derives from it stays in its device-resident counts - the host enqueues a whole cycle and
+// looks at the counts once, at the end
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxBands = 16;
+
+enum : int
+{
+    BAND_ERR_SEND_OVERFLOW = 1,  // more particles crossed an edge than the exchange boxes hold
+    BAND_ERR_PARTICLE_CAP = 2,   // the band's particles do not fit its capacity
+    BAND_ERR_BIRTH_CAP = 4,      // its share of the birth particles does not fit
+    BAND_ERR_TIMEOUT = 8,        // a neighbour's message did not arrive
+};
+
+struct BandCounts
+{
+    int n_sort;           // particles after the neighbours' records have joined (sort, per-cell sums, CDF)
+    int n_lo, n_hi;       // records received from the lower / upper neighbour
+    int sent_lo, sent_hi; // records sent
+    int B;                // birth particles of this band
+    int birth_slot_base;  // global number of its first birth slot
+    int n_out;            // resampled particles of this band
+    int err;              // BAND_ERR_* bits
+    int pad;
+    long long out_base;   // global number of its first output slot
+    double born_local, born_base, born_total;
+    double weight_local, cdf_base, weight_total;
+};
+
+struct BandMail // lives on the band's GPU, written by the other bands' kernels (one writer per word)
+{
+    unsigned long long sent_from_lo; // (sequence number << 32) | records in the lower neighbour's upper send box
+    unsigned long long sent_from_hi;
+    unsigned long long pad[2];
+    double born[kMaxBands];          // normaliser shares of all bands, tagged with the cycle's sequence number
+    double weight[kMaxBands];
+    unsigned int born_seq[kMaxBands];
+    unsigned int weight_seq[kMaxBands];
+};
+
+// first and one-past-last slot of a band in a slot numbering that spans all bands: slots are handed out in proportion
+// to mass, slot end of a prefix = int(float(prefix) * scale) exactly as the kernels evaluate it per cell
+__host__ __device__ inline void band_slot_range(double before, double local, double total, int count_glob, int* first, int* past)
+{
+    if (!(total > 0.0))
+    {
+        *first = *past = 0;
+        return;
+    }
+    const float scale = (float)count_glob / (float)total;
+    *first = (int)((float)before * scale);
+    *past = (int)((float)(before + local) * scale);
+    if (*past < *first)
+        *past = *first;
+}
+
+// the output slots of the whole grid whose resampling offsets fall into a band's part of the global CDF
+__host__ __device__ inline void band_output_range(uint64_t seed, uint32_t cycle, bool systematic, long long n_glob, double weight_before,
+                                                  double weight_local, double weight_total, long long* first, long long* past)
+{
+    long long i_lo = 0, i_hi = 0;
+    if (weight_total > 0.0 && n_glob > 0 && weight_local > 0.0)
+    {
+        const double step = weight_total / (double)n_glob;
+        const uint32_t s_lo = (uint32_t)seed, s_hi = (uint32_t)(seed >> 32);
+        const float u0 = systematic ? u01_half_open(philox4x32_10(0u, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x) : 0.0f;
+        // smallest slot whose offset ((i + u) * step, the expression of resample_offset) exceeds x; offsets ascend with i
+        const double bound[2] = {weight_before, weight_before + weight_local}; // (== the next band's weight_before: same addition)
+        long long found[2];
+        for (int k = 0; k < 2; k++)
+        {
+            long long lo = 0, hi = n_glob;
+            while (lo < hi)
+            {
+                const long long mid = lo + ((hi - lo) >> 1);
+                const float u = systematic ? u0 : u01_half_open(philox4x32_10((uint32_t)mid, STAGE_RESAMPLE, cycle, 0u, s_lo, s_hi).x);
+                if (((double)mid + (double)u) * step > bound[k])
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            found[k] = lo;
+        }
+        i_lo = weight_before > 0.0 ? found[0] : 0;
+        i_hi = bound[1] >= weight_total ? n_glob : found[1];
+        if (i_hi < i_lo)
+            i_hi = i_lo;
+    }
+    *first = i_lo;
+    *past = i_hi;
+}
+
 struct CycleShift // ego-motion compensation of this cycle (dogm.cu:175-178)
 {
     int active;
@@ -202,6 +295,17 @@ struct dogm_handle
         int halo_rows;
         int halo_valid;            // the orchestrator filled the halo rows for this cycle
         double born_local, weight_local; // host copies of this band's normaliser shares
+        // device-paced cycle (dogm_band_group): see BandCounts / BandMail
+        dogm_b200::BandCounts* cnt;       // device
+        dogm_b200::BandCounts* cnt_host;  // pinned copy, valid after the end-of-cycle synchronisation
+        dogm_b200::BandMail* mail;        // this band's mailbox (device)
+        dogm_b200::BandMail* peer_mail[dogm_b200::kMaxBands]; // all bands' mailboxes in band order (peer-accessible)
+        int group_size, group_rank;
+        const dogm_b200::BandCounts* dev_cnt; // non-null while the stages of a device-paced cycle are being enqueued
+        uint32_t seq;                      // sequence number of the running cycle's messages
+        int n_pred;                        // particle count the running cycle's prediction worked on
+        // launch sizes of the device-paced cycle: estimates from the previous cycle (the kernels loop, so any value is safe)
+        int est_recv, est_birth, est_out, est_forced;
     } band;
     int device;
     int sm_count;
@@ -421,6 +525,13 @@ int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of 
 int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
 int run_band_outbox(dogm_handle* h); // compacts the particles k_predict flagged into the send boxes, in slot order
 int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi);
+// device-paced band cycle (kernels_particles.cu): the three message exchanges and the pull of the neighbours' records
+int run_band_publish_sent(dogm_handle* h);
+int run_band_collect_sent(dogm_handle* h, int n_pred);
+int run_band_pull(dogm_handle* h, int n_pred, const void* outbox_lo, const void* outbox_hi, const float* edge_lo, const float* edge_hi);
+int run_band_publish_share(dogm_handle* h, int which); // 0: born mass, 1: joint weight
+int run_band_collect_born(dogm_handle* h);
+int run_band_collect_weight(dogm_handle* h);
 void set_particle_counts(dogm_handle* h, int n, int b); // band mode: current counts and everything derived from them
 int materialize_meas(dogm_handle* h);      // kernels_meas.cu: runs a pending cartesian resampling into h->meas
 int run_extract_free_mass(dogm_handle* h); // GridCell AoS -> free_cur after dogm_set_grid_cells

@@ -360,6 +360,7 @@ struct BirthArgs
     double* grp_word;      // [n_groups]
     uint32_t epoch;
     double* total_out;     // DeviceScalars::born_total
+    const BandCounts* cnt; // device-paced band cycle: this band's birth count and slot base live on the device
 };
 
 // Developer build (-DDOGM_PHASE_TRACE): phase stamps of k_birth_particles (thread 0 of every CTA), see tools/phase_trace.py
@@ -393,12 +394,10 @@ int debug_phase_read_cells(void* out_host, size_t bytes)
 
 // initBirthParticlesKernel (init.cu:46-67) + initNewParticlesKernel1 (init_new_particles.cu:126-155, with the
 // deterministic ownership rule "slot s belongs to cell j iff start_j <= s <= end_j") + initNewParticlesKernel2 (:157-195)
-__global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
+__device__ __forceinline__ void birth_block(const BirthArgs& a, const int vblock, const int n_birth, double* s_grp)
 {
-    pdl_prologue(K_BIRTH_PARTICLES * 2);
-    extern __shared__ double s_grp[]; // [n_groups + 1] exclusive prefix of the group sums; the last entry is the total
     __shared__ double s_scan[kWarpsPerBlock];
-    const int s = blockIdx.x * kBlock + threadIdx.x;
+    const int s = vblock * kBlock + threadIdx.x;
     if (a.pub_host && s == 0)
     {
         const int found = __ldcg(a.pub_count);
@@ -408,7 +407,7 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     }
     // the velocity draw does not depend on the slot distribution: it overlaps the ticket and the group scans
     float2 vel = make_float2(0.0f, 0.0f);
-    if (s < a.B)
+    if (s < n_birth)
     {
         if (a.noise_injected)
             vel = a.noise[s];
@@ -420,13 +419,18 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     }
     PHASE_STAMP_C(blockIdx.x, 0, 0);
     SlotView v = a.slots;
+    if (a.cnt)
+    {
+        v.base_off = a.cnt->born_base;
+        v.slot_base = a.cnt->birth_slot_base;
+    }
     double born_total;
     if (a.n_groups > 0)
     {
         // The first CTAs of the grid scan one group of 256 block sums each (fixed order inside a group) and publish the group
         // sum; they wait for nobody and are dispatched before every CTA behind them, so every wait below ends.  Every CTA then
         // adds up the group sums in group order.
-        for (int g = (int)blockIdx.x; g < a.n_groups; g += (int)gridDim.x)
+        for (int g = vblock; g < a.n_groups; g += (int)gridDim.x)
         {
             const int j = g * kBlkGroup + (int)threadIdx.x;
             const double val = j < v.n_blocks ? v.blk_sum[j] : 0.0;
@@ -474,12 +478,12 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
         __syncthreads();
         v.grp_off = s_grp;
         born_total = s_grp[a.n_groups];
-        if (blockIdx.x == 0 && threadIdx.x == 0)
+        if (vblock == 0 && threadIdx.x == 0)
             *a.total_out = born_total;
     }
     else
         born_total = a.scal->born_total;
-    if (s >= a.B)
+    if (s >= n_birth)
         return;
     v.scale = (float)a.B_glob / (float)born_total;
     PHASE_STAMP_C(blockIdx.x, 1, __float_as_uint(v.scale));
@@ -511,6 +515,21 @@ __global__ void __launch_bounds__(kBlock) k_birth_particles(BirthArgs a)
     a.birth.weight[s] = weight;
     a.birth.state[s] = make_float4(x, y, vel.x, vel.y);
     PHASE_STAMP_C(blockIdx.x, 4, 0);
+}
+
+__global__ void __launch_bounds__(kBlock) k_birth_particles(const BirthArgs a)
+{
+    pdl_prologue(K_BIRTH_PARTICLES * 2);
+    extern __shared__ double s_grp[]; // [n_groups + 1] exclusive prefix of the group sums; the last entry is the total
+    if (!a.cnt)
+    {
+        birth_block(a, (int)blockIdx.x, a.B, s_grp);
+        return;
+    }
+    // device-paced band cycle: the band's birth count is read from the device, the grid is the host's estimate (no fused scan here)
+    const int n_birth = a.cnt->B;
+    for (int b = blockIdx.x; b * kBlock < n_birth || b == 0; b += gridDim.x)
+        birth_block(a, b, n_birth, s_grp);
 }
 
 // =========================================================================================================
@@ -806,7 +825,7 @@ int run_birth(dogm_handle* h)
 
 int run_birth_fill(dogm_handle* h, bool fused_scan)
 {
-    if (h->B <= 0)
+    if (h->B <= 0) // (device-paced band cycle: the band's capacity, which sizes the grid)
         return 0;
     BirthArgs a;
     a.B = h->B;
@@ -841,6 +860,7 @@ int run_birth_fill(dogm_handle* h, bool fused_scan)
     a.grp_word = h->grp_word;
     a.epoch = 0;
     a.total_out = &h->scal->born_total;
+    a.cnt = h->band.dev_cnt;
     size_t smem = sizeof(double);
     if (fused_scan)
     {

@@ -184,53 +184,67 @@ __global__ void __launch_bounds__(kWideBlock) k_soa_to_rec(const float4* __restr
 
 // pass-0 histogram of keys that are already in place (assignment called twice in a row)
 __global__ void __launch_bounds__(kWideBlock) k_key_tile_hist(const int* __restrict__ key, int n, uint32_t* hist, int bins,
-                                                              uint32_t mask)
+                                                              uint32_t mask, const int* n_dev)
 {
     pdl_prologue(K_TILE_HIST * 2);
+    if (n_dev)
+        n = *n_dev; // device-paced band cycle: the count is only known on the device; the grid is an estimate, the CTAs loop
     extern __shared__ uint32_t s_hist[];
-    for (int b = threadIdx.x; b < bins; b += kWideBlock)
-        s_hist[b] = 0u;
-    __syncthreads();
-    const int base = blockIdx.x * kTileItems;
-#pragma unroll
-    for (int j = 0; j < kTileItems / kWideBlock; j++)
+    const int tiles = (n + kTileItems - 1) / kTileItems;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
     {
-        const int i = base + j * kWideBlock + threadIdx.x;
-        if (i < n)
-            atomicAdd(&s_hist[(uint32_t)key[i] & mask], 1u);
+        for (int b = threadIdx.x; b < bins; b += kWideBlock)
+            s_hist[b] = 0u;
+        __syncthreads();
+        const int base = tile * kTileItems;
+#pragma unroll
+        for (int j = 0; j < kTileItems / kWideBlock; j++)
+        {
+            const int i = base + j * kWideBlock + threadIdx.x;
+            if (i < n)
+                atomicAdd(&s_hist[(uint32_t)key[i] & mask], 1u);
+        }
+        __syncthreads();
+        uint32_t* row = hist + (size_t)tile * bins;
+        for (int b = threadIdx.x; b < bins; b += kWideBlock)
+            row[b] = s_hist[b];
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t* row = hist + (size_t)blockIdx.x * bins;
-    for (int b = threadIdx.x; b < bins; b += kWideBlock)
-        row[b] = s_hist[b];
 }
 
 // histogram of a later pass over the pairs the previous pass has just written (they are still in L2); cheaper than
 // 2e6 global atomics issued from the previous scatter (21 us against 6 us at 2e6 particles)
 __global__ void __launch_bounds__(kWideBlock) k_pair_tile_hist(const int2* __restrict__ pair, int n, uint32_t* hist, int bins,
-                                                               int shift, uint32_t mask)
+                                                               int shift, uint32_t mask, const int* n_dev)
 {
     pdl_prologue(K_TILE_HIST * 2 + 1);
+    if (n_dev)
+        n = *n_dev;
     extern __shared__ uint32_t s_hist[];
-    for (int b = threadIdx.x; b < bins; b += kWideBlock)
-        s_hist[b] = 0u;
-    __syncthreads();
-    const int base = blockIdx.x * kTileItems;
-    int keys[kTileItems / kWideBlock];
-#pragma unroll
-    for (int j = 0; j < kTileItems / kWideBlock; j++)
+    const int tiles = (n + kTileItems - 1) / kTileItems;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
     {
-        const int i = base + j * kWideBlock + threadIdx.x;
-        keys[j] = i < n ? __ldg(&pair[i].x) : -1;
-    }
+        for (int b = threadIdx.x; b < bins; b += kWideBlock)
+            s_hist[b] = 0u;
+        __syncthreads();
+        const int base = tile * kTileItems;
+        int keys[kTileItems / kWideBlock];
 #pragma unroll
-    for (int j = 0; j < kTileItems / kWideBlock; j++)
-        if (keys[j] >= 0)
-            atomicAdd(&s_hist[((uint32_t)keys[j] >> shift) & mask], 1u);
-    __syncthreads();
-    uint32_t* row = hist + (size_t)blockIdx.x * bins;
-    for (int b = threadIdx.x; b < bins; b += kWideBlock)
-        row[b] = s_hist[b];
+        for (int j = 0; j < kTileItems / kWideBlock; j++)
+        {
+            const int i = base + j * kWideBlock + threadIdx.x;
+            keys[j] = i < n ? __ldg(&pair[i].x) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < kTileItems / kWideBlock; j++)
+            if (keys[j] >= 0)
+                atomicAdd(&s_hist[((uint32_t)keys[j] >> shift) & mask], 1u);
+        __syncthreads();
+        uint32_t* row = hist + (size_t)tile * bins;
+        for (int b = threadIdx.x; b < bins; b += kWideBlock)
+            row[b] = s_hist[b];
+        __syncthreads();
+    }
 }
 
 // records -> the reference's SoA block (read-out between stages: getParticles after prediction / assignment);
@@ -287,9 +301,11 @@ __device__ __forceinline__ unsigned long long await_u64(const unsigned long long
 // first term needs the totals of the CTAs before: every CTA publishes the sum of its 32 bins and adds up the words of
 // its predecessors (at most 64 CTAs, all resident; integers, so the order of the additions does not matter).
 __global__ void __launch_bounds__(kWideBlock) k_hist_scan(uint32_t* __restrict__ table, int tiles, int bins,
-                                                          unsigned long long* chain, uint32_t epoch)
+                                                          unsigned long long* chain, uint32_t epoch, const int* n_dev)
 {
     pdl_prologue(K_HIST_SCAN * 2 + (bins > 1024 ? 0 : 1));
+    if (n_dev)
+        tiles = (*n_dev + kTileItems - 1) / kTileItems;
     __shared__ uint32_t s_part[kScanWarps][32];
     __shared__ uint32_t s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -401,14 +417,12 @@ struct ScatterArgs
     uint32_t mask;
     int bins;
     const uint32_t* table; // this pass: final position of the first key per (tile, digit), from k_hist_scan
+    const int* n_dev;      // device-paced band cycle: the item count lives on the device (n is an upper bound for the grid)
 };
 
 template <bool FIRST>
-__global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
+__device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int tile, unsigned short* s_cnt /* [warps][bins] */)
 {
-    pdl_prologue(K_SCATTER * 2 + (FIRST ? 0 : 1));
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned short* s_cnt = (unsigned short*)s_raw; // [warps][bins]
 
     const int* __restrict__ key_in = a.key_in;
     const int2* __restrict__ pair_in = a.pair_in;
@@ -417,7 +431,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned full = 0xffffffffu;
     const unsigned lt = lanemask_lt();
-    const int warp_base = blockIdx.x * kTileItems + warp * (kTileItems / kWarpsPerBlock);
+    const int warp_base = tile * kTileItems + warp * (kTileItems / kWarpsPerBlock);
 
     // all key loads of the warp's 16 rounds are in flight while the rank counters are cleared
     int keys[kRoundsPerWarp];
@@ -504,7 +518,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
 
     // store phase: the inputs are read again (L1 / L2 hits) instead of being kept in registers across the ranking;
     // all loads of a batch of 8 are issued before the first store (the stores could alias them for the compiler)
-    const uint32_t* __restrict__ row = a.table + (size_t)blockIdx.x * a.bins; // final position of this tile's first key per bin
+    const uint32_t* __restrict__ row = a.table + (size_t)tile * a.bins; // final position of this tile's first key per bin
 #pragma unroll
     for (int half = 0; half < 2; half++)
     {
@@ -545,6 +559,30 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(ScatterArgs a)
             if (i < a.n)
                 pair_out[dest[q]] = make_int2(key[q], slot[q]);
         }
+    }
+}
+
+// LOOP = false: one CTA per tile (the grid is the number of tiles).  LOOP = true (device-paced band cycle): the item count is
+// read from the device, the grid is the host's estimate and the CTAs walk over the tiles.
+template <bool FIRST, bool LOOP>
+__global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
+{
+    pdl_prologue(K_SCATTER * 2 + (FIRST ? 0 : 1));
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned short* s_cnt = (unsigned short*)s_raw;
+    if (!LOOP)
+    {
+        scatter_tile<FIRST>(a_in, (int)blockIdx.x, s_cnt);
+        return;
+    }
+    ScatterArgs a = a_in;
+    if (a.n_dev)
+        a.n = *a.n_dev;
+    const int tiles = (a.n + kTileItems - 1) / kTileItems;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    {
+        scatter_tile<FIRST>(a, tile, s_cnt);
+        __syncthreads();
     }
 }
 
@@ -626,13 +664,11 @@ constexpr int kSegPerLane = kSegChunk / 32; // 8 consecutive sorted positions pe
 #ifndef DOGM_SEGSUM_MINBLOCKS
 #define DOGM_SEGSUM_MINBLOCKS 1
 #endif
-__global__ void __launch_bounds__(kBlock, DOGM_SEGSUM_MINBLOCKS) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
-                                                   int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
-                                                   SegPiece* trail, int* flags, float* __restrict__ sw)
+__device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, const PRec* __restrict__ rec, const int n, int* cell_start,
+                                             int* cell_end, CellSums* sums, SegPiece* lead, SegPiece* trail, int* flags,
+                                             float* __restrict__ sw, const int chunk)
 {
-    pdl_prologue(K_SEGSUM * 2);
     const int lane = threadIdx.x & 31;
-    const int chunk = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int base = chunk * kSegChunk;
     if (base >= n)
         return;
@@ -804,20 +840,38 @@ __global__ void __launch_bounds__(kBlock, DOGM_SEGSUM_MINBLOCKS) k_segsum(const 
     }
 }
 
+__global__ void __launch_bounds__(kBlock, DOGM_SEGSUM_MINBLOCKS) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
+                                                   int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
+                                                   SegPiece* trail, int* flags, float* __restrict__ sw, const int* n_dev)
+{
+    pdl_prologue(K_SEGSUM * 2);
+    const int chunk0 = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (!n_dev)
+    {
+        segsum_chunk(spair, rec, n, cell_start, cell_end, sums, lead, trail, flags, sw, chunk0);
+        return;
+    }
+    // device-paced band cycle: the count lives on the device, the grid is the host's estimate, the warps walk over the chunks
+    n = *n_dev;
+    for (int chunk = chunk0; chunk * kSegChunk < n; chunk += gridDim.x * kWarpsPerBlock)
+        segsum_chunk(spair, rec, n, cell_start, cell_end, sums, lead, trail, flags, sw, chunk);
+}
+
 // segments that span chunk borders: the chunk holding the head adds up the pieces in chunk order
 __global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spair, int n_chunks, CellSums* sums,
                                                    const SegPiece* __restrict__ lead, const SegPiece* __restrict__ trail,
-                                                   const int* __restrict__ flags, int* zero_word)
+                                                   const int* __restrict__ flags, int* zero_word, const int* n_dev)
 {
     pdl_prologue(K_SEGFIX * 2);
+    if (n_dev)
+        n_chunks = (*n_dev + kSegChunk - 1) / kSegChunk;
     if (zero_word && blockIdx.x == 0 && threadIdx.x == 0)
         *zero_word = 0; // the dynamic-cell counter the cell kernel appends to (no memset node between the kernels)
-    const int c = blockIdx.x * kBlock + threadIdx.x;
-    if (c >= n_chunks)
-        return;
+    for (int c = blockIdx.x * kBlock + threadIdx.x; c < n_chunks; c += gridDim.x * kBlock) // (one round unless the grid is an estimate)
+    {
     const int f = flags[c];
     if (!(f & SEG_TRAIL) || (f & SEG_THROUGH))
-        return;
+        continue;
     SegPiece acc = trail[c];
     int c2 = c + 1;
     while (c2 < n_chunks)
@@ -842,6 +896,7 @@ __global__ void __launch_bounds__(kBlock) k_segfix(const int2* __restrict__ spai
     v.s4 = acc.s4;
     v.s5 = acc.s5;
     store_cell_sums(sums, k, v);
+    }
 }
 
 // =========================================================================================================
@@ -931,6 +986,7 @@ struct ChainArgs
     const float* resample_u;
     uint64_t seed;
     uint32_t cycle;
+    const BandCounts* cnt; // device-paced band cycle: particle counts (hence the number of tiles) live on the device
 };
 
 // the k-th block of 256 output slots starts at this offset (same expression as resample_offset for slot 256 k)
@@ -987,9 +1043,17 @@ __device__ __forceinline__ double await_f64_bounded(const double* p, uint32_t ep
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(ChainArgs a)
+__global__ void __launch_bounds__(kBlock, 4) k_cdf_chain(const ChainArgs a_in)
 {
     pdl_prologue(K_CDF_CHAIN * 2);
+    ChainArgs a = a_in;
+    if (a.cnt)
+    {
+        a.c.N = a.cnt->n_sort;
+        a.c.n = a.cnt->n_sort + a.cnt->B;
+        a.tiles = (a.c.n + kCdfTile - 1) / kCdfTile;
+        a.flat = a.tiles <= kChainFlat * kBlock ? 1 : 0;
+    }
     __shared__ double s_w[kWarpsPerBlock];
     __shared__ double s_red[kWarpsPerBlock];
     __shared__ double s_total, s_step, s_inv, s_u;
@@ -1359,6 +1423,7 @@ struct ResampleArgs
     const float* resample_u;
     uint64_t seed;
     uint32_t cycle;
+    const BandCounts* cnt; // device-paced band cycle: counts and this band's part of the global draw live on the device
 };
 
 // One CTA resamples 1024 consecutive output slots, four per thread.  Their offsets ascend, so all ancestors lie in a short
@@ -1402,15 +1467,13 @@ constexpr int kResOutputs = kBlock * kResPer;  // output slots per CTA
 #ifndef DOGM_RES_MINBLOCKS
 #define DOGM_RES_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(ResampleArgs a)
+// the 1024 output slots of block `blk`
+__device__ __forceinline__ void resample_block(const ResampleArgs& a, const int blk)
 {
-    pdl_prologue(K_RESAMPLE * 2);
     __shared__ double s_cdf[kResWindow];
     __shared__ __align__(16) int s_anc[kResOutputs];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
-    // the CTAs at the end of the CDF (birth particles: several window slides) take longest: they go first
-    const int blk = (int)(gridDim.x - 1 - blockIdx.x);
     const int out0 = blk * kResOutputs;
     PHASE_STAMP(1, blockIdx.x, 0, 0);
     // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
@@ -1630,6 +1693,32 @@ __global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(Resampl
     PHASE_STAMP(1, blockIdx.x, 6, 0);
 }
 
+__global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(const ResampleArgs a_in)
+{
+    pdl_prologue(K_RESAMPLE * 2);
+    if (!a_in.cnt)
+    { // the CTAs at the end of the CDF (birth particles: several window slides) take longest: they go first
+        resample_block(a_in, (int)(gridDim.x - 1 - blockIdx.x));
+        return;
+    }
+    // device-paced band cycle: counts and this band's part of the global draw are read from the device; the grid is the host's
+    // estimate, the CTAs walk over the blocks of output slots
+    ResampleArgs a = a_in;
+    a.N = a.cnt->n_sort;
+    a.n_cdf = a.cnt->n_sort + a.cnt->B;
+    a.N_out = a.cnt->n_out;
+    a.out_base = a.cnt->out_base;
+    a.cdf_base = a.cnt->cdf_base;
+    if (a.n_cdf <= 0)
+        return;
+    const int blocks = (a.N_out + kResOutputs - 1) / kResOutputs;
+    for (int b = blockIdx.x; b < blocks; b += gridDim.x)
+    {
+        resample_block(a, blocks - 1 - b);
+        __syncthreads();
+    }
+}
+
 // ancestor search on a caller-supplied float CDF: thrust::lower_bound of resampling.cu:45 (+ clamp)
 __global__ void __launch_bounds__(kBlock) k_search_f32(const float* __restrict__ cdf, int n_cdf,
                                                        const float* __restrict__ draws, int n_draws, int* out)
@@ -1748,9 +1837,10 @@ int run_predict(dogm_handle* h, float dt)
 
 int run_assignment(dogm_handle* h)
 {
-    const int N = h->N;
+    const int N = h->N; // (device-paced band cycle: an upper bound that sizes the grids; the kernels read the count itself)
     if (N <= 0)
         return 0;
+    const int* n_dev = h->band.dev_cnt ? &h->band.dev_cnt->n_sort : nullptr;
     // reinitGridParticleIndices (init.cu:86-93): cell_start is all -1 here: k_init_grid set it and the cell kernel
     // resets every entry it consumes; only when the ranges were never consumed (stage API) a memset is needed
     if (h->ranges_in_soa)
@@ -1768,7 +1858,7 @@ int run_assignment(dogm_handle* h)
             launch_chained(h->stream, k_soa_to_rec, h->tiles, kWideBlock, smem, h->pa.state, h->pa.idx, h->pa.weight, h->pa.assoc, h->rec,
                                                                     h->key0, N, h->hist[0], h->digit_bins[0], mask);
         else
-            launch_chained(h->stream, k_key_tile_hist, h->tiles, kWideBlock, smem, h->key0, N, h->hist[0], h->digit_bins[0], mask);
+            launch_chained(h->stream, k_key_tile_hist, h->tiles, kWideBlock, smem, h->key0, N, h->hist[0], h->digit_bins[0], mask, n_dev);
         h->rec_valid = true;
     }
     for (int p = 0; p < h->passes; p++)
@@ -1778,12 +1868,12 @@ int run_assignment(dogm_handle* h)
         {
             LaunchScope ls(h, K_TILE_HIST, 8.0 * N);
             launch_chained(h->stream, k_pair_tile_hist, h->tiles, kWideBlock, (size_t)bins * sizeof(uint32_t), h->pairs[(p - 1) & 1],
-                           N, h->hist[p], bins, h->digit_shift[p], (uint32_t)(bins - 1));
+                           N, h->hist[p], bins, h->digit_shift[p], (uint32_t)(bins - 1), n_dev);
         }
         {
             LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
             launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[p], h->tiles, bins,
-                           (unsigned long long*)h->bin_base[p], ++h->scan_epoch[p]);
+                           (unsigned long long*)h->bin_base[p], ++h->scan_epoch[p], n_dev);
         }
         ScatterArgs a;
         a.key_in = h->key0;
@@ -1794,13 +1884,21 @@ int run_assignment(dogm_handle* h)
         a.mask = (uint32_t)(bins - 1);
         a.bins = bins;
         a.table = h->hist[p];
+        a.n_dev = n_dev;
         const size_t smem = (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
             LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
-            if (p == 0)
-                launch_chained(h->stream, k_scatter<true>, h->tiles, kBlock, smem, a);
+            if (n_dev)
+            {
+                if (p == 0)
+                    launch_chained(h->stream, k_scatter<true, true>, h->tiles, kBlock, smem, a);
+                else
+                    launch_chained(h->stream, k_scatter<false, true>, h->tiles, kBlock, smem, a);
+            }
+            else if (p == 0)
+                launch_chained(h->stream, k_scatter<true, false>, h->tiles, kBlock, smem, a);
             else
-                launch_chained(h->stream, k_scatter<false>, h->tiles, kBlock, smem, a);
+                launch_chained(h->stream, k_scatter<false, false>, h->tiles, kBlock, smem, a);
         }
     }
     h->spair = h->pairs[(h->passes - 1) & 1];
@@ -1810,12 +1908,12 @@ int run_assignment(dogm_handle* h)
     {
         LaunchScope ls(h, K_SEGSUM, 44.0 * N);
         launch_chained(h->stream, k_segsum, div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, 
-            h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw);
+            h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw, n_dev);
     }
     {
         LaunchScope ls(h, K_SEGFIX, 0.0);
         launch_chained(h->stream, k_segfix, div_up(h->n_chunks, kBlock), kBlock, 0, h->spair, h->n_chunks, h->cell_sums, h->seg_lead,
-                                                                      h->seg_trail, h->seg_flags, h->dyn_filter_on ? h->dyn_count : nullptr);
+                                                                      h->seg_trail, h->seg_flags, h->dyn_filter_on ? h->dyn_count : nullptr, n_dev);
     }
     h->sorted_valid = true;
     return (int)cudaGetLastError();
@@ -1878,10 +1976,11 @@ int configure_kernels()
 {
     const int max_bins = 1 << kMaxDigitBits;
     const int smem = max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
-    int e = (int)cudaFuncSetAttribute(k_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e)
-        return e;
-    return (int)cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int e = (int)cudaFuncSetAttribute(k_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return e;
 }
 
 int run_cdf(dogm_handle* h)
@@ -1889,7 +1988,7 @@ int run_cdf(dogm_handle* h)
     const int N = h->N, n = h->N + h->B;
     if (n <= 0)
         return 0;
-    if (N > 0 && !h->sorted_valid)
+    if (N > 0 && !h->sorted_valid && !h->band.dev_cnt)
         return DOGM_ERR_NOT_INITIALIZED; // the CDF reads the sorted weights of dogm_particle_assignment
     CdfArgs ca;
     ca.wa = h->weight_array;
@@ -1917,12 +2016,22 @@ int run_cdf(dogm_handle* h)
 #ifdef DOGM_AB_NO_CLAIMS
     ch.res_start = nullptr;
 #endif
+    ch.cnt = h->band.dev_cnt;
     if (h->band.enabled)
     { // the number of tiles changes from cycle to cycle, so the parity of the published words cannot alternate: the
       // words are cleared and every launch publishes with parity 1
-        cudaMemsetAsync(h->tile_sum, 0, (size_t)h->n_cdf_tiles * sizeof(double), h->stream);
-        cudaMemsetAsync(h->tile_off, 0, ((size_t)h->n_cdf_tiles + 3) * sizeof(double), h->stream);
+        // (device-paced cycle: n_cdf_tiles is an estimate, the words are cleared for the band's capacity)
+        const size_t clear_tiles = ch.cnt ? (size_t)div_up((long long)h->band.n_cap + h->band.b_cap > 0 ? (long long)h->band.n_cap + h->band.b_cap : 1, kCdfTile)
+                                          : (size_t)h->n_cdf_tiles;
+        cudaMemsetAsync(h->tile_sum, 0, clear_tiles * sizeof(double), h->stream);
+        cudaMemsetAsync(h->tile_off, 0, (clear_tiles + 3) * sizeof(double), h->stream);
         ch.epoch = 1u;
+        if (ch.cnt)
+        { // the number of tickets a launch draws is not known to the host either: the ticket starts from 0 every cycle
+            cudaMemsetAsync(h->chain_flags, 0, sizeof(uint32_t), h->stream);
+            h->chain_ticket_base = 0;
+            ch.ticket_base = 0;
+        }
     }
     ch.total_word = h->tile_off + (h->n_cdf_tiles / kChainGroup + 1);
     ch.res_blocks = div_up(N > 0 ? N : 1, kBlock);
@@ -1932,7 +2041,8 @@ int run_cdf(dogm_handle* h)
     ch.seed = h->opts.seed;
     ch.cycle = h->cycle;
     const int grid = h->n_cdf_tiles < h->chain_capacity ? h->n_cdf_tiles : h->chain_capacity;
-    h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
+    if (!ch.cnt)
+        h->chain_ticket_base += (uint32_t)(h->n_cdf_tiles + grid); // every CTA draws one ticket past the end
     {
         LaunchScope ls(h, K_CDF_CHAIN, fused ? 24.0 * N + 12.0 * h->B : 12.0 * n);
         if (fused)
@@ -1968,7 +2078,14 @@ int run_resample_gather(dogm_handle* h)
     a.resample_u = h->resample_u;
     a.seed = h->opts.seed;
     a.cycle = h->cycle;
-    if (n_out > 0 && n > 0)
+    a.cnt = h->band.dev_cnt;
+    if (a.cnt)
+    { // device-paced band cycle: the grid is sized for an estimate, the kernel reads what it really has to do and loops
+        const int est = h->band.est_out > 0 ? h->band.est_out : 1;
+        LaunchScope ls(h, K_RESAMPLE, 69.0 * est);
+        launch_chained(h->stream, k_resample, div_up(est, kResOutputs), kBlock, 0, a);
+    }
+    else if (n_out > 0 && n > 0)
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * n_out);
         launch_chained(h->stream, k_resample, div_up(n_out, kResOutputs), kBlock, 0, a);
@@ -2111,6 +2228,358 @@ __global__ void __launch_bounds__(kBlock) k_band_append(const PRec* __restrict__
     o[0] = rec_lo(lo.x, lo.y, cell, __float_as_uint(lo.w));
     o[1] = hi2;
     key0[n_cur + k] = cell;
+}
+
+
+// =========================================================================================================
+// device-paced band cycle: the bands' messages travel GPU to GPU.  Every exchange is a pair of one-warp kernels: the
+// publisher stores this band's share into the other bands' mailboxes (peer stores, value first, then the cycle's
+// sequence number behind a system-wide fence); the collector waits until the shares it needs carry the sequence number,
+// derives the band's counts from them - in band order, with the very expressions the host-paced phases use - and only
+// then lets its dependents launch.  Only the collectors ever spin, one warp each, so several bands on ONE GPU cannot
+// starve each other of SM slots; there the orchestrator also enqueues all publishers of an exchange before any of its
+// collectors (streams of one GPU may share a hardware queue: a collector must never sit in front of a publisher it waits
+// for).  The waits are bounded (a lost peer ends in an error flag, not in a hung GPU).
+// =========================================================================================================
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_sys_u32(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_u32(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kBandWaitNs = 4000000000ull; // 4 s: far beyond any cycle, short enough not to look like a hang
+
+struct BandLink
+{
+    BandMail* mail[kMaxBands]; // all bands' mailboxes in band order
+    int R, me;
+    uint32_t seq;
+    BandCounts* cnt;
+};
+
+// after prediction + outbox compaction: tell the neighbours how many records wait in the send boxes ...
+__global__ void __launch_bounds__(32) k_band_publish_sent(BandLink l, const double* __restrict__ out_total, int n_pred, int send_cap)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // (the collector behind waits for this kernel to finish)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0)
+    {
+        int err = 0;
+        int s_lo = n_pred > 0 ? (int)out_total[0] : 0, s_hi = n_pred > 0 ? (int)out_total[1] : 0;
+        if (s_lo > send_cap || s_hi > send_cap)
+        {
+            err |= BAND_ERR_SEND_OVERFLOW;
+            s_lo = min(s_lo, send_cap);
+            s_hi = min(s_hi, send_cap);
+        }
+        l.cnt->sent_lo = s_lo;
+        l.cnt->sent_hi = s_hi;
+        l.cnt->err = err; // (first kernel of the cycle that writes the flags)
+        __threadfence_system(); // the send boxes (written by the kernel in front) are visible before the counts
+        if (l.me > 0)
+            st_sys_u64(&l.mail[l.me - 1]->sent_from_hi, ((unsigned long long)l.seq << 32) | (unsigned)s_lo);
+        if (l.me + 1 < l.R)
+            st_sys_u64(&l.mail[l.me + 1]->sent_from_lo, ((unsigned long long)l.seq << 32) | (unsigned)s_hi);
+    }
+}
+
+// ... and learn how many they sent
+__global__ void __launch_bounds__(32) k_band_collect_sent(BandLink l, int n_pred, int n_cap)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0)
+    {
+        int err = 0;
+        int n_lo = 0, n_hi = 0;
+        const unsigned long long t0 = global_ns();
+        const BandMail* mine = l.mail[l.me];
+        bool need_lo = l.me > 0, need_hi = l.me + 1 < l.R;
+        while (need_lo || need_hi)
+        {
+            if (need_lo)
+            {
+                const unsigned long long w = ld_sys_u64(&mine->sent_from_lo);
+                if ((uint32_t)(w >> 32) == l.seq)
+                {
+                    n_lo = (int)(uint32_t)w;
+                    need_lo = false;
+                }
+            }
+            if (need_hi)
+            {
+                const unsigned long long w = ld_sys_u64(&mine->sent_from_hi);
+                if ((uint32_t)(w >> 32) == l.seq)
+                {
+                    n_hi = (int)(uint32_t)w;
+                    need_hi = false;
+                }
+            }
+            if ((need_lo || need_hi) && global_ns() - t0 > kBandWaitNs)
+            {
+                err |= BAND_ERR_TIMEOUT;
+                break;
+            }
+        }
+        __threadfence_system();
+        int n_sort = n_pred + n_lo + n_hi;
+        if (n_sort > n_cap)
+        {
+            err |= BAND_ERR_PARTICLE_CAP;
+            n_hi = max(0, min(n_hi, n_cap - n_pred - n_lo));
+            n_lo = max(0, min(n_lo, n_cap - n_pred));
+            n_sort = n_pred + n_lo + n_hi;
+        }
+        l.cnt->n_lo = n_lo;
+        l.cnt->n_hi = n_hi;
+        l.cnt->n_sort = n_sort;
+        if (err)
+            l.cnt->err |= err;
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// the neighbours' records (read from their send boxes over NVLink) join this band's records; the rows of the neighbours'
+// previous free masses an ego-motion shift pulls in are copied into the halo buffers
+__global__ void __launch_bounds__(kBlock) k_band_pull(const BandCounts* __restrict__ cnt, const PRec* in_lo, const PRec* in_hi,
+                                                      PRec* __restrict__ rec, int* __restrict__ key0, int n_pred, int gs, int row0,
+                                                      int rows, const float* edge_lo, const float* edge_hi, float* halo_lo,
+                                                      float* halo_hi, int halo_elems)
+{
+    pdl_prologue(K_MISC * 2);
+    const int n_lo = cnt->n_lo, n_hi = cnt->n_hi;
+    const int stride = gridDim.x * kBlock;
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < n_lo + n_hi; k += stride)
+    {
+        const float4* src = reinterpret_cast<const float4*>(k < n_lo ? in_lo + k : in_hi + (k - n_lo));
+        const float4 lo = __ldcg(src), hi = __ldcg(src + 1);
+        const int px = min(max(__float2int_rz(lo.x), 0), gs - 1);
+        const int py_raw = min(max(__float2int_rz(lo.y), 0), gs - 1) - row0;
+        const int py = min(max(py_raw, 0), rows - 1);
+        float4 hi2 = hi;
+        if (py_raw != py)
+            hi2.z = 0.0f; // (see k_band_append)
+        const int cell = px + gs * py;
+        float4* o = reinterpret_cast<float4*>(rec + n_pred + k);
+        o[0] = rec_lo(lo.x, lo.y, cell, __float_as_uint(lo.w));
+        o[1] = hi2;
+        key0[n_pred + k] = cell;
+    }
+    const int quads = halo_elems / 4; // (a row length that is no multiple of 4 leaves a tail for the scalar loop)
+    if (edge_lo)
+    {
+        for (int k = blockIdx.x * kBlock + threadIdx.x; k < quads; k += stride)
+            reinterpret_cast<float4*>(halo_lo)[k] = __ldcg(reinterpret_cast<const float4*>(edge_lo) + k);
+        for (int k = quads * 4 + blockIdx.x * kBlock + threadIdx.x; k < halo_elems; k += stride)
+            halo_lo[k] = __ldcg(edge_lo + k);
+    }
+    if (edge_hi)
+    {
+        for (int k = blockIdx.x * kBlock + threadIdx.x; k < quads; k += stride)
+            reinterpret_cast<float4*>(halo_hi)[k] = __ldcg(reinterpret_cast<const float4*>(edge_hi) + k);
+        for (int k = quads * 4 + blockIdx.x * kBlock + threadIdx.x; k < halo_elems; k += stride)
+            halo_hi[k] = __ldcg(edge_hi + k);
+    }
+}
+
+// publishes this band's entry of a normaliser (which = 0: born mass, 1: joint weight) into every band's mailbox: lane k serves
+// band k - value, system-wide fence, then the tag
+__global__ void __launch_bounds__(32) k_band_publish_share(BandLink l, int which, const DeviceScalars* scal)
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool any = which == 0 || l.cnt->n_sort + l.cnt->B > 0; // (no CDF tile ran: nobody wrote the total)
+    const double share = which ? (any ? scal->weight_total : 0.0) : scal->born_total;
+    const int lane = threadIdx.x;
+    if (lane == 0)
+    {
+        if (which)
+            l.cnt->weight_local = share;
+        else
+            l.cnt->born_local = share;
+    }
+    if (lane < l.R)
+    {
+        BandMail* m = l.mail[lane];
+        st_sys_u64(reinterpret_cast<unsigned long long*>(which ? &m->weight[l.me] : &m->born[l.me]),
+                   (unsigned long long)__double_as_longlong(share));
+    }
+    __threadfence_system();
+    if (lane < l.R)
+    {
+        BandMail* m = l.mail[lane];
+        st_sys_u32(which ? &m->weight_seq[l.me] : &m->born_seq[l.me], l.seq);
+    }
+}
+
+// waits for all bands' entries of a normaliser in this band's own mailbox; sums in band order: every band computes the same doubles
+__device__ __forceinline__ int band_collect(const BandLink& l, int which, double* before, double* total)
+{
+    const int lane = threadIdx.x;
+    int err = 0;
+    double v = 0.0;
+    if (lane < l.R)
+    {
+        const BandMail* mine = l.mail[l.me];
+        const unsigned long long t0 = global_ns();
+        while (ld_sys_u32(which ? &mine->weight_seq[lane] : &mine->born_seq[lane]) != l.seq)
+            if (global_ns() - t0 > kBandWaitNs)
+            {
+                err = BAND_ERR_TIMEOUT;
+                break;
+            }
+        __threadfence_system();
+        v = __longlong_as_double((long long)ld_sys_u64(reinterpret_cast<const unsigned long long*>(which ? &mine->weight[lane] : &mine->born[lane])));
+    }
+    err = __reduce_or_sync(0xffffffffu, err);
+    double acc = 0.0, b = 0.0;
+    for (int k = 0; k < l.R; k++)
+    {
+        const double vk = __shfl_sync(0xffffffffu, v, k);
+        if (k == l.me)
+            b = acc;
+        acc = acc + vk;
+    }
+    *before = b;
+    *total = acc;
+    return err;
+}
+
+// after the occupancy update: born mass of the whole grid, this band's birth slots
+__global__ void __launch_bounds__(32) k_band_collect_born(BandLink l, DeviceScalars* scal, int b_glob, int b_cap)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    double before, total;
+    int err = band_collect(l, 0, &before, &total);
+    if (threadIdx.x == 0)
+    {
+        const double local = l.cnt->born_local;
+        int first, past;
+        band_slot_range(before, local, total, b_glob, &first, &past);
+        int b = past - first;
+        if (b > b_cap)
+        {
+            err |= BAND_ERR_BIRTH_CAP;
+            b = b_cap;
+        }
+        l.cnt->born_base = before;
+        l.cnt->born_total = total;
+        l.cnt->birth_slot_base = first;
+        l.cnt->B = b;
+        if (err)
+            l.cnt->err |= err;
+        scal->born_total = total;
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// after the joint CDF: joint weight of the whole grid, the output slots this band draws
+__global__ void __launch_bounds__(32) k_band_collect_weight(BandLink l, DeviceScalars* scal, uint64_t seed, uint32_t cycle, int systematic,
+                                                            int n_glob, int n_cap)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    double before, total;
+    int err = band_collect(l, 1, &before, &total);
+    if (threadIdx.x == 0)
+    {
+        const double local = l.cnt->weight_local;
+        long long i_lo, i_hi;
+        band_output_range(seed, cycle, systematic != 0, (long long)n_glob, before, local, total, &i_lo, &i_hi);
+        long long n_out = i_hi - i_lo;
+        if (n_out > n_cap)
+        {
+            err |= BAND_ERR_PARTICLE_CAP;
+            n_out = n_cap;
+        }
+        l.cnt->cdf_base = before;
+        l.cnt->weight_total = total;
+        l.cnt->out_base = i_lo;
+        l.cnt->n_out = (int)n_out;
+        if (err)
+            l.cnt->err |= err;
+        scal->weight_total = total;
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+static BandLink make_link(dogm_handle* h)
+{
+    BandLink l;
+    for (int k = 0; k < kMaxBands; k++)
+        l.mail[k] = h->band.peer_mail[k];
+    l.R = h->band.group_size;
+    l.me = h->band.group_rank;
+    l.seq = h->band.seq;
+    l.cnt = h->band.cnt;
+    return l;
+}
+
+int run_band_publish_sent(dogm_handle* h)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    launch_chained(h->stream, k_band_publish_sent, 1, 32, 0, make_link(h), h->band.out_total, h->N, h->band.send_cap);
+    return (int)cudaGetLastError();
+}
+
+int run_band_collect_sent(dogm_handle* h, int n_pred)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    launch_chained(h->stream, k_band_collect_sent, 1, 32, 0, make_link(h), n_pred, h->band.n_cap);
+    return (int)cudaGetLastError();
+}
+
+int run_band_pull(dogm_handle* h, int n_pred, const void* outbox_lo, const void* outbox_hi, const float* edge_lo, const float* edge_hi)
+{
+    const int halo_elems = h->band.halo_rows * h->gs;
+    const long long work = (long long)2 * h->band.send_cap > halo_elems / 4 ? (long long)2 * h->band.send_cap : halo_elems / 4;
+    int grid = div_up(work > 0 ? work : 1, kBlock);
+    if (grid > 4 * h->sm_count)
+        grid = 4 * h->sm_count;
+    LaunchScope ls(h, K_MISC, 68.0 * h->band.send_cap);
+    launch_chained(h->stream, k_band_pull, grid, kBlock, 0, h->band.cnt, (const PRec*)outbox_lo, (const PRec*)outbox_hi, h->rec, h->key0,
+                   n_pred, h->gs, h->band.row0, h->band.rows, edge_lo, edge_hi, h->band.halo[0], h->band.halo[1], halo_elems);
+    return (int)cudaGetLastError();
+}
+
+int run_band_publish_share(dogm_handle* h, int which)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    launch_chained(h->stream, k_band_publish_share, 1, 32, 0, make_link(h), which, (const DeviceScalars*)h->scal);
+    return (int)cudaGetLastError();
+}
+
+int run_band_collect_born(dogm_handle* h)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    launch_chained(h->stream, k_band_collect_born, 1, 32, 0, make_link(h), h->scal, h->band.b_glob, h->band.b_cap);
+    return (int)cudaGetLastError();
+}
+
+int run_band_collect_weight(dogm_handle* h)
+{
+    LaunchScope ls(h, K_MISC, 0.0);
+    launch_chained(h->stream, k_band_collect_weight, 1, 32, 0, make_link(h), h->scal, h->opts.seed, h->cycle,
+                   h->opts.resample_mode == DOGM_RESAMPLE_SYSTEMATIC ? 1 : 0, h->band.n_glob, h->band.n_cap);
+    return (int)cudaGetLastError();
 }
 
 int run_band_outbox(dogm_handle* h)

@@ -232,6 +232,39 @@ void dogm_band_group_destroy(dogm_band_group* g);
 int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* const* measurement_bands, float new_x, float new_y,
                            float new_yaw, float dt, int* particles_out, dogm_band_cycle_info* info);
 
+/* How a group drives its cycles.  DEVICE_PACED (the default when every band's GPU can reach every other's memory): each band
+ * enqueues its whole cycle at once; the particles that change band, the halo rows and the two normalisers travel GPU to GPU -
+ * a band's kernels read its neighbours' send boxes directly, every band stores its normaliser share into every band's mailbox
+ * and single-block kernels wait for the shares in the stream - and the host synchronises once, at the end of the cycle.
+ * HOST_PACED: the phase calls above, one host synchronisation and one barrier per phase.  Same results bit for bit. */
+#define DOGM_BAND_GROUP_HOST_PACED 0
+#define DOGM_BAND_GROUP_DEVICE_PACED 1
+int dogm_band_group_set_mode(dogm_band_group* g, int mode);
+int dogm_band_group_get_mode(const dogm_band_group* g);
+
+/* The building blocks of the device-paced cycle, for an orchestrator of its own (one call per band and cycle each):
+ * dogm_band_link tells a band its rank and all bands' mailboxes (dogm_band_mailbox; every band's GPU needs peer access to the
+ * others'); dogm_band_cycle_enqueue enqueues the cycle (the neighbours' DOGM_BAND_SEND_* boxes and DOGM_BAND_EDGE_* rows are read
+ * in place by this band's kernels; the first cycle still runs through dogm_band_init_*); dogm_band_cycle_finish waits for it
+ * and returns the band's new particle count (DOGM_ERR_INVALID_ARGUMENT: a capacity was exceeded).
+ * `stages`: DOGM_BAND_STAGE_ALL enqueues the whole cycle.  Each of the four stages ends by publishing a message to the other
+ * bands and the next begins by waiting for theirs inside the stream.  Bands that share ONE GPU must be enqueued stage by
+ * stage - stage k of every band before stage k + 1 of any (their streams may share a hardware queue, and a waiting kernel
+ * must never sit in front of the publisher it waits for); bands on GPUs of their own take DOGM_BAND_STAGE_ALL. */
+#define DOGM_BAND_STAGE_PREDICT 1  /* prediction, outbox, record counts -> neighbours */
+#define DOGM_BAND_STAGE_UPDATE 2   /* neighbours' records and halo rows, sort, per-cell sums, occupancy update, born mass -> all */
+#define DOGM_BAND_STAGE_BIRTH 4    /* birth particles, joint CDF, joint weight -> all */
+#define DOGM_BAND_STAGE_RESAMPLE 8 /* this band's part of the global draw */
+#define DOGM_BAND_STAGE_ALL 15
+void* dogm_band_mailbox(dogm_handle* h);
+int dogm_band_link(dogm_handle* h, int rank, int n_bands, void* const* mailboxes);
+int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_meas_cell* measurement_band, int on_device, float new_x,
+                            float new_y, float new_yaw, float dt, const void* outbox_of_lower_neighbour,
+                            const void* outbox_of_upper_neighbour, const void* edge_rows_of_lower_neighbour,
+                            const void* edge_rows_of_upper_neighbour);
+int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* sent_lo, int* sent_hi, double* born_total,
+                           double* weight_total);
+
 /* out_ms[band * 5 + phase]: what every band itself spent in the phases of the last cycle (host wall clock, without the waiting
  * at the barriers) - the input for placing the band edges */
 int dogm_band_group_band_times(const dogm_band_group* g, float* out_ms);

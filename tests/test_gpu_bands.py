@@ -37,15 +37,28 @@ def run_plain(gpu, grids, poses, seed=77):
     return d
 
 
-def run_banded(gpu, grids, poses, bands, seed=77, native=True):
-    bd = gpu.BandedDOGM(make_params(gpu, SIZE, RES, N, B), bands, seed=seed, native=native)
+def run_banded(gpu, grids, poses, bands, seed=77, native=True, device_paced=None, devices=None):
+    bd = gpu.BandedDOGM(make_params(gpu, SIZE, RES, N, B), bands, seed=seed, native=native, device_paced=device_paced, devices=devices)
     dev = gpu.device_alloc(grids[0].nbytes)
     history = []
+    per_dev = {}
+    if devices is not None:  # every band reads its rows of the measurement grid from its own GPU
+        for d in sorted(set(devices)):
+            gpu.set_device(d)
+            per_dev[d] = gpu.device_alloc(grids[0].nbytes)
     for g, (x, y) in zip(grids, poses):
-        gpu.memcpy_h2d(dev, g)
-        ptrs = [dev + bd.row0[r] * bd.G * 16 for r in range(bands)]
+        if devices is None:
+            gpu.memcpy_h2d(dev, g)
+            ptrs = [dev + bd.row0[r] * bd.G * 16 for r in range(bands)]
+        else:
+            for d, p in per_dev.items():
+                gpu.set_device(d)
+                gpu.memcpy_h2d(p, g)
+            ptrs = [per_dev[devices[r]] + bd.row0[r] * bd.G * 16 for r in range(bands)]
         history.append(bd.update_grid(ptrs, x, y, 0.0, 0.1))
+    gpu.set_device(0)
     gpu.device_free(dev)
+    bd._extra_buffers = per_dev  # (freed with the process; kept alive while the bands exist)
     return bd, history
 
 
@@ -160,6 +173,72 @@ def test_native_band_group_equals_the_phase_calls(gpu):
         bd.close()
     assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
     for r in range(3):
+        for a, b in zip(out[0][1][r], out[1][1][r]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
+    assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))
+
+
+def _snapshot(bd, bands):
+    parts = [tuple(np.ascontiguousarray(a).copy() for a in bd.get_particles(r)) for r in range(bands)]
+    return parts, bd.get_grid_cells().copy(), dict(bd.last_totals)
+
+
+@pytest.mark.parametrize("bands,vx,vy", [(1, 0.0, 4.0), (2, 0.0, 4.0), (3, 3.0, 0.0), (4, -2.0, 6.0)])
+def test_device_paced_cycle_equals_the_host_paced_phases(gpu, bands, vx, vy):
+    """The device-paced group (whole cycle enqueued at once; counts, records, halo rows and normalisers exchanged GPU to GPU by
+    the kernels themselves) and the host-paced phases end in bit-identical particles, maps, counts and normalisers."""
+    grids, ps = scans(gpu, 7), poses(7, vy, vx)
+    out = []
+    for paced in (True, False):
+        bd, hist = run_banded(gpu, grids, ps, bands, device_paced=paced)
+        assert bd.device_paced == paced
+        out.append((hist,) + _snapshot(bd, bands))
+        if bands > 1:
+            lo, hi = bd.last_migration
+            assert sum(lo) + sum(hi) > 0
+        bd.close()
+    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
+    assert out[0][3] == out[1][3]
+    for r in range(bands):
+        for a, b in zip(out[0][1][r], out[1][1][r]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
+    assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))
+
+
+def test_device_paced_launch_estimates_do_not_matter(gpu, monkeypatch):
+    """The device-paced cycle sizes its launches from estimates (the counts live on the device) and the kernels loop: with
+    absurdly small estimates the result is the same bit for bit."""
+    grids, ps = scans(gpu, 6), poses(6, vy=5.0, vx=1.0)
+    out = []
+    for est in (None, "3000"):
+        if est:
+            monkeypatch.setenv("DOGM_B200_BAND_EST", est)
+        bd, hist = run_banded(gpu, grids, ps, 3, device_paced=True)
+        out.append((hist,) + _snapshot(bd, 3))
+        bd.close()
+    monkeypatch.delenv("DOGM_B200_BAND_EST", raising=False)
+    assert out[0][0] == out[1][0] and out[0][3] == out[1][3]
+    for r in range(3):
+        for a, b in zip(out[0][1][r], out[1][1][r]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
+    assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))
+
+
+def test_bands_on_two_gpus_equal_bands_on_one(gpu):
+    """Two bands on two GPUs (records, halo rows and normalisers cross NVLink: peer loads and stores from inside the kernels)
+    end in the same bits as the same two bands on one GPU."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    grids, ps = scans(gpu, 7), poses(7, vy=5.0, vx=1.0)
+    out = []
+    for devices in ([0, 1], [0, 0]):
+        bd, hist = run_banded(gpu, grids, ps, 2, device_paced=True, devices=devices)
+        assert bd.device_paced
+        out.append((hist,) + _snapshot(bd, 2))
+        bd.close()
+    assert out[0][0] == out[1][0]
+    assert out[0][3] == out[1][3]
+    for r in range(2):
         for a, b in zip(out[0][1][r], out[1][1][r]):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
     assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))

@@ -39,7 +39,8 @@ for R, method in runs:
     rows = None
     if row_load is not None and R > 1:
         rows = gpu.balanced_rows_by_phase(row_hist, R) if method == "phase" else gpu.balanced_rows(row_load, R)
-    bd = gpu.BandedDOGM(params, R, devices=list(range(R)), seed=123456, rows=rows, slack=2.5)
+    paced = {"host": False, "device": True}.get(os.environ.get("BAND_PACED", ""), None)
+    bd = gpu.BandedDOGM(params, R, devices=list(range(R)), seed=123456, rows=rows, slack=2.5, device_paced=paced)
     meas = []  # per band: its rows of every scan, resident on the band's GPU
     for r in range(R):
         gpu.set_device(r)
@@ -67,7 +68,7 @@ for R, method in runs:
         counts = cycle()
     t = (time.perf_counter() - t0) / K
     lo, hi = bd.last_migration
-    print(f"{name}: {R} band(s) on {R} GPU(s), edges by {method if R > 1 else '-'}, rows {bd.rows}: {1e3 * t:8.3f} ms/cycle, {1.0 / t:8.1f} cycles/s; particles per band {counts}, "
+    print(f"{name}: {R} band(s) on {R} GPU(s), {'device' if bd.device_paced else 'host'}-paced, edges by {method if R > 1 else '-'}, rows {bd.rows}: {1e3 * t:8.3f} ms/cycle, {1.0 / t:8.1f} cycles/s; particles per band {counts}, "
           f"migrated last cycle {sum(lo) + sum(hi)}; phases [predict, exchange, update, birth+cdf, resample] ms "
           f"{[round(v, 2) for v in bd.last_phase_ms]}; peer access {bd.peer_access}")
     if getattr(bd, "last_band_ms", None):
