@@ -268,6 +268,15 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     keep_first(alloc_zero((void**)&h->cell_prefix, C * sizeof(double)));
     keep_first(alloc_zero((void**)&h->blk_sum, (size_t)h->n_cell_blocks * sizeof(double)));
     keep_first(alloc_zero((void**)&h->blk_off, (size_t)h->n_cell_blocks * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->blk_age[0], (size_t)h->n_cell_blocks));
+    keep_first(alloc_zero((void**)&h->blk_age[1], (size_t)h->n_cell_blocks));
+    {
+        // the shortcut pays where the grid is much larger than what the sensor sees; below ~4e6 cells the cell kernel is bound
+        // by latency, not by its stores, and the bookkeeping costs more than the skipped blocks save (measured at 1.44e6 cells).
+        // DOGM_B200_NO_QUIET = 1 / 0 forces it off / on (A/B runs, tests)
+        const char* nq = getenv("DOGM_B200_NO_QUIET");
+        h->quiet_off = nq ? nq[0] == '1' : h->C < 4000000;
+    }
     keep_first(alloc_zero((void**)&h->grp_word, (size_t)h->n_blk_groups * sizeof(double)));
     keep_first(alloc_zero((void**)&h->grp_zero, ((size_t)h->n_blk_groups + 1) * sizeof(double)));
     for (int p = 0; p < kMaxPasses; p++)
@@ -389,6 +398,8 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->cell_prefix);
     cudaFree(h->blk_sum);
     cudaFree(h->blk_off);
+    cudaFree(h->blk_age[0]);
+    cudaFree(h->blk_age[1]);
     cudaFree(h->grp_word);
     cudaFree(h->grp_zero);
     for (int p = 0; p < kMaxPasses; p++)
@@ -906,6 +917,7 @@ extern "C" int dogm_set_grid_cells(dogm_handle* h, const dogm_grid_cell* cells, 
     if (!h || !cells)
         return DOGM_ERR_INVALID_ARGUMENT;
     h->dyn_list_valid = false;
+    DOGM_CHECK(cudaMemsetAsync(h->blk_age[0], 0, (size_t)h->n_cell_blocks, h->stream)); // (no block is known to be empty any more)
     DOGM_CHECK((cudaError_t)copy_in(h->grid, cells, (size_t)h->C * sizeof(dogm_grid_cell), on_device, h->stream));
     int e = run_extract_free_mass(h);
     if (e)
@@ -919,6 +931,7 @@ extern "C" int dogm_set_measurement_cells(dogm_handle* h, const dogm_meas_cell* 
     if (!h || !cells)
         return DOGM_ERR_INVALID_ARGUMENT;
     h->lazy_meas.pending = false;
+    DOGM_CHECK(cudaMemsetAsync(h->blk_age[0], 0, (size_t)h->n_cell_blocks, h->stream));
     DOGM_CHECK((cudaError_t)copy_in(h->meas, cells, (size_t)h->C * sizeof(dogm_meas_cell), on_device, h->stream));
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -355,6 +355,12 @@ struct dogm_handle
     double* blk_sum;   // born-mass sum per 256-cell block
     double* blk_off;   // exclusive prefix of blk_sum: inside the block's group of 256 (birth kernel) or complete (k_blocksum_scan)
     int n_cell_blocks;
+    // Shortcut of the cell kernel for blocks of 256 cells in which nothing happens (no particles, no measurement, no free mass
+    // left from the cycle before - most of a large grid): blk_age counts for how many cycles in a row a block's outputs have
+    // been the empty record (0, 1, 2 = "for at least two": both free-mass buffers, the grid cells, born masses and prefix of
+    // the block hold exactly what the kernel would write again).
+    uint8_t* blk_age[2]; // read (previous cycle) / written (this cycle), swapped per cell-kernel launch
+    bool quiet_off;       // the cell kernel runs without the shortcut (small grids; DOGM_B200_NO_QUIET)
     int n_blk_groups;  // groups of 256 blocks
     double* grp_word;  // [n_blk_groups] group sums published by the scanning CTAs of the birth kernel (parity words)
     double* grp_zero;  // [n_blk_groups + 1] zeros: the group offsets when blk_off holds complete offsets

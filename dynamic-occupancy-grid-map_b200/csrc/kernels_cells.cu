@@ -49,6 +49,9 @@ struct CellArgs
     const float4* geom;
     const float2* polar;
     int polar_K, polar_H;
+    // shortcut for blocks in which nothing happens (dogm_handle::blk_age): ages of the previous cycle (read) and of this one (written)
+    const uint8_t* age_prev;
+    uint8_t* age_next;
 };
 
 #ifndef DOGM_CELL_MINBLOCKS
@@ -57,7 +60,8 @@ struct CellArgs
 #ifndef DOGM_CELL_MINBLOCKS_LAZY
 #define DOGM_CELL_MINBLOCKS_LAZY 8
 #endif
-template <bool kLazyMeas>
+// kQuiet: with the shortcut for blocks in which nothing happens (large grids; on a small grid it only costs its bookkeeping)
+template <bool kLazyMeas, bool kQuiet>
 __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LAZY : DOGM_CELL_MINBLOCKS) k_cell(CellArgs a)
 {
     pdl_prologue(K_CELL * 2);
@@ -71,11 +75,14 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
     float rho_b = 0.0f;
     bool dyn_hit = false;
     dogm_dynamic_cell dyn_rec;
+    // all loads that do not depend on the cell being occupied go out together, ahead of the first store
+    float4 zq = make_float4(0.0f, 0.0f, 1.0f, 1.0f);
+    int start = -1;
+    float free_prev = 0.0f;
+    const int age = kQuiet ? a.age_prev[blockIdx.x] : 0;
     if (valid)
     {
-        // all loads that do not depend on the cell being occupied go out together, ahead of the first store
-        const int start = a.cell_start[c];
-        float4 zq;
+        start = a.cell_start[c];
         if constexpr (kLazyMeas)
             zq = meas_cell_from_polar(__ldcs(a.geom + c), a.polar, a.polar_K, a.polar_H);
         else
@@ -83,12 +90,10 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
         // ego-motion compensation of the grid (updatePose dogm.cu:175-193, moveMapKernel
         // ego_motion_compensation.cu:25-43): of all cell fields only free_mass survives into the next cycle,
         // so the shift is a shifted read of the previous free masses; vacated cells read 0 (dogm.cu:185)
-        float free_prev;
         if (a.shift_active)
         {
             const int x = c % a.gs, y = c / a.gs + a.row0;
             const int nx = x + a.x_move, ny = y + a.y_move;
-            free_prev = 0.0f;
             if (nx > 0 && nx < a.gs && ny > 0 && ny < a.gs)
             {
                 const int nl = ny - a.row0; // row inside this band
@@ -104,6 +109,24 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
         {
             free_prev = __ldg(a.free_cur + c);
         }
+    }
+    const bool z_none = zq.x == 0.0f && zq.y == 0.0f && zq.z == 1.0f && zq.w == 1.0f;
+    // a cell in which nothing happens: no particles, no measurement, no free mass left - its outputs are the empty record
+    const bool cell_idle = start < 0 && free_prev == 0.0f && z_none;
+    // Shortcut: the whole block has been like that for the last two cycles (both free-mass buffers, the grid cells, the born
+    // masses, the prefix and the handle's measurement copy already hold what would be written) and is again: nothing to
+    // compute, nothing to store.  (Most of a large grid lies outside the sensor's field of view.)
+    if (kQuiet && age >= 2) // (block-uniform)
+    {
+        if (__syncthreads_and(cell_idle))
+        {
+            if (threadIdx.x == 0)
+                a.age_next[blockIdx.x] = 2;
+            return;
+        }
+    }
+    if (valid)
+    {
         const bool occupied = start >= 0;
         int end = -1;
         CellSums cs;
@@ -237,6 +260,12 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
     const double incl = block_inclusive_scan_f64(valid ? (double)rho_b : 0.0, s_scan, &total);
     if (valid)
         a.prefix[c] = incl;
+    if (kQuiet)
+    {
+        const int idle = __syncthreads_and(cell_idle);
+        if (threadIdx.x == 0)
+            a.age_next[blockIdx.x] = idle ? (uint8_t)(age >= 1 ? 2 : 1) : (uint8_t)0;
+    }
     if (threadIdx.x == 0)
         a.blk_sum[blockIdx.x] = total;
 }
@@ -781,6 +810,13 @@ int run_occupancy_update(dogm_handle* h, float dt)
     a.geom = nullptr;
     a.polar = nullptr;
     a.polar_K = a.polar_H = 0;
+    a.age_prev = h->blk_age[0];
+    a.age_next = h->blk_age[1];
+    {
+        uint8_t* t = h->blk_age[0];
+        h->blk_age[0] = h->blk_age[1];
+        h->blk_age[1] = t;
+    }
     const bool lazy = h->lazy_meas.pending && !h->meas_src;
     if (lazy)
     {
@@ -795,10 +831,18 @@ int run_occupancy_update(dogm_handle* h, float dt)
     h->cell_kernel_done = false;
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
+        const bool quiet = !h->quiet_off;
         if (lazy)
-            launch_chained(h->stream, k_cell<true>, h->n_cell_blocks, kCellBlock, 0, a);
+        {
+            if (quiet)
+                launch_chained(h->stream, k_cell<true, true>, h->n_cell_blocks, kCellBlock, 0, a);
+            else
+                launch_chained(h->stream, k_cell<true, false>, h->n_cell_blocks, kCellBlock, 0, a);
+        }
+        else if (quiet)
+            launch_chained(h->stream, k_cell<false, true>, h->n_cell_blocks, kCellBlock, 0, a);
         else
-            launch_chained(h->stream, k_cell<false>, h->n_cell_blocks, kCellBlock, 0, a);
+            launch_chained(h->stream, k_cell<false, false>, h->n_cell_blocks, kCellBlock, 0, a);
     }
     h->shift_grid_pending = false;
     h->meas_src = nullptr;

@@ -840,13 +840,14 @@ __device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, con
     }
 }
 
+template <bool LOOP>
 __global__ void __launch_bounds__(kBlock, DOGM_SEGSUM_MINBLOCKS) k_segsum(const int2* __restrict__ spair, const PRec* __restrict__ rec, int n,
                                                    int* cell_start, int* cell_end, CellSums* sums, SegPiece* lead,
                                                    SegPiece* trail, int* flags, float* __restrict__ sw, const int* n_dev)
 {
     pdl_prologue(K_SEGSUM * 2);
     const int chunk0 = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    if (!n_dev)
+    if (!LOOP)
     {
         segsum_chunk(spair, rec, n, cell_start, cell_end, sums, lead, trail, flags, sw, chunk0);
         return;
@@ -1693,10 +1694,11 @@ __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int 
     PHASE_STAMP(1, blockIdx.x, 6, 0);
 }
 
+template <bool DEV>
 __global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(const ResampleArgs a_in)
 {
     pdl_prologue(K_RESAMPLE * 2);
-    if (!a_in.cnt)
+    if (!DEV)
     { // the CTAs at the end of the CDF (birth particles: several window slides) take longest: they go first
         resample_block(a_in, (int)(gridDim.x - 1 - blockIdx.x));
         return;
@@ -1907,8 +1909,12 @@ int run_assignment(dogm_handle* h)
     // per-cell sums + start/end over the sorted order
     {
         LaunchScope ls(h, K_SEGSUM, 44.0 * N);
-        launch_chained(h->stream, k_segsum, div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, 
-            h->spair, h->rec, N, h->cell_start, h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw, n_dev);
+        if (n_dev)
+            launch_chained(h->stream, k_segsum<true>, div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->spair, h->rec, N, h->cell_start,
+                           h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw, n_dev);
+        else
+            launch_chained(h->stream, k_segsum<false>, div_up(h->n_chunks, kWarpsPerBlock), kBlock, 0, h->spair, h->rec, N, h->cell_start,
+                           h->cell_end, h->cell_sums, h->seg_lead, h->seg_trail, h->seg_flags, h->sw, n_dev);
     }
     {
         LaunchScope ls(h, K_SEGFIX, 0.0);
@@ -2083,12 +2089,12 @@ int run_resample_gather(dogm_handle* h)
     { // device-paced band cycle: the grid is sized for an estimate, the kernel reads what it really has to do and loops
         const int est = h->band.est_out > 0 ? h->band.est_out : 1;
         LaunchScope ls(h, K_RESAMPLE, 69.0 * est);
-        launch_chained(h->stream, k_resample, div_up(est, kResOutputs), kBlock, 0, a);
+        launch_chained(h->stream, k_resample<true>, div_up(est, kResOutputs), kBlock, 0, a);
     }
     else if (n_out > 0 && n > 0)
     {
         LaunchScope ls(h, K_RESAMPLE, 69.0 * n_out);
-        launch_chained(h->stream, k_resample, div_up(n_out, kResOutputs), kBlock, 0, a);
+        launch_chained(h->stream, k_resample<false>, div_up(n_out, kResOutputs), kBlock, 0, a);
     }
     // publish (dogm.cu:128): the next population was written straight into particle_array
     h->pa_current = true;

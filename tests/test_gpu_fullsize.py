@@ -161,3 +161,41 @@ def test_no_birth_particles_and_single_particle(gpu, orc):
             assert np.array_equal(d.get_particles().grid_cell_idx, o.particles.grid_cell_idx)
             assert np.array_equal(d.get_resampled_indices(), o.resampled_idx)
             assert np.allclose(d.get_grid_cells()["occ_mass"], o.grid_cells["occ_mass"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("vx,vy,device_meas", [(0.0, 4.0, False), (3.0, -2.0, True), (0.0, 0.0, True)])
+def test_quiet_block_shortcut_is_bit_identical_to_the_dense_path(gpu, monkeypatch, vx, vy, device_meas):
+    """The cell kernel skips blocks of 256 cells in which nothing happens for the third cycle in a row (no particles, no
+    measurement, no free mass left; most of the grid outside the sensor's field of view).  With the shortcut switched off
+    (DOGM_B200_NO_QUIET=1) every cell is computed and stored every cycle: grid cells, measurement copy, born masses, particles
+    and birth particles must be the same bits, with ego-motion shifts in any direction and both ways of passing the grid."""
+    size, res, n, b = 102.4, 0.2, 300_000, 30_000  # 512 x 512 cells
+    rng = np.random.default_rng(5)
+    scans = [scene_meas(gpu, rng, 200, size, res) for _ in range(3)]
+    out = []
+    for off in ("1", "0"):
+        monkeypatch.setenv("DOGM_B200_NO_QUIET", off)
+        d = gpu.DOGM(make_params(gpu, size, res, n, b))
+        d.set_options(seed=99, resample_mode=gpu.RESAMPLE_SYSTEMATIC, noise_mode=gpu.NOISE_PHILOX)
+        dev = gpu.device_alloc(scans[0].nbytes)
+        snaps = []
+        for c in range(9):
+            m = scans[c % 3]
+            if device_meas:
+                gpu.memcpy_h2d(dev, m)
+                d.update_grid(dev, vx * 0.1 * (c + 1), vy * 0.1 * (c + 1), 0.0, 0.1, device=True)
+            else:
+                d.update_grid(m, vx * 0.1 * (c + 1), vy * 0.1 * (c + 1), 0.0, 0.1, device=False)
+            if c in (3, 8):
+                snaps.append((d.get_grid_cells().copy(), d.get_measurement_cells().copy(), d.get_born_masses().copy(),
+                              d.get_particles().block.copy(), d.get_birth_particles().block.copy()))
+        gpu.device_free(dev)
+        d.close()
+        out.append(snaps)
+    monkeypatch.delenv("DOGM_B200_NO_QUIET", raising=False)
+    for dense, quick in zip(*out):
+        for x, y in zip(dense, quick):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    # the test is not vacuous: a large part of the grid sees no measurement at all
+    cells = out[0][-1][0]
+    assert np.mean((cells["occ_mass"] == 0) & (cells["free_mass"] == 0)) > 0.1
