@@ -224,6 +224,8 @@ _SYMBOLS = [
     ("dogm_band_group_set_mode", C.c_int, [_P, C.c_int]),
     ("dogm_band_group_get_mode", C.c_int, [_P]),
     ("dogm_band_mailbox", C.c_void_p, [_P]),
+    ("dogm_band_set_profile", C.c_int, [_P, C.c_int]),
+    ("dogm_band_stage_times", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("dogm_band_link", C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("dogm_band_cycle_enqueue", C.c_int, [_P, C.c_int, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
     ("dogm_band_cycle_finish", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -928,6 +930,12 @@ class BandedDOGM:
         self.last_counts = counts
         self.last_totals = {"born": total_b, "weight": total_w}
         return counts
+
+    def set_profile(self, enable: bool):
+        """device-paced cycles: record events at the stage boundaries of every band (last_band_ms then holds device times)"""
+        for r in range(self.R):
+            self._on(r)
+            _check(self._lib.dogm_band_set_profile(self.h[r], 1 if enable else 0), "dogm_band_set_profile")
 
     def band_handle(self, r):
         return self.h[r]

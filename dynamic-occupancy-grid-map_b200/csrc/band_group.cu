@@ -144,7 +144,6 @@ void run_cycle(dogm_band_group* g, int r)
                     g->barrier->wait();
             }
         }
-        g->band_ms[(size_t)r * 5 + 0] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         int n_out = 0, a = 0, b = 0;
         double born = 0.0, weight = 0.0;
         const int e2 = dogm_band_cycle_finish(h, &n_out, &a, &b, &born, &weight); // (also drains the stream after a failed enqueue)
@@ -157,9 +156,15 @@ void run_cycle(dogm_band_group* g, int r)
             g->born_total = born;
             g->weight_total = weight;
         }
-        for (int k = 1; k < 5; k++)
-            g->band_ms[(size_t)r * 5 + k] = 0.0f;
-        g->band_ms[(size_t)r * 5 + 4] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        { // device time of the four stages when the bands are profiled (dogm_band_set_profile), zeros otherwise
+            float st[4] = {0, 0, 0, 0};
+            dogm_band_stage_times(h, st);
+            g->band_ms[(size_t)r * 5 + 0] = st[0];
+            g->band_ms[(size_t)r * 5 + 1] = 0.0f;
+            g->band_ms[(size_t)r * 5 + 2] = st[1];
+            g->band_ms[(size_t)r * 5 + 3] = st[2];
+            g->band_ms[(size_t)r * 5 + 4] = st[3];
+        }
         for (int k = 1; k <= 5; k++)
             mark(k);
         return;

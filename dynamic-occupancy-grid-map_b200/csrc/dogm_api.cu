@@ -169,6 +169,11 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->band.dev_cnt = nullptr;
     h->band.seq = 0;
     h->band.n_pred = 0;
+    h->band.profile = false;
+    for (int k = 0; k < 5; k++)
+        h->band.stage_ev[k] = nullptr;
+    for (int k = 0; k < 4; k++)
+        h->band.stage_ms[k] = 0.0f;
     h->band.est_recv = 65536;
     h->band.est_birth = band ? band->birth_capacity : 0;
     h->band.est_out = band ? band->particle_capacity : 0;
@@ -294,7 +299,7 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     keep_first(alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
     keep_first(alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int)));
     keep_first(alloc_zero((void**)&h->cdf, (N + B) * sizeof(double)));
-    keep_first(alloc_zero((void**)&h->tile_sum, (size_t)h->n_cdf_tiles * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->tile_sum, ((size_t)h->n_cdf_tiles + 3) * sizeof(double)));
     keep_first(alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 3) * sizeof(double)));
     keep_first(alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int)));
     if (!e)
@@ -431,6 +436,9 @@ extern "C" void dogm_destroy(dogm_handle* h)
     if (h->band.pin)
         cudaFreeHost(h->band.pin);
     cudaFree(h->band.cnt);
+    for (int k = 0; k < 5; k++)
+        if (h->band.stage_ev[k])
+            cudaEventDestroy(h->band.stage_ev[k]);
     cudaFree(h->band.mail);
     if (h->band.cnt_host)
         cudaFreeHost(h->band.cnt_host);
@@ -1422,8 +1430,13 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
     const int R = h->band.group_size, me = h->band.group_rank;
     if ((me > 0 && !outbox_of_lower_neighbour) || (me + 1 < R && !outbox_of_upper_neighbour))
         return DOGM_ERR_INVALID_ARGUMENT;
+    auto stamp = [&](int k) { // stage boundaries on the band's stream (profiling only: an event node interrupts the launch chain)
+        if (h->band.profile)
+            cudaEventRecord(h->band.stage_ev[k], h->stream);
+    };
     if (stages & DOGM_BAND_STAGE_PREDICT)
     { // prediction, the records that leave, their counts to the neighbours
+        stamp(0);
         h->band.seq++;
         update_pose(h, new_x, new_y, new_yaw);
         h->band.n_pred = h->N;
@@ -1434,6 +1447,7 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
             return e;
         if ((e = run_band_publish_sent(h)))
             return e;
+        stamp(1);
     }
     if (stages & DOGM_BAND_STAGE_UPDATE)
     { // the neighbours' counts and records; sort, per-cell sums, occupancy update; this band's born mass to all bands
@@ -1477,6 +1491,7 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
         h->band.dev_cnt = nullptr;
         if (e)
             return e; // (the other bands run into the bounded waits of their collectors)
+        stamp(2);
     }
     if (stages & DOGM_BAND_STAGE_BIRTH)
     { // born mass of the whole grid; birth particles; joint CDF; this band's joint weight to all bands
@@ -1488,6 +1503,7 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
         h->band.dev_cnt = nullptr;
         if (e)
             return e;
+        stamp(3);
     }
     if (stages & DOGM_BAND_STAGE_RESAMPLE)
     { // joint weight of the whole grid; this band's part of the draw
@@ -1497,9 +1513,30 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
         h->band.dev_cnt = nullptr;
         if (e)
             return e;
+        stamp(4);
         DOGM_CHECK(cudaMemcpyAsync(h->band.cnt_host, h->band.cnt, sizeof(BandCounts), cudaMemcpyDeviceToHost, h->stream));
         h->cycle++;
     }
+    return 0;
+}
+
+extern "C" int dogm_band_set_profile(dogm_handle* h, int enable)
+{
+    if (!h || !h->band.enabled)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (enable && !h->band.stage_ev[0])
+        for (int k = 0; k < 5; k++)
+            DOGM_CHECK(cudaEventCreate(&h->band.stage_ev[k]));
+    h->band.profile = enable != 0;
+    return 0;
+}
+
+extern "C" int dogm_band_stage_times(const dogm_handle* h, float* out_ms4)
+{
+    if (!h || !h->band.enabled || !out_ms4)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < 4; k++)
+        out_ms4[k] = h->band.stage_ms[k];
     return 0;
 }
 
@@ -1510,6 +1547,12 @@ extern "C" int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* s
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     const BandCounts c = *h->band.cnt_host;
+    for (int k = 0; k < 4; k++)
+    {
+        h->band.stage_ms[k] = 0.0f;
+        if (h->band.profile)
+            cudaEventElapsedTime(&h->band.stage_ms[k], h->band.stage_ev[k], h->band.stage_ev[k + 1]);
+    }
     set_particle_counts(h, c.n_out, c.B);
     if (h->band.est_forced <= 0)
     { // launch sizes of the next cycle: what this one needed plus a margin

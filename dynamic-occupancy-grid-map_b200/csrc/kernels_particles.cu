@@ -54,6 +54,7 @@ struct PredictArgs
     uint32_t* hist; // [tiles][bins] pass-0 histogram
     int bins;
     uint32_t mask;
+    double* leave_cnt[2]; // band mode: per tile, the particles leaving through the lower / upper edge (input of the outbox scan)
 };
 
 __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t slot, uint32_t cycle, float sigma_pos,
@@ -75,8 +76,11 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
     pdl_prologue(K_PREDICT * 2);
     extern __shared__ uint32_t s_hist[];
+    __shared__ uint32_t s_leave[2];
     for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         s_hist[b] = 0u;
+    if (threadIdx.x < 2)
+        s_leave[threadIdx.x] = 0u;
     __syncthreads();
 
     const float4* __restrict__ state = a.state;
@@ -132,7 +136,11 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
                 py = py < 0 ? 0 : a.rows - 1;
             }
             if (a.mig)
+            {
                 a.mig[i] = leaves;
+                if (leaves)
+                    atomicAdd(&s_leave[leaves - 1], 1u); // (few particles cross an edge: a handful of atomics per tile)
+            }
             const int cell = px + a.gs * py;
             float4* o = reinterpret_cast<float4*>(out + i);
             o[0] = rec_lo(x, y, cell, as);
@@ -145,6 +153,8 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
     uint32_t* row = a.hist + (size_t)blockIdx.x * a.bins;
     for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         row[b] = s_hist[b];
+    if (a.mig && threadIdx.x < 2)
+        a.leave_cnt[threadIdx.x][blockIdx.x] = (double)s_leave[threadIdx.x];
 }
 
 // SoA -> records without prediction (+ pass-0 histogram): the entry into the sort when the keys did not come from
@@ -1821,6 +1831,8 @@ int run_predict(dogm_handle* h, float dt)
     a.hist = h->hist[0];
     a.bins = h->digit_bins[0];
     a.mask = (uint32_t)(h->digit_bins[0] - 1);
+    a.leave_cnt[0] = h->band.out_cnt[0];
+    a.leave_cnt[1] = h->band.out_cnt[1];
     const size_t smem = (size_t)a.bins * sizeof(uint32_t);
     {
         LaunchScope ls(h, K_PREDICT, 57.0 * h->N);
@@ -2029,14 +2041,17 @@ int run_cdf(dogm_handle* h)
         // (device-paced cycle: n_cdf_tiles is an estimate, the words are cleared for the band's capacity)
         const size_t clear_tiles = ch.cnt ? (size_t)div_up((long long)h->band.n_cap + h->band.b_cap > 0 ? (long long)h->band.n_cap + h->band.b_cap : 1, kCdfTile)
                                           : (size_t)h->n_cdf_tiles;
-        cudaMemsetAsync(h->tile_sum, 0, clear_tiles * sizeof(double), h->stream);
-        cudaMemsetAsync(h->tile_off, 0, (clear_tiles + 3) * sizeof(double), h->stream);
         ch.epoch = 1u;
         if (ch.cnt)
-        { // the number of tickets a launch draws is not known to the host either: the ticket starts from 0 every cycle
-            cudaMemsetAsync(h->chain_flags, 0, sizeof(uint32_t), h->stream);
+        { // (device-paced cycle: cleared by k_band_collect_born, which also resets the ticket - the number of tickets a launch
+          //  draws is not known to the host either, so the ticket starts from 0 every cycle)
             h->chain_ticket_base = 0;
             ch.ticket_base = 0;
+        }
+        else
+        {
+            cudaMemsetAsync(h->tile_sum, 0, clear_tiles * sizeof(double), h->stream);
+            cudaMemsetAsync(h->tile_off, 0, (clear_tiles + 3) * sizeof(double), h->stream);
         }
     }
     ch.total_word = h->tile_off + (h->n_cdf_tiles / kChainGroup + 1);
@@ -2117,7 +2132,7 @@ int run_resampling(dogm_handle* h)
 // band mode: the particles that arrived from the neighbours (records with global coordinates in the two inboxes) become
 // the tail of this cycle's record list
 // Band mode, outbox: the slots k_predict flagged are compacted into the two send boxes in slot order.
-//   k_outbox_count: per tile of 4096 slots the number of particles leaving through either edge (as doubles: the tile
+//   k_predict     : per tile of 4096 slots the number of particles leaving through either edge (as doubles: the tile
 //                   offsets come from the same single-CTA scan the born masses use)
 //   k_outbox_write: rank inside the tile (block scan in slot order) + tile offset -> position in the box
 constexpr int kOutboxPer = kTileItems / kBlock; // 16 consecutive slots per thread
@@ -2144,26 +2159,54 @@ __device__ __forceinline__ unsigned long long outbox_thread_counts(const uint8_t
     return c; // low word: lower edge, high word: upper edge
 }
 
-__global__ void __launch_bounds__(kBlock) k_outbox_count(const uint8_t* __restrict__ mig, int n, double* cnt_lo, double* cnt_hi)
+// exclusive scans of the two per-tile count arrays (lower / upper edge) in one launch: CTA 0 and CTA 1, same code as k_blocksum_scan
+__global__ void __launch_bounds__(1024) k_outbox_scan(const double* __restrict__ in0, const double* __restrict__ in1, double* out0,
+                                                      double* out1, int n, double* totals)
 {
-    pdl_prologue(K_MISC * 2);
-    __shared__ unsigned long long s_w[kWarpsPerBlock];
-    uint8_t f[kOutboxPer];
-    unsigned long long c = outbox_thread_counts(mig, n, blockIdx.x * kTileItems + threadIdx.x * kOutboxPer, f);
+    pdl_prologue(K_BLOCKSUM_SCAN * 2 + 1);
+    const double* __restrict__ in = blockIdx.x ? in1 : in0;
+    double* __restrict__ out_excl = blockIdx.x ? out1 : out0;
+    __shared__ double s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + 1023) / 1024;
+    const int b0 = min((int)threadIdx.x * per, n), b1 = min(b0 + per, n);
+    double local = 0.0;
+    for (int b = b0; b < b1; b++)
+        local += in[b];
+    double incl = local;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1)
-        c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0)
-        s_w[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0)
+    for (int d = 1; d < 32; d <<= 1)
     {
-        unsigned long long t = 0;
-        for (int w = 0; w < kWarpsPerBlock; w++)
-            t += s_w[w];
-        cnt_lo[blockIdx.x] = (double)(uint32_t)t;
-        cnt_hi[blockIdx.x] = (double)(uint32_t)(t >> 32);
+        const double t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
     }
+    if (lane == 31)
+        s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        double wv = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const double t = __shfl_up_sync(0xffffffffu, wv, d);
+            if (lane >= d)
+                wv += t;
+        }
+        s_warp[lane] = wv;
+    }
+    __syncthreads();
+    const double warp_off = warp > 0 ? s_warp[warp - 1] : 0.0;
+    double excl = warp_off + (incl - local);
+    for (int b = b0; b < b1; b++)
+    {
+        const double v = in[b];
+        out_excl[b] = excl;
+        excl += v;
+    }
+    if (threadIdx.x == 1023)
+        totals[blockIdx.x] = s_warp[31];
 }
 
 __global__ void __launch_bounds__(kBlock) k_outbox_write(const uint8_t* __restrict__ mig, const PRec* __restrict__ rec, int n,
@@ -2471,11 +2514,25 @@ __device__ __forceinline__ int band_collect(const BandLink& l, int which, double
 }
 
 // after the occupancy update: born mass of the whole grid, this band's birth slots
-__global__ void __launch_bounds__(32) k_band_collect_born(BandLink l, DeviceScalars* scal, int b_glob, int b_cap)
+// (the other warps clear the words of the CDF chain meanwhile: the number of its tiles changes from cycle to cycle, see run_cdf)
+__global__ void __launch_bounds__(kBlock) k_band_collect_born(BandLink l, DeviceScalars* scal, int b_glob, int b_cap, double* clear_a,
+                                                              double* clear_b, int clear_n, uint32_t* ticket)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    double before, total;
-    int err = band_collect(l, 0, &before, &total);
+    if (threadIdx.x >= 32)
+    {
+        for (int k = threadIdx.x - 32; k < clear_n; k += kBlock - 32)
+        {
+            clear_a[k] = 0.0;
+            clear_b[k] = 0.0;
+        }
+        if (threadIdx.x == 32)
+            *ticket = 0u;
+    }
+    double before = 0.0, total = 0.0;
+    int err = 0;
+    if (threadIdx.x < 32)
+        err = band_collect(l, 0, &before, &total);
     if (threadIdx.x == 0)
     {
         const double local = l.cnt->born_local;
@@ -2495,6 +2552,7 @@ __global__ void __launch_bounds__(32) k_band_collect_born(BandLink l, DeviceScal
             l.cnt->err |= err;
         scal->born_total = total;
     }
+    __syncthreads();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
@@ -2576,7 +2634,10 @@ int run_band_publish_share(dogm_handle* h, int which)
 int run_band_collect_born(dogm_handle* h)
 {
     LaunchScope ls(h, K_MISC, 0.0);
-    launch_chained(h->stream, k_band_collect_born, 1, 32, 0, make_link(h), h->scal, h->band.b_glob, h->band.b_cap);
+    // the CDF chain's words for the band's capacity (+ 3 as in run_cdf), cleared here instead of by three memset nodes
+    const int clear_n = div_up((long long)h->band.n_cap + h->band.b_cap > 0 ? (long long)h->band.n_cap + h->band.b_cap : 1, kCdfTile) + 3;
+    launch_chained(h->stream, k_band_collect_born, 1, kBlock, 0, make_link(h), h->scal, h->band.b_glob, h->band.b_cap, h->tile_sum,
+                   h->tile_off, clear_n, h->chain_flags);
     return (int)cudaGetLastError();
 }
 
@@ -2592,13 +2653,13 @@ int run_band_outbox(dogm_handle* h)
 {
     const int n = h->N;
     const int tiles = div_up(n > 0 ? n : 1, kTileItems);
+    // (the per-tile counts of the leaving particles were written by k_predict)
     {
-        LaunchScope ls(h, K_MISC, 1.0 * n);
-        launch_chained(h->stream, k_outbox_count, tiles, kBlock, 0, h->band.mig, n, h->band.out_cnt[0], h->band.out_cnt[1]);
+        LaunchScope ls(h, K_BLOCKSUM_SCAN, 32.0 * tiles);
+        launch_chained(h->stream, k_outbox_scan, 2, 1024, 0, (const double*)h->band.out_cnt[0], (const double*)h->band.out_cnt[1],
+                       h->band.out_off[0], h->band.out_off[1], tiles, h->band.out_total);
     }
     int e = (int)cudaGetLastError();
-    e = e ? e : run_blocksum_scan(h, h->band.out_cnt[0], h->band.out_off[0], tiles, h->band.out_total);
-    e = e ? e : run_blocksum_scan(h, h->band.out_cnt[1], h->band.out_off[1], tiles, h->band.out_total + 1);
     if (e)
         return e;
     {

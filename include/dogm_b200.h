@@ -264,6 +264,12 @@ int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_meas_cell* me
                             const void* edge_rows_of_upper_neighbour);
 int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* sent_lo, int* sent_hi, double* born_total,
                            double* weight_total);
+/* Profiling of the device-paced cycle: with enable != 0 events are recorded on the band's stream at the four stage boundaries
+ * (they interrupt the launch chain, so a profiled cycle is a little slower); dogm_band_stage_times returns the device time
+ * of the stages of the last profiled cycle: predict + outbox, update (incl. the wait for the neighbours), birth + CDF (incl.
+ * the wait for the born masses), resample (incl. the wait for the joint weights). */
+int dogm_band_set_profile(dogm_handle* h, int enable);
+int dogm_band_stage_times(const dogm_handle* h, float* out_ms4);
 
 /* out_ms[band * 5 + phase]: what every band itself spent in the phases of the last cycle (host wall clock, without the waiting
  * at the barriers) - the input for placing the band edges */

@@ -3,7 +3,7 @@
 STEPS=${AB_STEPS:-100}
 for v in "$@"; do
   if [ "$v" = "-" ]; then unset DOGM_B200_LIB; else export DOGM_B200_LIB=build_ab/lib_$v.so; fi
-  timeout 300 python bench.py --steps $STEPS --warmup 10 --no-cpu-baseline ${AB_ARGS} 2>gpurun_out/ab_$v.err | tail -1 > gpurun_out/ab_$v.json
+  timeout 300 python bench.py --steps $STEPS --warmup 10 --no-cpu-baseline --no-band-scaling ${AB_ARGS} 2>gpurun_out/ab_$v.err | tail -1 > gpurun_out/ab_$v.json
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_$v.json"))

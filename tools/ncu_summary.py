@@ -1,7 +1,8 @@
 """Turns an `ncu --set full` report into the small, committed summaries under profiles/:
    <out>_kernels.csv  one line per profiled launch: duration, DRAM bytes, throughput %, occupancy, IPC, top stalls
-   traffic.json       dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel (read by bench.py -> roofline.traffic)
-Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01"""
+   traffic.json       {config: {kernel: {dram_bytes per launch, dram_pct, duration_us, launches_per_cycle}}} (read by bench.py ->
+                      roofline.traffic / cycle_dram / per_kernel_dram_pct; other configurations' entries are kept)
+Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r02 [config=nuss] [cycles profiled=2]"""
 import csv
 import io
 import json
@@ -13,6 +14,8 @@ import sys
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
+    config = sys.argv[3] if len(sys.argv) > 3 else "nuss"
+    cycles = float(sys.argv[4]) if len(sys.argv) > 4 else 2.0
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -52,12 +55,14 @@ def main():
             f"{int(num(r, 'smsp__inst_executed.sum'))}",
             " ".join(f"{n}={v:.1f}" for v, n in stalls),
         ])
-        a = agg.setdefault(short, {"launches": 0, "bytes": 0.0, "us": 0.0})
+        a = agg.setdefault(short, {"launches": 0, "bytes": 0.0, "us": 0.0, "pct": 0.0})
         a["launches"] += 1
         a["bytes"] += rd + wr
         a["us"] += dur
+        a["pct"] += num(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')
     for k, a in agg.items():
-        traffic[k] = a["bytes"] / a["launches"]
+        traffic[k] = {"dram_bytes": a["bytes"] / a["launches"], "dram_pct": round(a["pct"] / a["launches"], 1),
+                      "duration_us": round(a["us"] / a["launches"], 2), "launches_per_cycle": a["launches"] / cycles}
     os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
     with open(out + "_kernels.csv", "w", newline="") as f:
         w = csv.writer(f)
@@ -71,7 +76,16 @@ def main():
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
             w.writerow([k, a["launches"], f"{a['us']:.2f}", f"{a['us'] / total:.3f}", f"{a['bytes'] / a['launches']:.0f}"])
     tpath = os.path.join(os.path.dirname(out) or ".", "traffic.json")
-    json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
+    allcfg = {}
+    if os.path.exists(tpath):
+        try:
+            allcfg = json.load(open(tpath))
+            if allcfg and not all(isinstance(v, dict) and all(isinstance(x, dict) for x in v.values()) for v in allcfg.values()):
+                allcfg = {}  # the round-1 flat format
+        except Exception:
+            allcfg = {}
+    allcfg[config] = traffic
+    json.dump(allcfg, open(tpath, "w"), indent=1, sort_keys=True)
     print("wrote", out + "_kernels.csv", out + "_shares.csv", tpath)
 
 
