@@ -290,10 +290,52 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
         h->bin_base[p] = nullptr;
         h->scan_epoch[p] = 0;
     }
+    // bucket sort: when the grouping table [tiles][buckets] stays small (no bands: their particle counts change per cycle)
+    h->hist0_bucket = false;
+    h->bucket.enabled = false;
+    h->bucket.samples_valid = false;
+    h->bucket.bins = 0;
+    h->bucket.smp_raw = nullptr;
+    h->bucket.bkt = nullptr;
+    h->bucket.org = nullptr;
+    h->bucket.plan_key = h->bucket.plan_slot = h->bucket.plan_base = h->bucket.plan_pos = nullptr;
+    {
+        // one splitter per 2048 slots while that gives at most 1024 of them (buckets of ~2048 pairs: after the merge of the
+        // population's two sorted runs hardly any bucket exceeds the 4096 pairs the one-pass path of k_bucket_sort takes)
+        h->bucket.stride_shift = h->N <= 1024 * 2048 ? 11 : 12;
+        h->bucket.n_spl = (int)(((long long)h->N + (1ll << h->bucket.stride_shift) - 1) >> h->bucket.stride_shift);
+        if (h->bucket.n_spl < 1)
+            h->bucket.n_spl = 1;
+        const long long nb = (long long)h->bucket.n_spl + ((long long)h->C + 2047) / 2048 + 1;
+        const long long bins = (nb + 31) / 32 * 32;
+        // Off by default: measured at the headline size the three steps (plan 4 us, bucket numbers in the prediction +17 us,
+        // grouping pass 15 us, per-bucket sort ~50 us) lose against the two radix passes (50 us) - see DESIGN.md, negative results.
+        // DOGM_B200_SORT=bucket switches it on (tests run one parity case through it).
+        const char* mode = getenv("DOGM_B200_SORT");
+        const bool want = mode && !strcmp(mode, "bucket");
+        if (want && !band && h->N > 0 && h->tiles <= 1024 && bins <= (1 << kMaxDigitBits))
+        {
+            h->bucket.enabled = true;
+            h->bucket.bins = (int)bins;
+        }
+    }
     for (int p = 0; p < h->passes; p++)
     {
-        keep_first(alloc_zero((void**)&h->hist[p], (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t)));
-        keep_first(alloc_zero((void**)&h->bin_base[p], (size_t)h->digit_bins[p] * sizeof(uint32_t)));
+        size_t bins = (size_t)h->digit_bins[p];
+        if (p == 0 && h->bucket.enabled && (size_t)h->bucket.bins > bins)
+            bins = (size_t)h->bucket.bins;
+        keep_first(alloc_zero((void**)&h->hist[p], (size_t)h->tiles * bins * sizeof(uint32_t)));
+        keep_first(alloc_zero((void**)&h->bin_base[p], bins * sizeof(uint32_t)));
+    }
+    if (h->bucket.enabled)
+    {
+        keep_first(alloc_zero((void**)&h->bucket.smp_raw, (size_t)h->bucket.n_spl * sizeof(int)));
+        keep_first(alloc_zero((void**)&h->bucket.plan_key, (size_t)h->bucket.n_spl * sizeof(int)));
+        keep_first(alloc_zero((void**)&h->bucket.plan_slot, (size_t)h->bucket.n_spl * sizeof(int)));
+        keep_first(alloc_zero((void**)&h->bucket.plan_base, (size_t)h->bucket.n_spl * sizeof(int)));
+        keep_first(alloc_zero((void**)&h->bucket.plan_pos, (size_t)h->bucket.n_spl * sizeof(int)));
+        keep_first(alloc_zero((void**)&h->bucket.bkt, (N ? N : 1) * sizeof(uint16_t)));
+        keep_first(alloc_zero((void**)&h->bucket.org, (size_t)h->bucket.bins * sizeof(int)));
     }
     keep_first(alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
     keep_first(alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
@@ -412,6 +454,13 @@ extern "C" void dogm_destroy(dogm_handle* h)
         cudaFree(h->hist[p]);
         cudaFree(h->bin_base[p]);
     }
+    cudaFree(h->bucket.smp_raw);
+    cudaFree(h->bucket.plan_key);
+    cudaFree(h->bucket.plan_slot);
+    cudaFree(h->bucket.plan_base);
+    cudaFree(h->bucket.plan_pos);
+    cudaFree(h->bucket.bkt);
+    cudaFree(h->bucket.org);
     cudaFree(h->seg_lead);
     cudaFree(h->seg_trail);
     cudaFree(h->seg_flags);
@@ -904,6 +953,7 @@ extern "C" int dogm_set_particles(dogm_handle* h, const void* block, int on_devi
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK((cudaError_t)copy_in(h->pa.block, block, DOGM_PARTICLE_BLOCK_BYTES(h->N), on_device, h->stream));
     h->hist0_valid = false;
+    h->bucket.samples_valid = false;
     h->pa_current = true;
     h->rec_valid = false;
     h->sorted_valid = false;
@@ -1641,6 +1691,21 @@ extern "C" int dogm_debug_read(dogm_handle* h, const char* name, void* out_host,
     {
         src = h->res_start;
         have = (size_t)div_up(h->N > 0 ? h->N : 1, kBlock) * sizeof(int);
+    }
+    else if (!strcmp(name, "bucket_start") && h->bucket.enabled)
+    { // first position of every bucket in the grouping pass of the last assignment
+        src = h->hist[0];
+        have = (size_t)h->bucket.bins * sizeof(uint32_t);
+    }
+    else if (!strcmp(name, "bucket_org") && h->bucket.enabled)
+    {
+        src = h->bucket.org;
+        have = (size_t)h->bucket.bins * sizeof(int);
+    }
+    else if (!strcmp(name, "bucket_samples") && h->bucket.enabled)
+    {
+        src = h->bucket.smp_raw;
+        have = (size_t)h->bucket.n_spl * sizeof(int);
     }
     else if (!strcmp(name, "weight_total"))
     {

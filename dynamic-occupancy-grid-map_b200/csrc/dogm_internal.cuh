@@ -378,6 +378,21 @@ struct dogm_handle
     uint32_t scan_epoch[dogm_b200::kMaxPasses];
     int tiles;
     bool hist0_valid; // pass-0 tile histograms were produced by the prediction kernel for the current keys
+    bool hist0_bucket; // ... and they are histograms over the buckets of the bucket sort (not over the first radix digit)
+    // Bucket sort (kernels_particles.cu, "Bucket sort"): the population enters a cycle in cell order, so the cells of every
+    // 4096th particle are splitters for the new keys; grouping pass by bucket + one counting sort per bucket replace the radix
+    // passes.  Used when the keys come from the prediction kernel of a handle without bands and the tables stay small.
+    struct
+    {
+        bool enabled;
+        bool samples_valid; // smp_raw was written by the last resampling (else k_sample_keys reads the particle block)
+        int bins;           // buckets the tables are sized for (multiple of 32)
+        int n_spl, stride_shift; // one splitter sample per (1 << stride_shift) slots
+        int* smp_raw;       // [n_spl]
+        uint16_t* bkt;      // [N] bucket number per slot
+        int* org;           // [bins] first cell of every bucket
+        int *plan_key, *plan_slot, *plan_base, *plan_pos; // [n_spl] the cycle's splitters (k_bucket_plan)
+    } bucket;
 
     // segmented reduction
     int n_chunks;

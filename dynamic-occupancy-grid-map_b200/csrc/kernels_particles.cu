@@ -55,7 +55,234 @@ struct PredictArgs
     int bins;
     uint32_t mask;
     double* leave_cnt[2]; // band mode: per tile, the particles leaving through the lower / upper edge (input of the outbox scan)
+    // bucket sort (BUCKET variant): bucket number per particle, tile histogram over the buckets
+    uint16_t* bkt_out;  // [n] bucket number per slot
+    const int* plan_key; // the cycle's splitters (BucketPlan, below)
+    const int* plan_slot;
+    const int* plan_base;
+    const int* plan_pos;
+    int plan_n, plan_shift;
 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Bucket sort, steps 1 and 2 (a one-CTA plan kernel, then inside the prediction kernel).  The population enters a cycle in cell
+// order (resampling draws in the order of the sorted ancestors), and a prediction moves a particle by a few cells: the cell
+// indices of the particles in slots 0, stride, 2 stride, ... are splitters that cut the NEW keys into buckets of about
+// `stride` particles.  Where two splitters are more than kBucketSpan cells apart (sparse regions) the range is cut further, so
+// that a bucket never spans more than kBucketSpan cells: the per-bucket counting sort (k_bucket_sort) then needs counters for
+// kBucketSpan cells only.  Any splitters give a correct sort - they only decide how evenly the buckets fill.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kBucketSpan = 2048;
+constexpr int kBucketSpanBits = 11;
+
+// The splitters of a cycle (global memory, written by k_bucket_plan, read by k_predict through L1): sorted by (cell, slot), the
+// order of the sort itself - splitting by slot as well keeps a cell with tens of thousands of particles from ending up in one
+// bucket.  Range u holds the pairs from splitter u up to, not including, splitter u + 1 and is cut into nsub buckets of at
+// most kBucketSpan cells.
+struct BucketPlan
+{
+    int* key;   // [n_spl] cell of splitter u (key[0] = 0)
+    int* slot;  // [n_spl] its slot (slot[0] = 0)
+    int* base;  // [n_spl] number of the first bucket of range u
+    int* pos;   // [n_spl] where the sample of slots stride * t .. ended up among the splitters (start of the search)
+    int* org;   // [bins] first cell of every bucket
+    int n_spl, stride_shift, bins;
+};
+
+// one value per thread of a 1024-thread CTA: inclusive scans
+__device__ __forceinline__ int block1024_scan_max(int v, int* s_w)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d)
+            v = max(v, t);
+    }
+    if (lane == 31)
+        s_w[warp] = v;
+    __syncthreads();
+    int pre = INT_MIN;
+    for (int w = 0; w < warp; w++)
+        pre = max(pre, s_w[w]);
+    __syncthreads();
+    return max(v, pre);
+}
+__device__ __forceinline__ int block1024_scan_sum(int v, int* s_w, int* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d)
+            v += t;
+    }
+    if (lane == 31)
+        s_w[warp] = v;
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < 32; w++)
+    {
+        if (w < warp)
+            pre += s_w[w];
+        tot += s_w[w];
+    }
+    __syncthreads();
+    *total = tot;
+    return v + pre;
+}
+
+// One CTA per cycle, in front of the prediction.  The samples are the cells (before this prediction, moved by the pending
+// ego-motion shift) of the particles in slots 0, stride, 2 stride, ...  After a resampling the population is in cell order in
+// two runs - the copies of persistent particles, then the copies of birth particles - so the samples are two sorted lists:
+// they are merged by rank (one binary search per sample).  Any other input (a caller's particle set) gets a running maximum
+// instead: still valid splitters, just less even buckets.
+__global__ void __launch_bounds__(kWideBlock) k_bucket_plan(const int* __restrict__ smp_raw, BucketPlan pl, int delta, int C)
+{
+    pdl_prologue(K_MISC * 2 + 1);
+    __shared__ int s_key[kWideBlock], s_slot[kWideBlock], s_raw[kWideBlock];
+    __shared__ int s_w[32];
+    __shared__ int s_descents, s_break;
+    const int t = threadIdx.x, nt = pl.n_spl;
+    if (t == 0)
+    {
+        s_descents = 0;
+        s_break = nt;
+    }
+    int raw = INT_MAX;
+    if (t < nt)
+        raw = t == 0 ? 0 : min(max(__ldg(smp_raw + t) + delta, 0), C - 1);
+    s_raw[t] = raw;
+    __syncthreads();
+    if (t > 0 && t < nt && raw < s_raw[t - 1])
+    {
+        atomicAdd(&s_descents, 1);
+        atomicMin(&s_break, t);
+    }
+    __syncthreads();
+    const int descents = s_descents, brk = s_break;
+    int my_pos = t;
+    if (descents == 1)
+    { // two sorted runs [0, brk) and [brk, nt): rank of every sample in their merge (equal cells: the first run's come first)
+        int lo, hi;
+        if (t < brk)
+        { // + samples of the second run with a smaller cell
+            lo = brk, hi = nt;
+            while (lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                if (s_raw[mid] < raw)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            my_pos = t + (lo - brk);
+        }
+        else if (t < nt)
+        { // + samples of the first run with a cell <= mine
+            lo = 0, hi = brk;
+            while (lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                if (s_raw[mid] <= raw)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            my_pos = (t - brk) + lo;
+        }
+        if (t < nt)
+        {
+            s_key[my_pos] = raw;
+            s_slot[my_pos] = t << pl.stride_shift;
+        }
+        __syncthreads();
+    }
+    else
+    {
+        const int mx = descents == 0 ? raw : block1024_scan_max(t < nt ? raw : INT_MIN, s_w);
+        s_key[t] = t < nt ? mx : INT_MAX;
+        s_slot[t] = t << pl.stride_shift;
+        __syncthreads();
+    }
+    if (t < nt)
+        pl.pos[t] = my_pos;
+    // range t: from splitter t to splitter t + 1; the cell of splitter t + 1 itself can occur in it, hence the + 1
+    const int lo_c = t < nt ? s_key[t] : 0;
+    const int hi_c = t + 1 < nt ? s_key[t + 1] : C - 1;
+    const int nsub = t < nt ? (hi_c - lo_c) / kBucketSpan + 1 : 0;
+    int total;
+    const int incl = block1024_scan_sum(nsub, s_w, &total);
+    if (t < nt)
+    {
+        pl.key[t] = lo_c;
+        pl.slot[t] = t == 0 ? 0 : s_slot[t];
+        pl.base[t] = incl - nsub;
+        for (int k = 0; k < nsub; k++)
+            if (incl - nsub + k < pl.bins)
+                pl.org[incl - nsub + k] = lo_c + k * kBucketSpan;
+    }
+}
+
+// splitter u <= (key, slot) in the order of the sort?
+__device__ __forceinline__ bool splitter_le(const BucketPlan& pl, int u, int key, int slot)
+{
+    const int c = __ldg(pl.key + u);
+    return c < key || (c == key && __ldg(pl.slot + u) <= slot);
+}
+
+// the bucket of (key, slot): the last range whose splitter is <= the pair (splitter 0 = (0, 0) is <= everything).  A prediction
+// moves a particle by a few cells, so the search gallops away from the splitter its own slot's sample became: two or three
+// probes as a rule, all of them L1 hits (the particles of a CTA search the same neighbourhood).
+__device__ __forceinline__ int bucket_of(const BucketPlan& pl, int key, int slot)
+{
+    const int nt = pl.n_spl;
+    int lo, hi; // invariant: splitter lo <= item < splitter hi (hi == nt: none)
+    const int u0 = __ldg(pl.pos + min(slot >> pl.stride_shift, nt - 1));
+    if (splitter_le(pl, u0, key, slot))
+    {
+        lo = u0;
+        int step = 1;
+        hi = nt;
+        while (lo + step < nt)
+        {
+            if (!splitter_le(pl, lo + step, key, slot))
+            {
+                hi = lo + step;
+                break;
+            }
+            lo += step;
+            step <<= 1;
+        }
+    }
+    else
+    {
+        hi = u0;
+        int step = 1;
+        lo = 0;
+        while (hi - step > 0)
+        {
+            if (splitter_le(pl, hi - step, key, slot))
+            {
+                lo = hi - step;
+                break;
+            }
+            hi -= step;
+            step <<= 1;
+        }
+    }
+    while (hi - lo > 1)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (splitter_le(pl, mid, key, slot))
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return __ldg(pl.base + lo) + ((key - __ldg(pl.key + lo)) >> kBucketSpanBits);
+}
 
 __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t slot, uint32_t cycle, float sigma_pos,
                                                        float sigma_vel)
@@ -70,18 +297,24 @@ __device__ __forceinline__ float4 predict_noise_philox(uint64_t seed, uint32_t s
 // reference's separate kernel.  x' = (x + dt*vx) + noise: three roundings, the GLM mat4*vec4 grouping of predict.cu:33.
 // One CTA of 1024 threads per sort tile (4 particles per thread): the tile's pass-0 digit histogram comes for free.
 // Output: the particle as a 32-byte record in slot order (it never moves again inside the cycle) and its cell
-// index in a compact key array (the only thing the sort passes touch).
-template <bool INJECTED>
+// index in a compact key array (the only thing the sort passes touch).  BUCKET: also the particle's bucket number, and the
+// tile histogram is over the buckets (bucket sort, above).
+template <bool INJECTED, bool BUCKET>
 __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
 {
     pdl_prologue(K_PREDICT * 2);
     extern __shared__ uint32_t s_hist[];
     __shared__ uint32_t s_leave[2];
-    for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
-        s_hist[b] = 0u;
-    if (threadIdx.x < 2)
-        s_leave[threadIdx.x] = 0u;
-    __syncthreads();
+    constexpr int kPer = kTileItems / kWideBlock;
+    BucketPlan pl;
+    pl.key = const_cast<int*>(a.plan_key);
+    pl.slot = const_cast<int*>(a.plan_slot);
+    pl.base = const_cast<int*>(a.plan_base);
+    pl.pos = const_cast<int*>(a.plan_pos);
+    pl.org = nullptr;
+    pl.n_spl = a.plan_n;
+    pl.stride_shift = a.plan_shift;
+    pl.bins = a.bins;
 
     const float4* __restrict__ state = a.state;
     const float* __restrict__ weight = a.weight;
@@ -92,8 +325,15 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
     const int base = blockIdx.x * kTileItems;
     const float hi = (float)(a.gs - 1);
     const float xm = (float)a.x_move, ym = (float)a.y_move;
+
+    for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
+        s_hist[b] = 0u;
+    if (threadIdx.x < 2)
+        s_leave[threadIdx.x] = 0u;
+    __syncthreads();
+
 #pragma unroll
-    for (int j = 0; j < kTileItems / kWideBlock; j++)
+    for (int j = 0; j < kPer; j++)
     {
         const int i = base + j * kWideBlock + threadIdx.x;
         if (i < a.n)
@@ -146,7 +386,14 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
             o[0] = rec_lo(x, y, cell, as);
             o[1] = make_float4(vx, vy, w, w_leaving);
             key_out[i] = cell;
-            atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
+            if (BUCKET)
+            {
+                const int bk = bucket_of(pl, cell, i);
+                a.bkt_out[i] = (uint16_t)bk;
+                atomicAdd(&s_hist[bk], 1u);
+            }
+            else
+                atomicAdd(&s_hist[(uint32_t)cell & a.mask], 1u);
         }
     }
     __syncthreads();
@@ -155,6 +402,15 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
         row[b] = s_hist[b];
     if (a.mig && threadIdx.x < 2)
         a.leave_cnt[threadIdx.x][blockIdx.x] = (double)s_leave[threadIdx.x];
+}
+
+// splitter samples straight from the particle block (first cycle, after dogm_set_particles: resampling has not left them)
+__global__ void __launch_bounds__(kBlock) k_sample_keys(const int* __restrict__ idx, int n, int* smp_raw, int stride_shift)
+{
+    pdl_prologue(K_MISC * 2);
+    const int u = blockIdx.x * kBlock + threadIdx.x;
+    if (((long long)u << stride_shift) < n)
+        smp_raw[u] = idx[(size_t)u << stride_shift];
 }
 
 // SoA -> records without prediction (+ pass-0 histogram): the entry into the sort when the keys did not come from
@@ -428,11 +684,19 @@ struct ScatterArgs
     int bins;
     const uint32_t* table; // this pass: final position of the first key per (tile, digit), from k_hist_scan
     const int* n_dev;      // device-paced band cycle: the item count lives on the device (n is an upper bound for the grid)
+    const uint16_t* digit_in; // SRC 2: the digit (bucket number) per slot
 };
 
-template <bool FIRST>
+// SRC 0: first radix pass (keys in slot order, digits nearly all different: ballot ranking)
+// SRC 1: later radix passes ((key, slot) pairs grouped by cell already: MATCH.ANY ranking)
+// SRC 2: grouping pass of the bucket sort (keys in slot order + the bucket number k_predict computed per slot; a warp's
+//        particles fall into a handful of buckets: MATCH.ANY ranking, long contiguous runs in the output)
+template <int SRC>
 __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int tile, unsigned short* s_cnt /* [warps][bins] */)
 {
+    constexpr bool FIRST = SRC == 0;
+    constexpr bool DIG = SRC == 2;
+    const uint16_t* __restrict__ digit_in = a.digit_in;
 
     const int* __restrict__ key_in = a.key_in;
     const int2* __restrict__ pair_in = a.pair_in;
@@ -449,7 +713,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
     for (int r = 0; r < kRoundsPerWarp; r++)
     {
         const int i = warp_base + r * 32 + lane;
-        keys[r] = (i < a.n) ? (FIRST ? key_in[i] : pair_in[i].x) : 0;
+        keys[r] = (i < a.n) ? (DIG ? (int)digit_in[i] : (FIRST ? key_in[i] : pair_in[i].x)) : 0; // (DIG: shift 0, mask 0xffff)
     }
     {
         uint4* z = reinterpret_cast<uint4*>(s_cnt); // bins is a multiple of 32: the counter block is a multiple of 16 B
@@ -533,17 +797,22 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
     for (int half = 0; half < 2; half++)
     {
         int key[8], slot[8];
+        uint32_t dig[DIG ? 8 : 1];
 #pragma unroll
         for (int q = 0; q < 8; q++)
         {
             const int i = warp_base + (half * 8 + q) * 32 + lane;
             key[q] = 0;
             slot[q] = i;
+            if (DIG)
+                dig[q] = 0;
             if (i < a.n)
             {
-                if (FIRST)
+                if (FIRST || DIG)
                 {
                     key[q] = __ldg(key_in + i);
+                    if (DIG)
+                        dig[q] = __ldg(digit_in + i);
                 }
                 else
                 {
@@ -558,7 +827,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
         for (int q = 0; q < 8; q++)
         {
             const int r = half * 8 + q;
-            const uint32_t digit = ((uint32_t)key[q] >> a.shift) & a.mask;
+            const uint32_t digit = DIG ? dig[DIG ? q : 0] : (((uint32_t)key[q] >> a.shift) & a.mask);
             const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
             dest[q] = __ldg(row + digit) + my_cnt[digit] + rk;
         }
@@ -574,15 +843,15 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
 
 // LOOP = false: one CTA per tile (the grid is the number of tiles).  LOOP = true (device-paced band cycle): the item count is
 // read from the device, the grid is the host's estimate and the CTAs walk over the tiles.
-template <bool FIRST, bool LOOP>
+template <int SRC, bool LOOP>
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
 {
-    pdl_prologue(K_SCATTER * 2 + (FIRST ? 0 : 1));
+    pdl_prologue(K_SCATTER * 2 + (SRC == 1 ? 1 : 0));
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned short* s_cnt = (unsigned short*)s_raw;
     if (!LOOP)
     {
-        scatter_tile<FIRST>(a_in, (int)blockIdx.x, s_cnt);
+        scatter_tile<SRC>(a_in, (int)blockIdx.x, s_cnt);
         return;
     }
     ScatterArgs a = a_in;
@@ -591,7 +860,236 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
     const int tiles = (a.n + kTileItems - 1) / kTileItems;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
     {
-        scatter_tile<FIRST>(a, tile, s_cnt);
+        scatter_tile<SRC>(a, tile, s_cnt);
+        __syncthreads();
+    }
+}
+
+// =========================================================================================================
+// Bucket sort, step 3: one CTA per bucket sorts its (key, slot) pairs by key, keeping the slot order inside a key (the pairs
+// of a bucket arrive in slot order from the grouping pass).  A bucket spans at most kBucketSpan cells, so this is one counting
+// pass over the local key  key - first cell of the bucket:  rank inside the warp by ballots (the local keys of neighbouring
+// slots are nearly all different), per-warp u16 counters, prefix over the warps, exclusive scan over the cells.  The usual
+// bucket (up to 4096 pairs) is sorted into shared memory and written out as one contiguous stretch; a larger one (a cell
+// with thousands of particles) goes chunk by chunk straight to its final positions.
+// Replaces the second radix pass with its tile histogram and table scan; no table, no global counters.
+// =========================================================================================================
+struct BucketSortArgs
+{
+    const int2* pair_in;    // grouped by bucket, slot order inside a bucket
+    int2* pair_out;         // sorted by (cell, slot)
+    const uint32_t* start;  // [bins] first position of every bucket (row 0 of the scanned grouping table)
+    const int* org;         // [bins] first cell of every bucket
+    int bins, n;
+};
+
+constexpr int kBucketSmemBytes = kWarpsPerBlock * kBucketSpan * 2 + 2 * kBucketSpan * 4 + kTileItems * 2 + kTileItems * 4;
+
+// ranks of one chunk of up to 4096 pairs starting at `in` (the warp's 512 in 16 rounds).  On exit: rank2 = rank of every item among
+// the items of its warp with the same local key (two per register), s_cnt[w][k] = items with local key k in the warps before w,
+// s_tot[k] = items of the chunk with local key k.
+__device__ __forceinline__ void bucket_rank_chunk(const int2* __restrict__ in, const int cnt, const int org, unsigned short* s_cnt,
+                                                  uint32_t* s_tot, uint32_t (&rank2)[kRoundsPerWarp / 2])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu, lt = lanemask_lt();
+    const int wb = warp * (kTileItems / kWarpsPerBlock);
+    int lk[kRoundsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const int j = wb + r * 32 + lane;
+        lk[r] = j < cnt ? __ldg(&in[j].x) - org : 0;
+    }
+    {
+        uint4* z = reinterpret_cast<uint4*>(s_cnt);
+        for (int b = threadIdx.x; b < kWarpsPerBlock * kBucketSpan * 2 / 16; b += kBlock)
+            z[b] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    unsigned short* my_cnt = s_cnt + warp * kBucketSpan;
+    uint32_t peers[kRoundsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const bool valid = wb + r * 32 + lane < cnt;
+        uint32_t p = __ballot_sync(full, valid);
+#pragma unroll
+        for (int b = 0; b < kBucketSpanBits; b++)
+        {
+            const bool bit = ((uint32_t)lk[r] >> b) & 1u;
+            const uint32_t m = __ballot_sync(full, bit);
+            p &= bit ? m : ~m;
+        }
+        peers[r] = p;
+    }
+#pragma unroll
+    for (int r = 0; r < kRoundsPerWarp; r++)
+    {
+        const bool valid = wb + r * 32 + lane < cnt;
+        uint32_t old = 0;
+        if (valid)
+            old = my_cnt[lk[r]];
+        __syncwarp();
+        if (valid && (peers[r] & lt) == 0)
+            my_cnt[lk[r]] = (unsigned short)(old + __popc(peers[r]));
+        const uint32_t rk = old + __popc(peers[r] & lt);
+        if (r & 1)
+            rank2[r >> 1] |= rk << 16;
+        else
+            rank2[r >> 1] = rk;
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBucketSpan; b += kBlock)
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerBlock; w++)
+        {
+            const uint32_t c = s_cnt[w * kBucketSpan + b];
+            s_cnt[w * kBucketSpan + b] = (unsigned short)run;
+            run += c;
+        }
+        s_tot[b] = run;
+    }
+    __syncthreads();
+}
+
+// exclusive scan of the kBucketSpan counters in place (thread t owns the 8 consecutive counters 8 t .. 8 t + 7)
+__device__ __forceinline__ void bucket_scan_counts(uint32_t* s_tot, uint32_t* s_ws)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* v = reinterpret_cast<uint4*>(s_tot) + 2 * threadIdx.x;
+    uint4 a = v[0], b = v[1];
+    const uint32_t sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += t;
+    }
+    if (lane == 31)
+        s_ws[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; w++)
+        if (w < warp)
+            pre += s_ws[w];
+    uint32_t run = pre + incl - sum;
+    uint4 oa, ob;
+    oa.x = run; run += a.x;
+    oa.y = run; run += a.y;
+    oa.z = run; run += a.z;
+    oa.w = run; run += a.w;
+    ob.x = run; run += b.x;
+    ob.y = run; run += b.y;
+    ob.z = run; run += b.z;
+    ob.w = run;
+    v[0] = oa;
+    v[1] = ob;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock, 3) k_bucket_sort(const BucketSortArgs a)
+{
+    pdl_prologue(K_SCATTER * 2 + 1);
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned short* s_cnt = (unsigned short*)s_raw;                                   // [warps][span]
+    uint32_t* s_tot = (uint32_t*)(s_raw + kWarpsPerBlock * kBucketSpan * 2);          // [span] counts, then offsets
+    uint32_t* s_fill = s_tot + kBucketSpan;                                           // [span] (large buckets)
+    uint32_t* s_sl = s_fill + kBucketSpan;                                            // [4096] sorted slots
+    unsigned short* s_lk = (unsigned short*)(s_sl + kTileItems);                      // [4096] sorted local keys
+    __shared__ uint32_t s_ws[kWarpsPerBlock];
+    const int b = blockIdx.x;
+    const int p0 = (int)a.start[b];
+    const int p1 = b + 1 < a.bins ? (int)a.start[b + 1] : a.n;
+    const int count = p1 - p0;
+    if (count <= 0)
+        return;
+    const int org = a.org[b];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wb = warp * (kTileItems / kWarpsPerBlock);
+    const int2* __restrict__ in = a.pair_in + p0;
+    uint32_t rank2[kRoundsPerWarp / 2];
+    if (count <= kTileItems)
+    {
+        bucket_rank_chunk(in, count, org, s_cnt, s_tot, rank2);
+        bucket_scan_counts(s_tot, s_ws);
+        const unsigned short* my_cnt = s_cnt + warp * kBucketSpan;
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+        {
+            int2 pr[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                const int j = wb + (half * 8 + q) * 32 + lane;
+                pr[q] = j < count ? __ldg(in + j) : make_int2(org, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+            {
+                const int r = half * 8 + q;
+                const int j = wb + r * 32 + lane;
+                if (j < count)
+                {
+                    const int k = pr[q].x - org;
+                    const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
+                    const uint32_t lp = s_tot[k] + my_cnt[k] + rk;
+                    s_sl[lp] = (uint32_t)pr[q].y;
+                    s_lk[lp] = (unsigned short)k;
+                }
+            }
+        }
+        __syncthreads();
+        int2* __restrict__ out = a.pair_out + p0;
+        for (int j = threadIdx.x; j < count; j += kBlock)
+            out[j] = make_int2(org + (int)s_lk[j], (int)s_sl[j]);
+        return;
+    }
+    // ---- a large bucket: the counts of all its chunks first, then chunk by chunk to the final positions
+    for (int k = threadIdx.x; k < kBucketSpan; k += kBlock)
+    {
+        s_tot[k] = 0u;
+        s_fill[k] = 0u;
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < count; j0 += kBlock)
+    { // (warp-aggregated: a cell with thousands of particles would otherwise serialise on one counter)
+        const int j = j0 + threadIdx.x;
+        const bool valid = j < count;
+        const int k = valid ? __ldg(&in[j].x) - org : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (valid && (peers & lanemask_lt()) == 0)
+            atomicAdd(&s_tot[k], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    bucket_scan_counts(s_tot, s_ws);
+    uint32_t* s_ctot = s_sl; // (the staging area is not used on this path)
+    for (int c0 = 0; c0 < count; c0 += kTileItems)
+    {
+        const int cnt = min(kTileItems, count - c0);
+        bucket_rank_chunk(in + c0, cnt, org, s_cnt, s_ctot, rank2);
+        const unsigned short* my_cnt = s_cnt + warp * kBucketSpan;
+#pragma unroll
+        for (int r = 0; r < kRoundsPerWarp; r++)
+        {
+            const int j = wb + r * 32 + lane;
+            if (j < cnt)
+            {
+                const int2 pr = __ldg(in + c0 + j);
+                const int k = pr.x - org;
+                const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
+                a.pair_out[p0 + s_tot[k] + s_fill[k] + my_cnt[k] + rk] = pr;
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < kBucketSpan; k += kBlock)
+            s_fill[k] += s_ctot[k];
         __syncthreads();
     }
 }
@@ -1435,6 +1933,8 @@ struct ResampleArgs
     uint64_t seed;
     uint32_t cycle;
     const BandCounts* cnt; // device-paced band cycle: counts and this band's part of the global draw live on the device
+    int* samples;          // bucket sort: cell index of the particle in every stride-th output slot (splitters of the next cycle), or null
+    int sample_mask, sample_shift; // stride = 1024 << sample_shift, mask = (1 << sample_shift) - 1
 };
 
 // One CTA resamples 1024 consecutive output slots, four per thread.  Their offsets ascend, so all ancestors lie in a short
@@ -1688,6 +2188,8 @@ __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int 
     }
     PHASE_STAMP(1, blockIdx.x, 5, __float_as_uint(st[kResPer - 1].w) ^ __float_as_uint(st[0].x));
     const float w_new = __fdiv_rn(joint_max, (float)a.N_glob);
+    if (a.samples && threadIdx.x == 0 && (blk & a.sample_mask) == 0)
+        a.samples[blk >> a.sample_shift] = cell[0]; // output slot out0 = 1024 blk is a multiple of the sample stride
 #pragma unroll
     for (int j = 0; j < kResPer; j++)
     {
@@ -1833,16 +2335,55 @@ int run_predict(dogm_handle* h, float dt)
     a.mask = (uint32_t)(h->digit_bins[0] - 1);
     a.leave_cnt[0] = h->band.out_cnt[0];
     a.leave_cnt[1] = h->band.out_cnt[1];
+    const bool bucket = h->bucket.enabled;
+    a.bkt_out = h->bucket.bkt;
+    a.plan_key = h->bucket.plan_key;
+    a.plan_slot = h->bucket.plan_slot;
+    a.plan_base = h->bucket.plan_base;
+    a.plan_pos = h->bucket.plan_pos;
+    a.plan_n = h->bucket.n_spl;
+    a.plan_shift = h->bucket.stride_shift;
+    if (bucket)
+    {
+        a.bins = h->bucket.bins;
+        a.mask = 0xffffffffu;
+        if (!h->bucket.samples_valid)
+        {
+            LaunchScope ls(h, K_MISC, 0.0);
+            launch_chained(h->stream, k_sample_keys, div_up(h->bucket.n_spl, kBlock), kBlock, 0, (const int*)h->pa.idx, h->N,
+                           h->bucket.smp_raw, h->bucket.stride_shift);
+        }
+        BucketPlan pl;
+        pl.key = h->bucket.plan_key;
+        pl.slot = h->bucket.plan_slot;
+        pl.base = h->bucket.plan_base;
+        pl.pos = h->bucket.plan_pos;
+        pl.org = h->bucket.org;
+        pl.n_spl = h->bucket.n_spl;
+        pl.stride_shift = h->bucket.stride_shift;
+        pl.bins = h->bucket.bins;
+        LaunchScope ls(h, K_MISC, 0.0);
+        launch_chained(h->stream, k_bucket_plan, 1, kWideBlock, 0, (const int*)h->bucket.smp_raw, pl,
+                       a.shift_active ? -(a.x_move + a.gs * a.y_move) : 0, h->C);
+    }
     const size_t smem = (size_t)a.bins * sizeof(uint32_t);
     {
-        LaunchScope ls(h, K_PREDICT, 57.0 * h->N);
+        LaunchScope ls(h, K_PREDICT, (bucket ? 59.0 : 57.0) * h->N);
         if (h->opts.noise_mode == DOGM_NOISE_INJECTED)
-            launch_chained(h->stream, k_predict<true>, h->tiles, kWideBlock, smem, a);
+        {
+            if (bucket)
+                launch_chained(h->stream, k_predict<true, true>, h->tiles, kWideBlock, smem, a);
+            else
+                launch_chained(h->stream, k_predict<true, false>, h->tiles, kWideBlock, smem, a);
+        }
+        else if (bucket)
+            launch_chained(h->stream, k_predict<false, true>, h->tiles, kWideBlock, smem, a);
         else
-            launch_chained(h->stream, k_predict<false>, h->tiles, kWideBlock, smem, a);
+            launch_chained(h->stream, k_predict<false, false>, h->tiles, kWideBlock, smem, a);
     }
     h->shift_particles_pending = false;
     h->hist0_valid = true;
+    h->hist0_bucket = bucket;
     h->pa_current = false; // the predicted particles are the records now
     h->rec_valid = true;
     h->sorted_valid = false;
@@ -1875,7 +2416,43 @@ int run_assignment(dogm_handle* h)
             launch_chained(h->stream, k_key_tile_hist, h->tiles, kWideBlock, smem, h->key0, N, h->hist[0], h->digit_bins[0], mask, n_dev);
         h->rec_valid = true;
     }
-    for (int p = 0; p < h->passes; p++)
+    const bool bucket = h->hist0_valid && h->hist0_bucket;
+    if (bucket)
+    { // bucket sort: scan of the grouping table, grouping pass (stable, by bucket), one counting sort per bucket
+        const int bins = h->bucket.bins;
+        {
+            LaunchScope ls(h, K_HIST_SCAN, 8.0 * h->tiles * bins);
+            launch_chained(h->stream, k_hist_scan, bins / 32, kWideBlock, 0, h->hist[0], h->tiles, bins,
+                           (unsigned long long*)h->bin_base[0], ++h->scan_epoch[0], n_dev);
+        }
+        ScatterArgs a;
+        a.key_in = h->key0;
+        a.pair_in = nullptr;
+        a.pair_out = h->pairs[0];
+        a.n = N;
+        a.shift = 0;
+        a.mask = 0xffffu;
+        a.bins = bins;
+        a.table = h->hist[0];
+        a.n_dev = nullptr;
+        a.digit_in = h->bucket.bkt;
+        {
+            LaunchScope ls(h, K_SCATTER, 14.0 * N);
+            launch_chained(h->stream, k_scatter<2, false>, h->tiles, kBlock, (size_t)bins * kWarpsPerBlock * sizeof(unsigned short), a);
+        }
+        BucketSortArgs bs;
+        bs.pair_in = h->pairs[0];
+        bs.pair_out = h->pairs[1];
+        bs.start = h->hist[0]; // row 0 of the scanned table: keys in front of every bucket
+        bs.org = h->bucket.org;
+        bs.bins = bins;
+        bs.n = N;
+        {
+            LaunchScope ls(h, K_SCATTER, 16.0 * N);
+            launch_chained(h->stream, k_bucket_sort, bins, kBlock, (size_t)kBucketSmemBytes, bs);
+        }
+    }
+    for (int p = 0; p < (bucket ? 0 : h->passes); p++)
     {
         const int bins = h->digit_bins[p];
         if (p > 0)
@@ -1899,24 +2476,26 @@ int run_assignment(dogm_handle* h)
         a.bins = bins;
         a.table = h->hist[p];
         a.n_dev = n_dev;
+        a.digit_in = nullptr;
         const size_t smem = (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
             LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
             if (n_dev)
             {
                 if (p == 0)
-                    launch_chained(h->stream, k_scatter<true, true>, h->tiles, kBlock, smem, a);
+                    launch_chained(h->stream, k_scatter<0, true>, h->tiles, kBlock, smem, a);
                 else
-                    launch_chained(h->stream, k_scatter<false, true>, h->tiles, kBlock, smem, a);
+                    launch_chained(h->stream, k_scatter<1, true>, h->tiles, kBlock, smem, a);
             }
             else if (p == 0)
-                launch_chained(h->stream, k_scatter<true, false>, h->tiles, kBlock, smem, a);
+                launch_chained(h->stream, k_scatter<0, false>, h->tiles, kBlock, smem, a);
             else
-                launch_chained(h->stream, k_scatter<false, false>, h->tiles, kBlock, smem, a);
+                launch_chained(h->stream, k_scatter<1, false>, h->tiles, kBlock, smem, a);
         }
     }
-    h->spair = h->pairs[(h->passes - 1) & 1];
+    h->spair = bucket ? h->pairs[1] : h->pairs[(h->passes - 1) & 1];
     h->hist0_valid = false;
+    h->hist0_bucket = false;
     h->pa_current = false;
     // per-cell sums + start/end over the sorted order
     {
@@ -1994,10 +2573,12 @@ int configure_kernels()
 {
     const int max_bins = 1 << kMaxDigitBits;
     const int smem = max_bins * kWarpsPerBlock * (int)sizeof(unsigned short);
-    int e = (int)cudaFuncSetAttribute(k_scatter<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int e = (int)cudaFuncSetAttribute(k_scatter<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kBucketSmemBytes);
     return e;
 }
 
@@ -2100,6 +2681,10 @@ int run_resample_gather(dogm_handle* h)
     a.seed = h->opts.seed;
     a.cycle = h->cycle;
     a.cnt = h->band.dev_cnt;
+    a.samples = h->bucket.enabled ? h->bucket.smp_raw : nullptr;
+    a.sample_shift = h->bucket.stride_shift - 10;
+    a.sample_mask = (1 << a.sample_shift) - 1;
+    h->bucket.samples_valid = h->bucket.enabled && n_out > 0 && n > 0;
     if (a.cnt)
     { // device-paced band cycle: the grid is sized for an estimate, the kernel reads what it really has to do and loops
         const int est = h->band.est_out > 0 ? h->band.est_out : 1;

@@ -85,6 +85,16 @@ def test_free_running_two_pass_sort(gpu, orc):
     free_run(gpu, orc, 64.0, 0.5, 100000, 10000, cycles=5, seed=12, ego=(0.3, 0.8))
 
 
+@pytest.mark.parametrize("size,res,n,b,ego", [(64.0, 0.5, 100000, 10000, (0.3, 0.8)), (50.0, 0.2, 300000, 30000, (0.0, 0.4)),
+                                              (120.0, 0.25, 37000, 900, (-0.6, 0.2))])
+def test_free_running_bucket_sort(gpu, orc, monkeypatch, size, res, n, b, ego):
+    """The optional bucket sort (DOGM_B200_SORT=bucket: splitters from the population's own cell order, grouping pass by bucket,
+    one counting sort per bucket) against the oracle over free-running cycles, shifts included: same particle order, ranges,
+    ancestors and masses as the radix passes give."""
+    monkeypatch.setenv("DOGM_B200_SORT", "bucket")
+    free_run(gpu, orc, size, res, n, b, cycles=5, seed=21, ego=ego)
+
+
 def test_free_running_config1_reference_demo(gpu, orc):
     # BASELINE.json configs[0]: 250x250 grid, 3e5 persistent + 3e4 birth particles (README.md:20-22)
     free_run(gpu, orc, 50.0, 0.2, 300000, 30000, cycles=4, seed=13, ego=(0.0, 0.4))
