@@ -340,7 +340,7 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     keep_first(alloc_zero((void**)&h->seg_lead, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
     keep_first(alloc_zero((void**)&h->seg_trail, (size_t)(h->n_chunks + 1) * sizeof(SegPiece)));
     keep_first(alloc_zero((void**)&h->seg_flags, (size_t)(h->n_chunks + 1) * sizeof(int)));
-    keep_first(alloc_zero((void**)&h->cdf, (N + B) * sizeof(double)));
+    keep_first(alloc_zero((void**)&h->cdf, (N + B + 2) * sizeof(double))); // (+ padding: the bulk copy of a window reads whole 16 bytes)
     keep_first(alloc_zero((void**)&h->tile_sum, ((size_t)h->n_cdf_tiles + 3) * sizeof(double)));
     keep_first(alloc_zero((void**)&h->tile_off, ((size_t)h->n_cdf_tiles + 3) * sizeof(double)));
     keep_first(alloc_zero((void**)&h->res_start, ((size_t)div_up(h->N > 0 ? h->N : 1, kBlock)) * sizeof(int)));

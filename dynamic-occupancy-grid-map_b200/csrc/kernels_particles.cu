@@ -1976,35 +1976,94 @@ constexpr int kResPer = 4;                     // output slots per thread
 constexpr int kResOutputs = kBlock * kResPer;  // output slots per CTA
 
 #ifndef DOGM_RES_MINBLOCKS
-#define DOGM_RES_MINBLOCKS 5
+#define DOGM_RES_MINBLOCKS 6
 #endif
-// the 1024 output slots of block `blk`
+// shared-memory barrier + bulk copy (the copy engine moves the CDF window global -> shared: no registers, one instruction)
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the initialised barrier is visible to the copy engine
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, unsigned long long* bar)
+{ // 16-byte aligned addresses, size a multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// the 1024 output slots of block `blk`.  BULK: the CDF window is fetched by one bulk copy (cp.async.bulk + mbarrier) issued by
+// thread 0 instead of eight register-staged loads per thread (single-shot kernel only: the barrier is used once).
+template <bool BULK>
 __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int blk)
 {
-    __shared__ double s_cdf[kResWindow];
+    __shared__ __align__(16) double s_buf[kResWindow + 2]; // up to two entries in front of the window (16-byte aligned source)
     __shared__ __align__(16) int s_anc[kResOutputs];
     __shared__ double s_step, s_first;
     __shared__ float s_u0, s_jm;
+    __shared__ __align__(8) unsigned long long s_bar;
     const int out0 = blk * kResOutputs;
     PHASE_STAMP(1, blockIdx.x, 0, 0);
     // The window starts at lower_bound(first offset of the CTA).  k_cdf_chain has normally left that position in
-    // res_start (one entry per 256 output slots): every thread reads it and fetches its window entries straight away,
+    // res_start (one entry per 256 output slots): every thread reads it; the window entries are fetched straight away,
     // while thread 0 prepares the scalars; the claim is then checked against the CDF (entry before < first offset <= entry).
     int lo0 = 0x7f7f7f7f;
     if (a.res_start)
         lo0 = __ldcg(a.res_start + blk * kResPer);
     const bool claimed = lo0 >= 0 && lo0 < a.n_cdf;
     const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-    double win[kResWindow / kBlock];
+    // BULK: the copy starts at the even entry lo0a <= lo0 - 1, so that the entry in front of the window comes along
+    const int lo0a = (BULK && claimed && lo0 > 0) ? ((lo0 - 1) & ~1) : (claimed ? lo0 : 0);
+    const int off = BULK && claimed ? lo0 - lo0a : 0;
+    double* s_cdf = s_buf + off; // s_cdf[j] = cdf[lo0 + j]
+    double win[BULK ? 1 : kResWindow / kBlock];
     double before = -1.0;
-#pragma unroll
-    for (int k = 0; k < kResWindow / kBlock; k++)
+    int got = 0; // BULK: entries the copy delivers
+    if (BULK)
     {
-        const long long j = (long long)lo0 + k * kBlock + (int)threadIdx.x;
-        win[k] = (claimed && j < a.n_cdf) ? __ldcg(a.cdf + j) : kInf;
+        if (claimed)
+        {
+            got = min(kResWindow + off, a.n_cdf - lo0a);
+            if (threadIdx.x == 0)
+            {
+                const uint32_t bytes = (uint32_t)((got + 1) & ~1) * 8u; // (an odd count reads one entry of padding behind the CDF)
+                mbar_init(&s_bar, 1u);
+                mbar_expect_tx(&s_bar, bytes);
+                bulk_load(s_buf, a.cdf + lo0a, bytes, &s_bar);
+            }
+        }
     }
-    if (claimed && threadIdx.x == 0 && lo0 > 0)
-        before = __ldcg(a.cdf + lo0 - 1);
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < kResWindow / kBlock; k++)
+        {
+            const long long j = (long long)lo0 + k * kBlock + (int)threadIdx.x;
+            win[BULK ? 0 : k] = (claimed && j < a.n_cdf) ? __ldcg(a.cdf + j) : kInf;
+        }
+        if (claimed && threadIdx.x == 0 && lo0 > 0)
+            before = __ldcg(a.cdf + lo0 - 1);
+    }
     if (threadIdx.x == 0)
     {
         const double total = a.scal->weight_total;
@@ -2020,9 +2079,26 @@ __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int 
         s_first = a.mode == DOGM_RESAMPLE_STRATIFIED ? (double)(a.out_base + out0) * step - a.cdf_base
                                                      : resample_offset(a, out0, jm, u0, step);
     }
+    if (BULK)
+    {
+        if (claimed && threadIdx.x == 0)
+            mbar_wait(&s_bar, 0u); // (the other threads are released by the barrier below)
+        __syncthreads();
+        // the entries behind the end of the CDF read as +inf
+        for (int k = got + (int)threadIdx.x; k < kResWindow + 2; k += kBlock)
+            s_buf[k] = kInf;
+        if (claimed && threadIdx.x == 0)
+        {
+            before = lo0 > 0 ? s_cdf[-1] : -1.0;
+            win[0] = s_cdf[0];
+        }
+    }
+    else
+    {
 #pragma unroll
-    for (int k = 0; k < kResWindow / kBlock; k++)
-        s_cdf[k * kBlock + threadIdx.x] = win[k];
+        for (int k = 0; k < kResWindow / kBlock; k++)
+            s_cdf[k * kBlock + threadIdx.x] = win[BULK ? 0 : k];
+    }
     __syncthreads();
     PHASE_STAMP(1, blockIdx.x, 1, 0);
     const float joint_max = s_jm;
@@ -2052,6 +2128,7 @@ __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int 
             lo0 = nlo;
         }
         __syncthreads();
+        s_cdf = s_buf;
         for (int j = threadIdx.x; j < kResWindow; j += kBlock)
             s_cdf[j] = (lo0 + j < a.n_cdf) ? a.cdf[lo0 + j] : kInf;
         __syncthreads();
@@ -2212,7 +2289,7 @@ __global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(const R
     pdl_prologue(K_RESAMPLE * 2);
     if (!DEV)
     { // the CTAs at the end of the CDF (birth particles: several window slides) take longest: they go first
-        resample_block(a_in, (int)(gridDim.x - 1 - blockIdx.x));
+        resample_block<true>(a_in, (int)(gridDim.x - 1 - blockIdx.x));
         return;
     }
     // device-paced band cycle: counts and this band's part of the global draw are read from the device; the grid is the host's
@@ -2228,7 +2305,7 @@ __global__ void __launch_bounds__(kBlock, DOGM_RES_MINBLOCKS) k_resample(const R
     const int blocks = (a.N_out + kResOutputs - 1) / kResOutputs;
     for (int b = blockIdx.x; b < blocks; b += gridDim.x)
     {
-        resample_block(a, blocks - 1 - b);
+        resample_block<false>(a, blocks - 1 - b);
         __syncthreads();
     }
 }
