@@ -222,6 +222,8 @@ _SYMBOLS = [
     ("dogm_band_group_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
     ("dogm_band_group_destroy", None, [_P]),
     ("dogm_band_group_set_mode", C.c_int, [_P, C.c_int]),
+    ("dogm_band_set_state", C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float]),
+    ("dogm_band_group_mark_initialized", C.c_int, [_P]),
     ("dogm_band_group_get_mode", C.c_int, [_P]),
     ("dogm_band_mailbox", C.c_void_p, [_P]),
     ("dogm_band_set_profile", C.c_int, [_P, C.c_int]),
@@ -930,6 +932,24 @@ class BandedDOGM:
         self.last_counts = counts
         self.last_totals = {"born": total_b, "weight": total_w}
         return counts
+
+    def set_state(self, state, weight, associated, grid_cells, x, y, yaw):
+        """Parity hook: distributes a given particle set [n, 4] (global coordinates) and the grid cells of the whole grid over the
+        bands instead of running the first cycle's initialisation."""
+        state = np.ascontiguousarray(state, np.float32)
+        rows_of = np.clip(state[:, 1].astype(np.int64), 0, self.G - 1)
+        for r in range(self.R):
+            self._on(r)
+            sel = (rows_of >= self.row0[r]) & (rows_of < self.row0[r] + self.rows[r])
+            st = np.ascontiguousarray(state[sel])
+            w = np.ascontiguousarray(np.asarray(weight, np.float32)[sel])
+            a = np.ascontiguousarray(np.asarray(associated, np.uint8)[sel])
+            cells = np.ascontiguousarray(grid_cells[self.row0[r] * self.G:(self.row0[r] + self.rows[r]) * self.G])
+            _check(self._lib.dogm_band_set_state(self.h[r], len(st), _ptr(st), _ptr(w), _ptr(a), _ptr(cells), x, y, yaw),
+                   "dogm_band_set_state")
+        self.first = False
+        if self.group is not None:
+            _check(self._lib.dogm_band_group_mark_initialized(self.group), "dogm_band_group_mark_initialized")
 
     def set_profile(self, enable: bool):
         """device-paced cycles: record events at the stage boundaries of every band (last_band_ms then holds device times)"""

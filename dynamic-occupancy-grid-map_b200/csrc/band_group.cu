@@ -382,6 +382,14 @@ extern "C" int dogm_band_group_update(dogm_band_group* g, const dogm_meas_cell* 
     return e;
 }
 
+extern "C" int dogm_band_group_mark_initialized(dogm_band_group* g)
+{ // the bands were loaded with dogm_band_set_state: no first-cycle initialisation
+    if (!g)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    g->first = false;
+    return 0;
+}
+
 extern "C" int dogm_band_group_set_mode(dogm_band_group* g, int mode)
 {
     if (!g || (mode != DOGM_BAND_GROUP_HOST_PACED && mode != DOGM_BAND_GROUP_DEVICE_PACED))

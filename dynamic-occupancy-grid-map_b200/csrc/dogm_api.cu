@@ -1637,6 +1637,53 @@ extern "C" int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* s
     return 0;
 }
 
+// Parity hook: loads a band with a given state instead of the first cycle's initialisation - the particles that lie in its rows
+// (global coordinates; their cell indices are recomputed), the band's rows of the grid cells and the pose.
+extern "C" int dogm_band_set_state(dogm_handle* h, int n, const float* state_xyvv, const float* weight, const unsigned char* associated,
+                                   const dogm_grid_cell* grid_cells_band, float x, float y, float yaw)
+{
+    BAND_PROLOGUE();
+    if (n < 0 || n > h->band.n_cap || (n > 0 && (!state_xyvv || !weight)))
+        return DOGM_ERR_INVALID_ARGUMENT;
+    DOGM_CHECK(cudaStreamSynchronize(h->stream));
+    set_particle_counts(h, n, 0);
+    particle_set_assign(h->pa, h->pa.block, h->band.n_cap); // (the SoA block is laid out for the capacity)
+    if (n > 0)
+    {
+        std::vector<int> idx((size_t)n);
+        std::vector<unsigned char> as((size_t)n, 0);
+        for (int i = 0; i < n; i++)
+        {
+            int px = (int)state_xyvv[4 * i], py = (int)state_xyvv[4 * i + 1];
+            px = px < 0 ? 0 : (px > h->gs - 1 ? h->gs - 1 : px);
+            py = py < 0 ? 0 : (py > h->band.G - 1 ? h->band.G - 1 : py);
+            py -= h->band.row0;
+            if (py < 0 || py >= h->band.rows)
+                return DOGM_ERR_INVALID_ARGUMENT; // the particle does not lie in this band
+            idx[i] = px + h->gs * py;
+            if (associated)
+                as[i] = associated[i];
+        }
+        DOGM_CHECK(cudaMemcpy(h->pa.state, state_xyvv, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+        DOGM_CHECK(cudaMemcpy(h->pa.idx, idx.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        DOGM_CHECK(cudaMemcpy(h->pa.weight, weight, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+        DOGM_CHECK(cudaMemcpy(h->pa.assoc, as.data(), (size_t)n, cudaMemcpyHostToDevice));
+    }
+    h->pa_current = true;
+    h->rec_valid = false;
+    h->sorted_valid = false;
+    h->hist0_valid = false;
+    if (grid_cells_band && (e = dogm_set_grid_cells(h, grid_cells_band, 0)))
+        return e;
+    h->position_x = x;
+    h->position_y = y;
+    h->yaw = yaw;
+    h->first_pose_received = true;
+    h->first_measurement_received = true;
+    h->band.est_out = n + 8192 < h->band.n_cap ? n + 8192 : h->band.n_cap;
+    return 0;
+}
+
 extern "C" int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated)
 {
     BAND_PROLOGUE();

@@ -276,6 +276,11 @@ int dogm_band_stage_times(const dogm_handle* h, float* out_ms4);
 int dogm_band_group_band_times(const dogm_band_group* g, float* out_ms);
 
 int dogm_band_get_particles(dogm_handle* h, float* state_xyvv, int* cell_idx, float* weight, unsigned char* associated);
+/* Parity hooks: a band loaded with a given state (the particles that lie in its rows, in global coordinates; its rows of the grid
+ * cells; the pose) instead of the first cycle's initialisation, and a group told that its bands are initialised. */
+int dogm_band_set_state(dogm_handle* h, int n, const float* state_xyvv, const float* weight, const unsigned char* associated,
+                        const dogm_grid_cell* grid_cells_band, float x, float y, float yaw);
+int dogm_band_group_mark_initialized(dogm_band_group* g);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Read-out (blocking device-to-host copies, dogm.cu:133-159, dogm.h:111-139)

@@ -242,3 +242,66 @@ def test_bands_on_two_gpus_equal_bands_on_one(gpu):
         for a, b in zip(out[0][1][r], out[1][1][r]):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), f"band {r}"
     assert np.array_equal(out[0][2].view(np.uint8), out[1][2].view(np.uint8))
+
+
+@pytest.mark.parametrize("bands,paced", [(2, True), (4, True), (3, False)])
+def test_bands_with_injected_state_reproduce_the_single_grid_masses(gpu, bands, paced):
+    """An oracle for band mode: the single grid.  Both start one cycle from the SAME state (a realistic population and map
+    taken from a running filter, loaded through dogm_band_set_state / dogm_set_*), with the process noise switched off so
+    that the prediction is the same function on both sides.  The bands then hold the same particles per cell as the single
+    grid (some arrived over a band edge, in another order): every per-cell quantity that is an order-independent sum - the
+    predicted, updated, born and persistent masses, the born-mass array, the cell ranges' lengths - must be the same bits,
+    the joint weight total the same to double rounding, and the global particle count must be conserved."""
+    grids, ps = scans(gpu, 5), poses(5, vy=5.0, vx=2.0)
+    warm = run_plain(gpu, grids[:4], ps[:4])
+    P, G = warm.get_particles(), warm.get_grid_cells()
+    pose = (warm.get_position_x(), warm.get_position_y(), warm.get_yaw())
+    warm.close()
+    quiet = make_params(gpu, SIZE, RES, N, B, stddev_process_noise_position=0.0, stddev_process_noise_velocity=0.0)
+    (x, y) = ps[4]
+    # single grid
+    d = gpu.DOGM(quiet)
+    d.set_options(seed=5, resample_mode=gpu.RESAMPLE_SYSTEMATIC, noise_mode=gpu.NOISE_PHILOX)
+    d.update_measurement_grid(grids[3])  # (the first measurement initialises a population; it is replaced right away)
+    d.set_particles(P)
+    d.set_grid_cells(G)
+    d.set_pose(*pose)
+    d.update_grid(grids[4], x, y, 0.0, 0.1, device=False)
+    cells_single, born_single = d.get_grid_cells(), d.get_born_masses()
+    total_single = d.get_joint_weight_accum()[-1]
+    d.close()
+    # the bands
+    bd = gpu.BandedDOGM(quiet, bands, seed=5, device_paced=paced)
+    bd.set_state(P.state, P.weight, P.associated, G, *pose)
+    dev = gpu.device_alloc(grids[4].nbytes)
+    gpu.memcpy_h2d(dev, grids[4])
+    counts = bd.update_grid([dev + bd.row0[r] * bd.G * 16 for r in range(bands)], x, y, 0.0, 0.1)
+    cells_band = bd.get_grid_cells()
+    lo, hi = bd.last_migration
+    assert sum(lo) + sum(hi) > 0, "no particle crossed a band edge: the test would be vacuous"
+    assert N - bands <= sum(counts) <= N
+    for f in ("pred_occ_mass", "occ_mass", "free_mass", "new_born_occ_mass", "pers_occ_mass"):
+        assert np.array_equal(cells_band[f].view(np.uint32), cells_single[f].view(np.uint32)), f
+    n_single = np.where(cells_single["start_idx"] >= 0, cells_single["end_idx"] - cells_single["start_idx"] + 1, 0)
+    n_band = np.where(cells_band["start_idx"] >= 0, cells_band["end_idx"] - cells_band["start_idx"] + 1, 0)
+    # (a particle that left its band stays behind as a weightless ghost in the band's edge row until resampling drops it, so the
+    #  edge rows may count more particles than the single grid; a particle that left the GRID sideways has weight 0, sits in
+    #  the first or last column and is not sent on when it also crosses a band edge; everywhere else the counts are the same)
+    inner = np.ones((bd.G, bd.G), bool)
+    inner[:, 0] = inner[:, -1] = False
+    for r in range(bands):
+        inner[bd.row0[r]] = False
+        inner[bd.row0[r] + bd.rows[r] - 1] = False
+    inner = inner.ravel()
+    assert np.array_equal(n_single[inner], n_band[inner]), "the bands hold other particles per cell than the single grid"
+    # every migrated particle is counted twice in the bands' cell ranges: as the ghost it left behind and where it arrived
+    assert int(n_single.sum()) == N and int(n_band.sum()) == N + sum(lo) + sum(hi)
+    assert abs(bd.last_totals["weight"] - total_single) <= 1e-11 * total_single
+    born_total_single = float(born_single.astype(np.float64).sum())
+    assert abs(bd.last_totals["born"] - born_total_single) <= 1e-9 * max(born_total_single, 1.0)
+    # mean velocities: float sums in another order inside a cell
+    sel = cells_single["pers_occ_mass"] > 1e-3
+    assert np.allclose(cells_band["mean_x_vel"][sel], cells_single["mean_x_vel"][sel], rtol=1e-4, atol=1e-3)
+    assert np.allclose(cells_band["mean_y_vel"][sel], cells_single["mean_y_vel"][sel], rtol=1e-4, atol=1e-3)
+    gpu.device_free(dev)
+    bd.close()
