@@ -634,6 +634,9 @@ def run_ours(args, dist):
         gpu.device_free(p)
     gen.close()
     d.close()
+    # ---- the drop-in C++ class against the C ABI it wraps (what refresh() of the public members costs per cycle)
+    if dist.rank == 0 and dist.world == 1 and args.config == "nuss":
+        result["protocol"]["cxx_facade"] = facade_overhead()
     # ---- large grids band-partitioned over the box's GPUs (rank 0, after every rank has finished its replica work) ------------
     if not args.no_band_scaling and args.config == "nuss":
         dist.barrier()
@@ -738,6 +741,20 @@ def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, s
             rec["error"] = f"{type(ex).__name__}: {ex}"
         records.append(rec)
     return records
+
+
+def facade_overhead():
+    """tests/cpp/dogm_spec_b200 --time: updateGrid through dogm::DOGM (include/dogm/dogm.h) and through dogm_update_grid."""
+    exe = os.path.join(ROOT, "tests", "cpp", "dogm_spec_b200")
+    pkg = os.path.join(ROOT, "dynamic-occupancy-grid-map_b200")
+    try:
+        if not os.path.exists(exe):
+            subprocess.run(["g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), exe + ".cpp", "-o", exe, "-L", pkg,
+                            "-ldogm_b200", f"-Wl,-rpath,{pkg}"], check=True, capture_output=True, timeout=300)
+        out = subprocess.run([exe, "--time"], capture_output=True, text=True, timeout=300)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {ex}"}
 
 
 def host_share(config, median_ms):

@@ -138,9 +138,10 @@ class DOGM
         meas_cell_array = p.meas_cell_array;
         weight_array = p.weight_array;
         born_masses_array = p.born_masses_array;
-        particle_array = ParticlesSoA::view(p.particle_array, particle_count, true);
-        particle_array_next = ParticlesSoA::view(p.particle_array_next, particle_count, true);
-        birth_particle_array = ParticlesSoA::view(p.birth_particle_array, new_born_particle_count, true);
+        // (rebind, not operator=: assigning a ParticlesSoA copies the particles, as in the reference)
+        particle_array.rebind(p.particle_array, particle_count, true);
+        particle_array_next.rebind(p.particle_array_next, particle_count, true);
+        birth_particle_array.rebind(p.birth_particle_array, new_born_particle_count, true);
     }
 
     ::dogm_handle* handle = nullptr;

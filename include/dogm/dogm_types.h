@@ -121,12 +121,33 @@ struct ParticlesSoA
         else if (!device && other.device)
             dogm_memcpy_d2h(memory_block, other.memory_block, num_bytes);
         else
-        {
-            void* tmp = std::malloc(num_bytes ? num_bytes : 1);
-            dogm_memcpy_d2h(tmp, other.memory_block, num_bytes);
-            dogm_memcpy_h2d(memory_block, tmp, num_bytes);
-            std::free(tmp);
-        }
+            dogm_memcpy_d2d(memory_block, other.memory_block, num_bytes); // device to device, also across GPUs of this process
+    }
+
+    // dogm_types.h:118-126: assignment COPIES THE CONTENTS into this set's own block (sizes must match, like the reference's
+    // assert).  Only an empty set (size 0, nothing to copy into) adopts the other's block as a non-owning view - the
+    // reference would assert there.  The copy constructor stays memberwise, as in the reference (returning a set by value
+    // hands the block on).
+    ParticlesSoA(const ParticlesSoA&) = default;
+    ParticlesSoA& operator=(const ParticlesSoA& other)
+    {
+        if (this == &other)
+            return *this;
+        if (size == 0 || memory_block == nullptr)
+            rebind(other.memory_block, other.size, other.device);
+        else
+            copy(other);
+        return *this;
+    }
+
+    // points this set at a block owned by somebody else (what DOGM does with its public members after every call)
+    void rebind(void* block, int count, bool is_device)
+    {
+        memory_block = block;
+        size = count;
+        device = is_device;
+        owns = false;
+        assignPointers();
     }
 
   private:

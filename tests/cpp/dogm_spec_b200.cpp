@@ -7,6 +7,7 @@
 #include "simulator.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -269,8 +270,90 @@ static int test_streaming_loop()
     return 0;
 }
 
-int main()
+static int test_particles_soa_assignment()
+{ // dogm_types.h:103-126: copy() and operator= copy the particles into the target's own block (any mix of host and device);
+  // only an empty set adopts the other's block
+    const int n = 1000;
+    dogm::ParticlesSoA a(n, false), b(n, false), d1(n, true), d2(n, true);
+    for (int i = 0; i < n; i++)
+    {
+        a.state[i] = dogm::vec4((float)i, 2.0f * i, -1.0f, 0.5f);
+        a.grid_cell_idx[i] = 7 * i;
+        a.weight[i] = 1.0f / (float)(i + 1);
+        a.associated[i] = (i % 3) == 0;
+    }
+    std::memset(b.memory_block, 0, DOGM_PARTICLE_BLOCK_BYTES(n));
+    d1 = a;  // host -> device
+    d2 = d1; // device -> device (direct copy, no host bounce)
+    b = d2;  // device -> host
+    CHECK(b.memory_block != a.memory_block && d1.memory_block != d2.memory_block);
+    CHECK(std::memcmp(a.memory_block, b.memory_block, DOGM_PARTICLE_BLOCK_BYTES(n)) == 0);
+    dogm::ParticlesSoA c(n, false);
+    c = a; // host -> host
+    CHECK(c.memory_block != a.memory_block && std::memcmp(a.memory_block, c.memory_block, DOGM_PARTICLE_BLOCK_BYTES(n)) == 0);
+    dogm::ParticlesSoA empty;
+    empty = a; // nothing to copy into: a view
+    CHECK(empty.memory_block == a.memory_block && empty.size == n && !empty.owns);
+    a.free();
+    b.free();
+    c.free();
+    d1.free();
+    d2.free();
+    return 0;
+}
+
+// --time: one updateGrid cycle through the C++ class (updateGrid + the refresh of its public members) against the same call
+// through the C ABI, headline configuration, device-resident measurement grid; prints one JSON line
+static int time_facade()
 {
+    dogm::DOGM::Params p;
+    p.size = 120.0f;
+    p.resolution = 0.1f;
+    p.particle_count = 2000000;
+    p.new_born_particle_count = 200000;
+    p.persistence_prob = 0.99f;
+    p.stddev_process_noise_position = 0.1f;
+    p.stddev_process_noise_velocity = 1.0f;
+    p.birth_prob = 0.02f;
+    p.stddev_velocity = 30.0f;
+    p.init_max_velocity = 30.0f;
+    p.freespace_discount = 0.01f;
+    LaserMeasurementGrid::Params lp;
+    lp.fov = 120.0f;
+    lp.max_range = 120.0f;
+    lp.resolution = p.resolution;
+    lp.stddev_range = 0.5f;
+    LaserMeasurementGrid gen(lp, p.size, p.resolution);
+    std::vector<float> scan(480, INFINITY);
+    for (int i = 100; i < 380; i += 3)
+        scan[i] = 20.0f + 0.2f * (float)(i % 50);
+    dogm::MeasurementCell* meas = gen.generateGrid(scan);
+    double ms[2] = {0.0, 0.0};
+    const int cycles = 200;
+    for (int variant = 0; variant < 2; variant++)
+    {
+        dogm::DOGM map(p);
+        for (int k = 0; k < 10; k++)
+            map.updateGrid(meas, 0.0f, 0.4f * k, 0.0f, 0.1f, true);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int k = 10; k < 10 + cycles; k++)
+        {
+            if (variant == 0)
+                map.updateGrid(meas, 0.0f, 0.4f * k, 0.0f, 0.1f, true);
+            else
+                dogm_update_grid(map.native(), meas, 0.0f, 0.4f * k, 0.0f, 0.1f, 1);
+        }
+        ms[variant] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / cycles;
+    }
+    std::printf("{\"facade_update_grid_ms\": %.5f, \"c_abi_update_grid_ms\": %.5f, \"refresh_overhead_us\": %.2f, \"cycles\": %d}\n", ms[0],
+                ms[1], (ms[0] - ms[1]) * 1e3, cycles);
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc > 1 && !std::strcmp(argv[1], "--time"))
+        return dogm_device_count() < 1 ? 2 : time_facade();
     if (dogm_device_count() < 1)
     {
         std::printf("no CUDA device\n");
@@ -281,6 +364,7 @@ int main()
     rc |= test_demo_flow();
     rc |= test_demo_main();
     rc |= test_streaming_loop();
+    rc |= test_particles_soa_assignment();
     std::printf(rc == 0 ? "dogm_spec_b200: all passed\n" : "dogm_spec_b200: FAILED\n");
     return rc;
 }
