@@ -156,14 +156,14 @@ void run_cycle(dogm_band_group* g, int r)
             g->born_total = born;
             g->weight_total = weight;
         }
-        { // device time of the four stages when the bands are profiled (dogm_band_set_profile), zeros otherwise
-            float st[4] = {0, 0, 0, 0};
+        { // own work per stage when the bands are profiled (dogm_band_set_profile; the waits for other bands are left out), zeros otherwise
+            float st[7] = {0, 0, 0, 0, 0, 0, 0};
             dogm_band_stage_times(h, st);
             g->band_ms[(size_t)r * 5 + 0] = st[0];
-            g->band_ms[(size_t)r * 5 + 1] = 0.0f;
-            g->band_ms[(size_t)r * 5 + 2] = st[1];
-            g->band_ms[(size_t)r * 5 + 3] = st[2];
-            g->band_ms[(size_t)r * 5 + 4] = st[3];
+            g->band_ms[(size_t)r * 5 + 1] = st[1] + st[3] + st[5]; // waiting for the other bands
+            g->band_ms[(size_t)r * 5 + 2] = st[2];
+            g->band_ms[(size_t)r * 5 + 3] = st[4];
+            g->band_ms[(size_t)r * 5 + 4] = st[6];
         }
         for (int k = 1; k <= 5; k++)
             mark(k);

@@ -170,9 +170,9 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->band.seq = 0;
     h->band.n_pred = 0;
     h->band.profile = false;
-    for (int k = 0; k < 5; k++)
+    for (int k = 0; k < 8; k++)
         h->band.stage_ev[k] = nullptr;
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 7; k++)
         h->band.stage_ms[k] = 0.0f;
     h->band.est_recv = 65536;
     h->band.est_birth = band ? band->birth_capacity : 0;
@@ -485,7 +485,7 @@ extern "C" void dogm_destroy(dogm_handle* h)
     if (h->band.pin)
         cudaFreeHost(h->band.pin);
     cudaFree(h->band.cnt);
-    for (int k = 0; k < 5; k++)
+    for (int k = 0; k < 8; k++)
         if (h->band.stage_ev[k])
             cudaEventDestroy(h->band.stage_ev[k]);
     cudaFree(h->band.mail);
@@ -1504,6 +1504,7 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
         const int n_pred = h->band.n_pred;
         if ((e = run_band_collect_sent(h, n_pred)))
             return e;
+        stamp(2);
         const bool halo = h->band.halo_rows > 0;
         if (R > 1 && (e = run_band_pull(h, n_pred, outbox_of_lower_neighbour, outbox_of_upper_neighbour,
                                         halo ? (const float*)edge_rows_of_lower_neighbour : nullptr,
@@ -1541,29 +1542,31 @@ extern "C" int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_me
         h->band.dev_cnt = nullptr;
         if (e)
             return e; // (the other bands run into the bounded waits of their collectors)
-        stamp(2);
+        stamp(3);
     }
     if (stages & DOGM_BAND_STAGE_BIRTH)
     { // born mass of the whole grid; birth particles; joint CDF; this band's joint weight to all bands
         h->band.dev_cnt = h->band.cnt;
         e = run_band_collect_born(h);
+        stamp(4);
         e = e ? e : run_birth_fill(h);
         e = e ? e : run_cdf(h);
         e = e ? e : run_band_publish_share(h, 1);
         h->band.dev_cnt = nullptr;
         if (e)
             return e;
-        stamp(3);
+        stamp(5);
     }
     if (stages & DOGM_BAND_STAGE_RESAMPLE)
     { // joint weight of the whole grid; this band's part of the draw
         h->band.dev_cnt = h->band.cnt;
         e = run_band_collect_weight(h);
+        stamp(6);
         e = e ? e : run_resample_gather(h);
         h->band.dev_cnt = nullptr;
         if (e)
             return e;
-        stamp(4);
+        stamp(7);
         DOGM_CHECK(cudaMemcpyAsync(h->band.cnt_host, h->band.cnt, sizeof(BandCounts), cudaMemcpyDeviceToHost, h->stream));
         h->cycle++;
     }
@@ -1575,18 +1578,18 @@ extern "C" int dogm_band_set_profile(dogm_handle* h, int enable)
     if (!h || !h->band.enabled)
         return DOGM_ERR_INVALID_ARGUMENT;
     if (enable && !h->band.stage_ev[0])
-        for (int k = 0; k < 5; k++)
+        for (int k = 0; k < 8; k++)
             DOGM_CHECK(cudaEventCreate(&h->band.stage_ev[k]));
     h->band.profile = enable != 0;
     return 0;
 }
 
-extern "C" int dogm_band_stage_times(const dogm_handle* h, float* out_ms4)
+extern "C" int dogm_band_stage_times(const dogm_handle* h, float* out_ms7)
 {
-    if (!h || !h->band.enabled || !out_ms4)
+    if (!h || !h->band.enabled || !out_ms7)
         return DOGM_ERR_INVALID_ARGUMENT;
-    for (int k = 0; k < 4; k++)
-        out_ms4[k] = h->band.stage_ms[k];
+    for (int k = 0; k < 7; k++)
+        out_ms7[k] = h->band.stage_ms[k];
     return 0;
 }
 
@@ -1597,7 +1600,7 @@ extern "C" int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* s
         return DOGM_ERR_INVALID_ARGUMENT;
     DOGM_CHECK(cudaStreamSynchronize(h->stream));
     const BandCounts c = *h->band.cnt_host;
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 7; k++)
     {
         h->band.stage_ms[k] = 0.0f;
         if (h->band.profile)

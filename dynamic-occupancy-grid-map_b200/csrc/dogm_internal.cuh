@@ -307,8 +307,8 @@ struct dogm_handle
         // launch sizes of the device-paced cycle: estimates from the previous cycle (the kernels loop, so any value is safe)
         int est_recv, est_birth, est_out, est_forced;
         bool profile;                      // record events at the stage boundaries (dogm_band_set_profile)
-        cudaEvent_t stage_ev[5];
-        float stage_ms[4];                 // predict + outbox, update, birth + CDF, resample of the last profiled cycle
+        cudaEvent_t stage_ev[8];
+        float stage_ms[7];                 // work and wait intervals of the last profiled cycle (dogm_band_stage_times)
     } band;
     int device;
     int sm_count;

@@ -264,12 +264,14 @@ int dogm_band_cycle_enqueue(dogm_handle* h, int stages, const dogm_meas_cell* me
                             const void* edge_rows_of_upper_neighbour);
 int dogm_band_cycle_finish(dogm_handle* h, int* particles_out, int* sent_lo, int* sent_hi, double* born_total,
                            double* weight_total);
-/* Profiling of the device-paced cycle: with enable != 0 events are recorded on the band's stream at the four stage boundaries
- * (they interrupt the launch chain, so a profiled cycle is a little slower); dogm_band_stage_times returns the device time
- * of the stages of the last profiled cycle: predict + outbox, update (incl. the wait for the neighbours), birth + CDF (incl.
- * the wait for the born masses), resample (incl. the wait for the joint weights). */
+/* Profiling of the device-paced cycle: with enable != 0 events are recorded on the band's stream around the three waits for the
+ * other bands' messages (they interrupt the launch chain, so a profiled cycle is a little slower); dogm_band_stage_times returns
+ * seven device times of the last profiled cycle, in stream order: [0] prediction + outbox + record counts published,
+ * [1] WAIT for the neighbours' counts, [2] pull + sort + per-cell sums + occupancy update + born mass published, [3] WAIT for the
+ * born masses, [4] birth particles + CDF + joint weight published, [5] WAIT for the joint weights, [6] resampling.  The even
+ * entries are the band's own work (what the band edges have to balance), the odd ones what it lost waiting for slower bands. */
 int dogm_band_set_profile(dogm_handle* h, int enable);
-int dogm_band_stage_times(const dogm_handle* h, float* out_ms4);
+int dogm_band_stage_times(const dogm_handle* h, float* out_ms7);
 
 /* out_ms[band * 5 + phase]: what every band itself spent in the phases of the last cycle (host wall clock, without the waiting
  * at the barriers) - the input for placing the band edges */
