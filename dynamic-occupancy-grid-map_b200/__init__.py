@@ -672,18 +672,23 @@ def balanced_rows(row_load, n_bands: int, min_rows: int = 64):
 
 
 def balanced_rows_by_phase(particles_per_row, n_bands: int, cost_particle_phases: float = 43.0, cost_particle_update: float = 37.0,
-                           cost_cell_update: float = 25.0, min_rows: int = 64):
+                           cost_cell_update=25.0, min_rows: int = 64):
     """Band edges for a cycle that runs in phases with a barrier after each: the particle phases (prediction, birth + CDF,
     resampling) cost a band `cost_particle_phases` per particle, the update phase (sort, per-cell sums, cell kernel)
     `cost_particle_update` per particle plus `cost_cell_update` per cell (picoseconds, measured on one B200; only the ratios
     matter).  A cycle takes  max_b(particle phases) + max_b(update phase):  the edges minimise that sum, which one load figure per
     row (balanced_rows) cannot - a band of many empty rows is cheap in particles and expensive in cells.
     For every bound P on the particle phases the smallest feasible bound U on the update phase is found by bisection; feasibility
-    is a greedy sweep (a band takes rows while both bounds hold), exact for contiguous bands."""
+    is a greedy sweep (a band takes rows while both bounds hold), exact for contiguous bands.
+    `cost_cell_update` may be an array with one cost per row (per cell of that row): empty regions of a large grid cost the
+    cell kernel a fraction of what occupied ones do (its quiet-block shortcut), which a placement measured per band can tell.
+    The device-paced cycle (dogm_band_group) only meets ALL bands at the two normaliser exchanges; the prediction is coupled
+    to the neighbours alone, so it belongs to the update phase there: DEVICE_PACED_COSTS."""
     n_row = np.asarray(particles_per_row, np.float64)
     G = n_row.size
     cum_n = np.concatenate([[0.0], np.cumsum(n_row)])
-    cum_u = cost_particle_update * cum_n + cost_cell_update * G * np.arange(G + 1, dtype=np.float64)
+    cell_rows = np.broadcast_to(np.asarray(cost_cell_update, np.float64), (G,)) * G
+    cum_u = cost_particle_update * cum_n + np.concatenate([[0.0], np.cumsum(cell_rows)])
     total_n, total_u = cum_n[-1], cum_u[-1]
 
     def sweep(P, U):
@@ -725,6 +730,32 @@ def balanced_rows_by_phase(particles_per_row, n_bands: int, cost_particle_phases
         return balanced_rows(n_row + 1.0, n_bands, min_rows)
     cuts = best[1]
     return [cuts[i + 1] - cuts[i] for i in range(n_bands)]
+
+
+# picoseconds per particle in (birth + CDF + resampling), per particle in (prediction + sort + sums), per cell in the cell kernel
+DEVICE_PACED_COSTS = dict(cost_particle_phases=30.0, cost_particle_update=49.0, cost_cell_update=25.0)
+
+
+def band_costs_from_measurement(particles_per_band, rows, band_ms, G, cost_cell_default: float = 25.0):
+    """Costs for balanced_rows_by_phase from the bands' own stage times of a profiled placement (band_ms[b] = [predict, waits,
+    pull + sort + cells, birth + CDF, resample] in ms): the per-particle costs from the band with the most particles (its cell
+    part taken at the default cost), and one cell cost per band - what its update stage took beyond its particles - spread over
+    its rows.  Returns (cost_particle_phases, cost_particle_update, cost per row [G]) in ps, or None."""
+    ms = np.asarray(band_ms, np.float64)
+    n = np.asarray(particles_per_band, np.float64)
+    rows = np.asarray(rows, np.int64)
+    cells = rows.astype(np.float64) * G
+    if ms.ndim != 2 or ms.shape[0] != n.size or n.max() <= 0:
+        return None
+    ps = 1e9  # ms -> ps
+    b = int(np.argmax(n))
+    c_phase = float(np.median(((ms[:, 3] + ms[:, 4]) * ps / np.maximum(n, 1.0))[n > 0.25 * n.max()]))
+    a_b = (ms[:, 0] + ms[:, 2]) * ps
+    c_upd = (a_b[b] - cost_cell_default * cells[b]) / n[b]
+    if not (c_phase > 0 and c_upd > 0):
+        return None
+    c_cell_band = np.clip((a_b - c_upd * n) / np.maximum(cells, 1.0), 0.08 * cost_cell_default, 4.0 * cost_cell_default)
+    return c_phase, float(c_upd), np.repeat(c_cell_band, rows)
 
 
 def band_cycle_model(particles_per_row, rows, cost_particle_phases: float = 43.0, cost_particle_update: float = 37.0,

@@ -131,3 +131,42 @@ def test_band_edges_by_phase():
     # degenerate: no particles at all -> still a valid split
     rows0 = gpu.balanced_rows_by_phase(np.zeros(G), 4)
     assert len(rows0) == 4 and sum(rows0) == G and min(rows0) >= 64
+
+
+def test_band_edges_from_measured_costs():
+    """Closing the loop on the band edges: a synthetic 'machine' whose cell kernel is five times cheaper on rows without
+    particles (the quiet-block shortcut) times a placement; band_costs_from_measurement turns the bands' own stage times into
+    per-particle costs and one cell cost per band; the placement made with them is faster on that machine than the one made
+    with the default costs, and the per-row cell costs are accepted by the solver (tiles the rows, minimum height kept)."""
+    gpu = load_dogm_b200()
+    G, R = 4096, 8
+    y = np.arange(G, dtype=np.float64)
+    hist = np.exp(-(G - y) / 500.0)
+    hist[:2000] = 0.0
+    hist = hist / hist.sum() * 2e7
+
+    def machine(rows):
+        """per band [predict, waits, update, birth + CDF, resample] in ms and the cycle time (device-paced: max over the bands of
+        predict + update, then of birth + CDF, then of resampling)"""
+        cuts = np.concatenate([[0], np.cumsum(rows)]).astype(int)
+        ms = []
+        for b in range(len(rows)):
+            n = hist[cuts[b]:cuts[b + 1]].sum()
+            quiet = (hist[cuts[b]:cuts[b + 1]] == 0).sum() * G
+            busy = rows[b] * G - quiet
+            ms.append([12e-9 * n, 0.0, 37e-9 * n + 25e-9 * busy + 5e-9 * quiet, 13e-9 * n, 17e-9 * n])
+        ms = np.asarray(ms)
+        return ms, (ms[:, 0] + ms[:, 2]).max() + ms[:, 3].max() + ms[:, 4].max()
+
+    rows1 = gpu.balanced_rows_by_phase(hist, R, **gpu.DEVICE_PACED_COSTS)
+    ms1, t1 = machine(rows1)
+    cuts = np.concatenate([[0], np.cumsum(rows1)]).astype(int)
+    n_b = [hist[cuts[b]:cuts[b + 1]].sum() for b in range(R)]
+    costs = gpu.band_costs_from_measurement(n_b, rows1, ms1, G)
+    assert costs is not None and costs[2].shape == (G,)
+    assert abs(costs[0] - 30.0) < 1.0 and abs(costs[1] - 49.0) < 3.0
+    rows2 = gpu.balanced_rows_by_phase(hist, R, cost_particle_phases=costs[0], cost_particle_update=costs[1], cost_cell_update=costs[2])
+    assert len(rows2) == R and sum(rows2) == G and min(rows2) >= 64
+    _, t2 = machine(rows2)
+    assert t2 < 0.97 * t1, (t1, t2, rows1, rows2)
+    assert gpu.band_costs_from_measurement([0.0] * R, rows1, ms1, G) is None
