@@ -156,6 +156,8 @@ _SYMBOLS = [
     ("dogm_statistical_moments", C.c_int, [_P]),
     ("dogm_resampling", C.c_int, [_P]),
     ("dogm_get_grid_cells", C.c_int, [_P, _P]),
+    ("dogm_get_grid_cells_begin", C.c_int, [_P, _P]),
+    ("dogm_get_grid_cells_wait", C.c_int, [_P]),
     ("dogm_get_measurement_cells", C.c_int, [_P, _P]),
     ("dogm_get_particles", C.c_int, [_P, _P]),
     ("dogm_get_grid_size", C.c_int, [_P]),
@@ -394,6 +396,13 @@ class DOGM:
         out = np.empty(self.grid_cell_count, dtype=GRID_CELL_DTYPE) if out is None else out
         _check(self._lib.dogm_get_grid_cells(self._h, _ptr(out)), "dogm_get_grid_cells")
         return out
+
+    def get_grid_cells_begin(self, out: np.ndarray) -> None:
+        """pipelined getGridCells: starts the copy of the last cycle's cells into `out` (pinned) on the copy stream"""
+        _check(self._lib.dogm_get_grid_cells_begin(self._h, _ptr(out)), "dogm_get_grid_cells_begin")
+
+    def get_grid_cells_wait(self) -> None:
+        _check(self._lib.dogm_get_grid_cells_wait(self._h), "dogm_get_grid_cells_wait")
 
     def get_measurement_cells(self) -> np.ndarray:
         out = np.empty(self.grid_cell_count, dtype=MEAS_CELL_DTYPE)

@@ -194,6 +194,10 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     h->shift_particles_pending = h->shift_grid_pending = false;
     h->cycle = 0;
     h->hist0_valid = false;
+    h->grid_alt = nullptr;
+    h->copy_stream = nullptr;
+    h->grid_copy_busy[0] = h->grid_copy_busy[1] = false;
+    h->grid_swap_pending = false;
     h->launch_count = 0;
     h->timing = false;
     h->timer_ready = false;
@@ -433,6 +437,15 @@ extern "C" void dogm_destroy(dogm_handle* h)
     cudaFree(h->sw);
     cudaFree(h->birth.block);
     cudaFree(h->grid);
+    if (h->grid_alt)
+    {
+        cudaStreamSynchronize(h->copy_stream);
+        cudaFree(h->grid_alt);
+        cudaEventDestroy(h->cycle_done_ev);
+        cudaEventDestroy(h->grid_copy_ev[0]);
+        cudaEventDestroy(h->grid_copy_ev[1]);
+        cudaStreamDestroy(h->copy_stream);
+    }
     cudaFree(h->meas);
     cudaFree(h->weight_array);
     cudaFree(h->born_masses);
@@ -778,6 +791,46 @@ extern "C" int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host)
 {
     return copy_out(h, out_host, h ? h->grid : nullptr, h ? (size_t)h->C * sizeof(dogm_grid_cell) : 0);
 }
+// Pipelined getGridCells: the copy is enqueued on a stream of its own behind everything the handle has enqueued so far and
+// overlaps whatever is enqueued next (the next cycle's measurement upload and kernels); from then on the handle owns two
+// GridCell buffers and the cell kernel alternates between them.
+extern "C" int dogm_get_grid_cells_begin(dogm_handle* h, dogm_grid_cell* out_host)
+{
+    if (!h || !out_host)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (h->band.enabled)
+        return DOGM_ERR_UNSUPPORTED;
+    DOGM_CHECK(cudaSetDevice(h->device));
+    if (!h->grid_alt)
+    {
+        DOGM_CHECK(cudaMalloc((void**)&h->grid_alt, (size_t)h->C * sizeof(dogm_grid_cell)));
+        DOGM_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        DOGM_CHECK(cudaEventCreateWithFlags(&h->cycle_done_ev, cudaEventDisableTiming));
+        DOGM_CHECK(cudaEventCreateWithFlags(&h->grid_copy_ev[0], cudaEventDisableTiming));
+        DOGM_CHECK(cudaEventCreateWithFlags(&h->grid_copy_ev[1], cudaEventDisableTiming));
+        // (a caller may read cells of the other buffer through the stage API before the first full cycle has written it)
+        DOGM_CHECK(cudaMemcpyAsync(h->grid_alt, h->grid, (size_t)h->C * sizeof(dogm_grid_cell), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    DOGM_CHECK(cudaEventRecord(h->cycle_done_ev, h->stream));
+    DOGM_CHECK(cudaStreamWaitEvent(h->copy_stream, h->cycle_done_ev, 0));
+    DOGM_CHECK(cudaMemcpyAsync(out_host, h->grid, (size_t)h->C * sizeof(dogm_grid_cell), cudaMemcpyDeviceToHost, h->copy_stream));
+    DOGM_CHECK(cudaEventRecord(h->grid_copy_ev[0], h->copy_stream));
+    h->grid_copy_busy[0] = true;
+    h->grid_swap_pending = true;
+    return 0;
+}
+
+extern "C" int dogm_get_grid_cells_wait(dogm_handle* h)
+{
+    if (!h)
+        return DOGM_ERR_INVALID_ARGUMENT;
+    if (!h->grid_alt)
+        return 0;
+    DOGM_CHECK(cudaSetDevice(h->device));
+    DOGM_CHECK(cudaStreamSynchronize(h->copy_stream));
+    return 0;
+}
+
 extern "C" int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_host)
 {
     if (h && materialize_meas(h))

@@ -327,6 +327,14 @@ struct dogm_handle
     bool sorted_valid;            // spair / sw describe the current particles sorted by cell and the per-cell sums exist
     dogm_b200::ParticleSet birth; // birth_particle_array
     dogm_grid_cell* grid;
+    // pipelined read-out (dogm_get_grid_cells_begin / _wait): a second GridCell buffer the cell kernel alternates with, so that
+    // the copy of cycle n's cells to the host (copy stream) runs under cycle n + 1; null until the first _begin
+    dogm_grid_cell* grid_alt;
+    cudaStream_t copy_stream;
+    cudaEvent_t cycle_done_ev;     // main stream: everything enqueued before the read-out was started
+    cudaEvent_t grid_copy_ev[2];   // copy stream: the read-out of `grid` (0) / of the buffer now in `grid_alt` (1) has finished
+    bool grid_copy_busy[2];
+    bool grid_swap_pending;        // the next cell kernel writes the other buffer (set by _begin, done by run_occupancy_update)
     dogm_meas_cell* meas;
     float* weight_array;
     float* born_masses;

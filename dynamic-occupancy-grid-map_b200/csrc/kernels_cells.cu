@@ -767,6 +767,26 @@ int run_init_particles(dogm_handle* h)
 
 int run_occupancy_update(dogm_handle* h, float dt)
 {
+    if (h->grid_swap_pending)
+    { // pipelined read-out: the cells of the previous cycle are still on their way to the host; this cycle writes the other
+      // buffer (every field of every cell is written by the dense cell kernel, nothing of the old buffer is read), once the copy
+      // that last read THAT buffer has finished
+        h->grid_swap_pending = false;
+        dogm_grid_cell* t = h->grid;
+        h->grid = h->grid_alt;
+        h->grid_alt = t;
+        const cudaEvent_t e = h->grid_copy_ev[0];
+        h->grid_copy_ev[0] = h->grid_copy_ev[1];
+        h->grid_copy_ev[1] = e;
+        const bool b = h->grid_copy_busy[0];
+        h->grid_copy_busy[0] = h->grid_copy_busy[1];
+        h->grid_copy_busy[1] = b;
+        if (h->grid_copy_busy[0])
+        {
+            cudaStreamWaitEvent(h->stream, h->grid_copy_ev[0], 0);
+            h->grid_copy_busy[0] = false;
+        }
+    }
     CellArgs a;
     a.C = h->C;
     a.gs = h->gs;
@@ -831,7 +851,7 @@ int run_occupancy_update(dogm_handle* h, float dt)
     h->cell_kernel_done = false;
     {
         LaunchScope ls(h, K_CELL, 96.0 * h->C);
-        const bool quiet = !h->quiet_off;
+        const bool quiet = !h->quiet_off && !h->grid_alt; // (the shortcut relies on the ONE grid buffer holding last cycle's cells)
         if (lazy)
         {
             if (quiet)

@@ -51,6 +51,17 @@ class DOGM
         dogm_get_grid_cells(handle, cells.data());
         return cells;
     }
+    // getGridCells without stalling the filter (not in the reference): the cells of the last updateGrid start travelling into
+    // `pinned_out` (cudaMallocHost memory of grid_cell_count cells) and arrive under the following updateGrid calls;
+    // waitGridCells() returns when they are there.  grid_cell_array alternates between two device buffers from then on.
+    void getGridCellsAsync(GridCell* pinned_out)
+    {
+        dogm_get_grid_cells_begin(handle, pinned_out);
+    }
+    void waitGridCells()
+    {
+        dogm_get_grid_cells_wait(handle);
+    }
     std::vector<MeasurementCell> getMeasurementCells() const // dogm.cu:143-151
     {
         std::vector<MeasurementCell> cells(static_cast<size_t>(grid_cell_count));

@@ -288,6 +288,16 @@ int dogm_band_group_mark_initialized(dogm_band_group* g);
  * Read-out (blocking device-to-host copies, dogm.cu:133-159, dogm.h:111-139)
  * ---------------------------------------------------------------------------------------------------------- */
 int dogm_get_grid_cells(dogm_handle* h, dogm_grid_cell* out_host);        /* getGridCells: grid_cell_count * 64 B */
+/* getGridCells without stopping the filter (the reference's demo loop reads all cells after every updateGrid,
+ * demo/main.cpp:94-110 -> dogm.cu:133-141: 64 B per cell over PCIe, ten times the cycle itself at the 1200^2 size).
+ * _begin enqueues the copy of the cells of the cycle enqueued last into out_host (page-locked memory, or the copy is not
+ * asynchronous) on a copy stream of the handle and returns; the copy then runs under the dogm_update_grid* calls that follow:
+ * from the first _begin on the handle keeps two GridCell buffers and the cell kernel alternates between them
+ * (dogm_get_device_ptrs / the C++ class's grid_cell_array follow).  _wait returns when every copy begun so far has arrived.
+ *   update(n); begin(n, buf[n & 1]); ... update(n + 1); wait(); use buf[n & 1]; begin(n + 1, buf[(n + 1) & 1]); ...
+ * Not available on band handles (DOGM_ERR_UNSUPPORTED). */
+int dogm_get_grid_cells_begin(dogm_handle* h, dogm_grid_cell* out_host);
+int dogm_get_grid_cells_wait(dogm_handle* h);
 int dogm_get_measurement_cells(dogm_handle* h, dogm_meas_cell* out_host); /* getMeasurementCells: count * 16 B */
 int dogm_get_particles(dogm_handle* h, void* out_block);                  /* getParticles: particle block of N */
 int dogm_get_grid_size(const dogm_handle* h);                             /* getGridSize */

@@ -453,3 +453,47 @@ def test_degenerate_inputs_terminate(gpu, orc):
         d.update_grid(grid, 0.0, 0.0, 0.0, 0.1, device=False)
     d.close()
     gen.close()
+
+
+def test_pipelined_grid_cell_readback_equals_the_blocking_getter(gpu):
+    """dogm_get_grid_cells_begin / _wait (the copy of cycle n's cells runs under cycle n + 1, the cell kernel alternates between
+    two GridCell buffers): every cycle's cells arrive bit-identical to what dogm_get_grid_cells returns for a twin handle that
+    is driven with blocking calls; the device pointer of the grid cells follows the buffer the last cycle wrote; the blocking
+    getter still works in between; a read-out begun twice for one cycle delivers the same cells twice."""
+    size, res, n, b = 64.0, 0.5, 60000, 6000
+    p = make_params(gpu, size, res, n, b)
+    twins = []
+    for _ in range(2):
+        d = gpu.DOGM(p)
+        d.set_options(seed=99, noise_mode=gpu.NOISE_PHILOX, resample_mode=gpu.RESAMPLE_SYSTEMATIC)
+        twins.append(d)
+    a, pl = twins
+    gs, C = a.grid_size, a.grid_cell_count
+    rng = np.random.default_rng(5)
+    meas = [gpu.pinned_empty((C,), gpu.MEAS_CELL_DTYPE) for _ in range(3)]
+    for m in meas:
+        m[:] = synthetic_meas(gpu.MEAS_CELL_DTYPE, gs, rng)
+    bufs = [gpu.pinned_empty((C,), gpu.GRID_CELL_DTYPE) for _ in range(2)]
+    extra = gpu.pinned_empty((C,), gpu.GRID_CELL_DTYPE)
+    expected, ptrs = [], set()
+    cycles = 7
+    for c in range(cycles):
+        x, y = 0.3 * c, 0.7 * c
+        a.update_grid(meas[c % 3], x, y, 0.0, 0.1, device=False)
+        expected.append(a.get_grid_cells().copy())
+        pl.update_grid(meas[c % 3], x, y, 0.0, 0.1, device=False, sync=False)
+        if c > 0:
+            pl.get_grid_cells_wait()
+            assert np.array_equal(bufs[(c - 1) & 1].view(np.uint8), expected[c - 1].view(np.uint8)), f"cycle {c - 1}"
+        pl.get_grid_cells_begin(bufs[c & 1])
+        if c == 3:
+            pl.get_grid_cells_begin(extra)  # the same cycle once more
+            assert np.array_equal(pl.get_grid_cells().view(np.uint8), expected[c].view(np.uint8))  # and through the blocking getter
+        ptrs.add(int(pl.device_ptrs().grid_cell_array))
+    pl.get_grid_cells_wait()
+    assert np.array_equal(bufs[(cycles - 1) & 1].view(np.uint8), expected[-1].view(np.uint8))
+    assert np.array_equal(extra.view(np.uint8), expected[3].view(np.uint8))
+    assert len(ptrs) == 2  # two buffers in turn
+    assert_particles_equal(pl.get_particles(), a.get_particles(), "populations of the twins")
+    for d in twins:
+        d.close()
