@@ -46,7 +46,12 @@ def compare_after_cycle(d, o, p, tag):
     assert np.array_equal(d.get_resampled_indices(), o.resampled_idx), f"{tag}: ancestor indices differ"
     assert np.array_equal(d.get_weight_array().view(np.uint32), o.weight_array.view(np.uint32)), f"{tag}: weight_array"
     assert np.array_equal(d.get_born_masses().view(np.uint32), o.born_masses.view(np.uint32)), f"{tag}: born masses"
-    assert np.allclose(d.get_joint_weight_accum(), o.joint_weight_accum, rtol=1e-13, atol=0), f"{tag}: cdf"
+    # Both sides add the same float weights in double, the oracle one after the other, the kernel tile-wise.  While the weights
+    # span less than 2^29 the partial sums are exact in either order (24-bit addends, 53-bit accumulator) and the arrays are
+    # equal to the last bit; with very small weights in the set (a birth weight of 1e-12 next to persistent weights of 1e-4) the
+    # two orders round differently in the last bits: a serial double sum of k terms is off by about sqrt(k) * 2^-53 relative,
+    # 1e-13 at k = 3e5.  What decides the ancestors is checked bit for bit above.
+    assert np.allclose(d.get_joint_weight_accum(), o.joint_weight_accum, rtol=1e-12, atol=0), f"{tag}: cdf"
     assert_cells_match(d.get_grid_cells(), o.grid_cells, p.stddev_velocity)
     assert (d.get_position_x(), d.get_position_y(), d.get_yaw()) == o.position
 
