@@ -697,7 +697,7 @@ def fit_band_costs(info, G):
         return None
 
 
-def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, scans=2, max_placements=3):
+def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, scans=2, max_placements=2):
     """ONE grid over n_gpus GPUs against the same grid on one GPU in the same run.  Band edges from the 1-GPU run's particle
     row histogram (balanced_rows_by_phase); device-paced cycles (the bands' messages travel GPU to GPU, one host
     synchronisation per cycle); wall clock around the blocking group update, which is what a caller sees per cycle."""
@@ -718,11 +718,12 @@ def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, s
             gen.close()
             G = int(round(np.sqrt(grids[0].size)))
 
-            def run(bands, rows, profile):
-                bd = gpu.BandedDOGM(params, bands, devices=list(range(bands)), seed=123456, rows=rows, slack=2.5)
+            def run(bands, rows, profile, devices=None):
+                devices = list(range(bands)) if devices is None else list(devices)
+                bd = gpu.BandedDOGM(params, bands, devices=devices, seed=123456, rows=rows, slack=2.5)
                 meas = []
                 for r in range(bands):
-                    gpu.set_device(r)
+                    gpu.set_device(devices[r])
                     lo, hi = bd.row0[r] * bd.G, (bd.row0[r] + bd.rows[r]) * bd.G
                     ptrs = []
                     for g in grids:
@@ -768,7 +769,7 @@ def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, s
                     hist = np.bincount(np.clip(state[:, 1].astype(np.int64), 0, G - 1), minlength=G).astype(np.float64)
                     del state
                 for r in range(bands):
-                    gpu.set_device(r)
+                    gpu.set_device(devices[r])
                     for ptr in meas[r]:
                         gpu.device_free(ptr)
                 bd.close()
@@ -805,6 +806,41 @@ def band_scaling(gpu, n_gpus, configs=("highway", "metro"), cycles=12, warm=6, s
                     if last["ms_per_cycle"] < many["ms_per_cycle"]:
                         many = last
                 many["placements_tried"] = tried
+                # two bands per GPU, one from either end of the grid (paired_band_plan): a GPU then owns particle-heavy and
+                # cell-heavy rows alike and no stage waits for a band that is heavy in the other resource.
+                # (skipped where a cycle is so short that the staged submission the shared GPUs need - a host barrier per stage -
+                # costs more than the balance gains)
+                if R >= 2 and 2 * R <= 16 and many["ms_per_cycle"] >= 0.6:
+                    try:
+                        single = many
+                        pairs = []
+
+                        def try_pair(kw, label, source):
+                            rows_p, dev_p, _ = gpu.paired_band_plan(hist, R, **kw)
+                            if any(rows_p == q["rows"] for q in pairs):
+                                return None
+                            info, _ = run(2 * R, rows_p, profile=True, devices=dev_p)
+                            info["devices"] = dev_p
+                            info["edges"] = f"two bands per GPU (band b with band 2R-1-b), cuts from {label}"
+                            pairs.append({"rows": info["rows"], "ms_per_cycle": info["ms_per_cycle"], "costs": source})
+                            return info
+
+                        # (cuts from costs fitted to a measured placement were tried here as well: they lost every time against
+                        # the fixed costs - two bands that share a GPU stretch each other's stage times unevenly)
+                        cands = [try_pair(gpu.DEVICE_PACED_COSTS, "the default costs", "default"),
+                                 try_pair(dict(gpu.DEVICE_PACED_COSTS, cost_cell_update=19.0), "the default costs with the cell kernel at its "
+                                          "DRAM floor (120 B per cell)", "default, 19 ps per cell")]
+                        cands = [c for c in cands if c is not None]
+                        if cands:
+                            lead = min(cands, key=lambda c: c["ms_per_cycle"])
+                            rec["two_bands_per_gpu"] = {"tried": pairs, "devices": lead["devices"]}
+                            if lead["ms_per_cycle"] < single["ms_per_cycle"]:
+                                lead["placements_tried"] = tried
+                                lead["one_band_per_gpu"] = {"rows": single["rows"], "ms_per_cycle": single["ms_per_cycle"],
+                                                            "phases_ms": single.get("phases_ms")}
+                                many = lead
+                    except Exception as ex:
+                        rec["two_bands_per_gpu"] = {"error": f"{type(ex).__name__}: {ex}"}
                 many.pop("band_ms", None)
                 rec.update(many)
                 rec["speedup_vs_1gpu_same_run"] = one["ms_per_cycle"] / many["ms_per_cycle"]

@@ -767,6 +767,64 @@ def band_costs_from_measurement(particles_per_band, rows, band_ms, G, cost_cell_
     return c_phase, float(c_upd), np.repeat(c_cell_band, rows)
 
 
+def paired_band_plan(particles_per_row, n_gpus: int, cost_particle_phases: float = 30.0, cost_particle_update: float = 49.0,
+                     cost_cell_update=25.0, min_rows: int = 64):
+    """Two bands per GPU: 2 * n_gpus contiguous bands, band b and band 2 * n_gpus - 1 - b on the same GPU.  A scene seen by one
+    sensor is dense near it and empty far away; with one contiguous band per GPU a band is either heavy in particles (it sets the
+    pace of birth + CDF and of the resampling) or heavy in cells (it sets the pace of the cell kernel) and every stage waits for
+    another band.  A GPU that owns one band from either end gets its share of both.  The cuts minimise
+    max_gpu(particle phases) + max_gpu(update phase) for the given costs (descent over the cuts, steps from G / 16 down to one
+    row).  Returns (rows per band, device per band, modelled cycle time)."""
+    n_row = np.asarray(particles_per_row, np.float64)
+    G = n_row.size
+    R, B = n_gpus, 2 * n_gpus
+    if G < B * min_rows:
+        raise ValueError("grid too small for two bands per GPU")
+    cum_n = np.concatenate([[0.0], np.cumsum(n_row)])
+    cell_rows = np.broadcast_to(np.asarray(cost_cell_update, np.float64), (G,)) * G
+    cum_c = np.concatenate([[0.0], np.cumsum(cell_rows)])
+    cum_u = cost_particle_update * cum_n + cum_c
+    devices = [b if b < R else B - 1 - b for b in range(B)]
+
+    def model(cuts, tau=0.0):
+        n_b = np.diff(cum_n[cuts])
+        u_b = np.diff(cum_u[cuts])
+        p_g = cost_particle_phases * (n_b[:R] + n_b[::-1][:R])
+        u_g = u_b[:R] + u_b[::-1][:R]
+        if tau <= 0.0:
+            return p_g.max() + u_g.max()
+        # smooth maximum: a descent over the cuts does not stall on the plateaus of the hard one
+        return (p_g.max() + tau * np.log(np.exp((p_g - p_g.max()) / tau).sum())) + (u_g.max() + tau * np.log(np.exp((u_g - u_g.max()) / tau).sum()))
+
+    # start: equal update cost per band, minimum heights enforced from both ends
+    cuts = [0]
+    for b in range(1, B):
+        c = int(np.searchsorted(cum_u, cum_u[-1] * b / B))
+        cuts.append(min(max(c, cuts[-1] + min_rows), G - (B - b) * min_rows))
+    cuts.append(G)
+    cuts = np.asarray(cuts, np.int64)
+    scale = (cost_particle_phases * cum_n[-1] + cum_u[-1]) / R
+    for tau in (0.05 * scale, 0.02 * scale, 0.005 * scale, 0.001 * scale, 0.0):
+        best = model(cuts, tau)
+        step = max(1, G // 16)
+        while step >= 1:
+            improved = True
+            while improved:
+                improved = False
+                for i in range(1, B):
+                    for d in (-step, step):
+                        c = cuts[i] + d
+                        if c - cuts[i - 1] < min_rows or cuts[i + 1] - c < min_rows:
+                            continue
+                        trial = cuts.copy()
+                        trial[i] = c
+                        t = model(trial, tau)
+                        if t < best * (1.0 - 1e-9):
+                            cuts, best, improved = trial, t, True
+            step //= 2
+    return [int(v) for v in np.diff(cuts)], devices, float(model(cuts))
+
+
 def band_cycle_model(particles_per_row, rows, cost_particle_phases: float = 43.0, cost_particle_update: float = 37.0,
                      cost_cell_update: float = 25.0) -> float:
     """the modelled cycle time (same units as the costs) of a given split: max over bands per phase, summed"""

@@ -170,3 +170,25 @@ def test_band_edges_from_measured_costs():
     _, t2 = machine(rows2)
     assert t2 < 0.97 * t1, (t1, t2, rows1, rows2)
     assert gpu.band_costs_from_measurement([0.0] * R, rows1, ms1, G) is None
+
+
+def test_two_bands_per_gpu_plan():
+    """paired_band_plan: 2 R contiguous bands, band b and band 2 R - 1 - b on one GPU; the split tiles the rows with the minimum
+    height, every GPU gets two bands, and for a scene that is dense at one end the modelled cycle (slowest GPU per phase, summed)
+    beats the best split with one contiguous band per GPU."""
+    gpu = load_dogm_b200()
+    G, R = 16384, 8
+    y = np.arange(G, dtype=np.float64)
+    hist = np.exp(-(G - y) / 2500.0)
+    hist[:3000] *= 0.01
+    hist = hist / hist.sum() * 2e8
+    rows, devices, t_pair = gpu.paired_band_plan(hist, R)
+    assert len(rows) == 2 * R and sum(rows) == G and min(rows) >= 64
+    assert sorted(devices) == sorted(list(range(R)) * 2) and devices[0] == devices[-1] and devices[R - 1] == devices[R]
+    single = gpu.balanced_rows_by_phase(hist, R, **gpu.DEVICE_PACED_COSTS)
+    t_single = gpu.band_cycle_model(hist, single, **gpu.DEVICE_PACED_COSTS)
+    assert t_pair < 0.93 * t_single, (t_pair, t_single)
+    # uniform scene: nothing to gain, nothing lost
+    uni = np.full(G, 2e8 / G)
+    _, _, t_u = gpu.paired_band_plan(uni, R)
+    assert t_u <= 1.01 * gpu.band_cycle_model(uni, gpu.balanced_rows_by_phase(uni, R, **gpu.DEVICE_PACED_COSTS), **gpu.DEVICE_PACED_COSTS)
