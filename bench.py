@@ -501,7 +501,7 @@ def run_ours(args, dist):
     # ---- independent sensor streams on one GPU (BASELINE.json configs[3]: 64 streams over 8 GPUs = 8 per GPU): extra handles
     #      on their own CUDA streams fill the latency-bound gaps of a single cycle; reported next to the headline value
     streams_info = None
-    extra_handles = 3 if (C * 64 + cfg["n"] * 200) * 3 < 40e9 else 0
+    extra_handles = 7 if (C * 64 + cfg["n"] * 200) * 7 < 40e9 else 0  # 8 streams per GPU: 64 on a box of 8
     if extra_handles:
         others = []
         for s in range(extra_handles):

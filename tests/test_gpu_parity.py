@@ -56,13 +56,13 @@ def compare_after_cycle(d, o, p, tag):
     assert (d.get_position_x(), d.get_position_y(), d.get_yaw()) == o.position
 
 
-def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, **over):
+def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, systematic=False, **over):
     rng = np.random.default_rng(seed)
     p = make_params(gpu, size, res, n, b, **over)
     po = make_params(orc, size, res, n, b, **over)
     d = gpu.DOGM(p)
-    d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_INJECTED)
-    o = orc.OracleDOGM(po, resample_mode=orc.RESAMPLE_INJECTED)
+    d.set_options(noise_mode=gpu.NOISE_INJECTED, resample_mode=gpu.RESAMPLE_SYSTEMATIC if systematic else gpu.RESAMPLE_INJECTED)
+    o = orc.OracleDOGM(po, resample_mode=orc.RESAMPLE_SYSTEMATIC if systematic else orc.RESAMPLE_INJECTED)
     gs = d.grid_size
     assert gs == o.grid_size
     meas = None
@@ -98,6 +98,25 @@ def test_free_running_bucket_sort(gpu, orc, monkeypatch, size, res, n, b, ego):
     ancestors and masses as the radix passes give."""
     monkeypatch.setenv("DOGM_B200_SORT", "bucket")
     free_run(gpu, orc, size, res, n, b, cycles=5, seed=21, ego=ego)
+
+
+@pytest.mark.parametrize("size,res,n,b,ego,over", [
+    (64.0, 0.5, 100000, 10000, (0.3, 0.8), {}),
+    (50.0, 0.2, 300000, 30000, (0.0, 0.4), {}),            # the demo size
+    (120.0, 0.25, 37000, 900, (-0.6, 0.2), {}),            # few birth particles, ragged last tile
+    (9.0, 0.3, 1001, 77, (-0.7, 0.35), {}),                # not a multiple of anything
+    (10.0, 1.0, 2, 1, (1.5, -2.5), {}),                    # two particles
+    (33.0, 0.5, 4097, 513, (0.0, 0.0), {}),
+    (8.0, 0.5, 3000, 0, (0.0, 0.6), {}),                   # no birth particles at all
+    (4.0, 0.5, 30000, 3000, (0.0, 0.0), dict(stddev_process_noise_position=0.01, stddev_process_noise_velocity=0.1,
+                                             stddev_velocity=0.5, init_max_velocity=0.5)),  # 64 cells: long runs of copies
+])
+def test_free_running_systematic_resampling(gpu, orc, size, res, n, b, ego, over):
+    """Systematic resampling (BASELINE.json's production mode: one fraction for all offsets; window starts claimed by the CDF
+    kernel, search in shared memory) against the oracle's lower_bound on the same CDF with the same fraction: ancestors, the
+    next population and everything downstream bit for bit, over free-running cycles with shifts - ragged sizes, two particles,
+    no birth particles, long runs of copies of one ancestor."""
+    free_run(gpu, orc, size, res, n, b, cycles=5, seed=41, ego=ego, systematic=True, **over)
 
 
 def test_free_running_config1_reference_demo(gpu, orc):
