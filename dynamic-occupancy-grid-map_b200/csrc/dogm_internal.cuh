@@ -490,6 +490,35 @@ void launch_end(dogm_handle* h, int id);
 constexpr int kTraceSlots = 2 * K_COUNT;
 static __constant__ unsigned long long* c_trace; // one copy per translation unit, bound by trace_bind_*()
 
+// L2 eviction priorities per access (no set-aside, no access-policy window): the 64 MB of particle records are written by the
+// prediction and gathered twice later in the cycle (segmented sums, resampling) - they are stored and re-read as evict_last;
+// what is written once and not read again inside the cycle (the GridCell array) goes evict_first.
+__device__ __forceinline__ uint64_t l2_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint(float4* ptr, const float4 v, const uint64_t policy)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_hint(const float4* ptr, const uint64_t policy)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
+
 __device__ __forceinline__ void pdl_prologue(int trace_slot)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -253,7 +253,13 @@ __global__ void __launch_bounds__(kCellBlock, kLazyMeas ? DOGM_CELL_MINBLOCKS_LA
         {
             const int f = j * 32 + lane; // float4 index inside the warp's block: cell f/4, part f%4
             if (warp_cell0 + (f >> 2) < a.C)
+            {
+#ifdef DOGM_NO_L2_HINTS
                 gw[f] = s_out[warp][f & 3][f >> 2];
+#else
+                st_hint(gw + f, s_out[warp][f & 3][f >> 2], l2_evict_first()); // (nobody reads the cells again inside the cycle)
+#endif
+            }
         }
     }
     double total;

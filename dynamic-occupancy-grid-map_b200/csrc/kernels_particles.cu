@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
     const int base = blockIdx.x * kTileItems;
     const float hi = (float)(a.gs - 1);
     const float xm = (float)a.x_move, ym = (float)a.y_move;
+    const uint64_t keep = l2_evict_last(); // the records are gathered twice later in the cycle
 
     for (int b = threadIdx.x; b < a.bins; b += kWideBlock)
         s_hist[b] = 0u;
@@ -383,8 +384,13 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
             }
             const int cell = px + a.gs * py;
             float4* o = reinterpret_cast<float4*>(out + i);
+#ifdef DOGM_NO_L2_HINTS
             o[0] = rec_lo(x, y, cell, as);
             o[1] = make_float4(vx, vy, w, w_leaving);
+#else
+            st_hint(o, rec_lo(x, y, cell, as), keep);
+            st_hint(o + 1, make_float4(vx, vy, w, w_leaving), keep);
+#endif
             key_out[i] = cell;
             if (BUCKET)
             {
@@ -1215,6 +1221,7 @@ __device__ __forceinline__ void segsum_chunk(const int2* __restrict__ spair, con
     float4 hi[kSegPerLane]; // (vx, vy, w, -) of the lane's particles: eight independent sector reads in flight
 #pragma unroll
     for (int j = 0; j < kSegPerLane; j++)
+        // (a plain load: with an evict_last hint on this gather the kernel took 34 instead of 26 us)
         hi[j] = slot[j] >= 0 ? reinterpret_cast<const float4*>(rec + slot[j])[1] : make_float4(0.f, 0.f, 0.f, 0.f);
 
     int kprev = __shfl_up_sync(full, key[kSegPerLane - 1], 1);
@@ -2250,7 +2257,11 @@ __device__ __forceinline__ void resample_block(const ResampleArgs& a, const int 
         if (slot[j] >= 0)
         {
             const float4* p = reinterpret_cast<const float4*>(a.rec + slot[j]);
+#ifdef DOGM_NO_L2_HINTS
             const float4 rlo = __ldg(p), rhi = __ldg(p + 1);
+#else
+            const float4 rlo = ld_hint(p, l2_evict_first()), rhi = ld_hint(p + 1, l2_evict_first()); // (their last use)
+#endif
             st[j] = make_float4(rlo.x, rlo.y, rhi.x, rhi.y);
             cell[j] = __float_as_int(rlo.z);
             as[j] = __float_as_uint(rlo.w);
