@@ -280,17 +280,6 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     keep_first(alloc_zero((void**)&h->blk_age[0], (size_t)h->n_cell_blocks));
     keep_first(alloc_zero((void**)&h->blk_age[1], (size_t)h->n_cell_blocks));
     {
-        // developer switch: the device's L2 fetch granularity (32 / 64 / 128 bytes), see DESIGN.md section 5
-        const char* fg = getenv("DOGM_B200_L2_FETCH");
-        if (fg && atoi(fg) > 0)
-        {
-            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
-            size_t got = 0;
-            cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-            fprintf(stderr, "dogm_b200: L2 fetch granularity %zu bytes\n", got);
-        }
-    }
-    {
         // the shortcut pays where the grid is much larger than what the sensor sees; below ~4e6 cells the cell kernel is bound
         // by latency, not by its stores, and the bookkeeping costs more than the skipped blocks save (measured at 1.44e6 cells).
         // DOGM_B200_NO_QUIET = 1 / 0 forces it off / on (A/B runs, tests)
