@@ -601,7 +601,8 @@ def run_ours(args, dist):
             "achieved": dram_cycle / (ms_per_step * 1e-3) / 1e9,
             "frac": dram_cycle / (ms_per_step * 1e-3) / 1e9 / peak,
             "formula": "sum over the cycle's kernels of ncu dram__bytes_read + dram__bytes_write per launch (profiles/traffic.json, "
-                       "this configuration) / ms_per_step",
+                       "this configuration; ncu flushes the caches in front of every profiled kernel, so what a kernel finds in L2 from its "
+                       "predecessor counts as DRAM traffic here: an upper bound) / ms_per_step",
         },
         "per_kernel_dram_pct": None if not prof else {k: v.get("dram_pct") for k, v in prof.items() if k in kernels},
         "kernels_ms_per_cycle": {k: v["total_ms"] / K for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1]["total_ms"])},
