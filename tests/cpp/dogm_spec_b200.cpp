@@ -270,6 +270,51 @@ static int test_streaming_loop()
     return 0;
 }
 
+static int test_pipelined_grid_cells()
+{ // getGridCellsAsync / waitGridCells (the copy of cycle n's cells runs under cycle n + 1): the same cells as getGridCells(), the
+  // public grid_cell_array follows the buffer the last cycle wrote
+    dogm::GridParams p = spec_params();
+    p.size = 20.0f;
+    p.resolution = 0.2f;
+    p.particle_count = 20000;
+    p.new_born_particle_count = 2000;
+    dogm::LaserSensorParams lp;
+    lp.fov = 120.0f;
+    lp.max_range = 20.0f;
+    lp.resolution = p.resolution;
+    lp.stddev_range = 0.5f;
+    LaserMeasurementGrid generator(lp, p.size, p.resolution);
+    dogm::DOGM blocking(p), pipelined(p);
+    const size_t cells = (size_t)blocking.getGridSize() * blocking.getGridSize();
+    dogm::GridCell* buf[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; k++)
+        CHECK(dogm_host_alloc_pinned((void**)&buf[k], cells * sizeof(dogm::GridCell)) == 0);
+    std::vector<float> scan(40, INFINITY);
+    for (int i = 10; i < 30; i++)
+        scan[i] = 6.0f + 0.1f * i;
+    std::vector<std::vector<dogm::GridCell>> expected;
+    const dogm::GridCell* seen[2] = {nullptr, nullptr};
+    for (int step = 0; step < 6; step++)
+    {
+        dogm::MeasurementCell* meas = generator.generateGrid(scan);
+        blocking.updateGrid(meas, 0.0f, 0.4f * step, 0.0f, 0.1f, true);
+        expected.push_back(blocking.getGridCells());
+        pipelined.updateGrid(meas, 0.0f, 0.4f * step, 0.0f, 0.1f, true);
+        CHECK(pipelined.last_error == 0);
+        if (step > 0)
+        {
+            pipelined.waitGridCells();
+            CHECK(std::memcmp(buf[(step - 1) & 1], expected[step - 1].data(), cells * sizeof(dogm::GridCell)) == 0);
+        }
+        seen[step & 1] = pipelined.grid_cell_array;
+        pipelined.getGridCellsAsync(buf[step & 1]);
+    }
+    pipelined.waitGridCells();
+    CHECK(std::memcmp(buf[1], expected[5].data(), cells * sizeof(dogm::GridCell)) == 0);
+    CHECK(seen[0] != nullptr && seen[1] != nullptr && seen[0] != seen[1]);
+    return 0;
+}
+
 static int test_particles_soa_assignment()
 { // dogm_types.h:103-126: copy() and operator= copy the particles into the target's own block (any mix of host and device);
   // only an empty set adopts the other's block
@@ -365,6 +410,7 @@ int main(int argc, char** argv)
     rc |= test_demo_main();
     rc |= test_streaming_loop();
     rc |= test_particles_soa_assignment();
+    rc |= test_pipelined_grid_cells();
     std::printf(rc == 0 ? "dogm_spec_b200: all passed\n" : "dogm_spec_b200: FAILED\n");
     return rc;
 }

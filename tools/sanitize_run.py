@@ -36,6 +36,14 @@ for (size, res, n, b) in [(20.0, 0.25, 20000, 2000), (13.0, 0.5, 5001, 333)]:
     d.statistical_moments(); d.resampling()
     d.get_grid_cells(); d.get_measurement_cells(); d.get_birth_particles(); d.get_weight_array(); d.get_joint_weight_accum()
     d.get_resampled_indices(); d.export_philox_noise(3)
+    # pipelined read-out: copy stream, two GridCell buffers in turn
+    bufs = [gpu.pinned_empty((d.grid_cell_count,), gpu.GRID_CELL_DTYPE) for _ in range(2)]
+    for c in range(4):
+        z = np.where(rng.uniform(size=37) < 0.6, rng.uniform(2, size * 0.9, 37), np.inf).astype(np.float32)
+        d.update_grid(gen.generate_grid(z), 3.0 + 0.3 * c, 4.0, 0.0, 0.1, device=True, sync=False)
+        d.get_grid_cells_wait()
+        d.get_grid_cells_begin(bufs[c & 1])
+    d.get_grid_cells_wait()
     gen.close(); d.close()
 # band mode: two and three bands on one GPU (outbox compaction, append, halo rows, global normalisers)
 size, res, n, b = 24.0, 0.25, 30000, 3000
