@@ -76,7 +76,12 @@ static void plan_sort(dogm_handle* h)
     while ((1ll << bits) < (long long)h->C)
         bits++;
     h->key_bits = bits;
-    int passes = (bits + kMaxDigitBits - 1) / kMaxDigitBits;
+    // (DOGM_B200_MAX_DIGIT_BITS, tests: narrower digits make a small grid run the three-pass plan of the 16384^2 grid)
+    int max_bits = kMaxDigitBits;
+    if (const char* mb = getenv("DOGM_B200_MAX_DIGIT_BITS"))
+        if (atoi(mb) >= 5 && atoi(mb) <= kMaxDigitBits && (bits + atoi(mb) - 1) / atoi(mb) <= kMaxPasses)
+            max_bits = atoi(mb);
+    int passes = (bits + max_bits - 1) / max_bits;
     if (passes < 1)
         passes = 1;
     h->passes = passes;

@@ -39,11 +39,35 @@ def assert_cells_match(g, e, vel_scale):
         assert np.allclose(g[f], e[f], rtol=1e-3, atol=1e-4 * vel_scale * vel_scale), f
 
 
-def compare_after_cycle(d, o, p, tag):
+def compare_after_cycle(d, o, p, tag, ties=0, draws=None):
     N = d.particle_count
-    assert_particles_equal(d.get_particles(), o.particles, f"{tag} particles")
+    if ties:
+        # Millions of weights spanning more than 2^29: the double sums of the two sides round differently in their last bits
+        # (the comment at the CDF check below), and a draw that falls within that distance of a CDF entry picks the neighbouring
+        # ancestor.  At most `ties` such draws are accepted, each one checked to be such a tie; the populations must agree
+        # everywhere else, and the handle continues from the oracle's population so that the two stay in step.
+        ga, oa = d.get_resampled_indices(), o.resampled_idx
+        bad = np.flatnonzero(ga != oa)
+        assert bad.size <= ties, f"{tag}: {bad.size} ancestors differ"
+        gc, oc = d.get_joint_weight_accum(), o.joint_weight_accum
+        for i in bad:
+            lo, hi = min(ga[i], oa[i]), max(ga[i], oa[i])
+            assert hi - lo == 1, f"{tag}: slot {i}: ancestors {ga[i]} / {oa[i]} are not neighbours"
+            r = draws(i, gc[-1])
+            assert abs(gc[lo] - r) <= 1e-10 * abs(r) and abs(oc[lo] - r) <= 1e-10 * abs(r), f"{tag}: slot {i} is no tie"
+        gp, op = d.get_particles(), o.particles
+        keep = np.ones(N, bool)
+        keep[bad] = False
+        assert np.array_equal(gp.grid_cell_idx[keep], op.grid_cell_idx[keep]) and np.array_equal(gp.associated[keep], op.associated[keep])
+        assert np.array_equal(gp.state.view(np.uint32)[keep], op.state.view(np.uint32)[keep]), f"{tag}: states differ"
+        assert np.array_equal(gp.weight.view(np.uint32), op.weight.view(np.uint32)), f"{tag}: weights differ"
+        if bad.size:
+            d.set_particles(type(gp).from_arrays(op.state, op.grid_cell_idx, op.weight, op.associated))
+    else:
+        assert_particles_equal(d.get_particles(), o.particles, f"{tag} particles")
     assert_particles_equal(d.get_birth_particles(), o.birth_particles, f"{tag} birth particles")
-    assert np.array_equal(d.get_resampled_indices(), o.resampled_idx), f"{tag}: ancestor indices differ"
+    if not ties:
+        assert np.array_equal(d.get_resampled_indices(), o.resampled_idx), f"{tag}: ancestor indices differ"
     assert np.array_equal(d.get_weight_array().view(np.uint32), o.weight_array.view(np.uint32)), f"{tag}: weight_array"
     assert np.array_equal(d.get_born_masses().view(np.uint32), o.born_masses.view(np.uint32)), f"{tag}: born masses"
     # Both sides add the same float weights in double, the oracle one after the other, the kernel tile-wise.  While the weights
@@ -51,12 +75,12 @@ def compare_after_cycle(d, o, p, tag):
     # equal to the last bit; with very small weights in the set (a birth weight of 1e-12 next to persistent weights of 1e-4) the
     # two orders round differently in the last bits: a serial double sum of k terms is off by about sqrt(k) * 2^-53 relative,
     # 1e-13 at k = 3e5.  What decides the ancestors is checked bit for bit above.
-    assert np.allclose(d.get_joint_weight_accum(), o.joint_weight_accum, rtol=1e-12, atol=0), f"{tag}: cdf"
+    assert np.allclose(d.get_joint_weight_accum(), o.joint_weight_accum, rtol=1e-11 if ties else 1e-12, atol=0), f"{tag}: cdf"
     assert_cells_match(d.get_grid_cells(), o.grid_cells, p.stddev_velocity)
     assert (d.get_position_x(), d.get_position_y(), d.get_yaw()) == o.position
 
 
-def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, systematic=False, **over):
+def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, systematic=False, ties=0, **over):
     rng = np.random.default_rng(seed)
     p = make_params(gpu, size, res, n, b, **over)
     po = make_params(orc, size, res, n, b, **over)
@@ -75,7 +99,11 @@ def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, m
         x, y = ego[0] * c, ego[1] * c
         d.update_grid(meas, x, y, 0.0, dt, device=False)
         o.update_grid(meas.view(orc.MEAS_CELL_DTYPE), x, y, 0.0, dt)
-        compare_after_cycle(d, o, p, f"cycle {c}")
+        if systematic:  # the offset of output slot i: (i + u) * total / N in double (one fraction for all slots)
+            draws = lambda i, total, u=float(ru[0]): (float(i) + u) * (total / n)
+        else:  # injected: float(total) * u_i in float, resampling.cu:34-47
+            draws = lambda i, total, ru=ru: float(np.float32(total) * ru[i])
+        compare_after_cycle(d, o, p, f"cycle {c}", ties=ties, draws=draws)
     d.close()
     o.close()
 
@@ -117,6 +145,23 @@ def test_free_running_systematic_resampling(gpu, orc, size, res, n, b, ego, over
     next population and everything downstream bit for bit, over free-running cycles with shifts - ragged sizes, two particles,
     no birth particles, long runs of copies of one ancestor."""
     free_run(gpu, orc, size, res, n, b, cycles=5, seed=41, ego=ego, systematic=True, **over)
+
+
+def test_free_running_three_pass_sort(gpu, orc, monkeypatch):
+    """Cell keys of more than 24 bits (the 16384^2 grid: 28) are sorted in three passes; with the digit width limited to 5 bits
+    (DOGM_B200_MAX_DIGIT_BITS) a 128 x 128 grid (14 key bits) takes the same plan: same order, ranges, ancestors as the oracle."""
+    monkeypatch.setenv("DOGM_B200_MAX_DIGIT_BITS", "5")
+    free_run(gpu, orc, 64.0, 0.5, 100000, 10000, cycles=4, seed=19, ego=(0.3, 0.8))
+    free_run(gpu, orc, 64.0, 0.5, 4097, 513, cycles=3, seed=20, ego=(-0.5, 0.25), systematic=True)
+
+
+@pytest.mark.parametrize("systematic", [False, True])
+def test_free_running_more_cdf_tiles_than_resident_ctas(gpu, orc, systematic):
+    """4.4e6 joint-weight entries = 1075 CDF tiles: more than the chained scan keeps resident at once (its CTAs walk over the
+    tickets), more than the flat look-back takes (groups of 256 tiles + group prefixes), and no window starts for the
+    resampling CTAs (they search) - the paths the 4096^2 and 16384^2 grids run, here against the oracle; 260 particles per cell
+    on average, so most cells span several chunks of the segmented reduction."""
+    free_run(gpu, orc, 64.0, 0.5, 4_300_000, 100_000, cycles=3, seed=23, ego=(0.3, 0.8), systematic=systematic, ties=4)
 
 
 def test_free_running_config1_reference_demo(gpu, orc):
