@@ -80,7 +80,8 @@ def compare_after_cycle(d, o, p, tag, ties=0, draws=None):
     assert (d.get_position_x(), d.get_position_y(), d.get_yaw()) == o.position
 
 
-def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, systematic=False, ties=0, **over):
+def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, meas_every=1, systematic=False, ties=0, free_level=0.3,
+             **over):
     rng = np.random.default_rng(seed)
     p = make_params(gpu, size, res, n, b, **over)
     po = make_params(orc, size, res, n, b, **over)
@@ -92,7 +93,7 @@ def free_run(gpu, orc, size, res, n, b, cycles, seed, ego=(0.0, 0.45), dt=0.1, m
     meas = None
     for c in range(cycles):
         if c % meas_every == 0:
-            meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, gs, rng)
+            meas = synthetic_meas(gpu.MEAS_CELL_DTYPE, gs, rng, free_level=free_level)
         pn, bn, iv, ru = cycle_noise(rng, n, b, p)
         d.set_noise(pn, bn, iv, ru)
         o.set_noise(pn, bn, iv, ru)
@@ -162,6 +163,15 @@ def test_free_running_more_cdf_tiles_than_resident_ctas(gpu, orc, systematic):
     resampling CTAs (they search) - the paths the 4096^2 and 16384^2 grids run, here against the oracle; 260 particles per cell
     on average, so most cells span several chunks of the segmented reduction."""
     free_run(gpu, orc, 64.0, 0.5, 4_300_000, 100_000, cycles=3, seed=23, ego=(0.3, 0.8), systematic=systematic, ties=4)
+
+
+def test_free_running_4096_grid_12_bit_digits_and_quiet_blocks(gpu, orc):
+    """4096 x 4096 cells (BASELINE.json configs[2]'s grid) with few particles: 24 key bits = two sort passes of 4096 bins, the
+    widest digits there are, and from the third cycle on the cell kernel's shortcut for blocks in which nothing happens - both
+    against the oracle, cell by cell (the property tests of test_gpu_fullsize.py run this grid with its 2.2e7 particles)."""
+    # (no free mass outside the occupied blobs: most blocks of 256 cells see no particles, no measurement and no free mass)
+    free_run(gpu, orc, 409.6, 0.1, 200_000, 20_000, cycles=5, seed=29, ego=(0.0, 0.0), meas_every=5, free_level=0.0)
+    free_run(gpu, orc, 409.6, 0.1, 200_000, 20_000, cycles=2, seed=30, ego=(0.0, 0.45))
 
 
 def test_free_running_config1_reference_demo(gpu, orc):
