@@ -301,6 +301,10 @@ static int create_impl(const dogm_params* params, const dogm_band_config* band, 
     }
     // bucket sort: when the grouping table [tiles][buckets] stays small (no bands: their particle counts change per cycle)
     h->hist0_bucket = false;
+    {
+        const char* sm = getenv("DOGM_B200_SORT");
+        h->sort_fuse_off = sm && !strcmp(sm, "radix");
+    }
     h->bucket.enabled = false;
     h->bucket.samples_valid = false;
     h->bucket.bins = 0;

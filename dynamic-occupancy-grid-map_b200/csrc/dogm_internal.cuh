@@ -387,6 +387,7 @@ struct dogm_handle
     int tiles;
     bool hist0_valid; // pass-0 tile histograms were produced by the prediction kernel for the current keys
     bool hist0_bucket; // ... and they are histograms over the buckets of the bucket sort (not over the first radix digit)
+    bool sort_fuse_off; // DOGM_B200_SORT=radix: keep the separate table scans / pair histogram for few tiles as well (A/B, tests)
     // Bucket sort (kernels_particles.cu, "Bucket sort"): the population enters a cycle in cell order, so the cells of every
     // 4096th particle are splitters for the new keys; grouping pass by bucket + one counting sort per bucket replace the radix
     // passes.  Used when the keys come from the prediction kernel of a handle without bands and the tables stay small.
@@ -584,6 +585,7 @@ int run_birth_fill(dogm_handle* h, bool fused_scan = false); // birth particles 
 int run_resampling(dogm_handle* h);
 int run_cdf(dogm_handle* h);            // joint weight CDF only (first half of run_resampling)
 int run_resample_gather(dogm_handle* h); // ancestor search + gather (second half)
+bool sort_fused(const dogm_handle* h);
 int run_band_outbox(dogm_handle* h); // compacts the particles k_predict flagged into the send boxes, in slot order
 int run_band_append(dogm_handle* h, int n_from_lo, int n_from_hi);
 // device-paced band cycle (kernels_particles.cu): the three message exchanges and the pull of the neighbours' records

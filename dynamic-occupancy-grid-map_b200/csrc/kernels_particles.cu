@@ -55,6 +55,8 @@ struct PredictArgs
     int bins;
     uint32_t mask;
     double* leave_cnt[2]; // band mode: per tile, the particles leaving through the lower / upper edge (input of the outbox scan)
+    uint32_t* clear[2];   // few tiles (fused sort passes): the tile histograms of the later passes, cleared here (filled with atomics)
+    int clear_n[2];
     // bucket sort (BUCKET variant): bucket number per particle, tile histogram over the buckets
     uint16_t* bkt_out;  // [n] bucket number per slot
     const int* plan_key; // the cycle's splitters (BucketPlan, below)
@@ -331,6 +333,10 @@ __global__ void __launch_bounds__(kWideBlock) k_predict(PredictArgs a)
         s_hist[b] = 0u;
     if (threadIdx.x < 2)
         s_leave[threadIdx.x] = 0u;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        for (int b = blockIdx.x * kWideBlock + threadIdx.x; b < a.clear_n[k]; b += gridDim.x * kWideBlock)
+            a.clear[k][b] = 0u;
     __syncthreads();
 
 #pragma unroll
@@ -691,13 +697,19 @@ struct ScatterArgs
     const uint32_t* table; // this pass: final position of the first key per (tile, digit), from k_hist_scan
     const int* n_dev;      // device-paced band cycle: the item count lives on the device (n is an upper bound for the grid)
     const uint16_t* digit_in; // SRC 2: the digit (bucket number) per slot
+    // FUSE (few tiles: the cycle is bound by launch latency): `table` holds the raw counts [tiles][bins] and every CTA scans the
+    // columns itself; the tile histogram of the NEXT pass is added up with atomics while the pairs are stored (next_hist was
+    // cleared by the prediction kernel), so neither k_hist_scan nor k_pair_tile_hist is launched
+    int tiles;
+    uint32_t* next_hist; // [tiles][next_bins] or null (last pass)
+    int next_bins, next_shift;
 };
 
 // SRC 0: first radix pass (keys in slot order, digits nearly all different: ballot ranking)
 // SRC 1: later radix passes ((key, slot) pairs grouped by cell already: MATCH.ANY ranking)
 // SRC 2: grouping pass of the bucket sort (keys in slot order + the bucket number k_predict computed per slot; a warp's
 //        particles fall into a handful of buckets: MATCH.ANY ranking, long contiguous runs in the output)
-template <int SRC>
+template <int SRC, bool FUSE>
 __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int tile, unsigned short* s_cnt /* [warps][bins] */)
 {
     constexpr bool FIRST = SRC == 0;
@@ -726,6 +738,73 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
         const int nz = a.bins * kWarpsPerBlock * (int)sizeof(unsigned short) / (int)sizeof(uint4);
         for (int b = threadIdx.x; b < nz; b += kBlock)
             z[b] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // FUSE: final position of this tile's first key per digit = (keys with a smaller digit) + (same digit in earlier tiles),
+    // from the raw counts of all tiles (a few dozen rows, read by every CTA: they sit in L2)
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_cnt + a.bins * kWarpsPerBlock); // [bins] (FUSE only)
+    if (FUSE)
+    {
+        uint32_t* s_tot = s_row + a.bins;
+        __shared__ uint32_t s_ws[kWarpsPerBlock];
+        for (int b = threadIdx.x; b < a.bins; b += kBlock)
+        {
+            uint32_t before = 0, total = 0;
+            const uint32_t* col = a.table + b;
+            int t = 0;
+            for (; t + 16 <= a.tiles; t += 16)
+            { // (16 rows in flight per thread: the loop is a chain of L2 round trips)
+                uint32_t v[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    v[k] = __ldcg(col + (size_t)(t + k) * a.bins);
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                {
+                    total += v[k];
+                    before += t + k < tile ? v[k] : 0u;
+                }
+            }
+            for (; t < a.tiles; t++)
+            {
+                const uint32_t v = __ldcg(col + (size_t)t * a.bins);
+                total += v;
+                before += t < tile ? v : 0u;
+            }
+            s_row[b] = before;
+            s_tot[b] = total;
+        }
+        __syncthreads();
+        // exclusive scan of the digit totals: thread t owns `per` consecutive digits (bins <= 4 * 256)
+        const int per = a.bins >= kBlock ? a.bins / kBlock : 1;
+        const int e0 = (int)threadIdx.x * per;
+        uint32_t cnt[4], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            cnt[k] = (k < per && e0 + k < a.bins) ? s_tot[e0 + k] : 0u;
+            sum += cnt[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(full, incl, d);
+            if (lane >= d)
+                incl += u;
+        }
+        if (lane == 31)
+            s_ws[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < warp; w++)
+            run += s_ws[w];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < per && e0 + k < a.bins)
+            {
+                s_row[e0 + k] += run;
+                run += cnt[k];
+            }
     }
     __syncthreads();
 
@@ -798,7 +877,7 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
 
     // store phase: the inputs are read again (L1 / L2 hits) instead of being kept in registers across the ranking;
     // all loads of a batch of 8 are issued before the first store (the stores could alias them for the compiler)
-    const uint32_t* __restrict__ row = a.table + (size_t)tile * a.bins; // final position of this tile's first key per bin
+    const uint32_t* __restrict__ row = FUSE ? s_row : a.table + (size_t)tile * a.bins; // final position of this tile's first key per bin
 #pragma unroll
     for (int half = 0; half < 2; half++)
     {
@@ -835,21 +914,27 @@ __device__ __forceinline__ void scatter_tile(const ScatterArgs& a, const int til
             const int r = half * 8 + q;
             const uint32_t digit = DIG ? dig[DIG ? q : 0] : (((uint32_t)key[q] >> a.shift) & a.mask);
             const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
-            dest[q] = __ldg(row + digit) + my_cnt[digit] + rk;
+            dest[q] = (FUSE ? row[digit] : __ldg(row + digit)) + my_cnt[digit] + rk;
         }
 #pragma unroll
         for (int q = 0; q < 8; q++)
         {
             const int i = warp_base + (half * 8 + q) * 32 + lane;
             if (i < a.n)
+            {
                 pair_out[dest[q]] = make_int2(key[q], slot[q]);
+                if (FUSE && a.next_hist)
+                    atomicAdd(a.next_hist + (size_t)(dest[q] / kTileItems) * a.next_bins +
+                                  (((uint32_t)key[q] >> a.next_shift) & (uint32_t)(a.next_bins - 1)),
+                              1u);
+            }
         }
     }
 }
 
 // LOOP = false: one CTA per tile (the grid is the number of tiles).  LOOP = true (device-paced band cycle): the item count is
 // read from the device, the grid is the host's estimate and the CTAs walk over the tiles.
-template <int SRC, bool LOOP>
+template <int SRC, bool LOOP, bool FUSE = false>
 __global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
 {
     pdl_prologue(K_SCATTER * 2 + (SRC == 1 ? 1 : 0));
@@ -857,7 +942,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
     unsigned short* s_cnt = (unsigned short*)s_raw;
     if (!LOOP)
     {
-        scatter_tile<SRC>(a_in, (int)blockIdx.x, s_cnt);
+        scatter_tile<SRC, FUSE>(a_in, (int)blockIdx.x, s_cnt);
         return;
     }
     ScatterArgs a = a_in;
@@ -866,7 +951,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scatter(const ScatterArgs a_in)
     const int tiles = (a.n + kTileItems - 1) / kTileItems;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
     {
-        scatter_tile<SRC>(a, tile, s_cnt);
+        scatter_tile<SRC, false>(a, tile, s_cnt);
         __syncthreads();
     }
 }
@@ -2390,6 +2475,20 @@ int ensure_soa(dogm_handle* h)
     return (int)cudaGetLastError();
 }
 
+// Few tiles (the 250^2 demo size: 74): the cycle is bound by the latency of its dependent launches, and the table scans and the
+// pair histogram of the sort are three of them - the scatter kernels then scan the (small) tables themselves and count the next
+// pass's digits while they store (k_scatter FUSE).
+constexpr int kFuseMaxTiles = 128, kFuseMaxBins = 1024;
+bool sort_fused(const dogm_handle* h)
+{
+    if (h->band.enabled || h->bucket.enabled || h->tiles > kFuseMaxTiles || h->sort_fuse_off)
+        return false;
+    for (int p = 0; p < h->passes; p++)
+        if (h->digit_bins[p] > kFuseMaxBins)
+            return false;
+    return true;
+}
+
 int run_predict(dogm_handle* h, float dt)
 {
     if (h->N <= 0)
@@ -2423,6 +2522,12 @@ int run_predict(dogm_handle* h, float dt)
     a.mask = (uint32_t)(h->digit_bins[0] - 1);
     a.leave_cnt[0] = h->band.out_cnt[0];
     a.leave_cnt[1] = h->band.out_cnt[1];
+    for (int k = 0; k < 2; k++)
+    {
+        const bool on = sort_fused(h) && k + 1 < h->passes;
+        a.clear[k] = on ? h->hist[k + 1] : nullptr;
+        a.clear_n[k] = on ? h->tiles * h->digit_bins[k + 1] : 0;
+    }
     const bool bucket = h->bucket.enabled;
     a.bkt_out = h->bucket.bkt;
     a.plan_key = h->bucket.plan_key;
@@ -2504,6 +2609,12 @@ int run_assignment(dogm_handle* h)
             launch_chained(h->stream, k_key_tile_hist, h->tiles, kWideBlock, smem, h->key0, N, h->hist[0], h->digit_bins[0], mask, n_dev);
         h->rec_valid = true;
     }
+    const bool fused = sort_fused(h) && !n_dev;
+    if (fused && !h->hist0_valid)
+    { // (the tables of the later passes are cleared by the prediction kernel; without one in front of this sort, here)
+        for (int p = 1; p < h->passes; p++)
+            cudaMemsetAsync(h->hist[p], 0, (size_t)h->tiles * h->digit_bins[p] * sizeof(uint32_t), h->stream);
+    }
     const bool bucket = h->hist0_valid && h->hist0_bucket;
     if (bucket)
     { // bucket sort: scan of the grouping table, grouping pass (stable, by bucket), one counting sort per bucket
@@ -2523,6 +2634,10 @@ int run_assignment(dogm_handle* h)
         a.bins = bins;
         a.table = h->hist[0];
         a.n_dev = nullptr;
+        a.tiles = h->tiles;
+        a.next_hist = nullptr;
+        a.next_bins = 1;
+        a.next_shift = 0;
         a.digit_in = h->bucket.bkt;
         {
             LaunchScope ls(h, K_SCATTER, 14.0 * N);
@@ -2543,6 +2658,31 @@ int run_assignment(dogm_handle* h)
     for (int p = 0; p < (bucket ? 0 : h->passes); p++)
     {
         const int bins = h->digit_bins[p];
+        if (fused)
+        { // one launch per pass: table scan, ranking, scatter, next pass's tile histogram
+            ScatterArgs a;
+            a.key_in = h->key0;
+            a.pair_in = p > 0 ? h->pairs[(p - 1) & 1] : nullptr;
+            a.pair_out = h->pairs[p & 1];
+            a.n = N;
+            a.shift = h->digit_shift[p];
+            a.mask = (uint32_t)(bins - 1);
+            a.bins = bins;
+            a.table = h->hist[p];
+            a.n_dev = nullptr;
+            a.digit_in = nullptr;
+            a.tiles = h->tiles;
+            a.next_hist = p + 1 < h->passes ? h->hist[p + 1] : nullptr;
+            a.next_bins = p + 1 < h->passes ? h->digit_bins[p + 1] : 1;
+            a.next_shift = p + 1 < h->passes ? h->digit_shift[p + 1] : 0;
+            const size_t smem = (size_t)bins * kWarpsPerBlock * sizeof(unsigned short) + 2 * (size_t)bins * sizeof(uint32_t);
+            LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N + 4.0 * h->tiles * bins * h->tiles);
+            if (p == 0)
+                launch_chained(h->stream, k_scatter<0, false, true>, h->tiles, kBlock, smem, a);
+            else
+                launch_chained(h->stream, k_scatter<1, false, true>, h->tiles, kBlock, smem, a);
+            continue;
+        }
         if (p > 0)
         {
             LaunchScope ls(h, K_TILE_HIST, 8.0 * N);
@@ -2565,6 +2705,10 @@ int run_assignment(dogm_handle* h)
         a.table = h->hist[p];
         a.n_dev = n_dev;
         a.digit_in = nullptr;
+        a.tiles = h->tiles;
+        a.next_hist = nullptr;
+        a.next_bins = 1;
+        a.next_shift = 0;
         const size_t smem = (size_t)bins * kWarpsPerBlock * sizeof(unsigned short);
         {
             LaunchScope ls(h, K_SCATTER, (p == 0 ? 12.0 : 16.0) * N);
@@ -2667,6 +2811,8 @@ int configure_kernels()
     e = e ? e : (int)cudaFuncSetAttribute(k_scatter<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     e = e ? e : (int)cudaFuncSetAttribute(k_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     e = e ? e : (int)cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, kBucketSmemBytes);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = e ? e : (int)cudaFuncSetAttribute(k_scatter<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     return e;
 }
 

@@ -148,6 +148,16 @@ def test_free_running_systematic_resampling(gpu, orc, size, res, n, b, ego, over
     free_run(gpu, orc, size, res, n, b, cycles=5, seed=41, ego=ego, systematic=True, **over)
 
 
+@pytest.mark.parametrize("size,res,n,b,ego", [(64.0, 0.5, 100000, 10000, (0.3, 0.8)), (10.0, 0.25, 20000, 2000, (0.0, 0.45)),
+                                              (50.0, 0.2, 300000, 30000, (0.0, 0.4))])
+def test_free_running_separate_scan_kernels_at_small_sizes(gpu, orc, monkeypatch, size, res, n, b, ego):
+    """Up to 128 sort tiles the scatter kernels scan the tile histograms themselves and count the next pass's digits while they
+    store (k_scatter FUSE: three launches fewer per cycle - what every small case of this file runs).  DOGM_B200_SORT=radix keeps
+    the separate kernels the large sizes use (k_hist_scan, k_pair_tile_hist) at these sizes too: same results."""
+    monkeypatch.setenv("DOGM_B200_SORT", "radix")
+    free_run(gpu, orc, size, res, n, b, cycles=4, seed=51, ego=ego)
+
+
 def test_free_running_three_pass_sort(gpu, orc, monkeypatch):
     """Cell keys of more than 24 bits (the 16384^2 grid: 28) are sorted in three passes; with the digit width limited to 5 bits
     (DOGM_B200_MAX_DIGIT_BITS) a 128 x 128 grid (14 key bits) takes the same plan: same order, ranges, ancestors as the oracle."""
