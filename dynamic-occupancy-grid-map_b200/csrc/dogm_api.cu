@@ -1037,6 +1037,11 @@ extern "C" int dogm_set_grid_cells(dogm_handle* h, const dogm_grid_cell* cells, 
     if (!h || !cells)
         return DOGM_ERR_INVALID_ARGUMENT;
     h->dyn_list_valid = false;
+    if (h->grid_alt && h->grid_copy_busy[0])
+    { // a pipelined read-out of this buffer may still be on its way: it gets the cells it was begun for
+        DOGM_CHECK(cudaStreamWaitEvent(h->stream, h->grid_copy_ev[0], 0));
+        h->grid_copy_busy[0] = false;
+    }
     DOGM_CHECK(cudaMemsetAsync(h->blk_age[0], 0, (size_t)h->n_cell_blocks, h->stream)); // (no block is known to be empty any more)
     DOGM_CHECK((cudaError_t)copy_in(h->grid, cells, (size_t)h->C * sizeof(dogm_grid_cell), on_device, h->stream));
     int e = run_extract_free_mass(h);
